@@ -1,0 +1,390 @@
+// Trie-constrained beam search on the device: log-sum-exp, CSR trie gather, per-user top-2K,
+// BeamSearchScorer.process / finalize.  No host round trip per step.
+//
+// Semantics restated from transformers==4.26.0 (the reference's pinned dependency, reference
+// requirements.txt:1; reached through `super().generate(...)` at src/model/gram.py:93-99):
+//   beam_search          generation/utils.py     log_softmax over the FULL vocabulary, then the
+//                                                logits processor, then + beam_scores, view(B, K*V),
+//                                                topk(2K, sorted)
+//   PrefixConstrained... generation/logits_process.py   -inf mask outside Trie.get(prefix)
+//                                                (reference src/utils/generation_trie.py:44-68,89-95);
+//                                                the mask is applied AFTER the full-vocab
+//                                                log-softmax, scores are not renormalised
+//   BeamSearchScorer     generation/beam_search.py      process(): EOS candidates ranked < K become
+//                                                hypotheses, the first K non-EOS candidates become the
+//                                                next beams; BeamHypotheses.add / is_done; finalize()
+// Because only trie children can survive the mask, the candidate set of a user is the union of the
+// children of its K live trie nodes (<= K * max_fanout) instead of K*V masked scores.
+//
+// Documented divergence (SURVEY.md section 8(c) "tie/UB zones"): when a user has fewer than 2K finite
+// candidates HF's topk returns -inf entries whose token ids depend on torch.topk tie order; here such
+// fillers are dead beams (score -inf, token pad, never EOS).  They can only surface in the returned
+// top-K when the trie holds fewer than K reachable items.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace gram {
+
+// ------------------------------------------------------------------------------------------------
+// lse[row] = log(sum(exp(logits[row, :])))  computed as max + log(sum(exp(x - max)))
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) lse_rows_kernel(const float* __restrict__ logits, float* __restrict__ lse, int V) {
+  __shared__ float red[8];
+  __shared__ float bcast;
+  const float* x = logits + (size_t)blockIdx.x * V;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  float mx = -INFINITY;
+  for (int i = tid * 4; i < V; i += 1024) {
+    const float4 v = load4(x + i);
+    mx = fmaxf(fmaxf(mx, fmaxf(v.x, v.y)), fmaxf(v.z, v.w));
+  }
+  mx = warp_max(mx);
+  if (lane == 0) red[wid] = mx;
+  __syncthreads();
+  if (tid == 0) {
+    float m = red[0];
+    for (int i = 1; i < 8; ++i) m = fmaxf(m, red[i]);
+    bcast = m;
+  }
+  __syncthreads();
+  mx = bcast;
+  float sum = 0.f;
+  for (int i = tid * 4; i < V; i += 1024) {
+    const float4 v = load4(x + i);
+    sum += expf(v.x - mx) + expf(v.y - mx) + expf(v.z - mx) + expf(v.w - mx);
+  }
+  sum = warp_sum(sum);
+  __syncthreads();
+  if (lane == 0) red[wid] = sum;
+  __syncthreads();
+  if (tid == 0) {
+    float sacc = 0.f;
+    for (int i = 0; i < 8; ++i) sacc += red[i];
+    lse[blockIdx.x] = mx + logf(sacc);
+  }
+}
+
+cudaError_t lse_rows(const float* logits, float* lse, int R, int V, cudaStream_t s) {
+  if (R <= 0) return cudaSuccess;
+  if (V & 3) return cudaErrorInvalidValue;
+  lse_rows_kernel<<<R, 256, 0, s>>>(logits, lse, V);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+__global__ void beam_init_kernel(BeamState bs, int root, int users, int start_tok) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  const int R = users * bs.K;
+  if (r < R) {
+    bs.beam_score[0][r] = (r % bs.K == 0) ? 0.f : -1e9f;
+    bs.node[0][r] = root;
+    bs.seq[0][(size_t)r * bs.max_length] = start_tok;
+    bs.tok[r] = start_tok;
+  }
+  if (r < users) {
+    bs.n_hyp[r] = 0;
+    bs.worst[r] = 1e9;
+    bs.next_seqno[r] = 0;
+    bs.done[r] = 0;
+  }
+}
+
+cudaError_t beam_init(BeamState bs, TrieCSR trie, int users, int start_tok, cudaStream_t s) {
+  const int R = users * bs.K;
+  beam_init_kernel<<<(R + 255) / 256, 256, 0, s>>>(bs, trie.root, users, start_tok);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+// hypothesis container (BeamHypotheses of transformers 4.26, early_stopping=False)
+// ------------------------------------------------------------------------------------------------
+struct HypView {
+  double* score; int* len; int* seqno; int* tok;   // K+1 slots
+  int* n; double* worst; int* next_seqno;
+  int K, max_length;
+};
+
+__device__ inline HypView hyp_view(const BeamState& bs, int u) {
+  HypView hv;
+  const int S = bs.K + 1;
+  hv.score = bs.hyp_score + (size_t)u * S;
+  hv.len = bs.hyp_len + (size_t)u * S;
+  hv.seqno = bs.hyp_seqno + (size_t)u * S;
+  hv.tok = bs.hyp_tok + (size_t)u * S * bs.max_length;
+  hv.n = bs.n_hyp + u;
+  hv.worst = bs.worst + u;
+  hv.next_seqno = bs.next_seqno + u;
+  hv.K = bs.K;
+  hv.max_length = bs.max_length;
+  return hv;
+}
+
+// BeamHypotheses.add: score = sum_logprobs / len ** length_penalty (len counts the start token, not EOS)
+__device__ void hyp_add(HypView hv, const int* tokens, int len, float sum_logprobs, const double* len_pow) {
+  const double score = (double)sum_logprobs / len_pow[len];
+  int n = *hv.n;
+  if (n < hv.K || score > *hv.worst) {
+    hv.score[n] = score;
+    hv.len[n] = len;
+    hv.seqno[n] = (*hv.next_seqno)++;
+    for (int i = 0; i < len; ++i) hv.tok[(size_t)n * hv.max_length + i] = tokens[i];
+    ++n;
+    if (n > hv.K) {
+      // python: sorted([(s, idx)])[0] -> lowest score, earliest inserted among equals
+      int imin = 0;
+      for (int i = 1; i < n; ++i)
+        if (hv.score[i] < hv.score[imin] || (hv.score[i] == hv.score[imin] && hv.seqno[i] < hv.seqno[imin])) imin = i;
+      const int last = n - 1;
+      if (imin != last) {
+        hv.score[imin] = hv.score[last];
+        hv.len[imin] = hv.len[last];
+        hv.seqno[imin] = hv.seqno[last];
+        for (int i = 0; i < hv.len[last]; ++i)
+          hv.tok[(size_t)imin * hv.max_length + i] = hv.tok[(size_t)last * hv.max_length + i];
+      }
+      --n;
+      double w = hv.score[0];
+      for (int i = 1; i < n; ++i) w = fmin(w, hv.score[i]);
+      *hv.worst = w;
+    } else {
+      *hv.worst = fmin(score, *hv.worst);
+    }
+    *hv.n = n;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// one step: candidates -> top-2K -> scorer.  One CTA per user.
+// ------------------------------------------------------------------------------------------------
+constexpr int BEAM_THREADS = 256;
+constexpr int BEAM_KMAX = 64;
+
+size_t beam_step_smem(int cand_cap) { return (size_t)cand_cap * sizeof(unsigned long long); }
+
+__global__ void __launch_bounds__(BEAM_THREADS)
+beam_step_kernel(BeamState bs, TrieCSR trie, const float* __restrict__ logits, const float* __restrict__ lse,
+                 int users, int t, int cand_cap) {
+  extern __shared__ __align__(16) unsigned long long keys[];
+  __shared__ int pre[BEAM_KMAX + 1];
+  __shared__ int sel_parent[BEAM_KMAX], sel_tok[BEAM_KMAX], sel_node[BEAM_KMAX];
+  __shared__ float sel_score[BEAM_KMAX];
+  __shared__ int n_sort_s;
+
+  const int u = blockIdx.x, tid = threadIdx.x;
+  const int K = bs.K, V = bs.V, ML = bs.max_length;
+  const int R = users * K, base = u * K;
+  const int cur = t & 1, nxt = cur ^ 1;
+  const int cur_len = t + 1;
+  const float* score_c = bs.beam_score[cur];
+  const int* node_c = bs.node[cur];
+  const int* seq_c = bs.seq[cur];
+  const int* anc_c = bs.anc[cur];
+
+  if (bs.tap_lse) {
+    for (int b = tid; b < K; b += BEAM_THREADS) {
+      bs.tap_lse[(size_t)t * R + base + b] = lse[base + b];
+      bs.tap_score[(size_t)t * R + base + b] = score_c[base + b];
+    }
+    for (int i = tid; i < K * ML; i += BEAM_THREADS)
+      bs.tap_seq[((size_t)t * R + base) * ML + i] = (i % ML) < cur_len ? seq_c[(size_t)base * ML + i] : 0;
+  }
+
+  const bool frozen = bs.done[u] != 0;
+  if (frozen) {
+    // hypotheses of this user are final (scorer pads done batches); keep rows well-formed but dead
+    for (int b = tid; b < K; b += BEAM_THREADS) {
+      bs.beam_score[nxt][base + b] = 0.f;
+      bs.node[nxt][base + b] = -1;
+      bs.tok[base + b] = bs.pad;
+    }
+    for (int i = tid; i < K * ML; i += BEAM_THREADS) {
+      const int b = i / ML, j = i % ML;
+      bs.seq[nxt][(size_t)base * ML + i] = (j == cur_len) ? bs.pad : seq_c[(size_t)base * ML + i];
+      bs.anc[nxt][(size_t)base * ML + i] = (j == t) ? b : anc_c[(size_t)base * ML + i];
+    }
+    return;
+  }
+
+  // ---- enumerate candidates: children of every live beam's trie node ----
+  if (tid == 0) {
+    int run = 0;
+    for (int b = 0; b < K; ++b) {
+      pre[b] = run;
+      const int nd = node_c[base + b];
+      const float sc = score_c[base + b];
+      if (nd >= 0 && sc > -INFINITY) run += trie.child_offsets[nd + 1] - trie.child_offsets[nd];
+    }
+    pre[K] = run;
+    int n = 2;
+    while (n < run) n <<= 1;
+    n_sort_s = n;
+    if (run > cand_cap) { atomicExch(bs.err, 1); }
+  }
+  __syncthreads();
+  const int C = min(pre[K], cand_cap);
+  const int n_sort = min(n_sort_s, cand_cap);
+  for (int c = tid; c < n_sort; c += BEAM_THREADS) {
+    unsigned long long key = 0ull;
+    if (c < C) {
+      int b = 0;
+      while (pre[b + 1] <= c) ++b;                         // K <= 64, linear search
+      const int nd = node_c[base + b];
+      const int e = trie.child_offsets[nd] + (c - pre[b]);
+      const int tok = trie.child_tokens[e];
+      const int row = base + b;
+      float s = (logits[(size_t)row * V + tok] - lse[row]) + score_c[row];
+      if (!(s == s)) s = -INFINITY;
+      const unsigned int idx = (unsigned int)b * (unsigned int)V + (unsigned int)tok;
+      key = ((unsigned long long)float_key(s) << 32) | (unsigned long long)(0xFFFFFFFFu - idx);
+    }
+    keys[c] = key;
+  }
+  __syncthreads();
+  // ---- bitonic sort ascending (best candidate ends at n_sort-1) ----
+  for (int k = 2; k <= n_sort; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = tid; i < n_sort; i += BEAM_THREADS) {
+        const int ixj = i ^ j;
+        if (ixj > i) {
+          const unsigned long long a = keys[i], b = keys[ixj];
+          const bool up = ((i & k) == 0);
+          if ((a > b) == up) { keys[i] = b; keys[ixj] = a; }
+        }
+      }
+      __syncthreads();
+    }
+  }
+  // ---- BeamSearchScorer.process for this user ----
+  if (tid == 0) {
+    HypView hv = hyp_view(bs, u);
+    int slot = 0;
+    float best = -INFINITY;
+    for (int rank = 0; rank < 2 * K && slot < K; ++rank) {
+      float s = -INFINITY;
+      int b = 0, tok = bs.pad, child = -1;
+      if (rank < C) {
+        const unsigned long long key = keys[n_sort - 1 - rank];
+        s = key_float((unsigned int)(key >> 32));
+        const unsigned int idx = 0xFFFFFFFFu - (unsigned int)(key & 0xFFFFFFFFull);
+        b = (int)(idx / (unsigned int)V);
+        tok = (int)(idx % (unsigned int)V);
+        const int nd = node_c[base + b];
+        for (int e = trie.child_offsets[nd]; e < trie.child_offsets[nd + 1]; ++e)
+          if (trie.child_tokens[e] == tok) { child = trie.child_nodes[e]; break; }
+        if (s == -INFINITY) { tok = bs.pad; child = -1; }   // indistinguishable from a filler
+      }
+      if (rank == 0) best = s;
+      if (tok == bs.eos && s > -INFINITY) {
+        if (rank >= K) continue;
+        hyp_add(hv, seq_c + (size_t)(base + b) * ML, cur_len, s, bs.len_pow);
+      } else {
+        sel_parent[slot] = b; sel_tok[slot] = tok; sel_node[slot] = child; sel_score[slot] = s;
+        ++slot;
+      }
+    }
+    for (; slot < K; ++slot) { sel_parent[slot] = 0; sel_tok[slot] = bs.pad; sel_node[slot] = -1; sel_score[slot] = -INFINITY; }
+    // BeamHypotheses.is_done(best_sum_logprobs = max of the 2K candidate scores, cur_len)
+    if (*hv.n >= K) {
+      const double cur_score = (double)best / bs.len_pow[cur_len];
+      if (*hv.worst >= cur_score) bs.done[u] = 1;
+    }
+  }
+  __syncthreads();
+  for (int b = tid; b < K; b += BEAM_THREADS) {
+    bs.beam_score[nxt][base + b] = sel_score[b];
+    bs.node[nxt][base + b] = sel_node[b];
+    bs.tok[base + b] = sel_tok[b];
+  }
+  for (int i = tid; i < K * ML; i += BEAM_THREADS) {
+    const int b = i / ML, j = i % ML;
+    const int par = sel_parent[b];
+    int tokv = 0;
+    if (j < cur_len) tokv = seq_c[(size_t)(base + par) * ML + j];
+    else if (j == cur_len) tokv = sel_tok[b];
+    bs.seq[nxt][(size_t)base * ML + i] = tokv;
+    int a = 0;
+    if (j < t) a = anc_c[(size_t)(base + par) * ML + j];
+    else if (j == t) a = par;
+    bs.anc[nxt][(size_t)base * ML + i] = a;
+  }
+}
+
+cudaError_t beam_step(BeamState bs, TrieCSR trie, const float* logits, const float* lse, int users, int t,
+                      int cand_cap, cudaStream_t s) {
+  if (users <= 0) return cudaSuccess;
+  if (bs.K > BEAM_KMAX) return cudaErrorInvalidValue;
+  const size_t smem = beam_step_smem(cand_cap);
+  static size_t configured = 0;
+  if (smem > configured) {
+    cudaError_t e = cudaFuncSetAttribute(beam_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    configured = smem;
+  }
+  beam_step_kernel<<<users, BEAM_THREADS, smem, s>>>(bs, trie, logits, lse, users, t, cand_cap);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+// BeamSearchScorer.finalize: one thread per user (tiny, serial by nature)
+// ------------------------------------------------------------------------------------------------
+__global__ void beam_finalize_kernel(BeamState bs, int users, int t_final, int R_ret, long long* __restrict__ out_seq,
+                                     float* __restrict__ out_scores, int* __restrict__ out_width) {
+  const int u = blockIdx.x * blockDim.x + threadIdx.x;
+  if (u >= users) return;
+  const int K = bs.K, ML = bs.max_length;
+  const int cur = t_final & 1;              // buffers holding the beams after the last step
+  const int cur_len = t_final + 1;
+  HypView hv = hyp_view(bs, u);
+  if (!bs.done[u]) {
+    for (int j = 0; j < K; ++j) {
+      const int row = u * K + j;
+      hyp_add(hv, bs.seq[cur] + (size_t)row * ML, cur_len, bs.beam_score[cur][row], bs.len_pow);
+    }
+  }
+  // sorted(beams, key=score) ascending, stable; pop() from the end -> (score desc, insertion desc)
+  int n = *hv.n;
+  int width = 1;
+  for (int rnk = 0; rnk < R_ret; ++rnk) {
+    long long* o = out_seq + ((size_t)u * R_ret + rnk) * ML;
+    for (int i = 0; i < ML; ++i) o[i] = bs.pad;
+    if (n == 0) { out_scores[(size_t)u * R_ret + rnk] = -INFINITY; continue; }
+    int ib = 0;
+    for (int i = 1; i < n; ++i)
+      if (hv.score[i] > hv.score[ib] || (hv.score[i] == hv.score[ib] && hv.seqno[i] > hv.seqno[ib])) ib = i;
+    const int len = hv.len[ib];
+    for (int i = 0; i < len; ++i) o[i] = hv.tok[(size_t)ib * ML + i];
+    if (len < bs.gen_len) o[len] = bs.eos;
+    out_scores[(size_t)u * R_ret + rnk] = (float)hv.score[ib];
+    width = max(width, min(len + 1, bs.gen_len));
+    // remove ib (order of the remainder is irrelevant: seqno carries insertion order)
+    const int last = n - 1;
+    if (ib != last) {
+      hv.score[ib] = hv.score[last]; hv.len[ib] = hv.len[last]; hv.seqno[ib] = hv.seqno[last];
+      for (int i = 0; i < hv.len[last]; ++i) hv.tok[(size_t)ib * ML + i] = hv.tok[(size_t)last * ML + i];
+    }
+    --n;
+  }
+  atomicMax(out_width, width);
+}
+
+cudaError_t beam_finalize(BeamState bs, int users, int t_final, int R_ret, int64_t* out_seq, float* out_scores,
+                          int* out_width, cudaStream_t s) {
+  if (users <= 0) return cudaSuccess;
+  cudaError_t e = cudaMemsetAsync(out_width, 0, sizeof(int), s);
+  if (e != cudaSuccess) return e;
+  beam_finalize_kernel<<<(users + 63) / 64, 64, 0, s>>>(bs, users, t_final, R_ret, (long long*)out_seq, out_scores, out_width);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+__global__ void forced_step_kernel(BeamState bs, const long long* __restrict__ dec_ids, int q, int t, int R) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r < R) bs.tok[r] = (int)dec_ids[(size_t)r * q + t];
+}
+
+cudaError_t forced_step(BeamState bs, const int64_t* dec_ids, int q, int t, int R, cudaStream_t s) {
+  forced_step_kernel<<<(R + 255) / 256, 256, 0, s>>>(bs, (const long long*)dec_ids, q, t, R);
+  return cudaGetLastError();
+}
+
+}  // namespace gram

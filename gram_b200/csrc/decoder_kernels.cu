@@ -1,0 +1,292 @@
+// Decoder-side attention kernels.
+//
+//  * dec_self_attention: single-token causal self-attention over <= max_length cached positions
+//    (reference src/model/gram_t5_modeling.py:536-540 `cat` of past K/V, :572-621 attention,
+//    decoder layer-0 causal relative bias :397-477).  Instead of physically re-ordering the cache
+//    after every beam step (reference src/model/gram_t5.py:320-348, index_select on every tensor),
+//    each beam row carries an ancestry table anc[row][j] = "row of my user that wrote position j".
+//
+//  * cross_attention (kernel (b) of the north star): decoder cross-attention over the fused FiD
+//    memory (reference src/model/gram_t5_modeling.py:670-705, 549, 572-621).  The reference expands
+//    the encoder memory K-fold per beam (HF `_expand_inputs_for_generation`) and streams K/V of shape
+//    (B*K) x H x S x dk per layer per step; here the K beams of a user are the rows of ONE problem and
+//    the user's K/V -- written in place by the projection GEMM in packed [token][layer][K|V][head][dk]
+//    order, no concat copy -- is read once.  This file holds the CUDA-core version used by the fp32
+//    parity mode; cross_attention_mma.cu holds the bf16 tensor-core version.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace gram {
+
+// ------------------------------------------------------------------------------------------------
+// self-attention: one warp per (row, head)
+// ------------------------------------------------------------------------------------------------
+template <typename T, int DK>
+__global__ void __launch_bounds__(128)
+dec_self_attention_kernel(const T* __restrict__ qkv, T* __restrict__ cache_k, T* __restrict__ cache_v,
+                          const int* __restrict__ anc, int Tmax, const float* __restrict__ dec_bias, int n_dec,
+                          T* __restrict__ out, int R, int K, int H, int t) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= R * H) return;
+  const int r = warp / H, h = warp % H;
+  const int HD = H * DK;
+  const int ubase = (r / K) * K;
+  const T* qrow = qkv + (size_t)r * 3 * HD + h * DK;
+  // append this step's key/value (slot t, own row)
+  T* kslot = cache_k + ((size_t)t * R + r) * HD + h * DK;
+  T* vslot = cache_v + ((size_t)t * R + r) * HD + h * DK;
+  for (int d = lane; d < DK; d += 32) {
+    kslot[d] = qrow[HD + d];
+    vslot[d] = qrow[2 * HD + d];
+  }
+  __syncwarp();
+  __shared__ float qs_all[4][DK];
+  __shared__ float ps_all[4][64];
+  __shared__ int src_all[4][64];
+  float* qs = qs_all[threadIdx.x >> 5];
+  float* ps = ps_all[threadIdx.x >> 5];
+  int* src = src_all[threadIdx.x >> 5];
+  for (int d = lane; d < DK; d += 32) qs[d] = to_f32(qrow[d]);
+  const int npos = t + 1;                                   // <= 64
+  for (int j = lane; j < npos; j += 32) src[j] = (j == t) ? r : ubase + anc[(size_t)r * Tmax + j];
+  __syncwarp();
+  float sc[2];
+  float mx = -INFINITY;
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const int j = lane + 32 * i;
+    sc[i] = -INFINITY;
+    if (j < npos) {
+      const T* kr = cache_k + ((size_t)j * R + src[j]) * HD + h * DK;
+      float a = 0.f;
+#pragma unroll
+      for (int d = 0; d < DK; d += 4) {
+        const float4 kf = load4(kr + d);
+        a = fmaf(qs[d + 0], kf.x, a); a = fmaf(qs[d + 1], kf.y, a);
+        a = fmaf(qs[d + 2], kf.z, a); a = fmaf(qs[d + 3], kf.w, a);
+      }
+      const int dist = t - j;
+      sc[i] = a + dec_bias[h * n_dec + (dist < n_dec ? dist : n_dec - 1)];
+      mx = fmaxf(mx, sc[i]);
+    }
+  }
+  mx = warp_max(mx);
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    sc[i] = (sc[i] == -INFINITY) ? 0.f : expf(sc[i] - mx);
+    sum += sc[i];
+  }
+  sum = warp_sum(sum);
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const int j = lane + 32 * i;
+    if (j < 64) ps[j] = sc[i] / sum;
+  }
+  __syncwarp();
+  float o[(DK + 31) / 32];
+#pragma unroll
+  for (int e = 0; e < (DK + 31) / 32; ++e) o[e] = 0.f;
+  for (int j = 0; j < npos; ++j) {
+    const T* vr = cache_v + ((size_t)j * R + src[j]) * HD + h * DK;
+    const float pj = ps[j];
+#pragma unroll
+    for (int e = 0; e < (DK + 31) / 32; ++e) {
+      const int d = lane + 32 * e;
+      if (d < DK) o[e] = fmaf(pj, to_f32(vr[d]), o[e]);
+    }
+  }
+  T* orow = out + (size_t)r * HD + h * DK;
+#pragma unroll
+  for (int e = 0; e < (DK + 31) / 32; ++e) {
+    const int d = lane + 32 * e;
+    if (d < DK) orow[d] = from_f32<T>(o[e]);
+  }
+}
+
+template <typename T>
+static cudaError_t launch_dec_self(const void* qkv, void* ck, void* cv, const int* anc, int Tmax,
+                                   const float* dec_bias, int n_dec, void* out, int R, int K, int H, int dk, int t,
+                                   cudaStream_t s) {
+  const int warps = R * H;
+  const int grid = (warps + 3) / 4;
+  switch (dk) {
+    case 16: dec_self_attention_kernel<T, 16><<<grid, 128, 0, s>>>((const T*)qkv, (T*)ck, (T*)cv, anc, Tmax, dec_bias, n_dec, (T*)out, R, K, H, t); break;
+    case 32: dec_self_attention_kernel<T, 32><<<grid, 128, 0, s>>>((const T*)qkv, (T*)ck, (T*)cv, anc, Tmax, dec_bias, n_dec, (T*)out, R, K, H, t); break;
+    case 64: dec_self_attention_kernel<T, 64><<<grid, 128, 0, s>>>((const T*)qkv, (T*)ck, (T*)cv, anc, Tmax, dec_bias, n_dec, (T*)out, R, K, H, t); break;
+    default: return cudaErrorInvalidValue;
+  }
+  return cudaGetLastError();
+}
+
+cudaError_t dec_self_attention(int dtype, const void* qkv, void* cache_k, void* cache_v, const int* anc, int Tmax,
+                               const float* dec_bias, int n_dec, void* out, int R, int K, int H, int dk, int t,
+                               cudaStream_t s) {
+  if (R <= 0) return cudaSuccess;
+  if (t + 1 > 64) return cudaErrorInvalidValue;
+  if (dtype == 0) return launch_dec_self<float>(qkv, cache_k, cache_v, anc, Tmax, dec_bias, n_dec, out, R, K, H, dk, t, s);
+  return launch_dec_self<bf16>(qkv, cache_k, cache_v, anc, Tmax, dec_bias, n_dec, out, R, K, H, dk, t, s);
+}
+
+// ------------------------------------------------------------------------------------------------
+// cross-attention, CUDA-core version: one CTA per (user, head); the K beams are the query rows.
+// Tiles of TS memory rows are staged through shared memory with vectorised coalesced loads;
+// online (flash-style) softmax keeps one running max/sum per beam.
+// ------------------------------------------------------------------------------------------------
+constexpr int XA_THREADS = 128;
+constexpr int XA_TS = 32;        // memory rows per tile
+constexpr int XA_KMAX = 64;      // beams per user supported by this kernel
+
+template <typename T, int DK>
+__global__ void __launch_bounds__(XA_THREADS)
+cross_attention_kernel(const T* __restrict__ q, const T* __restrict__ kv, size_t kv_stride, int k_off, int v_off,
+                       const int* __restrict__ ustart, const uint8_t* __restrict__ tok_valid, T* __restrict__ out,
+                       int K, int H) {
+  constexpr int KS = DK + 4;                 // padded, keeps 16B alignment and conflict-free LDS.128
+  constexpr int G = XA_THREADS / DK;         // beam groups in the PV phase
+  constexpr int NBT = (XA_KMAX + G - 1) / G; // beams per thread in the PV phase
+  constexpr int NBS = XA_KMAX / 4;           // beams per thread in the score phase (4 groups of 32 rows)
+  const int u = blockIdx.x, h = blockIdx.y;
+  const int s_beg = ustart[u], s_end = ustart[u + 1];
+  const int HD = H * DK;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+
+  extern __shared__ __align__(16) float smem[];
+  float* qs = smem;                          // [K][DK]
+  float* Ks = qs + XA_KMAX * DK;             // [TS][KS]
+  float* Vs = Ks + XA_TS * KS;               // [TS][DK]
+  float* Ps = Vs + XA_TS * DK;               // [KMAX][TS]
+  float* m_s = Ps + XA_KMAX * XA_TS;         // [KMAX] running max
+  float* l_s = m_s + XA_KMAX;                // [KMAX] running sum
+  float* c_s = l_s + XA_KMAX;                // [KMAX] correction factor of this tile
+
+  for (int i = tid; i < K * DK; i += XA_THREADS) {
+    const int b = i / DK, d = i % DK;
+    qs[b * DK + d] = to_f32(q[(size_t)(u * K + b) * HD + h * DK + d]);
+  }
+  for (int i = tid; i < XA_KMAX; i += XA_THREADS) { m_s[i] = -INFINITY; l_s[i] = 0.f; c_s[i] = 0.f; }
+
+  float acc[NBT];
+#pragma unroll
+  for (int i = 0; i < NBT; ++i) acc[i] = 0.f;
+  const int pv_d = tid % DK, pv_g = tid / DK;
+  __syncthreads();
+
+  for (int s0 = s_beg; s0 < s_end; s0 += XA_TS) {
+    const int rows = min(XA_TS, s_end - s0);
+    // ---- stage K and V rows of this head ----
+    for (int i = tid; i < XA_TS * (DK / 4); i += XA_THREADS) {
+      const int j = i / (DK / 4), c = (i % (DK / 4)) * 4;
+      float4 kf = make_float4(0.f, 0.f, 0.f, 0.f), vf = kf;
+      if (j < rows) {
+        const T* base = kv + (size_t)(s0 + j) * kv_stride + h * DK + c;
+        kf = load4(base + k_off);
+        vf = load4(base + v_off);
+      }
+      *reinterpret_cast<float4*>(&Ks[j * KS + c]) = kf;
+      *reinterpret_cast<float4*>(&Vs[j * DK + c]) = vf;
+    }
+    __syncthreads();
+    // ---- scores: thread = (row j = lane, beam group = warp) ----
+    {
+      float sc[NBS];
+#pragma unroll
+      for (int i = 0; i < NBS; ++i) sc[i] = 0.f;
+      const int j = lane;
+#pragma unroll 4
+      for (int d = 0; d < DK; d += 4) {
+        const float4 kf = *reinterpret_cast<const float4*>(&Ks[j * KS + d]);
+#pragma unroll
+        for (int i = 0; i < NBS; ++i) {
+          const int b = wid + 4 * i;
+          if (b < K) {
+            const float4 qf = *reinterpret_cast<const float4*>(&qs[b * DK + d]);
+            sc[i] = fmaf(qf.x, kf.x, sc[i]); sc[i] = fmaf(qf.y, kf.y, sc[i]);
+            sc[i] = fmaf(qf.z, kf.z, sc[i]); sc[i] = fmaf(qf.w, kf.w, sc[i]);
+          }
+        }
+      }
+      const bool ok = (j < rows) && (tok_valid == nullptr || tok_valid[s0 + j]);
+      // ---- online softmax per beam (this warp owns beams wid, wid+4, ...) ----
+#pragma unroll
+      for (int i = 0; i < NBS; ++i) {
+        const int b = wid + 4 * i;
+        if (b < K) {                                        // warp-uniform
+          const float v = ok ? sc[i] : -INFINITY;
+          const float tmax = warp_max(v);
+          const float m_old = m_s[b];
+          const float m_new = fmaxf(m_old, tmax);
+          const float p = (v == -INFINITY) ? 0.f : expf(v - m_new);
+          const float psum = warp_sum(p);
+          Ps[b * XA_TS + j] = p;
+          if (lane == 0) {
+            const float corr = (m_old == -INFINITY) ? 0.f : expf(m_old - m_new);
+            c_s[b] = corr;
+            l_s[b] = l_s[b] * corr + psum;
+            m_s[b] = m_new;
+          }
+        }
+      }
+    }
+    __syncthreads();
+    // ---- PV: thread = (d = tid % DK, beam group = tid / DK) ----
+#pragma unroll
+    for (int i = 0; i < NBT; ++i) {
+      const int b = pv_g + G * i;
+      if (b < K) {
+        float a = acc[i] * c_s[b];
+#pragma unroll 8
+        for (int j = 0; j < XA_TS; j += 4) {
+          const float4 pf = *reinterpret_cast<const float4*>(&Ps[b * XA_TS + j]);
+          a = fmaf(pf.x, Vs[(j + 0) * DK + pv_d], a);
+          a = fmaf(pf.y, Vs[(j + 1) * DK + pv_d], a);
+          a = fmaf(pf.z, Vs[(j + 2) * DK + pv_d], a);
+          a = fmaf(pf.w, Vs[(j + 3) * DK + pv_d], a);
+        }
+        acc[i] = a;
+      }
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < NBT; ++i) {
+    const int b = pv_g + G * i;
+    if (b < K) {
+      const float l = l_s[b];
+      out[(size_t)(u * K + b) * HD + h * DK + pv_d] = from_f32<T>(l > 0.f ? acc[i] / l : 0.f);
+    }
+  }
+}
+
+template <typename T, int DK>
+static cudaError_t launch_cross(const void* q, const void* kv, size_t kv_stride, int k_off, int v_off,
+                                const int* ustart, const uint8_t* tok_valid, void* out, int users, int K, int H,
+                                cudaStream_t s) {
+  constexpr int KS = DK + 4;
+  const size_t smem = sizeof(float) * ((size_t)XA_KMAX * DK + XA_TS * KS + XA_TS * DK + XA_KMAX * XA_TS + 3 * XA_KMAX);
+  auto kern = cross_attention_kernel<T, DK>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  kern<<<dim3(users, H), XA_THREADS, smem, s>>>((const T*)q, (const T*)kv, kv_stride, k_off, v_off, ustart,
+                                                 tok_valid, (T*)out, K, H);
+  return cudaGetLastError();
+}
+
+cudaError_t cross_attention(int dtype, const void* q, const void* kv, size_t kv_stride, int k_off, int v_off,
+                            const int* ustart, const uint8_t* tok_valid, void* out, int users, int K, int H, int dk,
+                            cudaStream_t s) {
+  if (users <= 0) return cudaSuccess;
+  if (K > XA_KMAX) return cudaErrorInvalidValue;
+#define GRAM_XA(TT)                                                                                              \
+  switch (dk) {                                                                                                  \
+    case 16: return launch_cross<TT, 16>(q, kv, kv_stride, k_off, v_off, ustart, tok_valid, out, users, K, H, s); \
+    case 32: return launch_cross<TT, 32>(q, kv, kv_stride, k_off, v_off, ustart, tok_valid, out, users, K, H, s); \
+    case 64: return launch_cross<TT, 64>(q, kv, kv_stride, k_off, v_off, ustart, tok_valid, out, users, K, H, s); \
+    default: return cudaErrorInvalidValue;                                                                       \
+  }
+  if (dtype == 0) { GRAM_XA(float) }
+  GRAM_XA(bf16)
+#undef GRAM_XA
+}
+
+}  // namespace gram

@@ -1,0 +1,341 @@
+// Encoder-side kernels: valid-token packing, embedding gather, T5 RMS norm (+ passage-position
+// embedding), bidirectional per-passage self-attention, and the debug un-packer.
+//
+// Reference semantics (paths relative to the reference root):
+//   packing          src/model/gram.py:206-216 views B x (N*L) as (B*N) x L and encodes every passage
+//                    independently.  Masked keys receive finfo.min and contribute exactly 0 after the
+//                    fp32 softmax (src/model/gram_t5_modeling.py:1130,596-610), and masked memory
+//                    positions are invisible to the decoder (:1145-1147), so rows past the last valid
+//                    token of a passage -- and all-masked passages -- are skipped here, exactly.
+//   embedding        src/model/gram_t5_modeling.py:1091
+//   RMS norm         src/model/gram_t5_modeling.py:262-276 (fp32 variance, no mean subtraction)
+//   position add     src/model/gram.py:238-249
+//   attention        src/model/gram_t5_modeling.py:572-621 (no 1/sqrt(d) scale, additive relative bias
+//                    from layer 0 shared by all layers :1249, fp32 softmax)
+#include "common.cuh"
+#include "kernels.h"
+
+namespace gram {
+
+// ------------------------------------------------------------------------------------------------
+// packing
+// ------------------------------------------------------------------------------------------------
+__global__ void passage_len_kernel(const uint8_t* __restrict__ mask, int P, int L, int* __restrict__ plen) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= P) return;
+  const uint8_t* m = mask + (size_t)warp * L;
+  int last = 0;
+  for (int l = lane; l < L; l += 32)
+    if (m[l]) last = l + 1;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) last = max(last, __shfl_xor_sync(0xffffffffu, last, o));
+  if (lane == 0) plen[warp] = last;
+}
+
+// single-CTA exclusive scan (P is at most a few hundred thousand)
+__global__ void __launch_bounds__(1024) passage_scan_kernel(const int* __restrict__ plen, int P, int N, int B,
+                                                            int* __restrict__ poff, int* __restrict__ ustart,
+                                                            int* __restrict__ total) {
+  __shared__ int warp_sums[32];
+  __shared__ int carry_s;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int per = (P + 1023) / 1024;
+  const int beg = min(tid * per, P), end = min(beg + per, P);
+  int sum = 0;
+  for (int i = beg; i < end; ++i) sum += plen[i];
+  // block exclusive scan of `sum`
+  int incl = sum;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    int v = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += v;
+  }
+  if (lane == 31) warp_sums[wid] = incl;
+  __syncthreads();
+  if (wid == 0) {
+    int w = warp_sums[lane];
+    int wi = w;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      int v = __shfl_up_sync(0xffffffffu, wi, o);
+      if (lane >= o) wi += v;
+    }
+    warp_sums[lane] = wi - w;   // exclusive
+    if (lane == 31) carry_s = wi;
+  }
+  __syncthreads();
+  int run = warp_sums[wid] + incl - sum;
+  for (int i = beg; i < end; ++i) {
+    poff[i] = run;
+    if (i % N == 0) ustart[i / N] = run;
+    run += plen[i];
+  }
+  if (tid == 0) {
+    poff[P] = carry_s;
+    ustart[B] = carry_s;
+    *total = carry_s;
+  }
+}
+
+__global__ void passage_fill_kernel(const int64_t* __restrict__ ids, const uint8_t* __restrict__ mask, int N, int L,
+                                    PackMeta pm, int vocab_hi) {
+  const int p = blockIdx.x;
+  const int len = pm.plen[p], off = pm.poff[p];
+  for (int l = threadIdx.x; l < len; l += blockDim.x) {
+    const size_t src = (size_t)p * L + l;
+    long long id = ids[src];
+    pm.tok_id[off + l] = (int)id;
+    pm.tok_valid[off + l] = mask[src] ? 1 : 0;
+    pm.tok_pos[off + l] = p % N;
+    pm.row_src[off + l] = (int)src;
+  }
+}
+
+cudaError_t enc_pack(const int64_t* ids, const uint8_t* mask, int B, int N, int L, PackMeta pm, cudaStream_t s) {
+  const int P = B * N;
+  passage_len_kernel<<<(P * 32 + 255) / 256, 256, 0, s>>>(mask, P, L, pm.plen);
+  passage_scan_kernel<<<1, 1024, 0, s>>>(pm.plen, P, N, B, pm.poff, pm.ustart, pm.total);
+  passage_fill_kernel<<<P, 128, 0, s>>>(ids, mask, N, L, pm, 0);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+// embedding gather: x[row] = table[tok_id[row]]   (fp32 residual stream)
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void embed_rows_kernel(const T* __restrict__ table, const int* __restrict__ tok_id, float* __restrict__ x,
+                                  int M_imm, const int* __restrict__ m_ptr, int D) {
+  const int M = m_ptr ? *m_ptr : M_imm;
+  const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (row >= M) return;
+  const T* src = table + (size_t)tok_id[row] * D;
+  float* dst = x + (size_t)row * D;
+  for (int c = lane * 4; c < D; c += 128) store4(dst + c, load4(src + c));
+}
+
+cudaError_t embed_rows(int dtype, const void* table, const int* tok_id, float* x, int M_max, const int* m_ptr, int D,
+                       cudaStream_t s) {
+  if (M_max <= 0) return cudaSuccess;
+  const int grid = (M_max + 7) / 8;
+  if (dtype == 0) embed_rows_kernel<float><<<grid, 256, 0, s>>>((const float*)table, tok_id, x, M_max, m_ptr, D);
+  else embed_rows_kernel<bf16><<<grid, 256, 0, s>>>((const bf16*)table, tok_id, x, M_max, m_ptr, D);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+// RMS norm: one warp per row
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void rmsnorm_rows_kernel(const float* __restrict__ x, const float* __restrict__ w, T* __restrict__ y,
+                                    int M_imm, const int* __restrict__ m_ptr, int D, float eps, float scale,
+                                    const float* __restrict__ pos_table, const int* __restrict__ tok_pos) {
+  const int M = m_ptr ? *m_ptr : M_imm;
+  const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (row >= M) return;
+  const float* xr = x + (size_t)row * D;
+  float ss = 0.f;
+  for (int c = lane * 4; c < D; c += 128) {
+    const float4 v = load4(xr + c);
+    ss = fmaf(v.x, v.x, ss); ss = fmaf(v.y, v.y, ss); ss = fmaf(v.z, v.z, ss); ss = fmaf(v.w, v.w, ss);
+  }
+  ss = warp_sum(ss);
+  const float r = 1.0f / sqrtf(ss / (float)D + eps);
+  const float* pe = pos_table ? pos_table + (size_t)tok_pos[row] * D : nullptr;
+  T* yr = y + (size_t)row * D;
+  for (int c = lane * 4; c < D; c += 128) {
+    const float4 v = load4(xr + c);
+    const float4 g = load4(w + c);
+    float4 o;
+    o.x = g.x * (v.x * r); o.y = g.y * (v.y * r); o.z = g.z * (v.z * r); o.w = g.w * (v.w * r);
+    if (scale != 1.0f) { o.x *= scale; o.y *= scale; o.z *= scale; o.w *= scale; }
+    if (pe) {
+      const float4 q = load4(pe + c);
+      o.x += q.x; o.y += q.y; o.z += q.z; o.w += q.w;
+    }
+    store4(yr + c, o);
+  }
+}
+
+cudaError_t rmsnorm_rows(int dtype, const float* x, const float* w, void* y, int M_max, const int* m_ptr, int D,
+                         float eps, float scale, const float* pos_table, const int* tok_pos, cudaStream_t s) {
+  if (M_max <= 0) return cudaSuccess;
+  const int grid = (M_max + 7) / 8;
+  if (dtype == 0)
+    rmsnorm_rows_kernel<float><<<grid, 256, 0, s>>>(x, w, (float*)y, M_max, m_ptr, D, eps, scale, pos_table, tok_pos);
+  else
+    rmsnorm_rows_kernel<bf16><<<grid, 256, 0, s>>>(x, w, (bf16*)y, M_max, m_ptr, D, eps, scale, pos_table, tok_pos);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+// encoder self-attention, CUDA-core version: one CTA per (passage, head), one warp per query row.
+// K and V of the passage/head are staged in shared memory as fp32; a lane owns keys lane, lane+32, ...
+// ------------------------------------------------------------------------------------------------
+template <typename T, int DK, int NI>
+__global__ void __launch_bounds__(128)
+enc_attention_kernel(const T* __restrict__ qkv, T* __restrict__ out, const int* __restrict__ plen,
+                     const int* __restrict__ poff, const uint8_t* __restrict__ tok_valid,
+                     const float* __restrict__ bias_lut, int Lb, int H) {
+  constexpr int LK = NI * 32;
+  constexpr int KS = DK + 1;                       // padded K row: lanes read different rows, same column
+  const int p = blockIdx.x, h = blockIdx.y;
+  const int len = plen[p];
+  if (len == 0) return;
+  const int row0 = poff[p];
+  const int HD = H * DK;
+  const size_t ld = (size_t)3 * HD;
+
+  extern __shared__ __align__(16) float smem[];
+  float* Ks = smem;                                // [LK][KS]
+  float* Vs = Ks + LK * KS;                        // [LK][DK]
+  float* lut = Vs + LK * DK;                       // [2*Lb-1]
+  float* qs = lut + (2 * Lb - 1);                  // [4][DK]
+  float* ps = qs + 4 * DK;                         // [4][LK]
+  uint8_t* vs = reinterpret_cast<uint8_t*>(ps + 4 * LK);   // [LK]
+
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  for (int i = tid; i < len * (DK / 4); i += 128) {
+    const int j = i / (DK / 4), c = (i % (DK / 4)) * 4;
+    const T* base = qkv + (size_t)(row0 + j) * ld + h * DK + c;
+    const float4 kf = load4(base + HD);
+    const float4 vf = load4(base + 2 * HD);
+    Ks[j * KS + c + 0] = kf.x; Ks[j * KS + c + 1] = kf.y; Ks[j * KS + c + 2] = kf.z; Ks[j * KS + c + 3] = kf.w;
+    *reinterpret_cast<float4*>(&Vs[j * DK + c]) = vf;
+  }
+  for (int i = tid; i < 2 * Lb - 1; i += 128) lut[i] = bias_lut[(size_t)h * (2 * Lb - 1) + i];
+  for (int i = tid; i < len; i += 128) vs[i] = tok_valid[row0 + i];
+  __syncthreads();
+
+  for (int qi = wid; qi < len; qi += 4) {
+    // stage this query row
+    const T* qrow = qkv + (size_t)(row0 + qi) * ld + h * DK;
+    for (int d = lane; d < DK; d += 32) qs[wid * DK + d] = to_f32(qrow[d]);
+    __syncwarp();
+    float sc[NI];
+#pragma unroll
+    for (int i = 0; i < NI; ++i) sc[i] = 0.f;
+#pragma unroll 8
+    for (int d = 0; d < DK; ++d) {
+      const float qd = qs[wid * DK + d];
+#pragma unroll
+      for (int i = 0; i < NI; ++i) {
+        const int j = lane + 32 * i;
+        if (j < len) sc[i] = fmaf(qd, Ks[j * KS + d], sc[i]);
+      }
+    }
+    float mx = -INFINITY;
+#pragma unroll
+    for (int i = 0; i < NI; ++i) {
+      const int j = lane + 32 * i;
+      if (j < len && vs[j]) {
+        sc[i] += lut[j - qi + Lb - 1];
+        mx = fmaxf(mx, sc[i]);
+      } else {
+        sc[i] = -INFINITY;
+      }
+    }
+    mx = warp_max(mx);
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < NI; ++i) {
+      sc[i] = (sc[i] == -INFINITY) ? 0.f : expf(sc[i] - mx);
+      sum += sc[i];
+    }
+    sum = warp_sum(sum);
+#pragma unroll
+    for (int i = 0; i < NI; ++i) {
+      const int j = lane + 32 * i;
+      if (j < LK) ps[wid * LK + j] = sc[i] / sum;
+    }
+    __syncwarp();
+    // out[d] = sum_j p_j V[j][d]
+    float o[(DK + 31) / 32];
+#pragma unroll
+    for (int e = 0; e < (DK + 31) / 32; ++e) o[e] = 0.f;
+    for (int j = 0; j < len; ++j) {
+      const float pj = ps[wid * LK + j];
+#pragma unroll
+      for (int e = 0; e < (DK + 31) / 32; ++e) {
+        const int d = lane + 32 * e;
+        if (d < DK) o[e] = fmaf(pj, Vs[j * DK + d], o[e]);
+      }
+    }
+    T* orow = out + (size_t)(row0 + qi) * HD + h * DK;
+#pragma unroll
+    for (int e = 0; e < (DK + 31) / 32; ++e) {
+      const int d = lane + 32 * e;
+      if (d < DK) orow[d] = from_f32<T>(o[e]);
+    }
+    __syncwarp();
+  }
+}
+
+template <typename T, int DK, int NI>
+static cudaError_t launch_enc_attn(const void* qkv, void* out, const int* plen, const int* poff,
+                                   const uint8_t* tok_valid, const float* bias_lut, int Lb, int P, int H,
+                                   cudaStream_t s) {
+  constexpr int LK = NI * 32;
+  size_t smem = sizeof(float) * ((size_t)LK * (DK + 1) + (size_t)LK * DK + (2 * Lb - 1) + 4 * DK + 4 * LK) + LK + 16;
+  auto kern = enc_attention_kernel<T, DK, NI>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  kern<<<dim3(P, H), 128, smem, s>>>((const T*)qkv, (T*)out, plen, poff, tok_valid, bias_lut, Lb, H);
+  return cudaGetLastError();
+}
+
+template <typename T, int DK>
+static cudaError_t dispatch_enc_attn_ni(const void* qkv, void* out, const int* plen, const int* poff,
+                                        const uint8_t* tok_valid, const float* bias_lut, int Lb, int P, int H,
+                                        int Lmax, cudaStream_t s) {
+  if (Lmax <= 32) return launch_enc_attn<T, DK, 1>(qkv, out, plen, poff, tok_valid, bias_lut, Lb, P, H, s);
+  if (Lmax <= 64) return launch_enc_attn<T, DK, 2>(qkv, out, plen, poff, tok_valid, bias_lut, Lb, P, H, s);
+  if (Lmax <= 128) return launch_enc_attn<T, DK, 4>(qkv, out, plen, poff, tok_valid, bias_lut, Lb, P, H, s);
+  if (Lmax <= 256) return launch_enc_attn<T, DK, 8>(qkv, out, plen, poff, tok_valid, bias_lut, Lb, P, H, s);
+  return cudaErrorInvalidValue;
+}
+
+template <typename T>
+static cudaError_t dispatch_enc_attn_dk(const void* qkv, void* out, const int* plen, const int* poff,
+                                        const uint8_t* tok_valid, const float* bias_lut, int Lb, int P, int H,
+                                        int dk, int Lmax, cudaStream_t s) {
+  switch (dk) {
+    case 16: return dispatch_enc_attn_ni<T, 16>(qkv, out, plen, poff, tok_valid, bias_lut, Lb, P, H, Lmax, s);
+    case 32: return dispatch_enc_attn_ni<T, 32>(qkv, out, plen, poff, tok_valid, bias_lut, Lb, P, H, Lmax, s);
+    case 64: return dispatch_enc_attn_ni<T, 64>(qkv, out, plen, poff, tok_valid, bias_lut, Lb, P, H, Lmax, s);
+    default: return cudaErrorInvalidValue;
+  }
+}
+
+cudaError_t enc_attention(int dtype, const void* qkv, void* out, const int* plen, const int* poff,
+                          const uint8_t* tok_valid, const float* bias_lut, int Lb, int P, int H, int dk, int Lmax,
+                          cudaStream_t s) {
+  if (P <= 0) return cudaSuccess;
+  if (dtype == 0)
+    return dispatch_enc_attn_dk<float>(qkv, out, plen, poff, tok_valid, bias_lut, Lb, P, H, dk, Lmax, s);
+  return dispatch_enc_attn_dk<bf16>(qkv, out, plen, poff, tok_valid, bias_lut, Lb, P, H, dk, Lmax, s);
+}
+
+// ------------------------------------------------------------------------------------------------
+// debug tap: packed memory -> padded fp32 [B, N*L, D] (caller zero-fills first)
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void unpack_memory_kernel(const T* __restrict__ mem, const int* __restrict__ row_src,
+                                     float* __restrict__ out, int M_imm, const int* __restrict__ m_ptr, int D) {
+  const int M = m_ptr ? *m_ptr : M_imm;
+  const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (row >= M) return;
+  const T* src = mem + (size_t)row * D;
+  float* dst = out + (size_t)row_src[row] * D;
+  for (int c = lane * 4; c < D; c += 128) store4(dst + c, load4(src + c));
+}
+
+cudaError_t unpack_memory(int dtype, const void* mem, const int* row_src, float* out, int M_max, const int* m_ptr,
+                          int D, cudaStream_t s) {
+  if (M_max <= 0) return cudaSuccess;
+  const int grid = (M_max + 7) / 8;
+  if (dtype == 0) unpack_memory_kernel<float><<<grid, 256, 0, s>>>((const float*)mem, row_src, out, M_max, m_ptr, D);
+  else unpack_memory_kernel<bf16><<<grid, 256, 0, s>>>((const bf16*)mem, row_src, out, M_max, m_ptr, D);
+  return cudaGetLastError();
+}
+
+}  // namespace gram

@@ -1,0 +1,814 @@
+// gram_b200 engine: handle, weight/trie residency, the encode -> fused memory -> decode-step loop,
+// and the C ABI declared in include/gram_b200.h.
+//
+// Orchestration mirrors the reference call stack:
+//   GRAM.generate                      src/model/gram.py:74-107
+//     EncoderWrapper.forward           src/model/gram.py:200-256          -> encode()
+//     HF generate / beam_search loop   transformers 4.26 (third party)    -> generate() step loop
+//       GRAM.forward one token         src/model/gram_t5.py:118-287       -> decoder_step()
+//       log_softmax + trie + topk + scorer                                 -> lse_rows + beam_step
+//       _reorder_cache                 src/model/gram_t5.py:320-348       -> eliminated (ancestry table; cross
+//                                                                            K/V is per user, not per beam)
+// Everything is enqueued on the caller's stream; the only host synchronisation is the final copy-out
+// to host buffers.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <math.h>
+#include <string>
+#include <vector>
+#include <map>
+#include <set>
+
+#include "../../include/gram_b200.h"
+#include "common.cuh"
+#include "kernels.h"
+
+using namespace gram;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t bytes = 0;
+};
+
+struct LayerW {
+  void *qkv = nullptr, *o = nullptr, *wi = nullptr, *wo = nullptr;      // self-attn + FF
+  void *cq = nullptr, *co = nullptr;                                     // decoder cross-attn q / o
+  float *ln0 = nullptr, *ln1 = nullptr, *ln2 = nullptr;
+};
+
+}  // namespace
+
+struct gram_handle {
+  gram_config cfg;
+  int D, HD, F, V, H, dk, Le, Ld;
+  size_t esz;                 // bytes per stored element
+  int num_sms = 148;
+  std::string err;
+  std::vector<void*> allocs;
+  size_t alloc_bytes = 0;
+
+  // weights
+  void* shared = nullptr;     // [V, D]
+  void* lm_head = nullptr;    // [V, D] (== shared when tied weights were loaded once)
+  float* pos_emb = nullptr;   // [n_positions, D] fp32
+  float *enc_final_ln = nullptr, *dec_final_ln = nullptr;
+  std::vector<LayerW> enc, dec;
+  void* ckv_w = nullptr;      // [Ld*2*HD, D]  (ck_0 | cv_0 | ck_1 | ...)
+  float *enc_rel = nullptr, *dec_rel = nullptr;     // [buckets, H] fp32
+  float *enc_bias_lut = nullptr, *dec_bias_lut = nullptr;
+  int n_enc_lut = 0, n_dec_lut = 0, Lb = 0;
+  std::set<std::string> loaded;
+  bool buckets_set = false, weights_ready = false;
+  float* stage = nullptr;
+  size_t stage_elems = 0;
+
+  // trie
+  TrieCSR trie{};
+  bool trie_set = false;
+  int cand_cap = 0;
+
+  // encoder workspace
+  int64_t Mcap = 0;
+  PackMeta pm{};
+  int64_t* d_ids = nullptr;
+  uint8_t* d_mask = nullptr;
+  float* x = nullptr;
+  void *xn = nullptr, *qkv = nullptr, *ao = nullptr, *ff = nullptr, *mem = nullptr, *ckv = nullptr;
+  int enc_B = 0, enc_N = 0, enc_L = 0;
+  bool encoded = false;
+
+  // decoder workspace
+  int Rcap = 0;
+  float* dx = nullptr;
+  void *dxn = nullptr, *dqkv = nullptr, *dao = nullptr, *dq = nullptr, *dff = nullptr;
+  void *sk = nullptr, *sv = nullptr;     // [Ld][Tmax][Rcap][HD]
+  float *logits = nullptr, *lse = nullptr;
+  BeamState bs{};
+  double* d_len_pow = nullptr;
+  double* h_len_pow = nullptr;           // pinned
+  int64_t* d_out_seq = nullptr;
+  float* d_out_scores = nullptr;
+  int* d_out_width = nullptr;
+  int* h_flags = nullptr;                // pinned: [0]=err, [1]=width, [2]=total tokens
+  int* d_zero_anc = nullptr;
+  int64_t* d_dec_ids = nullptr;
+  int last_steps = 0, last_R = 0;
+
+  // measurement
+  int64_t launches = 0;
+  uint32_t prof_mask = 0;
+  std::vector<cudaEvent_t> ev_pool;
+  size_t ev_used = 0;
+  struct EvRec { int cls; cudaEvent_t a, b; };
+  std::vector<EvRec> ev_log;
+  int64_t cls_launches[GRAM_K_COUNT] = {0};
+};
+
+namespace {
+
+#define CK(call)                                                                                       \
+  do {                                                                                                 \
+    cudaError_t e_ = (call);                                                                           \
+    if (e_ != cudaSuccess) {                                                                           \
+      char buf_[512];                                                                                  \
+      snprintf(buf_, sizeof buf_, "%s failed at %s:%d: %s", #call, __FILE__, __LINE__, cudaGetErrorString(e_)); \
+      h->err = buf_;                                                                                   \
+      return GRAM_ERR_CUDA;                                                                            \
+    }                                                                                                  \
+  } while (0)
+
+int fail(gram_handle* h, int code, const std::string& msg) {
+  h->err = msg;
+  return code;
+}
+
+template <typename P>
+int dalloc(gram_handle* h, P** out, size_t bytes) {
+  void* p = nullptr;
+  if (bytes == 0) bytes = 16;
+  cudaError_t e = cudaMalloc(&p, bytes);
+  if (e != cudaSuccess) {
+    char b[256];
+    snprintf(b, sizeof b, "cudaMalloc(%zu bytes) failed: %s (handle already owns %zu bytes)", bytes,
+             cudaGetErrorString(e), h->alloc_bytes);
+    h->err = b;
+    return GRAM_ERR_CUDA;
+  }
+  h->allocs.push_back(p);
+  h->alloc_bytes += bytes;
+  *out = reinterpret_cast<P*>(p);
+  return GRAM_OK;
+}
+#define DA(ptr, bytes)                                         \
+  do {                                                         \
+    int rc_ = dalloc(h, &(ptr), (bytes));                      \
+    if (rc_) return rc_;                                       \
+  } while (0)
+
+bool is_device_ptr(const void* p) {
+  cudaPointerAttributes a;
+  cudaError_t e = cudaPointerGetAttributes(&a, p);
+  if (e != cudaSuccess) { cudaGetLastError(); return false; }
+  return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+
+// ---- launch bookkeeping -----------------------------------------------------------------------
+struct Scope {
+  gram_handle* h; int cls; cudaStream_t s; bool timed; cudaEvent_t a{}, b{};
+  Scope(gram_handle* h_, int cls_, cudaStream_t s_) : h(h_), cls(cls_), s(s_) {
+    h->launches++;
+    h->cls_launches[cls]++;
+    timed = (h->prof_mask >> cls) & 1u;
+    if (timed) {
+      while (h->ev_used + 2 > h->ev_pool.size()) {
+        cudaEvent_t e; cudaEventCreate(&e); h->ev_pool.push_back(e);
+      }
+      a = h->ev_pool[h->ev_used++]; b = h->ev_pool[h->ev_used++];
+      cudaEventRecord(a, s);
+    }
+  }
+  ~Scope() {
+    if (timed) { cudaEventRecord(b, s); h->ev_log.push_back({cls, a, b}); }
+  }
+};
+
+__global__ void convert_kernel_f32(const float* __restrict__ src, float* __restrict__ dst, size_t n) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = src[i];
+}
+__global__ void convert_kernel_bf16(const float* __restrict__ src, bf16* __restrict__ dst, size_t n) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = __float2bfloat16_rn(src[i]);
+}
+__global__ void build_lut_kernel(const float* __restrict__ rel, const int* __restrict__ buckets, int n, int H,
+                                 float* __restrict__ lut) {
+  // lut[h][i] = rel[buckets[i]][h]
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n * H) {
+    const int hh = i / n, j = i % n;
+    lut[i] = rel[buckets[j] * H + hh];
+  }
+}
+
+int gemm(gram_handle* h, int cls, int epi, const void* A, const void* W, void* C, int M_max, const int* m_ptr, int N,
+         int K, cudaStream_t s) {
+  Scope sc(h, cls, s);
+  cudaError_t e;
+  if (h->cfg.dtype == GRAM_DTYPE_BF16 && !(h->cfg.flags & GRAM_FLAG_SIMT_GEMM) && gemm_tc_supported(N, K)) {
+    e = gemm_tc(epi, A, W, C, M_max, m_ptr, N, K, h->num_sms, s);
+    if (e != cudaSuccess) {
+      h->err = std::string("tcgen05 gemm launch failed: ") + cudaGetErrorString(e) + " / " + gemm_tc_last_error();
+      return GRAM_ERR_CUDA;
+    }
+    return GRAM_OK;
+  }
+  e = gemm_simt(h->cfg.dtype, epi, A, W, C, M_max, m_ptr, N, K, s);
+  if (e != cudaSuccess) {
+    h->err = std::string("simt gemm launch failed: ") + cudaGetErrorString(e);
+    return GRAM_ERR_CUDA;
+  }
+  return GRAM_OK;
+}
+#define RC(call)                 \
+  do {                           \
+    int rc_ = (call);            \
+    if (rc_) return rc_;         \
+  } while (0)
+#define CKL(cls, call)                                                                      \
+  do {                                                                                      \
+    Scope sc_(h, (cls), s);                                                                 \
+    cudaError_t e_ = (call);                                                                \
+    if (e_ != cudaSuccess) {                                                                \
+      h->err = std::string(#call) + " failed: " + cudaGetErrorString(e_);                   \
+      return GRAM_ERR_CUDA;                                                                 \
+    }                                                                                       \
+  } while (0)
+
+// ---- weight name resolution ---------------------------------------------------------------------
+struct WeightSlot { void* dst; int64_t rows, cols; bool f32; };
+
+bool resolve_weight(gram_handle* h, const std::string& name, WeightSlot* ws) {
+  const int D = h->D, HD = h->HD, F = h->F, V = h->V;
+  const size_t esz = h->esz;
+  auto T = [&](void* base, size_t row_off, int64_t rows, int64_t cols) {
+    ws->dst = (char*)base + row_off * (size_t)cols * esz; ws->rows = rows; ws->cols = cols; ws->f32 = false; return true;
+  };
+  auto F32 = [&](float* base, int64_t rows, int64_t cols) {
+    ws->dst = base; ws->rows = rows; ws->cols = cols; ws->f32 = true; return true;
+  };
+  if (name == "shared") return T(h->shared, 0, V, D);
+  if (name == "lm_head") return T(h->lm_head, 0, V, D);
+  if (name == "pos_emb") return h->pos_emb ? F32(h->pos_emb, h->cfg.n_positions, D) : false;
+  if (name == "enc.final_ln") return F32(h->enc_final_ln, 1, D);
+  if (name == "dec.final_ln") return F32(h->dec_final_ln, 1, D);
+  char side[8]; int idx; char what[32];
+  if (sscanf(name.c_str(), "%3[a-z].%d.%31s", side, &idx, what) != 3) return false;
+  const bool is_enc = !strcmp(side, "enc");
+  if (!is_enc && strcmp(side, "dec")) return false;
+  if (idx < 0 || idx >= (is_enc ? h->Le : h->Ld)) return false;
+  LayerW& L = is_enc ? h->enc[idx] : h->dec[idx];
+  const std::string w = what;
+  if (w == "q") return T(L.qkv, 0, HD, D);
+  if (w == "k") return T(L.qkv, HD, HD, D);
+  if (w == "v") return T(L.qkv, 2 * (size_t)HD, HD, D);
+  if (w == "o") return T(L.o, 0, D, HD);
+  if (w == "wi") return T(L.wi, 0, F, D);
+  if (w == "wo") return T(L.wo, 0, D, F);
+  if (w == "ln0") return F32(L.ln0, 1, D);
+  if (w == "ln1") return F32(L.ln1, 1, D);
+  if (w == "rel_bias") {
+    if (idx != 0) return false;
+    return F32(is_enc ? h->enc_rel : h->dec_rel, h->cfg.rel_buckets, h->H);
+  }
+  if (is_enc) return false;
+  if (w == "ln2") return F32(L.ln2, 1, D);
+  if (w == "cq") return T(L.cq, 0, HD, D);
+  if (w == "co") return T(L.co, 0, D, HD);
+  if (w == "ck") return T(h->ckv_w, (size_t)idx * 2 * HD, HD, D);
+  if (w == "cv") return T(h->ckv_w, (size_t)idx * 2 * HD + HD, HD, D);
+  return false;
+}
+
+std::vector<std::string> required_weights(const gram_handle* h) {
+  std::vector<std::string> r = {"shared", "lm_head", "enc.final_ln", "dec.final_ln", "enc.0.rel_bias", "dec.0.rel_bias"};
+  if (h->cfg.n_positions > 0) r.push_back("pos_emb");
+  for (int i = 0; i < h->Le; ++i)
+    for (const char* w : {"q", "k", "v", "o", "wi", "wo", "ln0", "ln1"}) r.push_back("enc." + std::to_string(i) + "." + w);
+  for (int i = 0; i < h->Ld; ++i)
+    for (const char* w : {"q", "k", "v", "o", "cq", "ck", "cv", "co", "wi", "wo", "ln0", "ln1", "ln2"})
+      r.push_back("dec." + std::to_string(i) + "." + w);
+  return r;
+}
+
+int next_pow2(int v) { int n = 1; while (n < v) n <<= 1; return n; }
+
+// ---- encoder --------------------------------------------------------------------------------------
+int run_encode(gram_handle* h, const int64_t* ids, const uint8_t* mask, int B, int N, int L, cudaStream_t s) {
+  const gram_config& c = h->cfg;
+  if (!h->weights_ready) return fail(h, GRAM_ERR_STATE, "gram_encode: weights not finalised");
+  if (B <= 0 || N <= 0 || L <= 0) return fail(h, GRAM_ERR_INVALID, "gram_encode: empty batch");
+  if (B > c.max_users || N > c.max_passages || L > c.max_seq_len)
+    return fail(h, GRAM_ERR_INVALID, "gram_encode: B/N/L exceed the capacities given to gram_create");
+  if ((int64_t)B * N * L > h->Mcap) return fail(h, GRAM_ERR_INVALID, "gram_encode: B*N*L exceeds max_tokens");
+  if (c.n_positions > 0 && N > c.n_positions)
+    return fail(h, GRAM_ERR_INVALID, "gram_encode: more passages than rows in the position table");
+  const size_t n = (size_t)B * N * L;
+  const int64_t* dids = ids;
+  const uint8_t* dmask = mask;
+  if (!is_device_ptr(ids)) { CK(cudaMemcpyAsync(h->d_ids, ids, n * sizeof(int64_t), cudaMemcpyHostToDevice, s)); dids = h->d_ids; }
+  if (!is_device_ptr(mask)) { CK(cudaMemcpyAsync(h->d_mask, mask, n, cudaMemcpyHostToDevice, s)); dmask = h->d_mask; }
+  h->encoded = false;
+  h->enc_B = B; h->enc_N = N; h->enc_L = L;
+  const int Mmax = (int)n;
+  const int* mp = h->pm.total;
+  const int D = h->D, HD = h->HD, F = h->F;
+  CKL(GRAM_K_OTHER, enc_pack(dids, dmask, B, N, L, h->pm, s));
+  h->launches += 2;   // enc_pack issues three kernels
+  CKL(GRAM_K_OTHER, embed_rows(c.dtype, h->shared, h->pm.tok_id, h->x, Mmax, mp, D, s));
+  for (int l = 0; l < h->Le; ++l) {
+    const LayerW& W = h->enc[l];
+    CKL(GRAM_K_OTHER, rmsnorm_rows(c.dtype, h->x, W.ln0, h->xn, Mmax, mp, D, c.ln_eps, 1.f, nullptr, nullptr, s));
+    RC(gemm(h, GRAM_K_GEMM_ENC, EPI_STORE, h->xn, W.qkv, h->qkv, Mmax, mp, 3 * HD, D, s));
+    CKL(GRAM_K_ENC_ATTN, enc_attention(c.dtype, h->qkv, h->ao, h->pm.plen, h->pm.poff, h->pm.tok_valid,
+                                       h->enc_bias_lut, h->Lb, B * N, h->H, h->dk, L, s));
+    RC(gemm(h, GRAM_K_GEMM_ENC, EPI_RESID, h->ao, W.o, h->x, Mmax, mp, D, HD, s));
+    CKL(GRAM_K_OTHER, rmsnorm_rows(c.dtype, h->x, W.ln1, h->xn, Mmax, mp, D, c.ln_eps, 1.f, nullptr, nullptr, s));
+    RC(gemm(h, GRAM_K_GEMM_ENC, EPI_RELU, h->xn, W.wi, h->ff, Mmax, mp, F, D, s));
+    RC(gemm(h, GRAM_K_GEMM_ENC, EPI_RESID, h->ff, W.wo, h->x, Mmax, mp, D, F, s));
+  }
+  CKL(GRAM_K_OTHER, rmsnorm_rows(c.dtype, h->x, h->enc_final_ln, h->mem, Mmax, mp, D, c.ln_eps, 1.f,
+                                 h->pos_emb, h->pos_emb ? h->pm.tok_pos : nullptr, s));
+  // cross-attention K/V of every decoder layer, written in place in the layout kernel (b) reads
+  RC(gemm(h, GRAM_K_GEMM_KV, EPI_STORE, h->mem, h->ckv_w, h->ckv, Mmax, mp, h->Ld * 2 * HD, D, s));
+  h->encoded = true;
+  return GRAM_OK;
+}
+
+// ---- one decoder step (all layers + lm_head) for R rows ---------------------------------------------
+int decoder_step(gram_handle* h, int R, int K, int users, int t, const int* anc, cudaStream_t s) {
+  const gram_config& c = h->cfg;
+  const int D = h->D, HD = h->HD, F = h->F;
+  const size_t esz = h->esz;
+  const size_t layer_cache = (size_t)c.max_length * h->Rcap * HD * esz;
+  CKL(GRAM_K_OTHER, embed_rows(c.dtype, h->shared, h->bs.tok, h->dx, R, nullptr, D, s));
+  for (int l = 0; l < h->Ld; ++l) {
+    const LayerW& W = h->dec[l];
+    CKL(GRAM_K_OTHER, rmsnorm_rows(c.dtype, h->dx, W.ln0, h->dxn, R, nullptr, D, c.ln_eps, 1.f, nullptr, nullptr, s));
+    RC(gemm(h, GRAM_K_GEMM_DEC, EPI_STORE, h->dxn, W.qkv, h->dqkv, R, nullptr, 3 * HD, D, s));
+    // cache slices are indexed [t][R][HD] with the *current* R as the row pitch
+    CKL(GRAM_K_OTHER, dec_self_attention(c.dtype, h->dqkv, (char*)h->sk + l * layer_cache, (char*)h->sv + l * layer_cache,
+                                         anc, c.max_length, h->dec_bias_lut, h->n_dec_lut, h->dao, R, K, h->H, h->dk, t, s));
+    RC(gemm(h, GRAM_K_GEMM_DEC, EPI_RESID, h->dao, W.o, h->dx, R, nullptr, D, HD, s));
+    CKL(GRAM_K_OTHER, rmsnorm_rows(c.dtype, h->dx, W.ln1, h->dxn, R, nullptr, D, c.ln_eps, 1.f, nullptr, nullptr, s));
+    RC(gemm(h, GRAM_K_GEMM_DEC, EPI_STORE, h->dxn, W.cq, h->dq, R, nullptr, HD, D, s));
+    CKL(GRAM_K_CROSS_ATTN, cross_attention(c.dtype, h->dq, h->ckv, (size_t)h->Ld * 2 * HD, l * 2 * HD, l * 2 * HD + HD,
+                                           h->pm.ustart, h->pm.tok_valid, h->dao, users, K, h->H, h->dk, s));
+    RC(gemm(h, GRAM_K_GEMM_DEC, EPI_RESID, h->dao, W.co, h->dx, R, nullptr, D, HD, s));
+    CKL(GRAM_K_OTHER, rmsnorm_rows(c.dtype, h->dx, W.ln2, h->dxn, R, nullptr, D, c.ln_eps, 1.f, nullptr, nullptr, s));
+    RC(gemm(h, GRAM_K_GEMM_DEC, EPI_RELU, h->dxn, W.wi, h->dff, R, nullptr, F, D, s));
+    RC(gemm(h, GRAM_K_GEMM_DEC, EPI_RESID, h->dff, W.wo, h->dx, R, nullptr, D, F, s));
+  }
+  const float scale = c.tie_word_embeddings ? 1.0f / sqrtf((float)D) : 1.0f;
+  CKL(GRAM_K_OTHER, rmsnorm_rows(c.dtype, h->dx, h->dec_final_ln, h->dxn, R, nullptr, D, c.ln_eps, scale, nullptr, nullptr, s));
+  RC(gemm(h, GRAM_K_LM_HEAD, EPI_F32, h->dxn, h->lm_head, h->logits, R, nullptr, h->V, D, s));
+  return GRAM_OK;
+}
+
+}  // namespace
+
+// =====================================================================================================
+// C ABI
+// =====================================================================================================
+extern "C" {
+
+const char* gram_version(void) { return "gram_b200 0.1 (sm_100a)"; }
+
+const char* gram_last_error(const gram_handle* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+void gram_destroy(gram_handle* h) {
+  if (!h) return;
+  cudaSetDevice(h->cfg.device);
+  for (void* p : h->allocs) cudaFree(p);
+  for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
+  if (h->h_len_pow) cudaFreeHost(h->h_len_pow);
+  if (h->h_flags) cudaFreeHost(h->h_flags);
+  delete h;
+}
+
+int gram_create(const gram_config* cfg, gram_handle** out) {
+  if (!cfg || !out) { g_create_error = "gram_create: null argument"; return GRAM_ERR_INVALID; }
+  *out = nullptr;
+  gram_handle* h = new gram_handle();
+  h->cfg = *cfg;
+  const gram_config& c = h->cfg;
+  auto bail = [&](int code) { g_create_error = h->err; gram_destroy(h); return code; };
+  if (c.dtype != GRAM_DTYPE_F32 && c.dtype != GRAM_DTYPE_BF16) { h->err = "gram_create: dtype must be 0 (fp32) or 1 (bf16)"; return bail(GRAM_ERR_INVALID); }
+  if (c.vocab_size <= 0 || c.d_model <= 0 || c.d_kv <= 0 || c.d_ff <= 0 || c.num_layers <= 0 ||
+      c.num_decoder_layers <= 0 || c.num_heads <= 0 || c.max_users <= 0 || c.max_passages <= 0 ||
+      c.max_seq_len <= 0 || c.max_beams <= 0 || c.max_length < 2) {
+    h->err = "gram_create: non-positive dimension"; return bail(GRAM_ERR_INVALID);
+  }
+  if (c.d_kv != 16 && c.d_kv != 32 && c.d_kv != 64) { h->err = "gram_create: d_kv must be 16, 32 or 64"; return bail(GRAM_ERR_UNSUPPORTED); }
+  if ((c.d_model & 3) || (c.d_ff & 3) || (c.vocab_size & 3)) { h->err = "gram_create: d_model, d_ff and vocab_size must be multiples of 4"; return bail(GRAM_ERR_UNSUPPORTED); }
+  if (c.max_beams > 64) { h->err = "gram_create: max_beams > 64 is not supported"; return bail(GRAM_ERR_UNSUPPORTED); }
+  if (c.max_length > 64) { h->err = "gram_create: max_length > 64 is not supported"; return bail(GRAM_ERR_UNSUPPORTED); }
+  if (c.max_seq_len > 256) { h->err = "gram_create: max_seq_len > 256 is not supported"; return bail(GRAM_ERR_UNSUPPORTED); }
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    cudaGetLastError();
+    h->err = "gram_create: no CUDA device visible -- gram_b200 has no CPU fallback"; return bail(GRAM_ERR_CUDA);
+  }
+  if (c.device < 0 || c.device >= ndev) { h->err = "gram_create: bad device ordinal"; return bail(GRAM_ERR_INVALID); }
+  {
+    cudaError_t e = cudaSetDevice(c.device);
+    if (e != cudaSuccess) { h->err = std::string("cudaSetDevice: ") + cudaGetErrorString(e); return bail(GRAM_ERR_CUDA); }
+    cudaDeviceProp prop;
+    cudaGetDeviceProperties(&prop, c.device);
+    if (prop.major != 10) {
+      char b[256]; snprintf(b, sizeof b, "gram_create: device %d is sm_%d%d; this library is built for sm_100a only", c.device, prop.major, prop.minor);
+      h->err = b; return bail(GRAM_ERR_UNSUPPORTED);
+    }
+    h->num_sms = prop.multiProcessorCount;
+  }
+  h->D = c.d_model; h->dk = c.d_kv; h->H = c.num_heads; h->HD = c.num_heads * c.d_kv; h->F = c.d_ff; h->V = c.vocab_size;
+  h->Le = c.num_layers; h->Ld = c.num_decoder_layers;
+  h->esz = c.dtype == GRAM_DTYPE_F32 ? 4 : 2;
+  if (h->HD & 3) { h->err = "gram_create: num_heads*d_kv must be a multiple of 4"; return bail(GRAM_ERR_UNSUPPORTED); }
+  const size_t esz = h->esz;
+  const int D = h->D, HD = h->HD, F = h->F, V = h->V;
+  int rc;
+#define DAC(ptr, bytes) do { rc = dalloc(h, &(ptr), (bytes)); if (rc) return bail(rc); } while (0)
+  // ---- weights ----
+  DAC(h->shared, (size_t)V * D * esz);
+  DAC(h->lm_head, (size_t)V * D * esz);
+  if (c.n_positions > 0) DAC(h->pos_emb, (size_t)c.n_positions * D * 4);
+  DAC(h->enc_final_ln, (size_t)D * 4);
+  DAC(h->dec_final_ln, (size_t)D * 4);
+  DAC(h->enc_rel, (size_t)c.rel_buckets * h->H * 4);
+  DAC(h->dec_rel, (size_t)c.rel_buckets * h->H * 4);
+  h->enc.resize(h->Le); h->dec.resize(h->Ld);
+  for (int i = 0; i < h->Le; ++i) {
+    LayerW& L = h->enc[i];
+    DAC(L.qkv, (size_t)3 * HD * D * esz); DAC(L.o, (size_t)D * HD * esz);
+    DAC(L.wi, (size_t)F * D * esz); DAC(L.wo, (size_t)D * F * esz);
+    DAC(L.ln0, (size_t)D * 4); DAC(L.ln1, (size_t)D * 4);
+  }
+  for (int i = 0; i < h->Ld; ++i) {
+    LayerW& L = h->dec[i];
+    DAC(L.qkv, (size_t)3 * HD * D * esz); DAC(L.o, (size_t)D * HD * esz);
+    DAC(L.cq, (size_t)HD * D * esz); DAC(L.co, (size_t)D * HD * esz);
+    DAC(L.wi, (size_t)F * D * esz); DAC(L.wo, (size_t)D * F * esz);
+    DAC(L.ln0, (size_t)D * 4); DAC(L.ln1, (size_t)D * 4); DAC(L.ln2, (size_t)D * 4);
+  }
+  DAC(h->ckv_w, (size_t)h->Ld * 2 * HD * D * esz);
+  h->Lb = c.max_seq_len;
+  h->n_enc_lut = 2 * h->Lb - 1;
+  h->n_dec_lut = c.max_length;
+  DAC(h->enc_bias_lut, (size_t)h->H * h->n_enc_lut * 4);
+  DAC(h->dec_bias_lut, (size_t)h->H * h->n_dec_lut * 4);
+  // ---- encoder workspace ----
+  const int64_t full = (int64_t)c.max_users * c.max_passages * c.max_seq_len;
+  h->Mcap = (c.max_tokens > 0 && c.max_tokens < full) ? c.max_tokens : full;
+  if (h->Mcap > 0x7fffffff) { h->err = "gram_create: token capacity exceeds 2^31"; return bail(GRAM_ERR_UNSUPPORTED); }
+  const size_t Mc = (size_t)h->Mcap + 256;     // slack rows so vector loads/TMA boxes never leave the buffer
+  const size_t P = (size_t)c.max_users * c.max_passages;
+  DAC(h->pm.plen, P * 4); DAC(h->pm.poff, (P + 1) * 4); DAC(h->pm.ustart, ((size_t)c.max_users + 1) * 4);
+  DAC(h->pm.total, 16);
+  DAC(h->pm.tok_id, Mc * 4); DAC(h->pm.tok_pos, Mc * 4); DAC(h->pm.tok_valid, Mc); DAC(h->pm.row_src, Mc * 4);
+  DAC(h->d_ids, (size_t)full * 8); DAC(h->d_mask, (size_t)full);
+  DAC(h->x, Mc * D * 4);
+  DAC(h->xn, Mc * D * esz); DAC(h->qkv, Mc * 3 * HD * esz); DAC(h->ao, Mc * HD * esz);
+  DAC(h->ff, Mc * F * esz); DAC(h->mem, Mc * D * esz);
+  DAC(h->ckv, Mc * (size_t)h->Ld * 2 * HD * esz);
+  // ---- decoder workspace ----
+  h->Rcap = c.max_users * c.max_beams;
+  const size_t R = (size_t)h->Rcap + 128;
+  const int ML = c.max_length;
+  DAC(h->dx, R * D * 4);
+  DAC(h->dxn, R * D * esz); DAC(h->dqkv, R * 3 * HD * esz); DAC(h->dao, R * HD * esz); DAC(h->dq, R * HD * esz);
+  DAC(h->dff, R * F * esz);
+  DAC(h->sk, (size_t)h->Ld * ML * R * HD * esz); DAC(h->sv, (size_t)h->Ld * ML * R * HD * esz);
+  DAC(h->logits, R * V * 4); DAC(h->lse, R * 4);
+  BeamState& bs = h->bs;
+  bs.max_length = ML; bs.gen_len = ML; bs.V = V; bs.eos = c.eos_id; bs.pad = c.pad_id; bs.K = c.max_beams;
+  for (int i = 0; i < 2; ++i) {
+    DAC(bs.beam_score[i], R * 4); DAC(bs.node[i], R * 4); DAC(bs.seq[i], R * ML * 4); DAC(bs.anc[i], R * ML * 4);
+  }
+  DAC(bs.tok, R * 4);
+  const size_t U = c.max_users, S = (size_t)c.max_beams + 1;
+  DAC(bs.hyp_score, U * S * 8); DAC(bs.hyp_len, U * S * 4); DAC(bs.hyp_seqno, U * S * 4); DAC(bs.hyp_tok, U * S * ML * 4);
+  DAC(bs.n_hyp, U * 4); DAC(bs.worst, U * 8); DAC(bs.next_seqno, U * 4); DAC(bs.done, U * 4);
+  DAC(bs.err, 16);
+  DAC(h->d_len_pow, ((size_t)ML + 1) * 8);
+  bs.len_pow = h->d_len_pow;
+  bs.tap_lse = nullptr; bs.tap_score = nullptr; bs.tap_seq = nullptr;
+  if (c.flags & GRAM_FLAG_KEEP_LOGITS) {
+    DAC(bs.tap_lse, (size_t)ML * R * 4); DAC(bs.tap_score, (size_t)ML * R * 4); DAC(bs.tap_seq, (size_t)ML * R * ML * 4);
+  }
+  DAC(h->d_out_seq, U * c.max_beams * ML * 8); DAC(h->d_out_scores, U * c.max_beams * 4); DAC(h->d_out_width, 16);
+  DAC(h->d_zero_anc, R * ML * 4);
+  DAC(h->d_dec_ids, R * ML * 8);
+#undef DAC
+  if (cudaMemset(h->d_zero_anc, 0, R * ML * 4) != cudaSuccess || cudaMemset(bs.err, 0, 16) != cudaSuccess ||
+      cudaMemset(bs.anc[0], 0, R * ML * 4) != cudaSuccess || cudaMemset(bs.anc[1], 0, R * ML * 4) != cudaSuccess) {
+    h->err = "gram_create: cudaMemset failed"; return bail(GRAM_ERR_CUDA);
+  }
+  if (cudaMallocHost(&h->h_len_pow, ((size_t)ML + 1) * 8) != cudaSuccess || cudaMallocHost(&h->h_flags, 64) != cudaSuccess) {
+    h->err = "gram_create: cudaMallocHost failed"; return bail(GRAM_ERR_CUDA);
+  }
+  *out = h;
+  return GRAM_OK;
+}
+
+int gram_load_weight(gram_handle* h, const char* name, const float* data, const int64_t* shape, int32_t ndim) {
+  if (!h || !name || !data || !shape) return GRAM_ERR_INVALID;
+  CK(cudaSetDevice(h->cfg.device));
+  WeightSlot ws;
+  if (!resolve_weight(h, name, &ws)) return fail(h, GRAM_ERR_INVALID, std::string("gram_load_weight: unknown tensor name '") + name + "'");
+  int64_t rows = 1, cols = 1;
+  if (ndim == 1) { cols = shape[0]; }
+  else if (ndim == 2) { rows = shape[0]; cols = shape[1]; }
+  else return fail(h, GRAM_ERR_INVALID, "gram_load_weight: ndim must be 1 or 2");
+  if (rows != ws.rows || cols != ws.cols) {
+    char b[256];
+    snprintf(b, sizeof b, "gram_load_weight: '%s' has shape [%lld,%lld], expected [%lld,%lld]", name, (long long)rows,
+             (long long)cols, (long long)ws.rows, (long long)ws.cols);
+    return fail(h, GRAM_ERR_INVALID, b);
+  }
+  const size_t n = (size_t)rows * cols;
+  if (n > h->stage_elems) {
+    float* p = nullptr;
+    CK(cudaMalloc(&p, n * 4));
+    if (h->stage) cudaFree(h->stage);
+    h->stage = p; h->stage_elems = n;
+  }
+  CK(cudaMemcpy(h->stage, data, n * 4, cudaMemcpyHostToDevice));
+  const int grid = (int)((n + 255) / 256);
+  if (ws.f32 || h->cfg.dtype == GRAM_DTYPE_F32) convert_kernel_f32<<<grid, 256>>>(h->stage, (float*)ws.dst, n);
+  else convert_kernel_bf16<<<grid, 256>>>(h->stage, (bf16*)ws.dst, n);
+  CK(cudaGetLastError());
+  CK(cudaDeviceSynchronize());
+  h->loaded.insert(name);
+  h->weights_ready = false;
+  return GRAM_OK;
+}
+
+int gram_set_rel_buckets(gram_handle* h, const int32_t* enc_buckets, int32_t n_enc, const int32_t* dec_buckets,
+                         int32_t n_dec) {
+  if (!h || !enc_buckets || !dec_buckets) return GRAM_ERR_INVALID;
+  CK(cudaSetDevice(h->cfg.device));
+  if (n_enc != h->n_enc_lut || n_dec != h->n_dec_lut) {
+    char b[256];
+    snprintf(b, sizeof b, "gram_set_rel_buckets: expected n_enc=%d (2*max_seq_len-1) and n_dec=%d (max_length)", h->n_enc_lut, h->n_dec_lut);
+    return fail(h, GRAM_ERR_INVALID, b);
+  }
+  for (int i = 0; i < n_enc; ++i) if (enc_buckets[i] < 0 || enc_buckets[i] >= h->cfg.rel_buckets) return fail(h, GRAM_ERR_INVALID, "bucket out of range");
+  for (int i = 0; i < n_dec; ++i) if (dec_buckets[i] < 0 || dec_buckets[i] >= h->cfg.rel_buckets) return fail(h, GRAM_ERR_INVALID, "bucket out of range");
+  // stash the bucket ids in the (int-sized) LUT buffers; finalize turns them into bias values
+  CK(cudaMemcpy(h->enc_bias_lut, enc_buckets, (size_t)n_enc * 4, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(h->dec_bias_lut, dec_buckets, (size_t)n_dec * 4, cudaMemcpyHostToDevice));
+  h->buckets_set = true;
+  h->weights_ready = false;
+  return GRAM_OK;
+}
+
+int gram_finalize_weights(gram_handle* h) {
+  if (!h) return GRAM_ERR_INVALID;
+  CK(cudaSetDevice(h->cfg.device));
+  for (const std::string& n : required_weights(h))
+    if (!h->loaded.count(n)) return fail(h, GRAM_ERR_STATE, "gram_finalize_weights: tensor '" + n + "' was never loaded");
+  if (!h->buckets_set) return fail(h, GRAM_ERR_STATE, "gram_finalize_weights: gram_set_rel_buckets not called");
+  // bias LUTs: lut[h][i] = rel[bucket[i]][h]
+  int* tmp = nullptr;
+  const int nmax = h->n_enc_lut > h->n_dec_lut ? h->n_enc_lut : h->n_dec_lut;
+  CK(cudaMalloc(&tmp, (size_t)nmax * 4));
+  CK(cudaMemcpy(tmp, h->enc_bias_lut, (size_t)h->n_enc_lut * 4, cudaMemcpyDeviceToDevice));
+  build_lut_kernel<<<(h->n_enc_lut * h->H + 255) / 256, 256>>>(h->enc_rel, tmp, h->n_enc_lut, h->H, h->enc_bias_lut);
+  CK(cudaDeviceSynchronize());
+  CK(cudaMemcpy(tmp, h->dec_bias_lut, (size_t)h->n_dec_lut * 4, cudaMemcpyDeviceToDevice));
+  build_lut_kernel<<<(h->n_dec_lut * h->H + 255) / 256, 256>>>(h->dec_rel, tmp, h->n_dec_lut, h->H, h->dec_bias_lut);
+  CK(cudaDeviceSynchronize());
+  cudaFree(tmp);
+  if (h->stage) { cudaFree(h->stage); h->stage = nullptr; h->stage_elems = 0; }
+  h->buckets_set = false;    // LUT buffers now hold values; buckets must be re-sent before another finalize
+  h->weights_ready = true;
+  return GRAM_OK;
+}
+
+int gram_set_trie(gram_handle* h, const int32_t* child_offsets, const int32_t* child_tokens, const int32_t* child_nodes,
+                  int32_t n_nodes, int32_t n_edges, int32_t root_node) {
+  if (!h || !child_offsets || n_nodes <= 0 || n_edges < 0) return GRAM_ERR_INVALID;
+  if (n_edges > 0 && (!child_tokens || !child_nodes)) return GRAM_ERR_INVALID;
+  CK(cudaSetDevice(h->cfg.device));
+  if (root_node >= n_nodes) return fail(h, GRAM_ERR_INVALID, "gram_set_trie: root_node out of range");
+  if (child_offsets[0] != 0 || child_offsets[n_nodes] != n_edges) return fail(h, GRAM_ERR_INVALID, "gram_set_trie: malformed CSR offsets");
+  int max_fan = 0;
+  for (int i = 0; i < n_nodes; ++i) {
+    const int f = child_offsets[i + 1] - child_offsets[i];
+    if (f < 0) return fail(h, GRAM_ERR_INVALID, "gram_set_trie: offsets must be non-decreasing");
+    if (f > max_fan) max_fan = f;
+  }
+  for (int e = 0; e < n_edges; ++e) {
+    if (child_tokens[e] < 0 || child_tokens[e] >= h->V) return fail(h, GRAM_ERR_INVALID, "gram_set_trie: token id outside the vocabulary");
+    if (child_nodes[e] < 0 || child_nodes[e] >= n_nodes) return fail(h, GRAM_ERR_INVALID, "gram_set_trie: child node out of range");
+  }
+  const int cap = next_pow2((max_fan > 0 ? max_fan : 1) * h->cfg.max_beams);
+  if (beam_step_smem(cap) > 200 * 1024)
+    return fail(h, GRAM_ERR_UNSUPPORTED, "gram_set_trie: max_beams * max trie fan-out exceeds the shared-memory candidate buffer");
+  int *d_off = nullptr, *d_tok = nullptr, *d_node = nullptr;
+  DA(d_off, ((size_t)n_nodes + 1) * 4); DA(d_tok, ((size_t)n_edges + 1) * 4); DA(d_node, ((size_t)n_edges + 1) * 4);
+  CK(cudaMemcpy(d_off, child_offsets, ((size_t)n_nodes + 1) * 4, cudaMemcpyHostToDevice));
+  if (n_edges) {
+    CK(cudaMemcpy(d_tok, child_tokens, (size_t)n_edges * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(d_node, child_nodes, (size_t)n_edges * 4, cudaMemcpyHostToDevice));
+  }
+  h->trie.child_offsets = d_off; h->trie.child_tokens = d_tok; h->trie.child_nodes = d_node;
+  h->trie.n_nodes = n_nodes; h->trie.n_edges = n_edges; h->trie.root = root_node; h->trie.max_fanout = max_fan;
+  h->cand_cap = cap < 64 ? 64 : cap;
+  h->trie_set = true;
+  return GRAM_OK;
+}
+
+int gram_encode(gram_handle* h, const int64_t* ids, const uint8_t* mask, int32_t B, int32_t N, int32_t L, void* stream) {
+  if (!h || !ids || !mask) return GRAM_ERR_INVALID;
+  CK(cudaSetDevice(h->cfg.device));
+  h->launches = 0;
+  return run_encode(h, ids, mask, B, N, L, (cudaStream_t)stream);
+}
+
+int gram_generate(gram_handle* h, const int64_t* ids, const uint8_t* mask, int32_t B, int32_t N, int32_t L, int32_t K,
+                  int32_t R_ret, int32_t max_length, const double* len_pow, int64_t* out_seq, int32_t* out_width,
+                  float* out_scores, void* stream) {
+  if (!h || !len_pow || !out_seq || !out_scores || !out_width) return GRAM_ERR_INVALID;
+  CK(cudaSetDevice(h->cfg.device));
+  cudaStream_t s = (cudaStream_t)stream;
+  const gram_config& c = h->cfg;
+  if (!h->trie_set) return fail(h, GRAM_ERR_STATE, "gram_generate: no trie set (gram_set_trie)");
+  if (K <= 0 || K > c.max_beams) return fail(h, GRAM_ERR_INVALID, "gram_generate: num_beams exceeds max_beams");
+  if (R_ret <= 0 || R_ret > K) return fail(h, GRAM_ERR_INVALID, "`num_return_sequences` has to be smaller or equal to `num_beams`.");
+  if (max_length < 2 || max_length > c.max_length) return fail(h, GRAM_ERR_INVALID, "gram_generate: max_length outside [2, cfg.max_length]");
+  h->launches = 0;
+  if (ids) {
+    if (!mask) return GRAM_ERR_INVALID;
+    RC(run_encode(h, ids, mask, B, N, L, s));
+  } else {
+    if (!h->encoded) return fail(h, GRAM_ERR_STATE, "gram_generate: ids == NULL but nothing has been encoded");
+    B = h->enc_B;
+  }
+  const int users = B, R = B * K, T = max_length - 1;
+  // the candidate buffer was sized for cfg.max_beams; K <= max_beams so it is sufficient
+  BeamState bs = h->bs;
+  bs.K = K; bs.max_length = c.max_length; bs.gen_len = max_length;
+  memcpy(h->h_len_pow, len_pow, ((size_t)max_length + 1) * sizeof(double));
+  for (int i = max_length + 1; i <= c.max_length; ++i) h->h_len_pow[i] = 1.0;
+  CK(cudaMemcpyAsync(h->d_len_pow, h->h_len_pow, ((size_t)c.max_length + 1) * 8, cudaMemcpyHostToDevice, s));
+  CKL(GRAM_K_BEAM, beam_init(bs, h->trie, users, c.start_id, s));
+  for (int t = 0; t < T; ++t) {
+    RC(decoder_step(h, R, K, users, t, bs.anc[t & 1], s));
+    CKL(GRAM_K_LM_HEAD, lse_rows(h->logits, h->lse, R, h->V, s));
+    CKL(GRAM_K_BEAM, beam_step(bs, h->trie, h->logits, h->lse, users, t, h->cand_cap, s));
+  }
+  CKL(GRAM_K_BEAM, beam_finalize(bs, users, T, R_ret, h->d_out_seq, h->d_out_scores, h->d_out_width, s));
+  h->last_steps = T; h->last_R = R;
+  // ---- copy-out: the library's result layout is [B*R_ret, cfg.max_length]; the ABI promises max_length ----
+  const size_t rows = (size_t)users * R_ret;
+  const bool host_out = !is_device_ptr(out_seq);
+  if (max_length == c.max_length) {
+    CK(cudaMemcpyAsync(out_seq, h->d_out_seq, rows * max_length * 8, host_out ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice, s));
+  } else {
+    CK(cudaMemcpy2DAsync(out_seq, (size_t)max_length * 8, h->d_out_seq, (size_t)c.max_length * 8, (size_t)max_length * 8, rows,
+                         host_out ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice, s));
+  }
+  CK(cudaMemcpyAsync(out_scores, h->d_out_scores, rows * 4, is_device_ptr(out_scores) ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, s));
+  CK(cudaMemcpyAsync(out_width, h->d_out_width, 4, is_device_ptr(out_width) ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, s));
+  CK(cudaMemcpyAsync(&h->h_flags[0], bs.err, 4, cudaMemcpyDeviceToHost, s));
+  CK(cudaMemcpyAsync(&h->h_flags[2], h->pm.total, 4, cudaMemcpyDeviceToHost, s));
+  if (host_out || !is_device_ptr(out_scores) || !is_device_ptr(out_width)) {
+    CK(cudaStreamSynchronize(s));
+    if (h->h_flags[0] != 0) {
+      cudaMemsetAsync(bs.err, 0, 4, s);
+      return fail(h, GRAM_ERR_INVALID, "gram_generate: candidate buffer overflow (trie fan-out larger than declared)");
+    }
+  }
+  return GRAM_OK;
+}
+
+int gram_get_memory(gram_handle* h, float* out, void* stream) {
+  if (!h || !out) return GRAM_ERR_INVALID;
+  CK(cudaSetDevice(h->cfg.device));
+  cudaStream_t s = (cudaStream_t)stream;
+  if (!h->encoded) return fail(h, GRAM_ERR_STATE, "gram_get_memory: nothing encoded");
+  const size_t n = (size_t)h->enc_B * h->enc_N * h->enc_L * h->D;
+  float* dst = out;
+  float* tmp = nullptr;
+  const bool dev = is_device_ptr(out);
+  if (!dev) { CK(cudaMalloc(&tmp, n * 4)); dst = tmp; }
+  CK(cudaMemsetAsync(dst, 0, n * 4, s));
+  cudaError_t e = unpack_memory(h->cfg.dtype, h->mem, h->pm.row_src, dst, (int)((size_t)h->enc_B * h->enc_N * h->enc_L), h->pm.total, h->D, s);
+  if (e != cudaSuccess) { if (tmp) cudaFree(tmp); return fail(h, GRAM_ERR_CUDA, cudaGetErrorString(e)); }
+  if (!dev) {
+    CK(cudaMemcpyAsync(out, tmp, n * 4, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    cudaFree(tmp);
+  }
+  return GRAM_OK;
+}
+
+int gram_decoder_logits(gram_handle* h, const int64_t* dec_ids, int32_t q, float* out_logits, void* stream) {
+  if (!h || !dec_ids || !out_logits) return GRAM_ERR_INVALID;
+  CK(cudaSetDevice(h->cfg.device));
+  cudaStream_t s = (cudaStream_t)stream;
+  if (!h->encoded) return fail(h, GRAM_ERR_STATE, "gram_decoder_logits: nothing encoded");
+  if (q <= 0 || q > h->cfg.max_length) return fail(h, GRAM_ERR_INVALID, "gram_decoder_logits: q outside [1, max_length]");
+  const int B = h->enc_B, R = B;
+  const int64_t* dids = dec_ids;
+  if (!is_device_ptr(dec_ids)) {
+    CK(cudaMemcpyAsync(h->d_dec_ids, dec_ids, (size_t)R * q * 8, cudaMemcpyHostToDevice, s));
+    dids = h->d_dec_ids;
+  }
+  const bool dev = is_device_ptr(out_logits);
+  BeamState bs = h->bs;
+  bs.K = 1;
+  const size_t V = h->V;
+  for (int t = 0; t < q; ++t) {
+    CKL(GRAM_K_OTHER, forced_step(bs, dids, q, t, R, s));
+    RC(decoder_step(h, R, 1, B, t, h->d_zero_anc, s));
+    // logits [R, V] -> out[b][t][:]
+    CK(cudaMemcpy2DAsync(out_logits + (size_t)t * V, (size_t)q * V * 4, h->logits, V * 4, V * 4, R,
+                         dev ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, s));
+  }
+  if (!dev) CK(cudaStreamSynchronize(s));
+  return GRAM_OK;
+}
+
+int gram_get_step_taps(gram_handle* h, float* lse, float* beam_scores, int32_t* beam_tokens, int32_t* n_steps) {
+  if (!h) return GRAM_ERR_INVALID;
+  CK(cudaSetDevice(h->cfg.device));
+  if (!h->bs.tap_lse) return fail(h, GRAM_ERR_STATE, "gram_get_step_taps: handle was created without GRAM_FLAG_KEEP_LOGITS");
+  CK(cudaDeviceSynchronize());
+  const size_t n = (size_t)h->last_steps * h->last_R;
+  if (lse) CK(cudaMemcpy(lse, h->bs.tap_lse, n * 4, cudaMemcpyDefault));
+  if (beam_scores) CK(cudaMemcpy(beam_scores, h->bs.tap_score, n * 4, cudaMemcpyDefault));
+  if (beam_tokens) CK(cudaMemcpy(beam_tokens, h->bs.tap_seq, n * h->cfg.max_length * 4, cudaMemcpyDefault));
+  if (n_steps) *n_steps = h->last_steps;
+  return GRAM_OK;
+}
+
+int gram_get_stats(gram_handle* h, gram_stats* out) {
+  if (!h || !out) return GRAM_ERR_INVALID;
+  CK(cudaSetDevice(h->cfg.device));
+  int total = 0;
+  CK(cudaMemcpy(&total, h->pm.total, 4, cudaMemcpyDeviceToHost));
+  out->launches = h->launches;
+  out->packed_tokens = h->encoded ? total : 0;
+  out->kv_bytes = (int64_t)total * h->Ld * 2 * h->HD * (int64_t)h->esz;
+  out->workspace_bytes = (int64_t)h->alloc_bytes;
+  return GRAM_OK;
+}
+
+int gram_profile_begin(gram_handle* h, uint32_t class_mask) {
+  if (!h) return GRAM_ERR_INVALID;
+  CK(cudaSetDevice(h->cfg.device));
+  h->prof_mask = class_mask;
+  h->ev_used = 0;
+  h->ev_log.clear();
+  for (int i = 0; i < GRAM_K_COUNT; ++i) h->cls_launches[i] = 0;
+  // pre-create a pool so event creation never lands inside a timed region
+  while (h->ev_pool.size() < 8192) { cudaEvent_t e; CK(cudaEventCreate(&e)); h->ev_pool.push_back(e); }
+  return GRAM_OK;
+}
+
+int gram_profile_end(gram_handle* h, float* ms_per_class, int64_t* launches_per_class) {
+  if (!h) return GRAM_ERR_INVALID;
+  CK(cudaSetDevice(h->cfg.device));
+  CK(cudaDeviceSynchronize());
+  float acc[GRAM_K_COUNT] = {0};
+  for (const auto& r : h->ev_log) {
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, r.a, r.b));
+    acc[r.cls] += ms;
+  }
+  for (int i = 0; i < GRAM_K_COUNT; ++i) {
+    if (ms_per_class) ms_per_class[i] = acc[i];
+    if (launches_per_class) launches_per_class[i] = h->cls_launches[i];
+  }
+  h->prof_mask = 0;
+  h->ev_used = 0;
+  h->ev_log.clear();
+  return GRAM_OK;
+}
+
+int gram_op_gemm(int32_t device, int32_t dtype, int32_t impl, int32_t epilogue, const void* A, const void* W, void* C,
+                 int32_t M, int32_t N, int32_t K, void* stream) {
+  if (cudaSetDevice(device) != cudaSuccess) return GRAM_ERR_CUDA;
+  cudaError_t e;
+  if (impl == 1) {
+    if (dtype != GRAM_DTYPE_BF16 || !gemm_tc_supported(N, K)) { g_create_error = "gram_op_gemm: tcgen05 path needs bf16 and a supported (N,K)"; return GRAM_ERR_UNSUPPORTED; }
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    e = gemm_tc(epilogue, A, W, C, M, nullptr, N, K, sms, (cudaStream_t)stream);
+    if (e != cudaSuccess) { g_create_error = std::string("gemm_tc: ") + cudaGetErrorString(e) + " / " + gemm_tc_last_error(); return GRAM_ERR_CUDA; }
+    return GRAM_OK;
+  }
+  e = gemm_simt(dtype, epilogue, A, W, C, M, nullptr, N, K, (cudaStream_t)stream);
+  if (e != cudaSuccess) { g_create_error = std::string("gemm_simt: ") + cudaGetErrorString(e); return GRAM_ERR_CUDA; }
+  return GRAM_OK;
+}
+
+int gram_op_cross_attention(int32_t device, int32_t dtype, const void* q, const void* kv, const int32_t* user_start,
+                            const uint8_t* tok_valid, void* out, int32_t users, int32_t K, int32_t H, int32_t dk,
+                            void* stream) {
+  if (cudaSetDevice(device) != cudaSuccess) return GRAM_ERR_CUDA;
+  cudaError_t e = cross_attention(dtype, q, kv, (size_t)2 * H * dk, 0, H * dk, user_start, tok_valid, out, users, K, H, dk,
+                                  (cudaStream_t)stream);
+  if (e != cudaSuccess) { g_create_error = std::string("cross_attention: ") + cudaGetErrorString(e); return GRAM_ERR_CUDA; }
+  return GRAM_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,93 @@
+// Host-callable launchers of the gram_b200 kernels.  dtype: 0 = fp32 storage, 1 = bf16 storage
+// (activations/weights); accumulation and the residual stream are always fp32.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace gram {
+
+enum { EPI_STORE = 0, EPI_RELU = 1, EPI_RESID = 2, EPI_F32 = 3 };
+
+// ---- gemm_simt.cu ------------------------------------------------------------------------------
+// C[M,N] = A[M,K] * W[N,K]^T.  M = *m_ptr when m_ptr != nullptr (grid sized for M_max), else M_max.
+cudaError_t gemm_simt(int dtype, int epi, const void* A, const void* W, void* C, int M_max, const int* m_ptr,
+                      int N, int K, cudaStream_t s);
+
+// ---- gemm_tc.cu (tcgen05 / TMEM / TMA, bf16) -----------------------------------------------------
+struct TcGemmPlan;   // cached TMA descriptors for one (A, W, shape)
+bool gemm_tc_supported(int N, int K);
+cudaError_t gemm_tc(int epi, const void* A, const void* W, void* C, int M_max, const int* m_ptr, int N, int K,
+                    int num_sms, cudaStream_t s);
+const char* gemm_tc_last_error();
+
+// ---- encoder_kernels.cu --------------------------------------------------------------------------
+struct PackMeta {            // device-resident description of the packed (valid-token) layout
+  int* plen;                 // [P]    valid length of passage p (last valid index + 1)
+  int* poff;                 // [P+1]  first packed row of passage p
+  int* ustart;               // [B+1]  first packed row of user b
+  int* total;                // [1]    number of packed rows (M of every encoder GEMM)
+  int* tok_id;               // [Mcap] token id per packed row
+  int* tok_pos;              // [Mcap] passage index within the user (row of the position table)
+  uint8_t* tok_valid;        // [Mcap] attention-mask bit per packed row
+  int* row_src;              // [Mcap] flat index b*N*L + n*L + l of the packed row (for unpacking)
+};
+cudaError_t enc_pack(const int64_t* ids, const uint8_t* mask, int B, int N, int L, PackMeta pm, cudaStream_t s);
+cudaError_t embed_rows(int dtype, const void* table, const int* tok_id, float* x, int M_max, const int* m_ptr,
+                       int D, cudaStream_t s);
+// y = w * (x * rsqrt(mean(x^2)+eps)) * scale  [+ pos_table[tok_pos[row]]]   (x fp32 -> y dtype)
+cudaError_t rmsnorm_rows(int dtype, const float* x, const float* w, void* y, int M_max, const int* m_ptr, int D,
+                         float eps, float scale, const float* pos_table, const int* tok_pos, cudaStream_t s);
+// bidirectional self-attention of every (passage, head): qkv [M, 3*H*dk] -> out [M, H*dk]
+cudaError_t enc_attention(int dtype, const void* qkv, void* out, const int* plen, const int* poff,
+                          const uint8_t* tok_valid, const float* bias_lut /*[H, 2*Lb-1]*/, int Lb, int P, int H,
+                          int dk, int Lmax, cudaStream_t s);
+cudaError_t unpack_memory(int dtype, const void* mem, const int* row_src, float* out, int M_max, const int* m_ptr,
+                          int D, cudaStream_t s);
+
+// ---- decoder_kernels.cu --------------------------------------------------------------------------
+// single-token causal self-attention with an ancestry-indirected KV cache.
+//   qkv [R, 3*HD]; cache_k/v [Tmax][R][HD]; anc [R][Tmax] (row *within the user* holding position j);
+//   dec_bias [H][n_dec]; t = current position.  Writes this step's k/v into slot t.
+cudaError_t dec_self_attention(int dtype, const void* qkv, void* cache_k, void* cache_v, const int* anc, int Tmax,
+                               const float* dec_bias, int n_dec, void* out, int R, int K, int H, int dk, int t,
+                               cudaStream_t s);
+// cross-attention over the in-place packed K/V memory (kernel (b)).
+//   q [R, HD]; kv rows of `kv_stride` elements with K at column k_off and V at column v_off (+ h*dk);
+//   user u owns packed rows [ustart[u], ustart[u+1]); beams of user u are rows u*K .. u*K+K-1.
+cudaError_t cross_attention(int dtype, const void* q, const void* kv, size_t kv_stride, int k_off, int v_off,
+                            const int* ustart, const uint8_t* tok_valid, void* out, int users, int K, int H, int dk,
+                            cudaStream_t s);
+
+// ---- beam_kernels.cu -------------------------------------------------------------------------------
+struct TrieCSR {
+  const int* child_offsets; const int* child_tokens; const int* child_nodes;
+  int n_nodes; int n_edges; int root; int max_fanout;
+};
+struct BeamState {           // all device pointers; rows R = users*K
+  int K, max_length, V, eos, pad;   // max_length = row pitch of seq/anc/hyp_tok (capacity)
+  int gen_len;                       // max_length of the current generate call (<= max_length)
+  float* beam_score[2];      // [R]
+  int* node[2];              // [R]   trie node of the beam prefix, -1 = dead
+  int* seq[2];               // [R][max_length] token prefix
+  int* anc[2];               // [R][max_length] self-attention cache ancestry
+  int* tok;                  // [R]   input token of the next decoder step
+  // hypotheses (per user, K+1 slots)
+  double* hyp_score; int* hyp_len; int* hyp_seqno; int* hyp_tok;   // [U][K+1], ..., [U][K+1][max_length]
+  int* n_hyp; double* worst; int* next_seqno; int* done;            // [U]
+  int* err;                  // [1] sticky device-side error flag
+  const double* len_pow;     // [max_length+1]
+  // optional taps
+  float* tap_lse; float* tap_score; int* tap_seq;                   // [steps][R](...)
+};
+cudaError_t lse_rows(const float* logits, float* lse, int R, int V, cudaStream_t s);
+cudaError_t beam_init(BeamState bs, TrieCSR trie, int users, int start_tok, cudaStream_t s);
+// one beam-search step: PrefixConstrainedLogitsProcessor + topk(2K) + BeamSearchScorer.process
+cudaError_t beam_step(BeamState bs, TrieCSR trie, const float* logits, const float* lse, int users, int t,
+                      int cand_cap, cudaStream_t s);
+cudaError_t beam_finalize(BeamState bs, int users, int t_final, int R_ret, int64_t* out_seq, float* out_scores,
+                          int* out_width, cudaStream_t s);
+// teacher forcing: tok[r] = ids[r*q + t], anc[r][t'] = 0
+cudaError_t forced_step(BeamState bs, const int64_t* dec_ids, int q, int t, int R, cudaStream_t s);
+size_t beam_step_smem(int cand_cap);
+
+}  // namespace gram

@@ -1,0 +1,158 @@
+/*
+ * gram_b200 -- C ABI of the B200-native GRAM inference/scoring hot path.
+ *
+ * This is the drop-in boundary.  The reference has no native layer: its
+ * "FFI" for this path is the Python call `model_rec.generate(...)` made by the eval loop, which in
+ * turn drives torch/ATen kernels op by op.  Each entry point below states the reference interface it
+ * replaces (paths relative to the reference root).  All pointers are plain host or device pointers;
+ * no torch types cross this boundary.  Integer return codes: 0 = ok, non-zero = error (message via
+ * gram_last_error).  One handle per device; a handle is not re-entrant; all device work is issued on
+ * the caller-provided stream and there is no host synchronisation inside the decode-step loop.
+ */
+#ifndef GRAM_B200_H_
+#define GRAM_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct gram_handle gram_handle;
+
+enum { GRAM_DTYPE_F32 = 0, GRAM_DTYPE_BF16 = 1 };
+
+enum {
+  GRAM_OK = 0,
+  GRAM_ERR_INVALID = 1,   /* bad argument / shape / capacity exceeded */
+  GRAM_ERR_CUDA = 2,      /* a CUDA runtime call failed              */
+  GRAM_ERR_STATE = 3,     /* call order violated (weights/trie/encode missing) */
+  GRAM_ERR_UNSUPPORTED = 4
+};
+
+/* Model + capacity description.  Field meaning follows the reference's config object
+ * (src/model/gram_t5_config.py:85-105) and the GRAM additions (src/main_generative_gram.py:67-70). */
+typedef struct gram_config {
+  int32_t vocab_size, d_model, d_kv, d_ff;
+  int32_t num_layers, num_decoder_layers, num_heads;
+  int32_t rel_buckets, rel_max_distance;
+  float   ln_eps;
+  int32_t pad_id, eos_id, start_id;
+  int32_t tie_word_embeddings;     /* 1: scale decoder output by d_model**-0.5 (gram_t5.py:249-252) */
+  int32_t n_positions;             /* rows of the passage-position table (max_item_num+1); 0 = none  */
+  int32_t dtype;                   /* GRAM_DTYPE_F32 (parity mode) or GRAM_DTYPE_BF16                */
+  int32_t device;                  /* CUDA device ordinal */
+  /* capacities: workspaces are allocated once in gram_create, nothing is allocated per call */
+  int32_t max_users;               /* B per call */
+  int32_t max_passages;            /* N */
+  int32_t max_seq_len;             /* L */
+  int32_t max_beams;               /* K */
+  int32_t max_length;              /* decoder max_length (start token included) */
+  int64_t max_tokens;              /* cap on packed valid encoder tokens per call; 0 = B*N*L */
+  int32_t flags;                   /* GRAM_FLAG_* */
+} gram_config;
+
+enum {
+  GRAM_FLAG_SIMT_GEMM = 1,         /* force the CUDA-core GEMM even for bf16 (debug / A-B timing) */
+  GRAM_FLAG_KEEP_LOGITS = 2        /* materialise full-vocab logits every step (debug / parity)   */
+};
+
+/* ---- lifetime -------------------------------------------------------------------------------- */
+/* replaces: model.create_model("gram", config) + .to(device)   (src/model/__init__.py:9-24,
+ * src/main_generative_gram.py:158-163) */
+int gram_create(const gram_config* cfg, gram_handle** out);
+void gram_destroy(gram_handle* h);
+const char* gram_last_error(const gram_handle* h);   /* h may be NULL: last create error */
+const char* gram_version(void);
+
+/* ---- weights --------------------------------------------------------------------------------- */
+/* replaces: GRAM.load_t5(state_dict) / load_state_dict  (src/model/gram.py:162-165).
+ * `name` is a canonical tensor name (see gram_b200/weights.py for the mapping from the reference's
+ * state-dict keys): "shared", "lm_head", "pos_emb", "enc.final_ln", "dec.final_ln",
+ * "enc.<i>.{q,k,v,o,wi,wo,ln0,ln1,rel_bias}", "dec.<i>.{q,k,v,o,cq,ck,cv,co,wi,wo,ln0,ln1,ln2,rel_bias}".
+ * `data` is a HOST pointer to contiguous fp32 in the reference's layout (nn.Linear: [out,in]). */
+int gram_load_weight(gram_handle* h, const char* name, const float* data, const int64_t* shape, int32_t ndim);
+/* relative-position bucket tables, computed by the host with the reference's own torch fp32 ops
+ * (src/model/gram_t5_modeling.py:397-450; rounding-sensitive):
+ *   enc_buckets[r + (n_enc-1)/2] for r = mem - ctx in [-(L-1), L-1];  dec_buckets[dist], dist = ctx - mem >= 0 */
+int gram_set_rel_buckets(gram_handle* h, const int32_t* enc_buckets, int32_t n_enc,
+                         const int32_t* dec_buckets, int32_t n_dec);
+/* checks that every tensor arrived, builds fused/packed device layouts.  Call once after loading. */
+int gram_finalize_weights(gram_handle* h);
+
+/* ---- item trie ------------------------------------------------------------------------------- */
+/* replaces: Trie(sequences) + prefix_allowed_tokens_fn(trie) (src/utils/generation_trie.py:5-95) as
+ * consumed by PrefixConstrainedLogitsProcessor.  CSR: children of node n are
+ * child_tokens/child_nodes[child_offsets[n] .. child_offsets[n+1]).  `root_node` is the node reached
+ * by the decoder start token (Trie.get([0]) lists its children); -1 if absent. */
+int gram_set_trie(gram_handle* h, const int32_t* child_offsets, const int32_t* child_tokens,
+                  const int32_t* child_nodes, int32_t n_nodes, int32_t n_edges, int32_t root_node);
+
+/* ---- hot path -------------------------------------------------------------------------------- */
+/* replaces: EncoderWrapper.forward (src/model/gram.py:200-256) + the per-layer cross-attention K/V
+ * projection (src/model/gram_t5_modeling.py:531-534).  ids int64 [B,N,L], mask uint8/bool [B,N,L];
+ * host or device pointers.  Leaves the fused memory and K/V resident in the handle. */
+int gram_encode(gram_handle* h, const int64_t* ids, const uint8_t* mask, int32_t B, int32_t N, int32_t L,
+                void* stream);
+
+/* replaces: GRAM.generate(input_ids, attention_mask, max_length, prefix_allowed_tokens_fn=...,
+ * num_beams=K, num_return_sequences=R, length_penalty=...) (src/model/gram.py:74-107; call site
+ * src/runner/single_runner_gram.py:641-651) including transformers-4.26 beam_search /
+ * BeamSearchScorer / PrefixConstrainedLogitsProcessor.
+ *   len_pow[c] = float(c) ** length_penalty for c in [0, max_length]   (host-computed doubles)
+ *   out_seq    int64 [B*R, max_length], rows best-first per user, 0-padded, EOS after the id
+ *   out_scores fp32  [B*R]  (sum_logprobs / len**length_penalty)
+ *   out_width  int32 [1]    min(max hypothesis length + 1, max_length) as HF pads it
+ * Output pointers may be host or device.  If `ids` is NULL the batch encoded by the last
+ * gram_encode call is decoded. */
+int gram_generate(gram_handle* h, const int64_t* ids, const uint8_t* mask, int32_t B, int32_t N, int32_t L,
+                  int32_t K, int32_t R, int32_t max_length, const double* len_pow,
+                  int64_t* out_seq, int32_t* out_width, float* out_scores, void* stream);
+
+/* ---- parity / debug taps (same kernels, results copied out) ------------------------------------ */
+/* fused memory of the last gram_encode as fp32 [B, N*L, d_model]; positions that were skipped
+ * (masked tail of a passage, all-masked passages) are written as 0. Host or device pointer. */
+int gram_get_memory(gram_handle* h, float* out, void* stream);
+/* replaces: GRAM.forward(..., decoder_input_ids=dec_ids, encoder_outputs=...) teacher-forced logits
+ * (src/model/gram.py:51-69): dec_ids int64 [B,q] -> logits fp32 [B,q,V] through the cached
+ * single-token decode step. */
+int gram_decoder_logits(gram_handle* h, const int64_t* dec_ids, int32_t q, float* out_logits, void* stream);
+/* per-step taps of the last gram_generate (requires GRAM_FLAG_KEEP_LOGITS):
+ * lse fp32 [steps, B*K]; beam_scores fp32 [steps, B*K] (scores entering the step);
+ * beam tokens int32 [steps, B*K, max_length] (prefix entering the step). Any pointer may be NULL. */
+int gram_get_step_taps(gram_handle* h, float* lse, float* beam_scores, int32_t* beam_tokens, int32_t* n_steps);
+
+/* ---- measurement ------------------------------------------------------------------------------- */
+typedef struct gram_stats {
+  int64_t launches;          /* kernels launched by the last encode/generate call            */
+  int64_t packed_tokens;     /* valid encoder tokens of the last encode (needs a sync to read) */
+  int64_t kv_bytes;          /* bytes of cross-attention K/V resident for the last batch      */
+  int64_t workspace_bytes;   /* device memory owned by the handle                             */
+} gram_stats;
+int gram_get_stats(gram_handle* h, gram_stats* out);
+
+/* kernel classes for event timing */
+enum {
+  GRAM_K_GEMM_ENC = 0, GRAM_K_ENC_ATTN = 1, GRAM_K_GEMM_KV = 2, GRAM_K_GEMM_DEC = 3,
+  GRAM_K_CROSS_ATTN = 4, GRAM_K_LM_HEAD = 5, GRAM_K_BEAM = 6, GRAM_K_OTHER = 7, GRAM_K_COUNT = 8
+};
+/* mask: bit c set = bracket every launch of class c with CUDA events on the launching stream */
+int gram_profile_begin(gram_handle* h, uint32_t class_mask);
+/* synchronises the stream, returns per-class total milliseconds and launch counts, clears the log */
+int gram_profile_end(gram_handle* h, float* ms_per_class /*[GRAM_K_COUNT]*/, int64_t* launches_per_class);
+
+/* ---- single-operator entry points (unit parity tests and roofline measurement) ------------------ */
+/* C[M,N] = A[M,K] * W[N,K]^T on device pointers.  dtype as in gram_config; impl 0 = SIMT fp32-accumulate,
+ * 1 = tcgen05 (bf16 only).  epilogue: 0 store (dtype), 1 relu+store (dtype), 2 C_f32 += acc, 3 store fp32. */
+int gram_op_gemm(int32_t device, int32_t dtype, int32_t impl, int32_t epilogue, const void* A, const void* W,
+                 void* C, int32_t M, int32_t N, int32_t K, void* stream);
+/* decoder cross-attention over an in-place K/V memory: q [users*K, H*dk], kv [tokens, 2*H*dk] (K|V),
+ * user_start int32 [users+1], tok_valid uint8 [tokens], out [users*K, H*dk] (all dtype). */
+int gram_op_cross_attention(int32_t device, int32_t dtype, const void* q, const void* kv,
+                            const int32_t* user_start, const uint8_t* tok_valid, void* out,
+                            int32_t users, int32_t K, int32_t H, int32_t dk, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GRAM_B200_H_ */
