@@ -1,0 +1,363 @@
+#!/usr/bin/env python
+"""bench.py -- users/sec of the GRAM inference/scoring hot path on B200.
+
+    python bench.py --gpus N --steps K --warmup W            (N > 1: launched by torchrun, one rank per GPU)
+    python bench.py --impl reference --gpus N --steps K --warmup W
+
+Workload (BASELINE.json configs[1]): Beauty full test set, T5-small, beam 20, 20 returned sequences,
+max_length 10, bf16 -- passage-batched encoder -> fused FiD memory -> cross-attention decode ->
+trie-constrained beam search over the 12,101-item trie.  A "step" is one pass of the hot path over one
+batch of `--batch` test users (leave-one-out split of the shipped Beauty user sequences; surrogate
+tokenizer + synthetic metadata tokens + random-init tied weights, because no tokenizer / text /
+checkpoint exists offline -- see gram_b200/data.py).  Users are sharded across ranks with no
+data-path collective ("scaling": "weak": every rank processes `--batch` users per step).
+
+Keys of the JSON line (see the task contract): value = whole-job users/s with inputs already resident
+in HBM; e2e = the same through `GRAM.generate(...)` with pinned HOST tensors (H2D of ids/mask and D2H of
+the ranked ids/scores inside the timed region); roofline = the dominant kernel class (tensor-core GEMM)
+against MEASURED_PEAKS.json; cpu_baseline = the oracle port of the reference timed on this box's cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+BEAMS = 20
+DATASET = "Beauty"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=8)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=256, help="users per step per GPU")
+    ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--cpu-users", type=int, default=8, help="users timed for cpu_baseline (0 = skip)")
+    ap.add_argument("--simt", action="store_true", help="force the CUDA-core GEMM (A/B timing)")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+# --------------------------------------------------------------------------------------------------
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return dict(hbm=d["hbm_gbs"], tensor=d["bf16_tflops_sustained"], tensor_burst=d["bf16_tflops"], src="measured")
+    return dict(hbm=6650.0, tensor=1400.0, tensor_burst=1590.0, src="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index = index
+        self.rows = []
+        self._stop = threading.Event()
+        self._t = None
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                      "-i", str(self.index)], capture_output=True, text=True, timeout=5).stdout
+                if out.strip():
+                    self.rows.append([c.strip() for c in out.strip().split(",")])
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def __enter__(self):
+        self._t = threading.Thread(target=self._run, daemon=True)
+        self._t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        self._t.join(timeout=6)
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+            except Exception:
+                continue
+            for n, v in zip(names, r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return dict(sm_mhz=float(np.median(sm)) if sm else None, sm_max_mhz=max(mx) if mx else None,
+                    reasons=sorted(reasons), samples=len(sm))
+
+
+def build_workload(args, rank, world):
+    from gram_b200 import GramConfig, Trie, prefix_allowed_tokens_fn, synth
+    from gram_b200.data import GramTestData
+    data = GramTestData(DATASET)
+    cfg = GramConfig.t5_small(max_seq_len=data.L, max_item_num=data.max_his)
+    sd = synth.make_state_dict(cfg, seed=0)
+    cands = data.encoded_candidates()
+    max_length = max(len(c) for c in cands)
+    trie = Trie(cands)
+    fn = prefix_allowed_tokens_fn(trie)
+    return data, cfg, sd, cands, max_length, trie, fn
+
+
+def step_users(data, step, batch, rank, world):
+    """Users of one step on one rank: contiguous shards, wrapping around the 22,363-user test set."""
+    start = ((step * world + rank) * batch) % data.n_users
+    return [(start + i) % data.n_users for i in range(batch)]
+
+
+def flops_and_bytes(cfg, tokens, users, K, T, esz):
+    """Algorithmic work of one step (SURVEY.md section 8(d) formulas)."""
+    d, HD, F, V = cfg.d_model, cfg.inner_dim, cfg.d_ff, cfg.vocab_size
+    Le, Ld = cfg.num_layers, cfg.num_decoder_layers
+    rows = users * K
+    gemm_enc = tokens * Le * (8 * d * HD + 4 * d * F)
+    gemm_kv = tokens * Ld * 4 * d * HD
+    gemm_dec = T * rows * Ld * (12 * d * HD + 4 * d * F)
+    gemm_head = T * rows * 2 * d * V
+    xattn_bytes = T * Ld * 2 * tokens * HD * esz
+    return dict(gemm_enc=gemm_enc, gemm_kv=gemm_kv, gemm_dec=gemm_dec, gemm_head=gemm_head,
+                gemm_total=gemm_enc + gemm_kv + gemm_dec + gemm_head, xattn_bytes=xattn_bytes)
+
+
+# --------------------------------------------------------------------------------------------------
+def cpu_oracle_users_per_sec(data, cfg, sd, cands, max_length, users, warm=1):
+    """The reference's CPU path (oracle port: reference modules' math + restated HF-4.26 beam search,
+    eval_batch_size 1 as the reference runs it) timed on this box's host cores."""
+    from oracle.gram_oracle import OracleGRAM, OracleTrie
+    torch.set_num_threads(os.cpu_count() or 1)
+    ora = OracleGRAM(cfg, sd)
+    trie = OracleTrie(cands)
+    batches = []
+    for u in users:
+        b = data.collate([u])
+        batches.append((torch.from_numpy(b["item_text_ids"]), torch.from_numpy(b["item_text_masks"])))
+    for ids, mask in batches[:warm]:
+        ora.generate(ids, mask, max_length, trie, BEAMS, BEAMS, 1.0)
+    t0 = time.perf_counter()
+    for ids, mask in batches[warm:]:
+        ora.generate(ids, mask, max_length, trie, BEAMS, BEAMS, 1.0)
+    dt = time.perf_counter() - t0
+    n = len(batches) - warm
+    return n / dt, n, dt
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    data, cfg, sd, cands, max_length, trie, fn = build_workload(args, 0, 1)
+    per_step = 1                                   # users per step: a bounded sample of the 256-user batch
+    users = [u for s in range(args.warmup + args.steps) for u in step_users(data, s, args.batch, 0, 1)[:per_step]]
+    from oracle.gram_oracle import OracleGRAM, OracleTrie
+    torch.set_num_threads(os.cpu_count() or 1)
+    ora = OracleGRAM(cfg, sd)
+    otrie = OracleTrie(cands)
+    times = []
+    for s in range(args.warmup + args.steps):
+        t0 = time.perf_counter()
+        for u in users[s * per_step:(s + 1) * per_step]:
+            b = data.collate([u])
+            ora.generate(torch.from_numpy(b["item_text_ids"]), torch.from_numpy(b["item_text_masks"]), max_length,
+                         otrie, BEAMS, BEAMS, 1.0)
+        times.append(time.perf_counter() - t0)
+    timed = times[args.warmup:]
+    total = sum(timed)
+    value = per_step * args.steps / total
+    sample = (f"{per_step} users per step (eval_batch_size 1, as the reference runs) x {args.steps} steps of the "
+              f"Beauty test split, fp32, torch CPU")
+    line = dict(metric="users/sec, trie-constrained beam-20 Recall@10 eval", value=value, unit="users/s", n_gpus=args.gpus,
+                steps=args.steps, warmup=args.warmup, ms_per_step=1000 * total / args.steps, higher_is_better=True,
+                scaling="weak", vs_baseline=None, dtype="f32", data="synthetic", impl="reference",
+                config=workload_config(args, data, max_length),
+                cpu_baseline=dict(value=value, unit="users/s", cores=os.cpu_count(), kind="port", sample=sample),
+                e2e=dict(value=value, unit="users/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, data, max_length):
+    return dict(workload=f"{DATASET} full test set ({data.n_users} users, {data.n_items}-item trie), T5-small, beam {BEAMS}, "
+                         f"return {BEAMS}, max_length {max_length}, max_his {data.max_his} x {data.L} tokens",
+                users_per_step_per_gpu=args.batch, parallelism=f"user-sharded dp{args.gpus}",
+                inputs="surrogate tokenizer + synthetic metadata tokens + random-init tied weights (seed 0)",
+                cache="per-step working set (K/V memory + activations, > 8 GB) exceeds the 126 MB L2; every step uses different users")
+
+
+# --------------------------------------------------------------------------------------------------
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (gram_b200 has no CPU fallback)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+
+    from gram_b200 import GRAM, _cabi
+    data, cfg, sd, cands, max_length, trie, fn = build_workload(args, rank, world)
+    flags = _cabi.GRAM_FLAG_SIMT_GEMM if args.simt else 0
+    model = GRAM(cfg, dtype=args.dtype, device=dev, flags=flags)
+    model.load_state_dict(sd)
+    B, K, W, S = args.batch, BEAMS, args.warmup, args.steps
+    model.configure(max_users=B, max_beams=K, max_length=max_length, max_passages=data.max_his + 1, max_seq_len=data.L)
+    model.user_limit = B
+
+    # ---- inputs: host (pinned) and device copies for every step -----------------------------------
+    host_in, dev_in, tokens = [], [], []
+    for s in range(W + S):
+        b = data.collate(step_users(data, s, B, rank, world))
+        ids = torch.from_numpy(b["item_text_ids"]).pin_memory()
+        mask = torch.from_numpy(b["item_text_masks"]).pin_memory()
+        host_in.append((ids, mask))
+        dev_in.append((ids.to(dev), mask.to(dev)))
+        tokens.append(int(b["item_text_masks"].sum()))
+    out_seq = torch.zeros((B * K, max_length), dtype=torch.int64, device=dev)
+    out_scores = torch.zeros((B * K,), dtype=torch.float32, device=dev)
+    out_width = torch.zeros((1,), dtype=torch.int32, device=dev)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def kernel_step(i):
+        ids, mask = dev_in[i]
+        model.generate_into(ids, mask, max_length, trie, K, K, 1.0, out_seq, out_scores, out_width)
+
+    # ---- value: inputs resident in HBM ------------------------------------------------------------
+    for i in range(W):
+        kernel_step(i)
+    barrier()
+    gemm_classes = ["gemm_enc", "gemm_kv", "gemm_dec", "lm_head"]
+    model.profile_begin(gemm_classes)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clocks:
+        barrier()
+        ev0.record()
+        for i in range(W, W + S):
+            kernel_step(i)
+        ev1.record()
+        barrier()
+    ms = ev0.elapsed_time(ev1)
+    prof = model.profile_end()
+    if dist is not None:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    value = world * B * S / (ms / 1000.0)
+
+    # ---- per-class device time of the same steps (second pass, all classes bracketed) ----------------
+    model.profile_begin(None)
+    for i in range(W, W + S):
+        kernel_step(i)
+    prof_all = model.profile_end()
+
+    # ---- e2e: public API with pinned host tensors ----------------------------------------------------
+    e2e = None
+    if not args.no_e2e:
+        def e2e_step(i):
+            ids, mask = host_in[i]
+            return model.generate(input_ids=ids, attention_mask=mask, max_length=max_length, prefix_allowed_tokens_fn=fn,
+                                  num_beams=K, num_return_sequences=K, output_scores=True, return_dict_in_generate=True,
+                                  length_penalty=1.0)
+        for i in range(W):
+            e2e_step(i)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        res = None
+        for i in range(W, W + S):
+            res = e2e_step(i)
+        e1.record()
+        barrier()
+        ems = e0.elapsed_time(e1)
+        if dist is not None:
+            t = torch.tensor([ems], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ems = float(t.item())
+        ids0, mask0 = host_in[W]
+        e2e = dict(value=world * B * S / (ems / 1000.0), unit="users/s",
+                   h2d_bytes_per_step=int(ids0.numel() * 8 + mask0.numel()),
+                   d2h_bytes_per_step=int(B * K * max_length * 8 + B * K * 4 + 4),
+                   ms_per_step=ems / S)
+        assert res["sequences"].shape[0] == B * K
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel class -------------------------------------------------------
+    peaks = load_peaks()
+    esz = 2 if args.dtype == "bf16" else 4
+    T = max_length - 1
+    tok_timed = tokens[W:W + S]
+    work = [flops_and_bytes(cfg, t, B, K, T, esz) for t in tok_timed]
+    gemm_ms = sum(prof[c]["ms"] for c in gemm_classes)
+    gemm_launches = sum(prof[c]["launches"] for c in gemm_classes)
+    gemm_flops = sum(w["gemm_total"] for w in work)
+    achieved_tf = gemm_flops / (gemm_ms / 1000.0) / 1e12 if gemm_ms > 0 else 0.0
+    roofline = dict(bound="tensor", kernel="gemm (all nn.Linear of the path: encoder, K/V projection, decoder, lm_head)",
+                    achieved=achieved_tf, peak=peaks["tensor"], unit="TFLOP/s", frac=achieved_tf / peaks["tensor"],
+                    traffic=None, peak_source=f"{peaks['src']} sustained bf16", launches=gemm_launches,
+                    avg_launch_ms=gemm_ms / max(gemm_launches, 1), share_of_step=gemm_ms / ms)
+    xa_ms = prof_all["cross_attn"]["ms"]
+    xa_bytes = sum(w["xattn_bytes"] for w in work)
+    xa_gbs = xa_bytes / (xa_ms / 1000.0) / 1e9 if xa_ms > 0 else 0.0
+    total_all = sum(v["ms"] for v in prof_all.values())
+    kernels = {c: dict(ms_per_step=v["ms"] / S, launches_per_step=v["launches"] // S,
+                       share=v["ms"] / total_all if total_all else 0.0) for c, v in prof_all.items()}
+    roofline_cross = dict(bound="hbm", kernel="cross_attention", achieved=xa_gbs, peak=peaks["hbm"], unit="GB/s",
+                          frac=xa_gbs / peaks["hbm"], traffic=None)
+
+    # ---- CPU baseline (bounded sample) -----------------------------------------------------------------
+    cpu = None
+    if args.cpu_users > 0 and world == 1:
+        ups, n, dt = cpu_oracle_users_per_sec(data, cfg, sd, cands, max_length, step_users(data, W, B, 0, 1)[:args.cpu_users + 1])
+        cpu = dict(value=ups, unit="users/s", cores=os.cpu_count(), kind="port",
+                   sample=f"{n} users of the first timed batch, eval_batch_size 1, fp32 torch CPU, {dt:.1f} s")
+
+    line = dict(metric="users/sec, trie-constrained beam-20 Recall@10 eval", value=value, unit="users/s", n_gpus=world,
+                steps=S, warmup=W, ms_per_step=ms / S, higher_is_better=True, scaling="weak", vs_baseline=None,
+                dtype=args.dtype, data="synthetic", config=workload_config(args, data, max_length),
+                clocks=clocks.summary(), e2e=e2e, gpu_launches=int(model.stats()["launches"]) * S,
+                roofline=roofline, roofline_cross_attention=roofline_cross, kernel_classes=kernels,
+                cpu_baseline=cpu, tokens_per_step=float(np.mean(tok_timed)),
+                gemm_impl="simt" if (args.simt or args.dtype == "fp32") else "tcgen05")
+    print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

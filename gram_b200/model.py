@@ -274,6 +274,26 @@ class GRAM:
         return GenerateOutput(sequences=sequences, sequences_scores=scores, scores=None, beam_indices=None)
 
     @torch.no_grad()
+    def generate_into(self, input_ids, attention_mask, max_length, trie, num_beams, num_return_sequences,
+                      length_penalty, out_seq, out_scores, out_width):
+        """`generate` without the Python-side post-processing: one C-ABI call writing into caller
+        tensors (`out_seq` int64 [B*R, max_length], `out_scores` fp32 [B*R], `out_width` int32 [1]).
+        With device tensors nothing synchronises -- the bench's kernel-only loop uses this."""
+        ids, mask = self._prep_inputs(input_ids, attention_mask)
+        B, N, L = ids.shape
+        K, R = int(num_beams), int(num_return_sequences)
+        self._ensure(B, N, L, K, int(max_length))
+        self._set_trie(trie)
+        key = (int(max_length), float(length_penalty))
+        if getattr(self, "_len_pow_key", None) != key:
+            self._len_pow = (C.c_double * (max_length + 1))(*[float(c) ** float(length_penalty) if c > 0 else 1.0
+                                                              for c in range(max_length + 1)])
+            self._len_pow_key = key
+        _cabi.check(self._lib.gram_generate(
+            self._handle, _ptr(ids), _ptr(mask), B, N, L, K, R, int(max_length), self._len_pow,
+            _ptr(out_seq), _ptr(out_width), _ptr(out_scores), self._stream()), self._handle, "gram_generate")
+
+    @torch.no_grad()
     def encode(self, input_ids, attention_mask):
         """Fused FiD memory `[B, N*L, d_model]` fp32 (zeros at skipped positions) -- parity tap."""
         ids, mask = self._prep_inputs(input_ids, attention_mask)

@@ -75,7 +75,7 @@ def test_gemm_simt(dtype, shape, epi):
                           C.c_void_p(Cd.data_ptr()), M, N, K, None)
     assert rc == 0, lib.gram_last_error(None)
     torch.cuda.synchronize()
-    tol = 2e-6 if (dtype == "fp32" or epi >= 2) else 8e-3     # bf16 store rounding
+    tol = 5e-6 if (dtype == "fp32" or epi >= 2) else 8e-3     # bf16 store rounding
     assert rel_err(Cd, ref) < tol
 
 
