@@ -1,8 +1,349 @@
-// placeholder until the tcgen05 kernel lands
+// tcgen05 / TMEM / TMA GEMM for sm_100a:  C[M,N] = A[M,K] * W[N,K]^T, bf16 operands, fp32 accumulation.
+//
+// Every nn.Linear on the hot path runs through this kernel in bf16 mode (reference
+// src/model/gram_t5_modeling.py:305-310,369-372,553-569,622; src/model/gram_t5.py:254): encoder q|k|v, o, wi,
+// wo; the per-user cross-attention K/V projection of all decoder layers in one launch; decoder projections; and
+// the 32128-wide vocabulary head.  Both operands are K-major (activations [M,K] row-major, nn.Linear weights
+// [N,K] row-major), which is the native "TN" form of the 5th-generation tensor core.
+//
+// Structure (persistent, warp-specialised, one CTA per SM):
+//   warp 0      TMA producer: cp.async.bulk.tensor 128x64 bf16 boxes of A and W into a STAGES-deep shared-memory
+//               ring with 128-byte swizzle, completion signalled on mbarriers (expect_tx)
+//   warp 1      MMA issuer: one elected thread issues tcgen05.mma (M=128, N=128, K=16, kind::f16) reading the
+//               swizzled tiles through shared-memory descriptors, accumulating in TMEM; tcgen05.commit releases
+//               ring slots and publishes finished accumulators
+//   warps 2-5   epilogue: tcgen05.ld of the fp32 accumulator (each warp owns its 32-lane TMEM quadrant), fused
+//               ReLU / residual add / dtype conversion, vectorised global stores
+// TMEM holds two 128-column accumulators so the epilogue of tile i overlaps the MMAs of tile i+1.
+// M may live in device memory (*m_ptr): the packed encoder token count is only known on the device, so the
+// kernel derives its tile loop bound there and the host never synchronises.
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <mutex>
+#include <map>
+#include <tuple>
+#include <string>
+
 #include "common.cuh"
 #include "kernels.h"
+
 namespace gram {
-bool gemm_tc_supported(int, int) { return false; }
-cudaError_t gemm_tc(int, const void*, const void*, void*, int, const int*, int, int, int, cudaStream_t) { return cudaErrorNotSupported; }
-const char* gemm_tc_last_error() { return "not built"; }
+
+namespace tc {
+
+constexpr int BLOCK_M = 128, BLOCK_N = 128, BLOCK_K = 64, UMMA_K = 16;
+constexpr int STAGES = 6;
+constexpr int ACC_STAGES = 2;
+constexpr int TMEM_COLS = ACC_STAGES * BLOCK_N;            // 256, power of two
+constexpr int THREADS = 192;
+constexpr uint32_t A_BYTES = BLOCK_M * BLOCK_K * 2;        // 16 KiB
+constexpr uint32_t B_BYTES = BLOCK_N * BLOCK_K * 2;        // 16 KiB
+constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
+constexpr size_t SMEM_BYTES = (size_t)STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+
+// ---- PTX wrappers --------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
 }
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra WAIT_DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "WAIT_DONE:\n"
+      "}\n" ::"r"(bar), "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major, 128-byte-swizzled shared-memory matrix descriptor (sm_100 format): 8-row groups are 1024 B apart.
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);          // start address, 16-byte units          bits [0,14)
+  d |= (uint64_t)1 << 16;                                // leading byte offset (unused for SW128) bits [16,30)
+  d |= (uint64_t)(1024 >> 4) << 32;                      // stride byte offset = 1024 B            bits [32,46)
+  d |= (uint64_t)1 << 46;                                // descriptor version 1 (Blackwell)       bits [46,48)
+  d |= (uint64_t)2 << 61;                                // layout type: SWIZZLE_128B              bits [61,64)
+  return d;
+}
+// instruction descriptor: D=f32, A=B=bf16, both K-major, M=128, N=128
+constexpr uint32_t kInstrDesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BLOCK_N >> 3) << 17) |
+                                ((uint32_t)(BLOCK_M >> 4) << 24);
+
+template <int EPI>
+__global__ void __launch_bounds__(THREADS, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
+               void* __restrict__ Cv, int M_imm, const int* __restrict__ m_ptr, int N, int K) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;           // 1024-byte alignment for the 128B swizzle atoms
+  uint8_t* smem = smem_raw + (base - raw);
+  const uint32_t bars = base + STAGES * STAGE_BYTES;      // full[STAGES], empty[STAGES], tfull[2], tempty[2], tmem ptr
+  auto full_bar = [&](int s) { return bars + 8u * s; };
+  auto empty_bar = [&](int s) { return bars + 8u * (STAGES + s); };
+  auto tfull_bar = [&](int s) { return bars + 8u * (2 * STAGES + s); };
+  auto tempty_bar = [&](int s) { return bars + 8u * (2 * STAGES + ACC_STAGES + s); };
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + STAGES * STAGE_BYTES + 8 * (2 * STAGES + 2 * ACC_STAGES));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int M = m_ptr ? *m_ptr : M_imm;
+  const int num_m = (M + BLOCK_M - 1) / BLOCK_M, num_n = (N + BLOCK_N - 1) / BLOCK_N;
+  const int num_tiles = num_m * num_n;
+  const int num_kb = K / BLOCK_K;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
+    for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int s = 0; s < ACC_STAGES; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    int stage = 0; uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int m_blk = tile / num_n, n_blk = tile % num_n;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(empty_bar(stage), phase ^ 1u);
+        if (lane == 0) {
+          const uint32_t sa = base + stage * STAGE_BYTES, sb = sa + A_BYTES;
+          mbar_arrive_expect_tx(full_bar(stage), STAGE_BYTES);
+          tma_load_2d(sa, &map_a, full_bar(stage), kb * BLOCK_K, m_blk * BLOCK_M);
+          tma_load_2d(sb, &map_w, full_bar(stage), kb * BLOCK_K, n_blk * BLOCK_N);
+        }
+        __syncwarp();
+        if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    int stage = 0; uint32_t phase = 0;
+    int acc = 0; uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      mbar_wait(tempty_bar(acc), acc_phase ^ 1u);          // epilogue has drained this accumulator
+      tcgen05_fence_after();
+      const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BLOCK_N);
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(full_bar(stage), phase);                 // TMA bytes have landed
+        tcgen05_fence_after();
+        if (lane == 0) {
+          const uint32_t sa = base + stage * STAGE_BYTES, sb = sa + A_BYTES;
+          const uint64_t da = make_smem_desc(sa), db = make_smem_desc(sb);
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+            // advance 16 bf16 = 32 bytes inside the 128-byte swizzle row: +2 in 16-byte address units
+            umma_bf16(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), kInstrDesc, (kb | k) ? 1u : 0u);
+          }
+          umma_commit(empty_bar(stage));                   // frees the ring slot when these MMAs retire
+          if (kb == num_kb - 1) umma_commit(tfull_bar(acc));   // accumulator complete
+        }
+        __syncwarp();
+        if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+      }
+      if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1u; }
+    }
+  } else {
+    // ===================== epilogue (warps 2..5) =====================
+    const int quad = warp & 3;                             // TMEM lane quadrant this warp may access
+    int acc = 0; uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int m_blk = tile / num_n, n_blk = tile % num_n;
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tcgen05_fence_after();
+      const int row = m_blk * BLOCK_M + quad * 32 + lane;
+      const bool row_ok = row < M;
+#pragma unroll 1
+      for (int c = 0; c < BLOCK_N / 32; ++c) {
+        uint32_t r[32];
+        const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BLOCK_N + c * 32);
+        tmem_ld32(taddr, r);
+        tmem_ld_wait();
+        const int col0 = n_blk * BLOCK_N + c * 32;
+        if (row_ok && col0 < N) {
+          const size_t off = (size_t)row * N + col0;
+          if (EPI == EPI_STORE || EPI == EPI_RELU) {
+            bf16* dst = reinterpret_cast<bf16*>(Cv) + off;
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              if (col0 + g * 8 < N) {
+                uint32_t pk[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  float a = __uint_as_float(r[g * 8 + 2 * e]), b = __uint_as_float(r[g * 8 + 2 * e + 1]);
+                  if (EPI == EPI_RELU) { a = fmaxf(a, 0.f); b = fmaxf(b, 0.f); }
+                  __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+                  pk[e] = *reinterpret_cast<uint32_t*>(&v);
+                }
+                *reinterpret_cast<uint4*>(dst + g * 8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+              }
+            }
+          } else {
+            float* dst = reinterpret_cast<float*>(Cv) + off;
+#pragma unroll
+            for (int g = 0; g < 8; ++g) {
+              if (col0 + g * 4 < N) {
+                float4 v = make_float4(__uint_as_float(r[g * 4]), __uint_as_float(r[g * 4 + 1]),
+                                       __uint_as_float(r[g * 4 + 2]), __uint_as_float(r[g * 4 + 3]));
+                if (EPI == EPI_RESID) {
+                  const float4 o = *reinterpret_cast<const float4*>(dst + g * 4);
+                  v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
+                }
+                *reinterpret_cast<float4*>(dst + g * 4) = v;
+              }
+            }
+          }
+        }
+      }
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(acc));
+      if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1u; }
+    }
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tcgen05_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
+  }
+}
+
+// ---- host side ---------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+std::mutex g_mu;
+EncodeTiledFn g_encode = nullptr;
+std::string g_err;
+std::map<std::tuple<const void*, int, int>, CUtensorMap> g_maps;
+bool g_attr_set[4] = {false, false, false, false};
+
+bool get_encode() {
+  if (g_encode) return true;
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q);
+  if (e != cudaSuccess || q != cudaDriverEntryPointSuccess || !fn) {
+    g_err = std::string("cuTensorMapEncodeTiled entry point unavailable: ") + cudaGetErrorString(e);
+    cudaGetLastError();
+    return false;
+  }
+  g_encode = (EncodeTiledFn)fn;
+  return true;
+}
+
+// 2-D bf16 row-major [rows, cols] with a (128 rows x 64 cols) box and 128-byte swizzle
+bool get_map(const void* ptr, int rows, int cols, CUtensorMap* out) {
+  auto key = std::make_tuple(ptr, rows, cols);
+  auto it = g_maps.find(key);
+  if (it != g_maps.end()) { *out = it->second; return true; }
+  if (!get_encode()) return false;
+  CUtensorMap m;
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)cols * 2};
+  cuuint32_t box[2] = {(cuuint32_t)BLOCK_K, (cuuint32_t)BLOCK_M};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = g_encode(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    g_err = "cuTensorMapEncodeTiled failed with CUresult " + std::to_string((int)r);
+    return false;
+  }
+  if (g_maps.size() > 4096) g_maps.clear();
+  g_maps[key] = m;
+  *out = m;
+  return true;
+}
+
+template <int EPI>
+cudaError_t launch(const CUtensorMap& ma, const CUtensorMap& mw, void* C, int M_max, const int* m_ptr, int N, int K,
+                   int num_sms, cudaStream_t s) {
+  auto kern = gemm_tc_kernel<EPI>;
+  if (!g_attr_set[EPI]) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
+    if (e != cudaSuccess) return e;
+    g_attr_set[EPI] = true;
+  }
+  const int tiles = ((M_max + BLOCK_M - 1) / BLOCK_M) * ((N + BLOCK_N - 1) / BLOCK_N);
+  const int grid = tiles < num_sms ? tiles : num_sms;
+  kern<<<grid, THREADS, SMEM_BYTES, s>>>(ma, mw, C, M_max, m_ptr, N, K);
+  return cudaGetLastError();
+}
+
+}  // namespace tc
+
+bool gemm_tc_supported(int N, int K) { return (K % tc::BLOCK_K) == 0 && (N % 16) == 0 && N >= 16 && K >= tc::BLOCK_K; }
+
+const char* gemm_tc_last_error() { return tc::g_err.c_str(); }
+
+cudaError_t gemm_tc(int epi, const void* A, const void* W, void* C, int M_max, const int* m_ptr, int N, int K,
+                    int num_sms, cudaStream_t s) {
+  if (M_max <= 0) return cudaSuccess;
+  if (!gemm_tc_supported(N, K)) return cudaErrorInvalidValue;
+  std::lock_guard<std::mutex> lk(tc::g_mu);
+  CUtensorMap ma, mw;
+  if (!tc::get_map(A, M_max, K, &ma) || !tc::get_map(W, N, K, &mw)) return cudaErrorUnknown;
+  switch (epi) {
+    case EPI_STORE: return tc::launch<EPI_STORE>(ma, mw, C, M_max, m_ptr, N, K, num_sms, s);
+    case EPI_RELU: return tc::launch<EPI_RELU>(ma, mw, C, M_max, m_ptr, N, K, num_sms, s);
+    case EPI_RESID: return tc::launch<EPI_RESID>(ma, mw, C, M_max, m_ptr, N, K, num_sms, s);
+    case EPI_F32: return tc::launch<EPI_F32>(ma, mw, C, M_max, m_ptr, N, K, num_sms, s);
+    default: return cudaErrorInvalidValue;
+  }
+}
+
+}  // namespace gram
