@@ -12,7 +12,7 @@ import os
 _LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libgram_b200.so")
 
 GRAM_DTYPE_F32, GRAM_DTYPE_BF16 = 0, 1
-GRAM_FLAG_SIMT_GEMM, GRAM_FLAG_KEEP_LOGITS = 1, 2
+GRAM_FLAG_SIMT_GEMM, GRAM_FLAG_KEEP_LOGITS, GRAM_FLAG_SIMT_ATTN = 1, 2, 4
 K_CLASSES = ["gemm_enc", "enc_attn", "gemm_kv", "gemm_dec", "cross_attn", "lm_head", "beam", "other"]
 GRAM_K_COUNT = len(K_CLASSES)
 
@@ -104,7 +104,7 @@ def load_library():
     lib.gram_profile_end.restype = C.c_int
     lib.gram_op_gemm.argtypes = [i32, i32, i32, i32, vp, vp, vp, i32, i32, i32, vp]
     lib.gram_op_gemm.restype = C.c_int
-    lib.gram_op_cross_attention.argtypes = [i32, i32, vp, vp, i32p, u8p, vp, i32, i32, i32, i32, vp]
+    lib.gram_op_cross_attention.argtypes = [i32, i32, i32, vp, vp, i32, i32p, u8p, vp, i32, i32, i32, i32, vp]
     lib.gram_op_cross_attention.restype = C.c_int
     _lib = lib
     return lib

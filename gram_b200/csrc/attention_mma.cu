@@ -1,0 +1,519 @@
+// Tensor-core attention kernels for bf16 mode (mma.sync m16n8k16, fp32 accumulation, online softmax).
+//
+// cross_attention_mma  -- kernel (b) of the north star: decoder cross-attention over the fused FiD memory
+//   (reference src/model/gram_t5_modeling.py:670-705 with cached K/V :549, attention :572-621).  The K beams of
+//   a user are the M rows of ONE flash-decoding problem, so the user's K/V is streamed from HBM exactly once
+//   per layer per step (the reference streams it K times after `_expand_inputs_for_generation`, and copies it
+//   again in `_reorder_cache`, src/model/gram_t5.py:320-348).  K/V is read IN PLACE from the buffer the
+//   projection GEMM wrote ([token][layer][K|V][head][dk], no concat copy): a TMA producer warp streams
+//   64-row x 64-col boxes per head into a 3-stage 128B-swizzled shared-memory ring; four consumer warps (one
+//   head each) run QK^T and PV on the tensor cores straight out of the swizzled tiles via ldmatrix.
+//   This op is HBM-bound by design: per 2 KB row of K|V it does 2*2*32*512 padded flops, i.e. ~64 flop/B.
+//
+// enc_attention_mma    -- per-(passage, head) bidirectional self-attention of the encoder (reference
+//   src/model/gram_t5_modeling.py:572-621 with the layer-0 relative-position bias :452-477 shared by all
+//   layers :1249 and the key padding mask :1130).  Same tile math; K/V of the passage are staged once.
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <mutex>
+#include <map>
+#include <tuple>
+#include <string>
+
+#include "common.cuh"
+#include "kernels.h"
+
+namespace gram {
+namespace fa {
+
+constexpr int TS = 64;                 // memory rows per tile
+constexpr int DK = 64;                 // head dim (these kernels are specialised for d_kv = 64)
+constexpr int BOX_BYTES = TS * DK * 2; // 8 KiB: one head's 64x64 bf16 tile, 128-byte rows
+constexpr float LOG2E = 1.4426950408889634f;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "FA_WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra FA_WAIT_DONE;\n"
+      "bra FA_WAIT_LOOP;\n"
+      "FA_WAIT_DONE:\n"
+      "}\n" ::"r"(bar), "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x4_t(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
+}
+__device__ __forceinline__ void mma_bf16(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+// address of 16-byte chunk `chunk` of row `row` inside a 128B-swizzled [rows][64 bf16] tile (base 1024-aligned)
+__device__ __forceinline__ uint32_t swz(uint32_t base, int row, int chunk) {
+  return base + (uint32_t)(row * 128) + (uint32_t)(((chunk ^ (row & 7)) & 7) << 4);
+}
+
+// One 64-key tile of flash attention for MT 16-row query tiles held by one warp.
+//   qf      Q fragments [MT][4 k-steps][4]
+//   kbase   shared address of the K tile  [64 keys][64 d]   (swizzled)
+//   vbase   shared address of the V tile  [64 keys][64 d]   (swizzled)
+//   BiasFn  additive score term bias(row_in_warp_tile, key_in_tile) (0 for cross-attention)
+//   kmask   bit j set = key j of the tile is visible
+template <int MT, typename BiasFn>
+__device__ __forceinline__ void flash_tile(const uint32_t (&qf)[MT][4][4], uint32_t kbase, uint32_t vbase,
+                                           unsigned long long kmask, BiasFn bias, float (&o)[MT][8][4],
+                                           float (&m_run)[MT][2], float (&l_run)[MT][2], int lane) {
+  const int g = lane >> 2, q = lane & 3;
+  float s[MT][8][4];
+#pragma unroll
+  for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) s[mt][nt][e] = 0.f;
+  // ---- S = Q K^T ----
+#pragma unroll
+  for (int p = 0; p < 4; ++p) {            // pairs of 8-key n-tiles
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {       // 16-wide steps over d
+      uint32_t b0, b1, b2, b3;
+      const int row = p * 16 + (lane & 7) + ((lane >> 4) << 3);
+      const int chunk = ks * 2 + ((lane >> 3) & 1);
+      ldsm_x4(swz(kbase, row, chunk), b0, b1, b2, b3);
+#pragma unroll
+      for (int mt = 0; mt < MT; ++mt) {
+        mma_bf16(s[mt][2 * p], qf[mt][ks], b0, b1);
+        mma_bf16(s[mt][2 * p + 1], qf[mt][ks], b2, b3);
+      }
+    }
+  }
+  // ---- bias, mask, online softmax ----
+#pragma unroll
+  for (int mt = 0; mt < MT; ++mt) {
+    float mx[2] = {-INFINITY, -INFINITY};
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int col = nt * 8 + 2 * q + (e & 1);
+        const int rr = mt * 16 + g + ((e >> 1) << 3);
+        const bool vis = (kmask >> col) & 1ull;
+        const float v = vis ? s[mt][nt][e] + bias(rr, col) : -INFINITY;
+        s[mt][nt][e] = v;
+        mx[e >> 1] = fmaxf(mx[e >> 1], v);
+      }
+    }
+#pragma unroll
+    for (int hf = 0; hf < 2; ++hf) {
+      float t = mx[hf];
+      t = fmaxf(t, __shfl_xor_sync(0xffffffffu, t, 1));
+      t = fmaxf(t, __shfl_xor_sync(0xffffffffu, t, 2));
+      const float m_old = m_run[mt][hf];
+      const float m_new = fmaxf(m_old, t);
+      const float corr = (m_old == -INFINITY) ? 0.f : exp2f((m_old - m_new) * LOG2E);
+      m_run[mt][hf] = m_new;
+      l_run[mt][hf] *= corr;
+      const float mb = (m_new == -INFINITY) ? 0.f : m_new * LOG2E;
+      float psum = 0.f;
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+#pragma unroll
+        for (int e2 = 0; e2 < 2; ++e2) {
+          const int e = hf * 2 + e2;
+          const float p = exp2f(s[mt][nt][e] * LOG2E - mb);     // exp2(-inf) = 0 for masked keys
+          s[mt][nt][e] = p;
+          psum += p;
+        }
+        o[mt][nt][hf * 2] *= corr;
+        o[mt][nt][hf * 2 + 1] *= corr;
+      }
+      l_run[mt][hf] += psum;
+    }
+  }
+  // ---- O += P V ----
+#pragma unroll
+  for (int ks = 0; ks < 4; ++ks) {         // 16-key steps
+    uint32_t pa[MT][4];
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt) {
+      pa[mt][0] = pack_bf16(s[mt][2 * ks][0], s[mt][2 * ks][1]);
+      pa[mt][1] = pack_bf16(s[mt][2 * ks][2], s[mt][2 * ks][3]);
+      pa[mt][2] = pack_bf16(s[mt][2 * ks + 1][0], s[mt][2 * ks + 1][1]);
+      pa[mt][3] = pack_bf16(s[mt][2 * ks + 1][2], s[mt][2 * ks + 1][3]);
+    }
+#pragma unroll
+    for (int dp = 0; dp < 4; ++dp) {       // pairs of 8-wide d n-tiles
+      uint32_t b0, b1, b2, b3;
+      const int row = ks * 16 + (lane & 7) + (((lane >> 3) & 1) << 3);
+      const int chunk = dp * 2 + (lane >> 4);
+      ldsm_x4_t(swz(vbase, row, chunk), b0, b1, b2, b3);
+#pragma unroll
+      for (int mt = 0; mt < MT; ++mt) {
+        mma_bf16(o[mt][2 * dp], pa[mt], b0, b1);
+        mma_bf16(o[mt][2 * dp + 1], pa[mt], b2, b3);
+      }
+    }
+  }
+}
+
+struct NoBias {
+  __device__ __forceinline__ float operator()(int, int) const { return 0.f; }
+};
+
+// ================================================================================================
+// cross attention
+// ================================================================================================
+constexpr int XA_WARPS = 4;                                   // consumer warps per CTA
+constexpr int XA_THREADS = (XA_WARPS + 1) * 32;               // + 1 TMA producer warp
+constexpr int XA_STAGE_TARGET = 64 * 1024;
+
+// HEADS heads per CTA, BH beam-halves (32 beams each) per head: HEADS * BH == 4 consumer warps.
+//   K <= 32: <4, 1>  (64 KiB stages, 3 stages)      K <= 64: <2, 2>  (32 KiB stages, 6 stages)
+template <int HEADS, int BH>
+__global__ void __launch_bounds__(XA_THREADS, 1)
+cross_attention_mma_kernel(const __grid_constant__ CUtensorMap map_kv, const bf16* __restrict__ qg,
+                           bf16* __restrict__ out, const int* __restrict__ ustart,
+                           const uint8_t* __restrict__ tok_valid, int K, int H, int k_col0, int v_col0) {
+  constexpr int MT = 2;
+  constexpr int XA_HEADS = HEADS;
+  constexpr uint32_t XA_STAGE_BYTES = 2 * HEADS * BOX_BYTES;   // K boxes then V boxes
+  constexpr int XA_STAGES = 3 * XA_STAGE_TARGET / (int)XA_STAGE_BYTES;
+  static_assert(HEADS * BH == XA_WARPS, "four consumer warps");
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (base - raw);
+  const uint32_t bars = base + XA_STAGES * XA_STAGE_BYTES;     // full[ST], empty[ST]
+  unsigned long long* masks = reinterpret_cast<unsigned long long*>(smem + XA_STAGES * XA_STAGE_BYTES + 128);
+
+  const int u = blockIdx.x, hg = blockIdx.y;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int s_beg = ustart[u], s_end = ustart[u + 1];
+  const int n_tiles = (s_end - s_beg + TS - 1) / TS;
+  const int HD = H * DK;
+
+  if (threadIdx.x == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_kv) : "memory");
+    for (int s = 0; s < XA_STAGES; ++s) { mbar_init(bars + 8u * s, 1); mbar_init(bars + 8u * (XA_STAGES + s), XA_WARPS); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  if (warp == XA_WARPS) {
+    // ===================== TMA producer =====================
+    int stage = 0; uint32_t phase = 0;
+    for (int t = 0; t < n_tiles; ++t) {
+      mbar_wait(bars + 8u * (XA_STAGES + stage), phase ^ 1u);
+      const int s0 = s_beg + t * TS;
+      const int r0 = s0 + lane, r1 = s0 + 32 + lane;
+      const bool v0 = (r0 < s_end) && (tok_valid == nullptr || tok_valid[r0] != 0);
+      const bool v1 = (r1 < s_end) && (tok_valid == nullptr || tok_valid[r1] != 0);
+      const unsigned lo = __ballot_sync(0xffffffffu, v0), hi = __ballot_sync(0xffffffffu, v1);
+      if (lane == 0) {
+        masks[stage] = ((unsigned long long)hi << 32) | lo;
+        const uint32_t full = bars + 8u * stage;
+        const uint32_t sb = base + stage * XA_STAGE_BYTES;
+        mbar_arrive_expect_tx(full, XA_STAGE_BYTES);
+#pragma unroll
+        for (int hh = 0; hh < XA_HEADS; ++hh) {
+          const int col = (hg * XA_HEADS + hh) * DK;
+          tma_load_2d(sb + hh * BOX_BYTES, &map_kv, full, k_col0 + col, s0);
+          tma_load_2d(sb + (XA_HEADS + hh) * BOX_BYTES, &map_kv, full, v_col0 + col, s0);
+        }
+      }
+      __syncwarp();
+      if (++stage == XA_STAGES) { stage = 0; phase ^= 1u; }
+    }
+    return;
+  }
+
+  // ===================== consumers: warp = (head, beam half) =====================
+  const int hl = warp / BH, b_off = (warp % BH) * 32;
+  const int h = hg * XA_HEADS + hl;
+  const int g = lane >> 2, q = lane & 3;
+  uint32_t qf[MT][4][4];
+#pragma unroll
+  for (int mt = 0; mt < MT; ++mt) {
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int b = b_off + mt * 16 + g + ((e & 1) << 3);
+        const int d = ks * 16 + 2 * q + ((e >> 1) << 3);
+        uint32_t v = 0u;
+        if (b < K) v = *reinterpret_cast<const uint32_t*>(qg + (size_t)(u * K + b) * HD + h * DK + d);
+        qf[mt][ks][e] = v;
+      }
+    }
+  }
+  float o[MT][8][4];
+  float m_run[MT][2], l_run[MT][2];
+#pragma unroll
+  for (int mt = 0; mt < MT; ++mt) {
+    m_run[mt][0] = m_run[mt][1] = -INFINITY;
+    l_run[mt][0] = l_run[mt][1] = 0.f;
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) o[mt][nt][e] = 0.f;
+  }
+  int stage = 0; uint32_t phase = 0;
+  for (int t = 0; t < n_tiles; ++t) {
+    mbar_wait(bars + 8u * stage, phase);
+    const unsigned long long kmask = masks[stage];
+    const uint32_t sb = base + stage * XA_STAGE_BYTES;
+    flash_tile<MT>(qf, sb + hl * BOX_BYTES, sb + (XA_HEADS + hl) * BOX_BYTES, kmask, NoBias(), o, m_run, l_run, lane);
+    __syncwarp();
+    if (lane == 0) mbar_arrive(bars + 8u * (XA_STAGES + stage));
+    if (++stage == XA_STAGES) { stage = 0; phase ^= 1u; }
+  }
+  // ---- normalise and store ----
+#pragma unroll
+  for (int mt = 0; mt < MT; ++mt) {
+#pragma unroll
+    for (int hf = 0; hf < 2; ++hf) {
+      float l = l_run[mt][hf];
+      l += __shfl_xor_sync(0xffffffffu, l, 1);
+      l += __shfl_xor_sync(0xffffffffu, l, 2);
+      const float inv = l > 0.f ? 1.0f / l : 0.f;
+      const int b = b_off + mt * 16 + g + hf * 8;
+      if (b < K) {
+        bf16* orow = out + (size_t)(u * K + b) * HD + h * DK;
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt)
+          *reinterpret_cast<uint32_t*>(orow + nt * 8 + 2 * q) = pack_bf16(o[mt][nt][hf * 2] * inv, o[mt][nt][hf * 2 + 1] * inv);
+      }
+    }
+  }
+}
+
+// ================================================================================================
+// encoder self-attention: one CTA per (passage, head); warp w owns query rows [32w, 32w+32)
+// ================================================================================================
+constexpr int EA_THREADS = 128;
+
+struct RelBias {
+  const float* lut;   // shared memory, [2*Lb-1]
+  int off;            // key_tile_start - query_warp_start + Lb - 1
+  __device__ __forceinline__ float operator()(int rr, int col) const { return lut[off + col - rr]; }
+};
+
+template <int LT>     // key tiles of 64 the kernel is sized for (L <= 64*LT)
+__global__ void __launch_bounds__(EA_THREADS)
+enc_attention_mma_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, const int* __restrict__ plen,
+                         const int* __restrict__ poff, const uint8_t* __restrict__ tok_valid,
+                         const float* __restrict__ bias_lut, int Lb, int H) {
+  const int p = blockIdx.x, h = blockIdx.y;
+  const int len = plen[p];
+  if (len == 0) return;
+  const int row0 = poff[p];
+  const int HD = H * DK;
+  const size_t ld = (size_t)3 * HD;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (base - raw);
+  // [K tiles LT x 8 KiB][V tiles LT x 8 KiB][lut (2*Lb-1) floats][masks LT x u64]
+  const uint32_t kb = base, vb = base + LT * BOX_BYTES;
+  float* lut = reinterpret_cast<float*>(smem + 2 * LT * BOX_BYTES) + 32;   // 32 floats of slack below index 0 (padding rows)
+  unsigned long long* masks = reinterpret_cast<unsigned long long*>(smem + 2 * LT * BOX_BYTES + 128 + ((2 * Lb - 1) * 4 + 15) / 16 * 16);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int n_tiles = (len + TS - 1) / TS;
+
+  // stage K and V (16-byte chunks, swizzled like a TMA 128B-swizzle box); rows past `len` are zero-filled
+  for (int i = tid; i < n_tiles * TS * 8; i += EA_THREADS) {
+    const int r = i >> 3, c = i & 7;
+    uint4 kv4 = make_uint4(0, 0, 0, 0), vv4 = kv4;
+    if (r < len) {
+      const bf16* src = qkv + (size_t)(row0 + r) * ld + h * DK + c * 8;
+      kv4 = *reinterpret_cast<const uint4*>(src + HD);
+      vv4 = *reinterpret_cast<const uint4*>(src + 2 * HD);
+    }
+    const int tile = r >> 6, rr = r & 63;
+    *reinterpret_cast<uint4*>(smem + (swz(kb + tile * BOX_BYTES, rr, c) - base)) = kv4;
+    *reinterpret_cast<uint4*>(smem + (swz(vb + tile * BOX_BYTES, rr, c) - base)) = vv4;
+  }
+  for (int i = tid; i < 2 * Lb - 1; i += EA_THREADS) lut[i] = bias_lut[(size_t)h * (2 * Lb - 1) + i];
+  if (warp < n_tiles) {
+    const int r0 = warp * TS + lane, r1 = r0 + 32;
+    const bool v0 = r0 < len && tok_valid[row0 + r0] != 0;
+    const bool v1 = r1 < len && tok_valid[row0 + r1] != 0;
+    const unsigned lo = __ballot_sync(0xffffffffu, v0), hi = __ballot_sync(0xffffffffu, v1);
+    if (lane == 0) masks[warp] = ((unsigned long long)hi << 32) | lo;
+  }
+  __syncthreads();
+
+  const int g = lane >> 2, q = lane & 3;
+  for (int qb = warp * 32; qb < len; qb += 4 * 32) {          // 32 query rows per warp pass
+    uint32_t qf[2][4][4];
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int r = qb + mt * 16 + g + ((e & 1) << 3);
+          const int d = ks * 16 + 2 * q + ((e >> 1) << 3);
+          uint32_t v = 0u;
+          if (r < len) v = *reinterpret_cast<const uint32_t*>(qkv + (size_t)(row0 + r) * ld + h * DK + d);
+          qf[mt][ks][e] = v;
+        }
+    float o[2][8][4], m_run[2][2], l_run[2][2];
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt) {
+      m_run[mt][0] = m_run[mt][1] = -INFINITY;
+      l_run[mt][0] = l_run[mt][1] = 0.f;
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) o[mt][nt][e] = 0.f;
+    }
+    for (int t = 0; t < n_tiles; ++t) {
+      RelBias rb{lut, t * TS - qb + Lb - 1};
+      flash_tile<2>(qf, kb + t * BOX_BYTES, vb + t * BOX_BYTES, masks[t], rb, o, m_run, l_run, lane);
+    }
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+      for (int hf = 0; hf < 2; ++hf) {
+        float l = l_run[mt][hf];
+        l += __shfl_xor_sync(0xffffffffu, l, 1);
+        l += __shfl_xor_sync(0xffffffffu, l, 2);
+        const float inv = l > 0.f ? 1.0f / l : 0.f;
+        const int r = qb + mt * 16 + g + hf * 8;
+        if (r < len) {
+          bf16* orow = out + (size_t)(row0 + r) * HD + h * DK;
+#pragma unroll
+          for (int nt = 0; nt < 8; ++nt)
+            *reinterpret_cast<uint32_t*>(orow + nt * 8 + 2 * q) = pack_bf16(o[mt][nt][hf * 2] * inv, o[mt][nt][hf * 2 + 1] * inv);
+        }
+      }
+  }
+}
+
+// ---- host side -------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+std::mutex g_mu;
+EncodeTiledFn g_encode = nullptr;
+std::map<std::tuple<const void*, size_t, size_t>, CUtensorMap> g_maps;
+
+bool get_kv_map(const void* ptr, size_t rows, size_t cols, CUtensorMap* out) {
+  auto key = std::make_tuple(ptr, rows, cols);
+  auto it = g_maps.find(key);
+  if (it != g_maps.end()) { *out = it->second; return true; }
+  if (!g_encode) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qr;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qr) != cudaSuccess ||
+        qr != cudaDriverEntryPointSuccess || !fn) { cudaGetLastError(); return false; }
+    g_encode = (EncodeTiledFn)fn;
+  }
+  CUtensorMap m;
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)cols * 2};
+  cuuint32_t box[2] = {(cuuint32_t)DK, (cuuint32_t)TS};
+  cuuint32_t estr[2] = {1, 1};
+  if (g_encode(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) return false;
+  if (g_maps.size() > 1024) g_maps.clear();
+  g_maps[key] = m;
+  *out = m;
+  return true;
+}
+
+}  // namespace fa
+
+bool cross_attention_mma_supported(int K, int H, int dk) {
+  return dk == fa::DK && K <= 64 && (K <= 32 ? (H % 4) == 0 : (H % 2) == 0);
+}
+
+cudaError_t cross_attention_mma(const void* q, const void* kv, size_t kv_rows, size_t kv_stride, int k_off, int v_off,
+                                const int* ustart, const uint8_t* tok_valid, void* out, int users, int K, int H,
+                                cudaStream_t s) {
+  if (users <= 0) return cudaSuccess;
+  std::lock_guard<std::mutex> lk(fa::g_mu);
+  CUtensorMap map;
+  if (!fa::get_kv_map(kv, kv_rows, kv_stride, &map)) return cudaErrorUnknown;
+  constexpr size_t smem = (size_t)3 * fa::XA_STAGE_TARGET + 1024 + 256;
+  static bool attr[2] = {false, false};
+  if (K <= 32) {
+    auto kern = fa::cross_attention_mma_kernel<4, 1>;
+    if (!attr[0]) {
+      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return e;
+      attr[0] = true;
+    }
+    kern<<<dim3(users, H / 4), fa::XA_THREADS, smem, s>>>(map, (const bf16*)q, (bf16*)out, ustart, tok_valid, K, H, k_off, v_off);
+  } else {
+    auto kern = fa::cross_attention_mma_kernel<2, 2>;
+    if (!attr[1]) {
+      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return e;
+      attr[1] = true;
+    }
+    kern<<<dim3(users, H / 2), fa::XA_THREADS, smem, s>>>(map, (const bf16*)q, (bf16*)out, ustart, tok_valid, K, H, k_off, v_off);
+  }
+  return cudaGetLastError();
+}
+
+bool enc_attention_mma_supported(int dk, int Lmax) { return dk == fa::DK && Lmax <= 256; }
+
+cudaError_t enc_attention_mma(const void* qkv, void* out, const int* plen, const int* poff, const uint8_t* tok_valid,
+                              const float* bias_lut, int Lb, int P, int H, int Lmax, cudaStream_t s) {
+  if (P <= 0) return cudaSuccess;
+  const int LT = (Lmax + fa::TS - 1) / fa::TS;
+  const size_t lut_bytes = ((size_t)(2 * Lb - 1) * 4 + 15) / 16 * 16;
+  static bool attr[5] = {false, false, false, false, false};
+  dim3 grid(P, H);
+#define GRAM_EA(LTV)                                                                                         \
+  {                                                                                                          \
+    const size_t smem = (size_t)2 * LTV * fa::BOX_BYTES + 128 + lut_bytes + LTV * 8 + 1024 + 64;                   \
+    auto kern = fa::enc_attention_mma_kernel<LTV>;                                                           \
+    if (!attr[LTV]) {                                                                                        \
+      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);    \
+      if (e != cudaSuccess) return e;                                                                        \
+      attr[LTV] = true;                                                                                      \
+    }                                                                                                        \
+    kern<<<grid, fa::EA_THREADS, smem, s>>>((const bf16*)qkv, (bf16*)out, plen, poff, tok_valid, bias_lut, Lb, H); \
+  }
+  if (LT <= 1) GRAM_EA(1)
+  else if (LT == 2) GRAM_EA(2)
+  else if (LT == 3) GRAM_EA(3)
+  else GRAM_EA(4)
+#undef GRAM_EA
+  return cudaGetLastError();
+}
+
+}  // namespace gram

@@ -315,8 +315,13 @@ int run_encode(gram_handle* h, const int64_t* ids, const uint8_t* mask, int B, i
     const LayerW& W = h->enc[l];
     CKL(GRAM_K_OTHER, rmsnorm_rows(c.dtype, h->x, W.ln0, h->xn, Mmax, mp, D, c.ln_eps, 1.f, nullptr, nullptr, s));
     RC(gemm(h, GRAM_K_GEMM_ENC, EPI_STORE, h->xn, W.qkv, h->qkv, Mmax, mp, 3 * HD, D, s));
-    CKL(GRAM_K_ENC_ATTN, enc_attention(c.dtype, h->qkv, h->ao, h->pm.plen, h->pm.poff, h->pm.tok_valid,
-                                       h->enc_bias_lut, h->Lb, B * N, h->H, h->dk, L, s));
+    if (c.dtype == GRAM_DTYPE_BF16 && !(c.flags & GRAM_FLAG_SIMT_ATTN) && enc_attention_mma_supported(h->dk, L)) {
+      CKL(GRAM_K_ENC_ATTN, enc_attention_mma(h->qkv, h->ao, h->pm.plen, h->pm.poff, h->pm.tok_valid, h->enc_bias_lut,
+                                             h->Lb, B * N, h->H, L, s));
+    } else {
+      CKL(GRAM_K_ENC_ATTN, enc_attention(c.dtype, h->qkv, h->ao, h->pm.plen, h->pm.poff, h->pm.tok_valid,
+                                         h->enc_bias_lut, h->Lb, B * N, h->H, h->dk, L, s));
+    }
     RC(gemm(h, GRAM_K_GEMM_ENC, EPI_RESID, h->ao, W.o, h->x, Mmax, mp, D, HD, s));
     CKL(GRAM_K_OTHER, rmsnorm_rows(c.dtype, h->x, W.ln1, h->xn, Mmax, mp, D, c.ln_eps, 1.f, nullptr, nullptr, s));
     RC(gemm(h, GRAM_K_GEMM_ENC, EPI_RELU, h->xn, W.wi, h->ff, Mmax, mp, F, D, s));
@@ -347,8 +352,13 @@ int decoder_step(gram_handle* h, int R, int K, int users, int t, const int* anc,
     RC(gemm(h, GRAM_K_GEMM_DEC, EPI_RESID, h->dao, W.o, h->dx, R, nullptr, D, HD, s));
     CKL(GRAM_K_OTHER, rmsnorm_rows(c.dtype, h->dx, W.ln1, h->dxn, R, nullptr, D, c.ln_eps, 1.f, nullptr, nullptr, s));
     RC(gemm(h, GRAM_K_GEMM_DEC, EPI_STORE, h->dxn, W.cq, h->dq, R, nullptr, HD, D, s));
-    CKL(GRAM_K_CROSS_ATTN, cross_attention(c.dtype, h->dq, h->ckv, (size_t)h->Ld * 2 * HD, l * 2 * HD, l * 2 * HD + HD,
-                                           h->pm.ustart, h->pm.tok_valid, h->dao, users, K, h->H, h->dk, s));
+    if (c.dtype == GRAM_DTYPE_BF16 && !(c.flags & GRAM_FLAG_SIMT_ATTN) && cross_attention_mma_supported(K, h->H, h->dk)) {
+      CKL(GRAM_K_CROSS_ATTN, cross_attention_mma(h->dq, h->ckv, (size_t)h->Mcap + 256, (size_t)h->Ld * 2 * HD, l * 2 * HD,
+                                                 l * 2 * HD + HD, h->pm.ustart, h->pm.tok_valid, h->dao, users, K, h->H, s));
+    } else {
+      CKL(GRAM_K_CROSS_ATTN, cross_attention(c.dtype, h->dq, h->ckv, (size_t)h->Ld * 2 * HD, l * 2 * HD, l * 2 * HD + HD,
+                                             h->pm.ustart, h->pm.tok_valid, h->dao, users, K, h->H, h->dk, s));
+    }
     RC(gemm(h, GRAM_K_GEMM_DEC, EPI_RESID, h->dao, W.co, h->dx, R, nullptr, D, HD, s));
     CKL(GRAM_K_OTHER, rmsnorm_rows(c.dtype, h->dx, W.ln2, h->dxn, R, nullptr, D, c.ln_eps, 1.f, nullptr, nullptr, s));
     RC(gemm(h, GRAM_K_GEMM_DEC, EPI_RELU, h->dxn, W.wi, h->dff, R, nullptr, F, D, s));
@@ -495,7 +505,9 @@ int gram_create(const gram_config* cfg, gram_handle** out) {
   DAC(h->d_zero_anc, R * ML * 4);
   DAC(h->d_dec_ids, R * ML * 8);
 #undef DAC
-  if (cudaMemset(h->d_zero_anc, 0, R * ML * 4) != cudaSuccess || cudaMemset(bs.err, 0, 16) != cudaSuccess ||
+  // K/V rows past a user's range are read (and masked) by the TMA-fed attention kernel: they must be finite
+  if (cudaMemset(h->ckv, 0, Mc * (size_t)h->Ld * 2 * HD * esz) != cudaSuccess ||
+      cudaMemset(h->d_zero_anc, 0, R * ML * 4) != cudaSuccess || cudaMemset(bs.err, 0, 16) != cudaSuccess ||
       cudaMemset(bs.anc[0], 0, R * ML * 4) != cudaSuccess || cudaMemset(bs.anc[1], 0, R * ML * 4) != cudaSuccess) {
     h->err = "gram_create: cudaMemset failed"; return bail(GRAM_ERR_CUDA);
   }
@@ -801,12 +813,22 @@ int gram_op_gemm(int32_t device, int32_t dtype, int32_t impl, int32_t epilogue, 
   return GRAM_OK;
 }
 
-int gram_op_cross_attention(int32_t device, int32_t dtype, const void* q, const void* kv, const int32_t* user_start,
-                            const uint8_t* tok_valid, void* out, int32_t users, int32_t K, int32_t H, int32_t dk,
-                            void* stream) {
+int gram_op_cross_attention(int32_t device, int32_t dtype, int32_t impl, const void* q, const void* kv, int32_t kv_rows,
+                            const int32_t* user_start, const uint8_t* tok_valid, void* out, int32_t users, int32_t K,
+                            int32_t H, int32_t dk, void* stream) {
   if (cudaSetDevice(device) != cudaSuccess) return GRAM_ERR_CUDA;
-  cudaError_t e = cross_attention(dtype, q, kv, (size_t)2 * H * dk, 0, H * dk, user_start, tok_valid, out, users, K, H, dk,
-                                  (cudaStream_t)stream);
+  cudaError_t e;
+  if (impl == 1) {
+    if (dtype != GRAM_DTYPE_BF16 || !cross_attention_mma_supported(K, H, dk)) {
+      g_create_error = "gram_op_cross_attention: tensor-core path needs bf16, d_kv 64, K <= 64 and H % 4 == 0 (K <= 32) or H % 2 == 0";
+      return GRAM_ERR_UNSUPPORTED;
+    }
+    e = cross_attention_mma(q, kv, (size_t)kv_rows, (size_t)2 * H * dk, 0, H * dk, user_start, tok_valid, out, users, K, H,
+                            (cudaStream_t)stream);
+  } else {
+    e = cross_attention(dtype, q, kv, (size_t)2 * H * dk, 0, H * dk, user_start, tok_valid, out, users, K, H, dk,
+                        (cudaStream_t)stream);
+  }
   if (e != cudaSuccess) { g_create_error = std::string("cross_attention: ") + cudaGetErrorString(e); return GRAM_ERR_CUDA; }
   return GRAM_OK;
 }

@@ -58,6 +58,17 @@ cudaError_t cross_attention(int dtype, const void* q, const void* kv, size_t kv_
                             const int* ustart, const uint8_t* tok_valid, void* out, int users, int K, int H, int dk,
                             cudaStream_t s);
 
+// ---- attention_mma.cu (bf16, tensor cores) --------------------------------------------------------------
+bool cross_attention_mma_supported(int K, int H, int dk);
+// kv_rows = rows of the allocation behind `kv` (TMA bound); rows past a user's range are masked, so the buffer
+// must only hold finite values.
+cudaError_t cross_attention_mma(const void* q, const void* kv, size_t kv_rows, size_t kv_stride, int k_off, int v_off,
+                                const int* ustart, const uint8_t* tok_valid, void* out, int users, int K, int H,
+                                cudaStream_t s);
+bool enc_attention_mma_supported(int dk, int Lmax);
+cudaError_t enc_attention_mma(const void* qkv, void* out, const int* plen, const int* poff, const uint8_t* tok_valid,
+                              const float* bias_lut, int Lb, int P, int H, int Lmax, cudaStream_t s);
+
 // ---- beam_kernels.cu -------------------------------------------------------------------------------
 struct TrieCSR {
   const int* child_offsets; const int* child_tokens; const int* child_nodes;

@@ -54,7 +54,8 @@ typedef struct gram_config {
 
 enum {
   GRAM_FLAG_SIMT_GEMM = 1,         /* force the CUDA-core GEMM even for bf16 (debug / A-B timing) */
-  GRAM_FLAG_KEEP_LOGITS = 2        /* materialise full-vocab logits every step (debug / parity)   */
+  GRAM_FLAG_KEEP_LOGITS = 2,       /* record per-step taps (lse, beam scores, prefixes) for parity tests */
+  GRAM_FLAG_SIMT_ATTN = 4          /* force the CUDA-core attention kernels even for bf16 (A-B timing)   */
 };
 
 /* ---- lifetime -------------------------------------------------------------------------------- */
@@ -146,9 +147,10 @@ int gram_profile_end(gram_handle* h, float* ms_per_class /*[GRAM_K_COUNT]*/, int
  * 1 = tcgen05 (bf16 only).  epilogue: 0 store (dtype), 1 relu+store (dtype), 2 C_f32 += acc, 3 store fp32. */
 int gram_op_gemm(int32_t device, int32_t dtype, int32_t impl, int32_t epilogue, const void* A, const void* W,
                  void* C, int32_t M, int32_t N, int32_t K, void* stream);
-/* decoder cross-attention over an in-place K/V memory: q [users*K, H*dk], kv [tokens, 2*H*dk] (K|V),
- * user_start int32 [users+1], tok_valid uint8 [tokens], out [users*K, H*dk] (all dtype). */
-int gram_op_cross_attention(int32_t device, int32_t dtype, const void* q, const void* kv,
+/* decoder cross-attention over an in-place K/V memory: q [users*K, H*dk], kv [kv_rows, 2*H*dk] (K|V),
+ * user_start int32 [users+1], tok_valid uint8 [kv_rows] or NULL, out [users*K, H*dk] (all dtype).
+ * impl 0 = CUDA-core kernel (fp32 or bf16), 1 = TMA + tensor-core kernel (bf16). */
+int gram_op_cross_attention(int32_t device, int32_t dtype, int32_t impl, const void* q, const void* kv, int32_t kv_rows,
                             const int32_t* user_start, const uint8_t* tok_valid, void* out,
                             int32_t users, int32_t K, int32_t H, int32_t dk, void* stream);
 

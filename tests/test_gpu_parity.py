@@ -79,13 +79,15 @@ def test_gemm_simt(dtype, shape, epi):
     assert rel_err(Cd, ref) < tol
 
 
-@pytest.mark.parametrize("dtype", ["fp32", "bf16"])
-@pytest.mark.parametrize("dk,H,K", [(16, 4, 4), (64, 8, 20), (64, 12, 50)])
-def test_cross_attention_op(dtype, dk, H, K):
+@pytest.mark.parametrize("dtype,impl", [("fp32", 0), ("bf16", 0), ("bf16", 1)])
+@pytest.mark.parametrize("dk,H,K", [(16, 4, 4), (64, 8, 20), (64, 12, 50), (64, 8, 1), (64, 4, 33)])
+def test_cross_attention_op(dtype, impl, dk, H, K):
+    if impl == 1 and dk != 64:
+        pytest.skip("tensor-core kernel is specialised for d_kv = 64")
     from gram_b200 import _cabi
     lib = _cabi.load_library()
     users = 3
-    lens = [70, 33, 129]
+    lens = [70, 33, 257]
     ustart = np.concatenate([[0], np.cumsum(lens)]).astype(np.int32)
     T = int(ustart[-1])
     HD = H * dk
@@ -98,8 +100,8 @@ def test_cross_attention_op(dtype, dk, H, K):
     valid_d = valid.cuda()
     out = torch.zeros(users * K, HD, device="cuda", dtype=tdt)
     us_d = torch.from_numpy(ustart).cuda()
-    rc = lib.gram_op_cross_attention(0, 0 if dtype == "fp32" else 1, C.c_void_p(q.data_ptr()), C.c_void_p(kv.data_ptr()),
-                                     C.c_void_p(us_d.data_ptr()), C.c_void_p(valid_d.data_ptr()),
+    rc = lib.gram_op_cross_attention(0, 0 if dtype == "fp32" else 1, impl, C.c_void_p(q.data_ptr()),
+                                     C.c_void_p(kv.data_ptr()), T, C.c_void_p(us_d.data_ptr()), C.c_void_p(valid_d.data_ptr()),
                                      C.c_void_p(out.data_ptr()), users, K, H, dk, None)
     assert rc == 0, lib.gram_last_error(None)
     torch.cuda.synchronize()
@@ -113,7 +115,7 @@ def test_cross_attention_op(dtype, dk, H, K):
         s = s.masked_fill(valid[a:b][None, None, :] == 0, float("-inf"))
         p = torch.softmax(s, -1)
         ref[u * K:(u + 1) * K] = torch.einsum("hks,shd->khd", p, vv).reshape(K, HD)
-    assert rel_err(out, ref) < (1e-5 if dtype == "fp32" else 8e-3)
+    assert rel_err(out, ref) < (1e-5 if dtype == "fp32" else (8e-3 if impl == 0 else 1.5e-2))
 
 
 # ---------------------------------------------------------------------------------------------
