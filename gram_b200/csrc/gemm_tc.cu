@@ -13,7 +13,9 @@
 //               swizzled tiles through shared-memory descriptors, accumulating in TMEM; tcgen05.commit releases
 //               ring slots and publishes finished accumulators
 //   warps 2-5   epilogue: tcgen05.ld of the fp32 accumulator (each warp owns its 32-lane TMEM quadrant), fused
-//               ReLU / residual add / dtype conversion, vectorised global stores
+//               ReLU / dtype conversion, staged through a 128B-swizzled shared-memory tile and written with TMA
+//               bulk tensor stores; the residual add (x += A W^T) is a TMA reduce-add performed at the L2, so the
+//               SM never reads the residual stream
 // TMEM holds two 128-column accumulators so the epilogue of tile i overlaps the MMAs of tile i+1.
 // M may live in device memory (*m_ptr): the packed encoder token count is only known on the device, so the
 // kernel derives its tile loop bound there and the host never synchronises.
@@ -39,7 +41,8 @@ constexpr int THREADS = 192;
 constexpr uint32_t A_BYTES = BLOCK_M * BLOCK_K * 2;        // 16 KiB
 constexpr uint32_t B_BYTES = BLOCK_N * BLOCK_K * 2;        // 16 KiB
 constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
-constexpr size_t SMEM_BYTES = (size_t)STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+constexpr uint32_t CSTAGE_BYTES = 32 * 1024;               // epilogue staging: two 128-row x 128-byte boxes
+constexpr size_t SMEM_BYTES = (size_t)STAGES * STAGE_BYTES + CSTAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 
 // ---- PTX wrappers --------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -71,6 +74,19 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
       ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
       : "memory");
 }
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(map), "r"(src), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
+  asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(map), "r"(src), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 __device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
@@ -116,17 +132,18 @@ constexpr uint32_t kInstrDesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)
 template <int EPI>
 __global__ void __launch_bounds__(THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
-               void* __restrict__ Cv, int M_imm, const int* __restrict__ m_ptr, int N, int K) {
+               const __grid_constant__ CUtensorMap map_c, int M_imm, const int* __restrict__ m_ptr, int N, int K) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;           // 1024-byte alignment for the 128B swizzle atoms
   uint8_t* smem = smem_raw + (base - raw);
-  const uint32_t bars = base + STAGES * STAGE_BYTES;      // full[STAGES], empty[STAGES], tfull[2], tempty[2], tmem ptr
+  const uint32_t cstage = base + STAGES * STAGE_BYTES;    // epilogue staging (1024-aligned)
+  const uint32_t bars = cstage + CSTAGE_BYTES;            // full[STAGES], empty[STAGES], tfull[2], tempty[2], tmem ptr
   auto full_bar = [&](int s) { return bars + 8u * s; };
   auto empty_bar = [&](int s) { return bars + 8u * (STAGES + s); };
   auto tfull_bar = [&](int s) { return bars + 8u * (2 * STAGES + s); };
   auto tempty_bar = [&](int s) { return bars + 8u * (2 * STAGES + ACC_STAGES + s); };
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + STAGES * STAGE_BYTES + 8 * (2 * STAGES + 2 * ACC_STAGES));
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + STAGES * STAGE_BYTES + CSTAGE_BYTES + 8 * (2 * STAGES + 2 * ACC_STAGES));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int M = m_ptr ? *m_ptr : M_imm;
@@ -137,6 +154,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_c) : "memory");
     for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
     for (int s = 0; s < ACC_STAGES; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 4); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -197,60 +215,79 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   } else {
     // ===================== epilogue (warps 2..5) =====================
     const int quad = warp & 3;                             // TMEM lane quadrant this warp may access
+    const int r = quad * 32 + lane;                        // row of the tile this thread owns
+    const bool issuer = (warp == 2 && lane == 0);
+    constexpr bool kOutBf16 = (EPI == EPI_STORE || EPI == EPI_RELU);
+    constexpr int ROUNDS = kOutBf16 ? 1 : 2;               // 32 KiB of staging = 128 bf16 or 64 fp32 columns
+    constexpr int CHUNKS_PER_ROUND = (BLOCK_N / 32) / ROUNDS;
     int acc = 0; uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int m_blk = tile / num_n, n_blk = tile % num_n;
       mbar_wait(tfull_bar(acc), acc_phase);
       tcgen05_fence_after();
-      const int row = m_blk * BLOCK_M + quad * 32 + lane;
-      const bool row_ok = row < M;
 #pragma unroll 1
-      for (int c = 0; c < BLOCK_N / 32; ++c) {
-        uint32_t r[32];
-        const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BLOCK_N + c * 32);
-        tmem_ld32(taddr, r);
-        tmem_ld_wait();
-        const int col0 = n_blk * BLOCK_N + c * 32;
-        if (row_ok && col0 < N) {
-          const size_t off = (size_t)row * N + col0;
-          if (EPI == EPI_STORE || EPI == EPI_RELU) {
-            bf16* dst = reinterpret_cast<bf16*>(Cv) + off;
+      for (int rd = 0; rd < ROUNDS; ++rd) {
+        if (issuer) tma_store_wait_read();                 // previous bulk store has finished reading the staging tile
+        epi_bar();
+#pragma unroll 1
+        for (int cc = 0; cc < CHUNKS_PER_ROUND; ++cc) {
+          const int c = rd * CHUNKS_PER_ROUND + cc;        // 32-column chunk of the accumulator
+          uint32_t v[32];
+          const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BLOCK_N + c * 32);
+          tmem_ld32(taddr, v);
+          tmem_ld_wait();
+          if (kOutBf16) {
+            // box (c/2): 128 rows x 64 bf16 (128 B per row); this chunk is the 16-byte pieces (c%2)*4 .. +3
+            const uint32_t box = cstage + (uint32_t)(c >> 1) * 16384u + (uint32_t)r * 128u;
 #pragma unroll
             for (int g = 0; g < 4; ++g) {
-              if (col0 + g * 8 < N) {
-                uint32_t pk[4];
+              uint32_t pk[4];
 #pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                  float a = __uint_as_float(r[g * 8 + 2 * e]), b = __uint_as_float(r[g * 8 + 2 * e + 1]);
-                  if (EPI == EPI_RELU) { a = fmaxf(a, 0.f); b = fmaxf(b, 0.f); }
-                  __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
-                  pk[e] = *reinterpret_cast<uint32_t*>(&v);
-                }
-                *reinterpret_cast<uint4*>(dst + g * 8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+              for (int e = 0; e < 4; ++e) {
+                float a = __uint_as_float(v[g * 8 + 2 * e]), b = __uint_as_float(v[g * 8 + 2 * e + 1]);
+                if (EPI == EPI_RELU) { a = fmaxf(a, 0.f); b = fmaxf(b, 0.f); }
+                __nv_bfloat162 h2 = __floats2bfloat162_rn(a, b);
+                pk[e] = *reinterpret_cast<uint32_t*>(&h2);
               }
+              const uint32_t piece = (uint32_t)(((c & 1) * 4 + g) ^ (r & 7));
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(box + (piece << 4)), "r"(pk[0]), "r"(pk[1]),
+                           "r"(pk[2]), "r"(pk[3]) : "memory");
             }
           } else {
-            float* dst = reinterpret_cast<float*>(Cv) + off;
+            // box cc: 128 rows x 32 fp32 (128 B per row)
+            const uint32_t box = cstage + (uint32_t)cc * 16384u + (uint32_t)r * 128u;
 #pragma unroll
             for (int g = 0; g < 8; ++g) {
-              if (col0 + g * 4 < N) {
-                float4 v = make_float4(__uint_as_float(r[g * 4]), __uint_as_float(r[g * 4 + 1]),
-                                       __uint_as_float(r[g * 4 + 2]), __uint_as_float(r[g * 4 + 3]));
-                if (EPI == EPI_RESID) {
-                  const float4 o = *reinterpret_cast<const float4*>(dst + g * 4);
-                  v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
-                }
-                *reinterpret_cast<float4*>(dst + g * 4) = v;
-              }
+              const uint32_t piece = (uint32_t)(g ^ (r & 7));
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(box + (piece << 4)), "r"(v[g * 4]),
+                           "r"(v[g * 4 + 1]), "r"(v[g * 4 + 2]), "r"(v[g * 4 + 3]) : "memory");
             }
           }
         }
+        if (rd == ROUNDS - 1) {
+          // every tcgen05.ld of this accumulator has completed: hand it back to the MMA warp
+          tcgen05_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(tempty_bar(acc));
+        }
+        fence_async_smem();                                // generic-proxy writes -> visible to the async proxy
+        epi_bar();
+        if (issuer) {
+          const int row0 = m_blk * BLOCK_M;
+#pragma unroll
+          for (int bx = 0; bx < 2; ++bx) {
+            const int col0 = n_blk * BLOCK_N + (kOutBf16 ? bx * 64 : (rd * 2 + bx) * 32);
+            if (col0 < N) {
+              if (EPI == EPI_RESID) tma_reduce_add_2d(&map_c, cstage + bx * 16384u, col0, row0);
+              else tma_store_2d(&map_c, cstage + bx * 16384u, col0, row0);
+            }
+          }
+          tma_store_commit();
+        }
       }
-      tcgen05_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(tempty_bar(acc));
       if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1u; }
     }
+    if (issuer) tma_store_wait_all();
   }
   tcgen05_fence_before();
   __syncthreads();
@@ -285,18 +322,20 @@ bool get_encode() {
   return true;
 }
 
-// 2-D bf16 row-major [rows, cols] with a (128 rows x 64 cols) box and 128-byte swizzle
-bool get_map(const void* ptr, int rows, int cols, CUtensorMap* out) {
-  auto key = std::make_tuple(ptr, rows, cols);
+// 2-D row-major [rows, cols] tensor map with a (128 rows x 128 bytes) box and 128-byte swizzle.
+// kind 0: bf16 operand/output (box 64 columns), kind 1: fp32 output (box 32 columns)
+bool get_map(const void* ptr, int rows, int cols, int kind, CUtensorMap* out) {
+  auto key = std::make_tuple(ptr, rows, cols * 2 + kind);
   auto it = g_maps.find(key);
   if (it != g_maps.end()) { *out = it->second; return true; }
   if (!get_encode()) return false;
   CUtensorMap m;
   cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
-  cuuint64_t strides[1] = {(cuuint64_t)cols * 2};
-  cuuint32_t box[2] = {(cuuint32_t)BLOCK_K, (cuuint32_t)BLOCK_M};
+  cuuint64_t strides[1] = {(cuuint64_t)cols * (kind ? 4 : 2)};
+  cuuint32_t box[2] = {(cuuint32_t)(kind ? 32 : 64), (cuuint32_t)BLOCK_M};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = g_encode(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+  CUresult r = g_encode(&m, kind ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
+                        const_cast<void*>(ptr), dims, strides, box, estr,
                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
@@ -310,8 +349,8 @@ bool get_map(const void* ptr, int rows, int cols, CUtensorMap* out) {
 }
 
 template <int EPI>
-cudaError_t launch(const CUtensorMap& ma, const CUtensorMap& mw, void* C, int M_max, const int* m_ptr, int N, int K,
-                   int num_sms, cudaStream_t s) {
+cudaError_t launch(const CUtensorMap& ma, const CUtensorMap& mw, const CUtensorMap& mc, int M_max, const int* m_ptr,
+                   int N, int K, int num_sms, cudaStream_t s) {
   auto kern = gemm_tc_kernel<EPI>;
   if (!g_attr_set[EPI]) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
@@ -320,7 +359,7 @@ cudaError_t launch(const CUtensorMap& ma, const CUtensorMap& mw, void* C, int M_
   }
   const int tiles = ((M_max + BLOCK_M - 1) / BLOCK_M) * ((N + BLOCK_N - 1) / BLOCK_N);
   const int grid = tiles < num_sms ? tiles : num_sms;
-  kern<<<grid, THREADS, SMEM_BYTES, s>>>(ma, mw, C, M_max, m_ptr, N, K);
+  kern<<<grid, THREADS, SMEM_BYTES, s>>>(ma, mw, mc, M_max, m_ptr, N, K);
   return cudaGetLastError();
 }
 
@@ -335,13 +374,15 @@ cudaError_t gemm_tc(int epi, const void* A, const void* W, void* C, int M_max, c
   if (M_max <= 0) return cudaSuccess;
   if (!gemm_tc_supported(N, K)) return cudaErrorInvalidValue;
   std::lock_guard<std::mutex> lk(tc::g_mu);
-  CUtensorMap ma, mw;
-  if (!tc::get_map(A, M_max, K, &ma) || !tc::get_map(W, N, K, &mw)) return cudaErrorUnknown;
+  CUtensorMap ma, mw, mc;
+  const int ckind = (epi == EPI_STORE || epi == EPI_RELU) ? 0 : 1;
+  if (!tc::get_map(A, M_max, K, 0, &ma) || !tc::get_map(W, N, K, 0, &mw) || !tc::get_map(C, M_max, N, ckind, &mc))
+    return cudaErrorUnknown;
   switch (epi) {
-    case EPI_STORE: return tc::launch<EPI_STORE>(ma, mw, C, M_max, m_ptr, N, K, num_sms, s);
-    case EPI_RELU: return tc::launch<EPI_RELU>(ma, mw, C, M_max, m_ptr, N, K, num_sms, s);
-    case EPI_RESID: return tc::launch<EPI_RESID>(ma, mw, C, M_max, m_ptr, N, K, num_sms, s);
-    case EPI_F32: return tc::launch<EPI_F32>(ma, mw, C, M_max, m_ptr, N, K, num_sms, s);
+    case EPI_STORE: return tc::launch<EPI_STORE>(ma, mw, mc, M_max, m_ptr, N, K, num_sms, s);
+    case EPI_RELU: return tc::launch<EPI_RELU>(ma, mw, mc, M_max, m_ptr, N, K, num_sms, s);
+    case EPI_RESID: return tc::launch<EPI_RESID>(ma, mw, mc, M_max, m_ptr, N, K, num_sms, s);
+    case EPI_F32: return tc::launch<EPI_F32>(ma, mw, mc, M_max, m_ptr, N, K, num_sms, s);
     default: return cudaErrorInvalidValue;
   }
 }
