@@ -71,6 +71,28 @@ cudaError_t lse_rows(const float* logits, float* lse, int R, int V, cudaStream_t
   return cudaGetLastError();
 }
 
+__global__ void lse_combine_kernel(const float2* __restrict__ partial, float* __restrict__ lse, int R, int n_tiles) {
+  const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (row >= R) return;
+  const float2* p = partial + (size_t)row * n_tiles;
+  float mx = -INFINITY;
+  for (int i = lane; i < n_tiles; i += 32) mx = fmaxf(mx, p[i].x);
+  mx = warp_max(mx);
+  float sum = 0.f;
+  for (int i = lane; i < n_tiles; i += 32) {
+    const float2 v = p[i];
+    if (v.x > -INFINITY) sum += v.y * expf(v.x - mx);
+  }
+  sum = warp_sum(sum);
+  if (lane == 0) lse[row] = mx + logf(sum);
+}
+
+cudaError_t lse_combine(const void* partial, float* lse, int R, int n_tiles, cudaStream_t s) {
+  if (R <= 0) return cudaSuccess;
+  lse_combine_kernel<<<(R + 7) / 8, 256, 0, s>>>((const float2*)partial, lse, R, n_tiles);
+  return cudaGetLastError();
+}
+
 // ------------------------------------------------------------------------------------------------
 __global__ void beam_init_kernel(BeamState bs, int root, int users, int start_tok) {
   const int r = blockIdx.x * blockDim.x + threadIdx.x;
@@ -162,8 +184,8 @@ constexpr int BEAM_KMAX = 64;
 size_t beam_step_smem(int cand_cap) { return (size_t)cand_cap * sizeof(unsigned long long); }
 
 __global__ void __launch_bounds__(BEAM_THREADS)
-beam_step_kernel(BeamState bs, TrieCSR trie, const float* __restrict__ logits, const float* __restrict__ lse,
-                 int users, int t, int cand_cap) {
+beam_step_kernel(BeamState bs, TrieCSR trie, const float* __restrict__ logits, const bf16* __restrict__ hidden,
+                 const bf16* __restrict__ head, int D, const float* __restrict__ lse, int users, int t, int cand_cap) {
   extern __shared__ __align__(16) unsigned long long keys[];
   __shared__ int pre[BEAM_KMAX + 1];
   __shared__ int sel_parent[BEAM_KMAX], sel_tok[BEAM_KMAX], sel_node[BEAM_KMAX];
@@ -223,21 +245,57 @@ beam_step_kernel(BeamState bs, TrieCSR trie, const float* __restrict__ logits, c
   __syncthreads();
   const int C = min(pre[K], cand_cap);
   const int n_sort = min(n_sort_s, cand_cap);
-  for (int c = tid; c < n_sort; c += BEAM_THREADS) {
-    unsigned long long key = 0ull;
-    if (c < C) {
+  if (logits != nullptr) {
+    for (int c = tid; c < n_sort; c += BEAM_THREADS) {
+      unsigned long long key = 0ull;
+      if (c < C) {
+        int b = 0;
+        while (pre[b + 1] <= c) ++b;                         // K <= 64, linear search
+        const int nd = node_c[base + b];
+        const int e = trie.child_offsets[nd] + (c - pre[b]);
+        const int tok = trie.child_tokens[e];
+        const int row = base + b;
+        float s = (logits[(size_t)row * V + tok] - lse[row]) + score_c[row];
+        if (!(s == s)) s = -INFINITY;
+        const unsigned int idx = (unsigned int)b * (unsigned int)V + (unsigned int)tok;
+        key = ((unsigned long long)float_key(s) << 32) | (unsigned long long)(0xFFFFFFFFu - idx);
+      }
+      keys[c] = key;
+    }
+  } else {
+    // fused mode: one warp per candidate recomputes its logit = hidden[row] . head[token] (bf16 operands, fp32 sum)
+    const int wid = tid >> 5, lane = tid & 31;
+    for (int c = C + tid; c < n_sort; c += BEAM_THREADS) keys[c] = 0ull;
+    for (int c = wid; c < C; c += BEAM_THREADS / 32) {
       int b = 0;
-      while (pre[b + 1] <= c) ++b;                         // K <= 64, linear search
+      while (pre[b + 1] <= c) ++b;
       const int nd = node_c[base + b];
       const int e = trie.child_offsets[nd] + (c - pre[b]);
       const int tok = trie.child_tokens[e];
       const int row = base + b;
-      float s = (logits[(size_t)row * V + tok] - lse[row]) + score_c[row];
-      if (!(s == s)) s = -INFINITY;
-      const unsigned int idx = (unsigned int)b * (unsigned int)V + (unsigned int)tok;
-      key = ((unsigned long long)float_key(s) << 32) | (unsigned long long)(0xFFFFFFFFu - idx);
+      const bf16* hr = hidden + (size_t)row * D;
+      const bf16* er = head + (size_t)tok * D;
+      float a = 0.f;
+      for (int d = lane * 8; d < D; d += 256) {
+        const uint4 hv = *reinterpret_cast<const uint4*>(hr + d);
+        const uint4 ev = *reinterpret_cast<const uint4*>(er + d);
+        const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&hv);
+        const __nv_bfloat162* e2 = reinterpret_cast<const __nv_bfloat162*>(&ev);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float2 x = __bfloat1622float2(h2[i]), y = __bfloat1622float2(e2[i]);
+          a = fmaf(x.x, y.x, a);
+          a = fmaf(x.y, y.y, a);
+        }
+      }
+      a = warp_sum(a);
+      if (lane == 0) {
+        float s = (a - lse[row]) + score_c[row];
+        if (!(s == s)) s = -INFINITY;
+        const unsigned int idx = (unsigned int)b * (unsigned int)V + (unsigned int)tok;
+        keys[c] = ((unsigned long long)float_key(s) << 32) | (unsigned long long)(0xFFFFFFFFu - idx);
+      }
     }
-    keys[c] = key;
   }
   __syncthreads();
   // ---- bitonic sort ascending (best candidate ends at n_sort-1) ----
@@ -309,10 +367,11 @@ beam_step_kernel(BeamState bs, TrieCSR trie, const float* __restrict__ logits, c
   }
 }
 
-cudaError_t beam_step(BeamState bs, TrieCSR trie, const float* logits, const float* lse, int users, int t,
-                      int cand_cap, cudaStream_t s) {
+cudaError_t beam_step(BeamState bs, TrieCSR trie, const float* logits, const void* hidden, const void* head, int D,
+                      const float* lse, int users, int t, int cand_cap, cudaStream_t s) {
   if (users <= 0) return cudaSuccess;
   if (bs.K > BEAM_KMAX) return cudaErrorInvalidValue;
+  if (logits == nullptr && (hidden == nullptr || head == nullptr || (D & 7))) return cudaErrorInvalidValue;
   const size_t smem = beam_step_smem(cand_cap);
   static size_t configured = 0;
   if (smem > configured) {
@@ -320,7 +379,8 @@ cudaError_t beam_step(BeamState bs, TrieCSR trie, const float* logits, const flo
     if (e != cudaSuccess) return e;
     configured = smem;
   }
-  beam_step_kernel<<<users, BEAM_THREADS, smem, s>>>(bs, trie, logits, lse, users, t, cand_cap);
+  beam_step_kernel<<<users, BEAM_THREADS, smem, s>>>(bs, trie, logits, (const bf16*)hidden, (const bf16*)head, D, lse, users, t,
+                                                     cand_cap);
   return cudaGetLastError();
 }
 

@@ -89,6 +89,7 @@ struct gram_handle {
   void *dxn = nullptr, *dqkv = nullptr, *dao = nullptr, *dq = nullptr, *dff = nullptr;
   void *sk = nullptr, *sv = nullptr;     // [Ld][Tmax][Rcap][HD]
   float *logits = nullptr, *lse = nullptr;
+  void* lse_partial = nullptr;           // float2 [Rcap][ceil(V/128)]
   BeamState bs{};
   double* d_len_pow = nullptr;
   double* h_len_pow = nullptr;           // pinned
@@ -208,6 +209,7 @@ int gemm(gram_handle* h, int cls, int epi, const void* A, const void* W, void* C
     }
     return GRAM_OK;
   }
+  if (epi == EPI_LSE) { h->err = "EPI_LSE needs the tcgen05 GEMM"; return GRAM_ERR_STATE; }
   e = gemm_simt(h->cfg.dtype, epi, A, W, C, M_max, m_ptr, N, K, s);
   if (e != cudaSuccess) {
     h->err = std::string("simt gemm launch failed: ") + cudaGetErrorString(e);
@@ -336,7 +338,7 @@ int run_encode(gram_handle* h, const int64_t* ids, const uint8_t* mask, int B, i
 }
 
 // ---- one decoder step (all layers + lm_head) for R rows ---------------------------------------------
-int decoder_step(gram_handle* h, int R, int K, int users, int t, const int* anc, cudaStream_t s) {
+int decoder_step(gram_handle* h, int R, int K, int users, int t, const int* anc, bool fused_lse, cudaStream_t s) {
   const gram_config& c = h->cfg;
   const int D = h->D, HD = h->HD, F = h->F;
   const size_t esz = h->esz;
@@ -366,7 +368,13 @@ int decoder_step(gram_handle* h, int R, int K, int users, int t, const int* anc,
   }
   const float scale = c.tie_word_embeddings ? 1.0f / sqrtf((float)D) : 1.0f;
   CKL(GRAM_K_OTHER, rmsnorm_rows(c.dtype, h->dx, h->dec_final_ln, h->dxn, R, nullptr, D, c.ln_eps, scale, nullptr, nullptr, s));
-  RC(gemm(h, GRAM_K_LM_HEAD, EPI_F32, h->dxn, h->lm_head, h->logits, R, nullptr, h->V, D, s));
+  if (fused_lse) {
+    // kernel (c): vocabulary projection with the log-softmax statistics fused into the epilogue; logits never stored
+    RC(gemm(h, GRAM_K_LM_HEAD, EPI_LSE, h->dxn, h->lm_head, h->lse_partial, R, nullptr, h->V, D, s));
+    CKL(GRAM_K_LM_HEAD, lse_combine(h->lse_partial, h->lse, R, (h->V + 127) / 128, s));
+  } else {
+    RC(gemm(h, GRAM_K_LM_HEAD, EPI_F32, h->dxn, h->lm_head, h->logits, R, nullptr, h->V, D, s));
+  }
   return GRAM_OK;
 }
 
@@ -485,6 +493,7 @@ int gram_create(const gram_config* cfg, gram_handle** out) {
   DAC(h->dff, R * F * esz);
   DAC(h->sk, (size_t)h->Ld * ML * R * HD * esz); DAC(h->sv, (size_t)h->Ld * ML * R * HD * esz);
   DAC(h->logits, R * V * 4); DAC(h->lse, R * 4);
+  DAC(h->lse_partial, R * (size_t)((V + 127) / 128) * 8);
   BeamState& bs = h->bs;
   bs.max_length = ML; bs.gen_len = ML; bs.V = V; bs.eos = c.eos_id; bs.pad = c.pad_id; bs.K = c.max_beams;
   for (int i = 0; i < 2; ++i) {
@@ -661,10 +670,18 @@ int gram_generate(gram_handle* h, const int64_t* ids, const uint8_t* mask, int32
   for (int i = max_length + 1; i <= c.max_length; ++i) h->h_len_pow[i] = 1.0;
   CK(cudaMemcpyAsync(h->d_len_pow, h->h_len_pow, ((size_t)c.max_length + 1) * 8, cudaMemcpyHostToDevice, s));
   CKL(GRAM_K_BEAM, beam_init(bs, h->trie, users, c.start_id, s));
+  // fused head (bf16 + tcgen05 GEMM): log-softmax statistics come out of the GEMM epilogue and candidate logits are
+  // recomputed from the trie children only; otherwise (fp32 parity mode) full logits are materialised
+  const bool fused = c.dtype == GRAM_DTYPE_BF16 && !(c.flags & (GRAM_FLAG_SIMT_GEMM | GRAM_FLAG_KEEP_LOGITS)) &&
+                     gemm_tc_supported(h->V, h->D) && (h->D % 8) == 0;
   for (int t = 0; t < T; ++t) {
-    RC(decoder_step(h, R, K, users, t, bs.anc[t & 1], s));
-    CKL(GRAM_K_LM_HEAD, lse_rows(h->logits, h->lse, R, h->V, s));
-    CKL(GRAM_K_BEAM, beam_step(bs, h->trie, h->logits, h->lse, users, t, h->cand_cap, s));
+    RC(decoder_step(h, R, K, users, t, bs.anc[t & 1], fused, s));
+    if (fused) {
+      CKL(GRAM_K_BEAM, beam_step(bs, h->trie, nullptr, h->dxn, h->lm_head, h->D, h->lse, users, t, h->cand_cap, s));
+    } else {
+      CKL(GRAM_K_LM_HEAD, lse_rows(h->logits, h->lse, R, h->V, s));
+      CKL(GRAM_K_BEAM, beam_step(bs, h->trie, h->logits, nullptr, nullptr, h->D, h->lse, users, t, h->cand_cap, s));
+    }
   }
   CKL(GRAM_K_BEAM, beam_finalize(bs, users, T, R_ret, h->d_out_seq, h->d_out_scores, h->d_out_width, s));
   h->last_steps = T; h->last_R = R;
@@ -730,7 +747,7 @@ int gram_decoder_logits(gram_handle* h, const int64_t* dec_ids, int32_t q, float
   const size_t V = h->V;
   for (int t = 0; t < q; ++t) {
     CKL(GRAM_K_OTHER, forced_step(bs, dids, q, t, R, s));
-    RC(decoder_step(h, R, 1, B, t, h->d_zero_anc, s));
+    RC(decoder_step(h, R, 1, B, t, h->d_zero_anc, false, s));
     // logits [R, V] -> out[b][t][:]
     CK(cudaMemcpy2DAsync(out_logits + (size_t)t * V, (size_t)q * V * 4, h->logits, V * 4, V * 4, R,
                          dev ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, s));

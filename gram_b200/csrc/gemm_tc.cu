@@ -132,7 +132,8 @@ constexpr uint32_t kInstrDesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)
 template <int EPI>
 __global__ void __launch_bounds__(THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
-               const __grid_constant__ CUtensorMap map_c, int M_imm, const int* __restrict__ m_ptr, int N, int K) {
+               const __grid_constant__ CUtensorMap map_c, float2* __restrict__ lse_partial, int M_imm,
+               const int* __restrict__ m_ptr, int N, int K) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;           // 1024-byte alignment for the 128B swizzle atoms
@@ -225,6 +226,41 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       const int m_blk = tile / num_n, n_blk = tile % num_n;
       mbar_wait(tfull_bar(acc), acc_phase);
       tcgen05_fence_after();
+      if (EPI == EPI_LSE) {
+        // fused log-softmax statistics: per row, (max, sum exp(x - max)) over this tile's columns; the logits
+        // themselves are never written (reference computes log_softmax over the materialised [rows, V] logits)
+        float mx = -INFINITY, sum = 0.f;
+        const int row = m_blk * BLOCK_M + r;
+#pragma unroll 1
+        for (int c = 0; c < BLOCK_N / 32; ++c) {
+          uint32_t v[32];
+          const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BLOCK_N + c * 32);
+          tmem_ld32(taddr, v);
+          tmem_ld_wait();
+          const int col0 = n_blk * BLOCK_N + c * 32;
+          float cm = -INFINITY;
+#pragma unroll
+          for (int e = 0; e < 32; ++e) {
+            const float x = (col0 + e < N) ? __uint_as_float(v[e]) : -INFINITY;
+            v[e] = __float_as_uint(x);
+            cm = fmaxf(cm, x);
+          }
+          const float nm = fmaxf(mx, cm);
+          if (nm > -INFINITY) {
+            float cs = 0.f;
+#pragma unroll
+            for (int e = 0; e < 32; ++e) cs += exp2f((__uint_as_float(v[e]) - nm) * 1.4426950408889634f);
+            sum = sum * exp2f((mx - nm) * 1.4426950408889634f) + cs;
+            mx = nm;
+          }
+        }
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tempty_bar(acc));
+        if (row < M) lse_partial[(size_t)row * num_n + n_blk] = make_float2(mx, sum);
+        if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1u; }
+        continue;
+      }
 #pragma unroll 1
       for (int rd = 0; rd < ROUNDS; ++rd) {
         if (issuer) tma_store_wait_read();                 // previous bulk store has finished reading the staging tile
@@ -306,7 +342,7 @@ std::mutex g_mu;
 EncodeTiledFn g_encode = nullptr;
 std::string g_err;
 std::map<std::tuple<const void*, int, int>, CUtensorMap> g_maps;
-bool g_attr_set[4] = {false, false, false, false};
+bool g_attr_set[5] = {false, false, false, false, false};
 
 bool get_encode() {
   if (g_encode) return true;
@@ -349,8 +385,8 @@ bool get_map(const void* ptr, int rows, int cols, int kind, CUtensorMap* out) {
 }
 
 template <int EPI>
-cudaError_t launch(const CUtensorMap& ma, const CUtensorMap& mw, const CUtensorMap& mc, int M_max, const int* m_ptr,
-                   int N, int K, int num_sms, cudaStream_t s) {
+cudaError_t launch(const CUtensorMap& ma, const CUtensorMap& mw, const CUtensorMap& mc, float2* lse_partial, int M_max,
+                   const int* m_ptr, int N, int K, int num_sms, cudaStream_t s) {
   auto kern = gemm_tc_kernel<EPI>;
   if (!g_attr_set[EPI]) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
@@ -359,7 +395,7 @@ cudaError_t launch(const CUtensorMap& ma, const CUtensorMap& mw, const CUtensorM
   }
   const int tiles = ((M_max + BLOCK_M - 1) / BLOCK_M) * ((N + BLOCK_N - 1) / BLOCK_N);
   const int grid = tiles < num_sms ? tiles : num_sms;
-  kern<<<grid, THREADS, SMEM_BYTES, s>>>(ma, mw, mc, M_max, m_ptr, N, K);
+  kern<<<grid, THREADS, SMEM_BYTES, s>>>(ma, mw, mc, lse_partial, M_max, m_ptr, N, K);
   return cudaGetLastError();
 }
 
@@ -376,13 +412,14 @@ cudaError_t gemm_tc(int epi, const void* A, const void* W, void* C, int M_max, c
   std::lock_guard<std::mutex> lk(tc::g_mu);
   CUtensorMap ma, mw, mc;
   const int ckind = (epi == EPI_STORE || epi == EPI_RELU) ? 0 : 1;
-  if (!tc::get_map(A, M_max, K, 0, &ma) || !tc::get_map(W, N, K, 0, &mw) || !tc::get_map(C, M_max, N, ckind, &mc))
-    return cudaErrorUnknown;
+  if (!tc::get_map(A, M_max, K, 0, &ma) || !tc::get_map(W, N, K, 0, &mw)) return cudaErrorUnknown;
+  if (epi == EPI_LSE) return tc::launch<EPI_LSE>(ma, mw, ma, (float2*)C, M_max, m_ptr, N, K, num_sms, s);
+  if (!tc::get_map(C, M_max, N, ckind, &mc)) return cudaErrorUnknown;
   switch (epi) {
-    case EPI_STORE: return tc::launch<EPI_STORE>(ma, mw, mc, M_max, m_ptr, N, K, num_sms, s);
-    case EPI_RELU: return tc::launch<EPI_RELU>(ma, mw, mc, M_max, m_ptr, N, K, num_sms, s);
-    case EPI_RESID: return tc::launch<EPI_RESID>(ma, mw, mc, M_max, m_ptr, N, K, num_sms, s);
-    case EPI_F32: return tc::launch<EPI_F32>(ma, mw, mc, M_max, m_ptr, N, K, num_sms, s);
+    case EPI_STORE: return tc::launch<EPI_STORE>(ma, mw, mc, nullptr, M_max, m_ptr, N, K, num_sms, s);
+    case EPI_RELU: return tc::launch<EPI_RELU>(ma, mw, mc, nullptr, M_max, m_ptr, N, K, num_sms, s);
+    case EPI_RESID: return tc::launch<EPI_RESID>(ma, mw, mc, nullptr, M_max, m_ptr, N, K, num_sms, s);
+    case EPI_F32: return tc::launch<EPI_F32>(ma, mw, mc, nullptr, M_max, m_ptr, N, K, num_sms, s);
     default: return cudaErrorInvalidValue;
   }
 }

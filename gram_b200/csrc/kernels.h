@@ -6,7 +6,8 @@
 
 namespace gram {
 
-enum { EPI_STORE = 0, EPI_RELU = 1, EPI_RESID = 2, EPI_F32 = 3 };
+enum { EPI_STORE = 0, EPI_RELU = 1, EPI_RESID = 2, EPI_F32 = 3, EPI_LSE = 4 };
+// EPI_LSE (tcgen05 GEMM only): C is float2 [M, ceil(N/128)] of per-tile (max, sum exp(x - max)); no logits are stored
 
 // ---- gemm_simt.cu ------------------------------------------------------------------------------
 // C[M,N] = A[M,K] * W[N,K]^T.  M = *m_ptr when m_ptr != nullptr (grid sized for M_max), else M_max.
@@ -91,10 +92,15 @@ struct BeamState {           // all device pointers; rows R = users*K
   float* tap_lse; float* tap_score; int* tap_seq;                   // [steps][R](...)
 };
 cudaError_t lse_rows(const float* logits, float* lse, int R, int V, cudaStream_t s);
+// lse[row] from the per-tile (max, sumexp) partials of the EPI_LSE GEMM epilogue
+cudaError_t lse_combine(const void* partial, float* lse, int R, int n_tiles, cudaStream_t s);
 cudaError_t beam_init(BeamState bs, TrieCSR trie, int users, int start_tok, cudaStream_t s);
 // one beam-search step: PrefixConstrainedLogitsProcessor + topk(2K) + BeamSearchScorer.process
-cudaError_t beam_step(BeamState bs, TrieCSR trie, const float* logits, const float* lse, int users, int t,
-                      int cand_cap, cudaStream_t s);
+// logits != nullptr: gather candidate logits from the materialised [R,V] matrix (fp32 parity mode);
+// logits == nullptr: recompute them as dot(hidden[row], head[token]) from the bf16 decoder output `hidden` [R,D]
+// and the bf16 vocabulary head `head` [V,D] (fused mode: full-vocab logits are never written)
+cudaError_t beam_step(BeamState bs, TrieCSR trie, const float* logits, const void* hidden, const void* head, int D,
+                      const float* lse, int users, int t, int cand_cap, cudaStream_t s);
 cudaError_t beam_finalize(BeamState bs, int users, int t_final, int R_ret, int64_t* out_seq, float* out_scores,
                           int* out_width, cudaStream_t s);
 // teacher forcing: tok[r] = ids[r*q + t], anc[r][t'] = 0

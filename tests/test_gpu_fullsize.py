@@ -1,0 +1,146 @@
+"""GPU tests at BASELINE.json's full sizes (T5-small, real item tries, beam 20): exact parity against
+the oracle on a few users, and size-independent properties on whole batches:
+
+  * every returned sequence is an item of the trie (the device trie mask admits nothing else)
+  * scores are sorted best-first and equal sum-of-logprobs / length
+  * idempotence (same call twice -> same bits) and batch invariance (a user's ranking does not depend
+    on which other users share the batch) in fp32
+  * the eval loop's metrics are identical for batch sizes 1 (reference behaviour) and 16
+"""
+import numpy as np
+import pytest
+import torch
+
+from helpers import ROOT  # noqa: F401
+from gram_b200 import GRAM, GramConfig, Trie, prefix_allowed_tokens_fn, synth
+from gram_b200.data import GramTestData
+from gram_b200.runner import GramEvalLoader, GramRunner
+
+pytestmark = pytest.mark.gpu
+K = 20
+
+
+@pytest.fixture(scope="module")
+def beauty():
+    data = GramTestData("Beauty")
+    cfg = GramConfig.t5_small(max_seq_len=data.L, max_item_num=data.max_his)
+    sd = synth.make_state_dict(cfg, seed=0)
+    cands = data.encoded_candidates()
+    trie = Trie(cands)
+    return dict(data=data, cfg=cfg, sd=sd, cands=cands, trie=trie, fn=prefix_allowed_tokens_fn(trie),
+                max_length=max(len(c) for c in cands), cand_set={tuple(c) for c in cands})
+
+
+def _gen(model, b, users, device="cuda"):
+    batch = b["data"].collate(users)
+    ids = torch.from_numpy(batch["item_text_ids"]).to(device)
+    mask = torch.from_numpy(batch["item_text_masks"]).to(device)
+    out = model.generate(input_ids=ids, attention_mask=mask, max_length=b["max_length"], prefix_allowed_tokens_fn=b["fn"],
+                         num_beams=K, num_return_sequences=K, output_scores=True, return_dict_in_generate=True,
+                         length_penalty=1.0)
+    return out["sequences"].cpu().numpy(), out["sequences_scores"].cpu().numpy(), batch
+
+
+def _strip(row):
+    row = list(row)
+    return tuple(row[:row.index(1) + 1]) if 1 in row else tuple(row)
+
+
+@pytest.mark.parametrize("dtype", ["fp32", "bf16"])
+def test_full_size_batch_properties(beauty, dtype):
+    b = beauty
+    model = GRAM(b["cfg"], dtype=dtype, device="cuda:0")
+    model.load_state_dict(b["sd"])
+    users = list(range(100, 148))
+    seq, sc, _ = _gen(model, b, users)
+    assert seq.shape[0] == len(users) * K
+    for u in range(len(users)):
+        rows = [_strip(r) for r in seq[u * K:(u + 1) * K]]
+        assert all(r in b["cand_set"] for r in rows), "a returned id is not an item of the trie"
+        assert len(set(rows)) == K, "duplicate items in one user's ranking"
+        s = sc[u * K:(u + 1) * K]
+        assert np.all(s[:-1] >= s[1:]) and np.all(np.isfinite(s))
+    seq2, sc2, _ = _gen(model, b, users)
+    assert np.array_equal(seq, seq2) and np.array_equal(sc, sc2)          # idempotent, deterministic
+    if dtype == "fp32":
+        # batch invariance: users 100..103 alone vs inside the 48-user batch
+        seq3, sc3, _ = _gen(model, b, users[:4])
+        w = min(seq.shape[1], seq3.shape[1])
+        assert np.array_equal(seq3[:, :w], seq[:4 * K, :w])
+        assert np.allclose(sc3, sc[:4 * K], atol=1e-5)
+
+
+def test_full_size_fp32_matches_oracle(beauty):
+    """Two real Beauty users, T5-small, 12,101-item trie, beam 20: ranked ids identical to the oracle."""
+    from oracle.gram_oracle import OracleGRAM, OracleTrie
+    b = beauty
+    hist = [len(b["data"].split(u)[0]) for u in range(400)]
+    users = [int(np.argmin(hist)), int(np.argsort(hist)[len(hist) // 2])]      # a short and a median history
+    model = GRAM(b["cfg"], dtype="fp32", device="cuda:0")
+    model.load_state_dict(b["sd"])
+    seq, sc, batch = _gen(model, b, users)
+    ora = OracleGRAM(b["cfg"], b["sd"])
+    ref = ora.generate(torch.from_numpy(batch["item_text_ids"]), torch.from_numpy(batch["item_text_masks"]),
+                       b["max_length"], OracleTrie(b["cands"]), K, K, 1.0)
+    want = ref["sequences"].numpy()
+    gap = np.abs(np.diff(ref["sequences_scores"].numpy().reshape(len(users), K), axis=1)).min()
+    print(f"[full-size fp32] min rank gap in the oracle scores: {gap:.3e}")
+    assert seq.shape == want.shape and np.array_equal(seq, want)
+    assert np.abs(sc - ref["sequences_scores"].numpy()).max() < 2e-4
+    # bf16: report overlap of the top-10
+    m16 = GRAM(b["cfg"], dtype="bf16", device="cuda:0")
+    m16.load_state_dict(b["sd"])
+    seq16, _, _ = _gen(m16, b, users)
+    for u in range(len(users)):
+        g = {_strip(r) for r in want[u * K:u * K + 10]}
+        h = {_strip(r) for r in seq16[u * K:u * K + 10]}
+        print(f"[full-size bf16] user {users[u]} top-10 overlap {len(g & h) / 10:.1f}")
+        assert len(g & h) >= 5
+
+
+def test_eval_loop_batch_size_independent(beauty):
+    b = beauty
+    model = GRAM(b["cfg"], dtype="fp32", device="cuda:0")
+    model.load_state_dict(b["sd"])
+
+    class Args:
+        metrics = "hit@5,hit@10,ndcg@5,ndcg@10"
+        beam_size = K
+        length_penalty = 1.0
+        item_id_type = "split"
+
+    users = list(range(32))
+    res = []
+    for bs in (1, 16):
+        loader = GramEvalLoader(b["data"], batch_size=bs, users=users)
+        runner = GramRunner(model, b["data"].tokenizer, "cuda:0", Args())
+        res.append(runner.test_dataset_task(loader))
+    assert res[0]["test_total"] == res[1]["test_total"] == 32
+    assert np.array_equal(res[0]["hit_ranks"], res[1]["hit_ranks"])
+    assert res[0]["metrics"] == res[1]["metrics"]
+    p0 = [r[2] for r in res[0]["rows"]]
+    p1 = [r[2] for r in res[1]["rows"]]
+    assert p0 == p1                                                        # identical decoded rankings
+
+
+@pytest.mark.parametrize("dataset", ["Toys", "Sports", "Yelp"])
+def test_other_datasets_valid_items(dataset):
+    """BASELINE configs 3 and 4: the other shipped tries (different id lengths / fan-outs)."""
+    data = GramTestData(dataset, synthetic_users=64 if dataset == "Yelp" else 0)
+    cfg = GramConfig.t5_small(max_seq_len=data.L, max_item_num=data.max_his)
+    sd = synth.make_state_dict(cfg, seed=0)
+    cands = data.encoded_candidates()
+    fn = prefix_allowed_tokens_fn(Trie(cands))
+    ml = max(len(c) for c in cands)
+    model = GRAM(cfg, dtype="bf16", device="cuda:0")
+    model.load_state_dict(sd)
+    batch = data.collate(list(range(16)))
+    out = model.generate(input_ids=torch.from_numpy(batch["item_text_ids"]).cuda(),
+                         attention_mask=torch.from_numpy(batch["item_text_masks"]).cuda(), max_length=ml,
+                         prefix_allowed_tokens_fn=fn, num_beams=K, num_return_sequences=K, return_dict_in_generate=True)
+    cs = {tuple(c) for c in cands}
+    seq = out["sequences"].cpu().numpy()
+    assert seq.shape == (16 * K, ml)
+    assert all(_strip(r) in cs for r in seq)
+    sc = out["sequences_scores"].cpu().numpy().reshape(16, K)
+    assert np.all(sc[:, :-1] >= sc[:, 1:])
