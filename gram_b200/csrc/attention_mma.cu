@@ -319,7 +319,8 @@ cross_attention_mma_kernel(const __grid_constant__ CUtensorMap map_kv, const bf1
 // ================================================================================================
 // encoder self-attention: one CTA per (passage, head); warp w owns query rows [32w, 32w+32)
 // ================================================================================================
-constexpr int EA_THREADS = 128;
+constexpr int EA_THREADS = 256;        // 8 warps x 16 query rows: low register count -> more resident CTAs per SM
+constexpr int EA_MT = 1;
 
 struct RelBias {
   const float* lut;   // shared memory, [2*Lb-1]
@@ -328,7 +329,7 @@ struct RelBias {
 };
 
 template <int LT>     // key tiles of 64 the kernel is sized for (L <= 64*LT)
-__global__ void __launch_bounds__(EA_THREADS)
+__global__ void __launch_bounds__(EA_THREADS, 2)
 enc_attention_mma_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, const int* __restrict__ plen,
                          const int* __restrict__ poff, const uint8_t* __restrict__ tok_valid,
                          const float* __restrict__ bias_lut, int Lb, int H) {
@@ -363,7 +364,7 @@ enc_attention_mma_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, c
     *reinterpret_cast<uint4*>(smem + (swz(vb + tile * BOX_BYTES, rr, c) - base)) = vv4;
   }
   for (int i = tid; i < 2 * Lb - 1; i += EA_THREADS) lut[i] = bias_lut[(size_t)h * (2 * Lb - 1) + i];
-  if (warp < n_tiles) {
+  if (warp < n_tiles) {                                        // n_tiles <= 4 < 8 warps
     const int r0 = warp * TS + lane, r1 = r0 + 32;
     const bool v0 = r0 < len && tok_valid[row0 + r0] != 0;
     const bool v1 = r1 < len && tok_valid[row0 + r1] != 0;
@@ -373,10 +374,11 @@ enc_attention_mma_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, c
   __syncthreads();
 
   const int g = lane >> 2, q = lane & 3;
-  for (int qb = warp * 32; qb < len; qb += 4 * 32) {          // 32 query rows per warp pass
-    uint32_t qf[2][4][4];
+  constexpr int ROWS = EA_MT * 16;                              // query rows per warp pass
+  for (int qb = warp * ROWS; qb < len; qb += (EA_THREADS / 32) * ROWS) {
+    uint32_t qf[EA_MT][4][4];
 #pragma unroll
-    for (int mt = 0; mt < 2; ++mt)
+    for (int mt = 0; mt < EA_MT; ++mt)
 #pragma unroll
       for (int ks = 0; ks < 4; ++ks)
 #pragma unroll
@@ -387,9 +389,9 @@ enc_attention_mma_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, c
           if (r < len) v = *reinterpret_cast<const uint32_t*>(qkv + (size_t)(row0 + r) * ld + h * DK + d);
           qf[mt][ks][e] = v;
         }
-    float o[2][8][4], m_run[2][2], l_run[2][2];
+    float o[EA_MT][8][4], m_run[EA_MT][2], l_run[EA_MT][2];
 #pragma unroll
-    for (int mt = 0; mt < 2; ++mt) {
+    for (int mt = 0; mt < EA_MT; ++mt) {
       m_run[mt][0] = m_run[mt][1] = -INFINITY;
       l_run[mt][0] = l_run[mt][1] = 0.f;
 #pragma unroll
@@ -399,10 +401,10 @@ enc_attention_mma_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, c
     }
     for (int t = 0; t < n_tiles; ++t) {
       RelBias rb{lut, t * TS - qb + Lb - 1};
-      flash_tile<2>(qf, kb + t * BOX_BYTES, vb + t * BOX_BYTES, masks[t], rb, o, m_run, l_run, lane);
+      flash_tile<EA_MT>(qf, kb + t * BOX_BYTES, vb + t * BOX_BYTES, masks[t], rb, o, m_run, l_run, lane);
     }
 #pragma unroll
-    for (int mt = 0; mt < 2; ++mt)
+    for (int mt = 0; mt < EA_MT; ++mt)
 #pragma unroll
       for (int hf = 0; hf < 2; ++hf) {
         float l = l_run[mt][hf];

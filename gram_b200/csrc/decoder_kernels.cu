@@ -104,16 +104,115 @@ dec_self_attention_kernel(const T* __restrict__ qkv, T* __restrict__ cache_k, T*
   }
 }
 
+// d_kv = 64 specialisation with a short dependency chain: lane = (position group pg = lane/8, 16-byte chunk
+// c = lane%8).  After one round trip for q/k/v + the ancestry row, every K and V chunk the warp needs is requested
+// at once (addresses depend on the ancestry only), so a step costs two memory round trips instead of five.
+__device__ __forceinline__ void load8(const float* p, float (&v)[8]) {
+  const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+__device__ __forceinline__ void load8(const bf16* p, float (&v)[8]) {
+  const uint4 u = *reinterpret_cast<const uint4*>(p);
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { const float2 f = __bfloat1622float2(h[i]); v[2 * i] = f.x; v[2 * i + 1] = f.y; }
+}
+__device__ __forceinline__ void store8(float* p, const float (&v)[8]) {
+  *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+  *reinterpret_cast<float4*>(p + 4) = make_float4(v[4], v[5], v[6], v[7]);
+}
+__device__ __forceinline__ void store8(bf16* p, const float (&v)[8]) {
+  uint4 u;
+  __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+  *reinterpret_cast<uint4*>(p) = u;
+}
+
+// One warp = (row, 4 heads): lane = (head hq = lane/8, 16-byte chunk c = lane%8), positions are walked with an
+// online softmax, four positions' K and V chunks requested per iteration.  Work is proportional to t+1.
+template <typename T>
+__global__ void __launch_bounds__(128)
+dec_self_attention64_kernel(const T* __restrict__ qkv, T* __restrict__ cache_k, T* __restrict__ cache_v,
+                            const int* __restrict__ anc, int Tmax, const float* __restrict__ dec_bias, int n_dec,
+                            T* __restrict__ out, int R, int K, int H, int t) {
+  constexpr int DK = 64;
+  const int HQ = H >> 2;                                 // head quads per row
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= R * HQ) return;
+  const int r = warp / HQ, h = (warp % HQ) * 4 + (lane >> 3), c = lane & 7;
+  const int HD = H * DK;
+  const int ubase = (r / K) * K;
+  const size_t col = (size_t)h * DK + c * 8;
+  // ancestry of this row: lane j holds position j (and j + 32)
+  const int a0 = (lane < t) ? anc[(size_t)r * Tmax + lane] : 0;
+  const int a1 = (lane + 32 < t) ? anc[(size_t)r * Tmax + lane + 32] : 0;
+  const T* qrow = qkv + (size_t)r * 3 * HD + col;
+  float qv[8], kc[8], vc[8];
+  load8(qrow, qv);
+  load8(qrow + HD, kc);
+  load8(qrow + 2 * HD, vc);
+  store8(cache_k + ((size_t)t * R + r) * HD + col, kc);  // append this step's key/value (slot t, own row)
+  store8(cache_v + ((size_t)t * R + r) * HD + col, vc);
+  const float* bias = dec_bias + h * n_dec;
+  float m = -INFINITY, l = 0.f;
+  float acc[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+  auto absorb = [&](const float (&kx)[8], const float (&vx)[8], int j) {
+    float a = 0.f;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) a = fmaf(qv[e], kx[e], a);
+    a += __shfl_xor_sync(0xffffffffu, a, 1);
+    a += __shfl_xor_sync(0xffffffffu, a, 2);
+    a += __shfl_xor_sync(0xffffffffu, a, 4);
+    const int dist = t - j;
+    a += bias[dist < n_dec ? dist : n_dec - 1];
+    const float mn = fmaxf(m, a);
+    const float corr = expf(m - mn);                     // exp(-inf) = 0 on the first position
+    const float p = expf(a - mn);
+    l = l * corr + p;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[e] = fmaf(p, vx[e], acc[e] * corr);
+    m = mn;
+  };
+  for (int j0 = 0; j0 < t; j0 += 4) {
+    float kx[4][8], vx[4][8];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int j = j0 + u;                              // warp-uniform
+      if (j < t) {
+        const int sj = ubase + __shfl_sync(0xffffffffu, j < 32 ? a0 : a1, j & 31);
+        const size_t off = ((size_t)j * R + sj) * HD + col;
+        load8(cache_k + off, kx[u]);
+        load8(cache_v + off, vx[u]);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      if (j0 + u < t) absorb(kx[u], vx[u], j0 + u);
+  }
+  absorb(kc, vc, t);
+  const float inv = 1.0f / l;
+#pragma unroll
+  for (int e = 0; e < 8; ++e) acc[e] *= inv;
+  store8(out + (size_t)r * HD + col, acc);
+}
+
 template <typename T>
 static cudaError_t launch_dec_self(const void* qkv, void* ck, void* cv, const int* anc, int Tmax,
                                    const float* dec_bias, int n_dec, void* out, int R, int K, int H, int dk, int t,
                                    cudaStream_t s) {
-  const int warps = R * H;
+  const int warps = (dk == 64 && (H & 3) == 0) ? R * (H / 4) : R * H;
   const int grid = (warps + 3) / 4;
+  if (dk == 64 && (H & 3)) {
+    dec_self_attention_kernel<T, 64><<<grid, 128, 0, s>>>((const T*)qkv, (T*)ck, (T*)cv, anc, Tmax, dec_bias, n_dec, (T*)out, R, K, H, t);
+    return cudaGetLastError();
+  }
   switch (dk) {
     case 16: dec_self_attention_kernel<T, 16><<<grid, 128, 0, s>>>((const T*)qkv, (T*)ck, (T*)cv, anc, Tmax, dec_bias, n_dec, (T*)out, R, K, H, t); break;
     case 32: dec_self_attention_kernel<T, 32><<<grid, 128, 0, s>>>((const T*)qkv, (T*)ck, (T*)cv, anc, Tmax, dec_bias, n_dec, (T*)out, R, K, H, t); break;
-    case 64: dec_self_attention_kernel<T, 64><<<grid, 128, 0, s>>>((const T*)qkv, (T*)ck, (T*)cv, anc, Tmax, dec_bias, n_dec, (T*)out, R, K, H, t); break;
+    case 64: dec_self_attention64_kernel<T><<<grid, 128, 0, s>>>((const T*)qkv, (T*)ck, (T*)cv, anc, Tmax, dec_bias, n_dec, (T*)out, R, K, H, t); break;
     default: return cudaErrorInvalidValue;
   }
   return cudaGetLastError();

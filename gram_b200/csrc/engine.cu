@@ -315,7 +315,7 @@ int run_encode(gram_handle* h, const int64_t* ids, const uint8_t* mask, int B, i
   CKL(GRAM_K_OTHER, embed_rows(c.dtype, h->shared, h->pm.tok_id, h->x, Mmax, mp, D, s));
   for (int l = 0; l < h->Le; ++l) {
     const LayerW& W = h->enc[l];
-    CKL(GRAM_K_OTHER, rmsnorm_rows(c.dtype, h->x, W.ln0, h->xn, Mmax, mp, D, c.ln_eps, 1.f, nullptr, nullptr, s));
+    CKL(GRAM_K_NORM_ENC, rmsnorm_rows(c.dtype, h->x, W.ln0, h->xn, Mmax, mp, D, c.ln_eps, 1.f, nullptr, nullptr, s));
     RC(gemm(h, GRAM_K_GEMM_ENC, EPI_STORE, h->xn, W.qkv, h->qkv, Mmax, mp, 3 * HD, D, s));
     if (c.dtype == GRAM_DTYPE_BF16 && !(c.flags & GRAM_FLAG_SIMT_ATTN) && enc_attention_mma_supported(h->dk, L)) {
       CKL(GRAM_K_ENC_ATTN, enc_attention_mma(h->qkv, h->ao, h->pm.plen, h->pm.poff, h->pm.tok_valid, h->enc_bias_lut,
@@ -325,11 +325,11 @@ int run_encode(gram_handle* h, const int64_t* ids, const uint8_t* mask, int B, i
                                          h->enc_bias_lut, h->Lb, B * N, h->H, h->dk, L, s));
     }
     RC(gemm(h, GRAM_K_GEMM_ENC, EPI_RESID, h->ao, W.o, h->x, Mmax, mp, D, HD, s));
-    CKL(GRAM_K_OTHER, rmsnorm_rows(c.dtype, h->x, W.ln1, h->xn, Mmax, mp, D, c.ln_eps, 1.f, nullptr, nullptr, s));
+    CKL(GRAM_K_NORM_ENC, rmsnorm_rows(c.dtype, h->x, W.ln1, h->xn, Mmax, mp, D, c.ln_eps, 1.f, nullptr, nullptr, s));
     RC(gemm(h, GRAM_K_GEMM_ENC, EPI_RELU, h->xn, W.wi, h->ff, Mmax, mp, F, D, s));
     RC(gemm(h, GRAM_K_GEMM_ENC, EPI_RESID, h->ff, W.wo, h->x, Mmax, mp, D, F, s));
   }
-  CKL(GRAM_K_OTHER, rmsnorm_rows(c.dtype, h->x, h->enc_final_ln, h->mem, Mmax, mp, D, c.ln_eps, 1.f,
+  CKL(GRAM_K_NORM_ENC, rmsnorm_rows(c.dtype, h->x, h->enc_final_ln, h->mem, Mmax, mp, D, c.ln_eps, 1.f,
                                  h->pos_emb, h->pos_emb ? h->pm.tok_pos : nullptr, s));
   // cross-attention K/V of every decoder layer, written in place in the layout kernel (b) reads
   RC(gemm(h, GRAM_K_GEMM_KV, EPI_STORE, h->mem, h->ckv_w, h->ckv, Mmax, mp, h->Ld * 2 * HD, D, s));
@@ -346,13 +346,13 @@ int decoder_step(gram_handle* h, int R, int K, int users, int t, const int* anc,
   CKL(GRAM_K_OTHER, embed_rows(c.dtype, h->shared, h->bs.tok, h->dx, R, nullptr, D, s));
   for (int l = 0; l < h->Ld; ++l) {
     const LayerW& W = h->dec[l];
-    CKL(GRAM_K_OTHER, rmsnorm_rows(c.dtype, h->dx, W.ln0, h->dxn, R, nullptr, D, c.ln_eps, 1.f, nullptr, nullptr, s));
+    CKL(GRAM_K_NORM_DEC, rmsnorm_rows(c.dtype, h->dx, W.ln0, h->dxn, R, nullptr, D, c.ln_eps, 1.f, nullptr, nullptr, s));
     RC(gemm(h, GRAM_K_GEMM_DEC, EPI_STORE, h->dxn, W.qkv, h->dqkv, R, nullptr, 3 * HD, D, s));
     // cache slices are indexed [t][R][HD] with the *current* R as the row pitch
-    CKL(GRAM_K_OTHER, dec_self_attention(c.dtype, h->dqkv, (char*)h->sk + l * layer_cache, (char*)h->sv + l * layer_cache,
+    CKL(GRAM_K_SELF_ATTN, dec_self_attention(c.dtype, h->dqkv, (char*)h->sk + l * layer_cache, (char*)h->sv + l * layer_cache,
                                          anc, c.max_length, h->dec_bias_lut, h->n_dec_lut, h->dao, R, K, h->H, h->dk, t, s));
     RC(gemm(h, GRAM_K_GEMM_DEC, EPI_RESID, h->dao, W.o, h->dx, R, nullptr, D, HD, s));
-    CKL(GRAM_K_OTHER, rmsnorm_rows(c.dtype, h->dx, W.ln1, h->dxn, R, nullptr, D, c.ln_eps, 1.f, nullptr, nullptr, s));
+    CKL(GRAM_K_NORM_DEC, rmsnorm_rows(c.dtype, h->dx, W.ln1, h->dxn, R, nullptr, D, c.ln_eps, 1.f, nullptr, nullptr, s));
     RC(gemm(h, GRAM_K_GEMM_DEC, EPI_STORE, h->dxn, W.cq, h->dq, R, nullptr, HD, D, s));
     if (c.dtype == GRAM_DTYPE_BF16 && !(c.flags & GRAM_FLAG_SIMT_ATTN) && cross_attention_mma_supported(K, h->H, h->dk)) {
       CKL(GRAM_K_CROSS_ATTN, cross_attention_mma(h->dq, h->ckv, (size_t)h->Mcap + 256, (size_t)h->Ld * 2 * HD, l * 2 * HD,
@@ -362,12 +362,12 @@ int decoder_step(gram_handle* h, int R, int K, int users, int t, const int* anc,
                                              h->pm.ustart, h->pm.tok_valid, h->dao, users, K, h->H, h->dk, s));
     }
     RC(gemm(h, GRAM_K_GEMM_DEC, EPI_RESID, h->dao, W.co, h->dx, R, nullptr, D, HD, s));
-    CKL(GRAM_K_OTHER, rmsnorm_rows(c.dtype, h->dx, W.ln2, h->dxn, R, nullptr, D, c.ln_eps, 1.f, nullptr, nullptr, s));
+    CKL(GRAM_K_NORM_DEC, rmsnorm_rows(c.dtype, h->dx, W.ln2, h->dxn, R, nullptr, D, c.ln_eps, 1.f, nullptr, nullptr, s));
     RC(gemm(h, GRAM_K_GEMM_DEC, EPI_RELU, h->dxn, W.wi, h->dff, R, nullptr, F, D, s));
     RC(gemm(h, GRAM_K_GEMM_DEC, EPI_RESID, h->dff, W.wo, h->dx, R, nullptr, D, F, s));
   }
   const float scale = c.tie_word_embeddings ? 1.0f / sqrtf((float)D) : 1.0f;
-  CKL(GRAM_K_OTHER, rmsnorm_rows(c.dtype, h->dx, h->dec_final_ln, h->dxn, R, nullptr, D, c.ln_eps, scale, nullptr, nullptr, s));
+  CKL(GRAM_K_NORM_DEC, rmsnorm_rows(c.dtype, h->dx, h->dec_final_ln, h->dxn, R, nullptr, D, c.ln_eps, scale, nullptr, nullptr, s));
   if (fused_lse) {
     // kernel (c): vocabulary projection with the log-softmax statistics fused into the epilogue; logits never stored
     RC(gemm(h, GRAM_K_LM_HEAD, EPI_LSE, h->dxn, h->lm_head, h->lse_partial, R, nullptr, h->V, D, s));

@@ -135,7 +135,8 @@ int gram_get_stats(gram_handle* h, gram_stats* out);
 /* kernel classes for event timing */
 enum {
   GRAM_K_GEMM_ENC = 0, GRAM_K_ENC_ATTN = 1, GRAM_K_GEMM_KV = 2, GRAM_K_GEMM_DEC = 3,
-  GRAM_K_CROSS_ATTN = 4, GRAM_K_LM_HEAD = 5, GRAM_K_BEAM = 6, GRAM_K_OTHER = 7, GRAM_K_COUNT = 8
+  GRAM_K_CROSS_ATTN = 4, GRAM_K_LM_HEAD = 5, GRAM_K_BEAM = 6, GRAM_K_OTHER = 7, GRAM_K_SELF_ATTN = 8,
+  GRAM_K_NORM_ENC = 9, GRAM_K_NORM_DEC = 10, GRAM_K_COUNT = 11
 };
 /* mask: bit c set = bracket every launch of class c with CUDA events on the launching stream */
 int gram_profile_begin(gram_handle* h, uint32_t class_mask);
