@@ -33,16 +33,24 @@ namespace gram {
 
 namespace tc {
 
-constexpr int BLOCK_M = 128, BLOCK_N = 128, BLOCK_K = 64, UMMA_K = 16;
-constexpr int STAGES = 6;
+// Tile: 128 x BN x 64 with BN = 128 or 256.  BN = 256 moves (128 + 256) * 64 * 2 B of operands per 128*256*64 MACs
+// (85 MAC/B) instead of 64 MAC/B: the K = 512 GEMMs of this model are L2-bandwidth-bound at 128 x 128, so the wide
+// tile is used whenever the problem still yields at least two waves of tiles.
+constexpr int BLOCK_M = 128, BLOCK_K = 64, UMMA_K = 16;
 constexpr int ACC_STAGES = 2;
-constexpr int TMEM_COLS = ACC_STAGES * BLOCK_N;            // 256, power of two
 constexpr int THREADS = 192;
 constexpr uint32_t A_BYTES = BLOCK_M * BLOCK_K * 2;        // 16 KiB
-constexpr uint32_t B_BYTES = BLOCK_N * BLOCK_K * 2;        // 16 KiB
-constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
 constexpr uint32_t CSTAGE_BYTES = 32 * 1024;               // epilogue staging: two 128-row x 128-byte boxes
-constexpr size_t SMEM_BYTES = (size_t)STAGES * STAGE_BYTES + CSTAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+template <int BN> struct Cfg {
+  static constexpr int STAGES = BN == 128 ? 6 : 4;
+  static constexpr uint32_t B_BYTES = BN * BLOCK_K * 2;    // 16 or 32 KiB
+  static constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int TMEM_COLS = ACC_STAGES * BN;        // 256 or 512 (power of two)
+  static constexpr size_t SMEM_BYTES = (size_t)STAGES * STAGE_BYTES + CSTAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+  // instruction descriptor: D=f32, A=B=bf16, both K-major, M=128, N=BN
+  static constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) |
+                                    ((uint32_t)(BLOCK_M >> 4) << 24);
+};
 
 // ---- PTX wrappers --------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -125,15 +133,15 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
   d |= (uint64_t)2 << 61;                                // layout type: SWIZZLE_128B              bits [61,64)
   return d;
 }
-// instruction descriptor: D=f32, A=B=bf16, both K-major, M=128, N=128
-constexpr uint32_t kInstrDesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BLOCK_N >> 3) << 17) |
-                                ((uint32_t)(BLOCK_M >> 4) << 24);
-
-template <int EPI>
+template <int EPI, int BLOCK_N>
 __global__ void __launch_bounds__(THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
                const __grid_constant__ CUtensorMap map_c, float2* __restrict__ lse_partial, int M_imm,
                const int* __restrict__ m_ptr, int N, int K) {
+  constexpr int STAGES = Cfg<BLOCK_N>::STAGES;
+  constexpr uint32_t STAGE_BYTES = Cfg<BLOCK_N>::STAGE_BYTES;
+  constexpr int TMEM_COLS = Cfg<BLOCK_N>::TMEM_COLS;
+  constexpr uint32_t kInstrDesc = Cfg<BLOCK_N>::IDESC;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;           // 1024-byte alignment for the 128B swizzle atoms
@@ -219,8 +227,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     const int r = quad * 32 + lane;                        // row of the tile this thread owns
     const bool issuer = (warp == 2 && lane == 0);
     constexpr bool kOutBf16 = (EPI == EPI_STORE || EPI == EPI_RELU);
-    constexpr int ROUNDS = kOutBf16 ? 1 : 2;               // 32 KiB of staging = 128 bf16 or 64 fp32 columns
-    constexpr int CHUNKS_PER_ROUND = (BLOCK_N / 32) / ROUNDS;
+    constexpr int CHUNKS_PER_ROUND = kOutBf16 ? 4 : 2;     // 32 KiB of staging = 128 bf16 or 64 fp32 columns
+    constexpr int ROUNDS = (BLOCK_N / 32) / CHUNKS_PER_ROUND;
     int acc = 0; uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int m_blk = tile / num_n, n_blk = tile % num_n;
@@ -273,8 +281,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           tmem_ld32(taddr, v);
           tmem_ld_wait();
           if (kOutBf16) {
-            // box (c/2): 128 rows x 64 bf16 (128 B per row); this chunk is the 16-byte pieces (c%2)*4 .. +3
-            const uint32_t box = cstage + (uint32_t)(c >> 1) * 16384u + (uint32_t)r * 128u;
+            // box (cc/2): 128 rows x 64 bf16 (128 B per row); this chunk is the 16-byte pieces (c%2)*4 .. +3
+            const uint32_t box = cstage + (uint32_t)(cc >> 1) * 16384u + (uint32_t)r * 128u;
 #pragma unroll
             for (int g = 0; g < 4; ++g) {
               uint32_t pk[4];
@@ -312,7 +320,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           const int row0 = m_blk * BLOCK_M;
 #pragma unroll
           for (int bx = 0; bx < 2; ++bx) {
-            const int col0 = n_blk * BLOCK_N + (kOutBf16 ? bx * 64 : (rd * 2 + bx) * 32);
+            const int col0 = n_blk * BLOCK_N + (kOutBf16 ? (rd * 2 + bx) * 64 : (rd * 2 + bx) * 32);
             if (col0 < N) {
               if (EPI == EPI_RESID) tma_reduce_add_2d(&map_c, cstage + bx * 16384u, col0, row0);
               else tma_store_2d(&map_c, cstage + bx * 16384u, col0, row0);
@@ -341,8 +349,8 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
 std::mutex g_mu;
 EncodeTiledFn g_encode = nullptr;
 std::string g_err;
-std::map<std::tuple<const void*, int, int>, CUtensorMap> g_maps;
-bool g_attr_set[5] = {false, false, false, false, false};
+std::map<std::tuple<const void*, int, long long>, CUtensorMap> g_maps;
+bool g_attr_set[10] = {false, false, false, false, false, false, false, false, false, false};
 
 bool get_encode() {
   if (g_encode) return true;
@@ -358,17 +366,17 @@ bool get_encode() {
   return true;
 }
 
-// 2-D row-major [rows, cols] tensor map with a (128 rows x 128 bytes) box and 128-byte swizzle.
+// 2-D row-major [rows, cols] tensor map with a (box_rows x 128 bytes) box and 128-byte swizzle.
 // kind 0: bf16 operand/output (box 64 columns), kind 1: fp32 output (box 32 columns)
-bool get_map(const void* ptr, int rows, int cols, int kind, CUtensorMap* out) {
-  auto key = std::make_tuple(ptr, rows, cols * 2 + kind);
+bool get_map(const void* ptr, int rows, int cols, int kind, int box_rows, CUtensorMap* out) {
+  auto key = std::make_tuple(ptr, rows, ((long long)cols * 2 + kind) * 4 + (box_rows >> 7));
   auto it = g_maps.find(key);
   if (it != g_maps.end()) { *out = it->second; return true; }
   if (!get_encode()) return false;
   CUtensorMap m;
   cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
   cuuint64_t strides[1] = {(cuuint64_t)cols * (kind ? 4 : 2)};
-  cuuint32_t box[2] = {(cuuint32_t)(kind ? 32 : 64), (cuuint32_t)BLOCK_M};
+  cuuint32_t box[2] = {(cuuint32_t)(kind ? 32 : 64), (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = g_encode(&m, kind ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
                         const_cast<void*>(ptr), dims, strides, box, estr,
@@ -384,19 +392,28 @@ bool get_map(const void* ptr, int rows, int cols, int kind, CUtensorMap* out) {
   return true;
 }
 
-template <int EPI>
+template <int EPI, int BN>
 cudaError_t launch(const CUtensorMap& ma, const CUtensorMap& mw, const CUtensorMap& mc, float2* lse_partial, int M_max,
                    const int* m_ptr, int N, int K, int num_sms, cudaStream_t s) {
-  auto kern = gemm_tc_kernel<EPI>;
-  if (!g_attr_set[EPI]) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
+  auto kern = gemm_tc_kernel<EPI, BN>;
+  constexpr size_t smem = Cfg<BN>::SMEM_BYTES;
+  bool& done = g_attr_set[EPI * 2 + (BN == 256)];
+  if (!done) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    g_attr_set[EPI] = true;
+    done = true;
   }
-  const int tiles = ((M_max + BLOCK_M - 1) / BLOCK_M) * ((N + BLOCK_N - 1) / BLOCK_N);
+  const int tiles = ((M_max + BLOCK_M - 1) / BLOCK_M) * ((N + BN - 1) / BN);
   const int grid = tiles < num_sms ? tiles : num_sms;
-  kern<<<grid, THREADS, SMEM_BYTES, s>>>(ma, mw, mc, lse_partial, M_max, m_ptr, N, K);
+  kern<<<grid, THREADS, smem, s>>>(ma, mw, mc, lse_partial, M_max, m_ptr, N, K);
   return cudaGetLastError();
+}
+
+// wide tiles only when they still give every SM at least two tiles
+inline int pick_bn(int M_max, int N, int num_sms) {
+  if (N < 256) return 128;
+  const long long tiles256 = (long long)((M_max + BLOCK_M - 1) / BLOCK_M) * ((N + 255) / 256);
+  return tiles256 >= 2LL * num_sms ? 256 : 128;
 }
 
 }  // namespace tc
@@ -412,16 +429,21 @@ cudaError_t gemm_tc(int epi, const void* A, const void* W, void* C, int M_max, c
   std::lock_guard<std::mutex> lk(tc::g_mu);
   CUtensorMap ma, mw, mc;
   const int ckind = (epi == EPI_STORE || epi == EPI_RELU) ? 0 : 1;
-  if (!tc::get_map(A, M_max, K, 0, &ma) || !tc::get_map(W, N, K, 0, &mw)) return cudaErrorUnknown;
-  if (epi == EPI_LSE) return tc::launch<EPI_LSE>(ma, mw, ma, (float2*)C, M_max, m_ptr, N, K, num_sms, s);
-  if (!tc::get_map(C, M_max, N, ckind, &mc)) return cudaErrorUnknown;
+  const int bn = epi == EPI_LSE ? 128 : tc::pick_bn(M_max, N, num_sms);
+  if (!tc::get_map(A, M_max, K, 0, tc::BLOCK_M, &ma) || !tc::get_map(W, N, K, 0, bn, &mw)) return cudaErrorUnknown;
+  if (epi == EPI_LSE) return tc::launch<EPI_LSE, 128>(ma, mw, ma, (float2*)C, M_max, m_ptr, N, K, num_sms, s);
+  if (!tc::get_map(C, M_max, N, ckind, tc::BLOCK_M, &mc)) return cudaErrorUnknown;
+#define GRAM_TC_LAUNCH(E)                                                                               \
+  return bn == 256 ? tc::launch<E, 256>(ma, mw, mc, nullptr, M_max, m_ptr, N, K, num_sms, s)           \
+                   : tc::launch<E, 128>(ma, mw, mc, nullptr, M_max, m_ptr, N, K, num_sms, s)
   switch (epi) {
-    case EPI_STORE: return tc::launch<EPI_STORE>(ma, mw, mc, nullptr, M_max, m_ptr, N, K, num_sms, s);
-    case EPI_RELU: return tc::launch<EPI_RELU>(ma, mw, mc, nullptr, M_max, m_ptr, N, K, num_sms, s);
-    case EPI_RESID: return tc::launch<EPI_RESID>(ma, mw, mc, nullptr, M_max, m_ptr, N, K, num_sms, s);
-    case EPI_F32: return tc::launch<EPI_F32>(ma, mw, mc, nullptr, M_max, m_ptr, N, K, num_sms, s);
+    case EPI_STORE: GRAM_TC_LAUNCH(EPI_STORE);
+    case EPI_RELU: GRAM_TC_LAUNCH(EPI_RELU);
+    case EPI_RESID: GRAM_TC_LAUNCH(EPI_RESID);
+    case EPI_F32: GRAM_TC_LAUNCH(EPI_F32);
     default: return cudaErrorInvalidValue;
   }
+#undef GRAM_TC_LAUNCH
 }
 
 }  // namespace gram

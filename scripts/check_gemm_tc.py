@@ -56,7 +56,8 @@ if __name__ == "__main__":
     allok = True
     print("correctness (tcgen05 vs torch fp32 matmul of the same bf16 operands)")
     for (M, N, K) in [(128, 128, 64), (128, 128, 512), (1, 128, 64), (200, 512, 512), (77, 192, 64), (333, 1536, 512),
-                      (1000, 2048, 512), (513, 512, 2048), (129, 32128, 512), (700, 6144, 512), (4097, 768, 3072)]:
+                      (1000, 2048, 512), (513, 512, 2048), (129, 32128, 512), (700, 6144, 512), (4097, 768, 3072),
+                      (38000, 512, 512), (38001, 784, 128), (20000, 32128, 64)]:   # the last three take the 128x256 tile
         for epi in (0, 1, 2, 3):
             allok &= run(M, N, K, epi)
     print("ALL OK" if allok else "SOME FAILED")

@@ -79,6 +79,31 @@ def test_gemm_simt(dtype, shape, epi):
     assert rel_err(Cd, ref) < tol
 
 
+@pytest.mark.parametrize("shape", [(1, 128, 64), (77, 192, 64), (333, 1536, 512), (513, 512, 2048), (129, 32128, 512),
+                                   (38001, 784, 128), (20000, 1024, 64)])
+@pytest.mark.parametrize("epi", [0, 1, 2, 3])
+def test_gemm_tcgen05(shape, epi):
+    """tcgen05/TMEM/TMA GEMM (128x128 and 128x256 tiles, all epilogues incl. TMA reduce-add) vs fp64 matmul of the
+    same bf16 operands."""
+    from gram_b200 import _cabi
+    lib = _cabi.load_library()
+    M, N, K = shape
+    g = torch.Generator(device="cpu").manual_seed(M + 3 * N + K + epi)
+    Ad = torch.randn(M, K, generator=g).cuda().to(torch.bfloat16)
+    Wd = (torch.randn(N, K, generator=g) * (K ** -0.5)).cuda().to(torch.bfloat16)
+    ref = Ad.double() @ Wd.double().t()
+    if epi == 1:
+        ref = ref.clamp_min(0)
+    Cd = torch.zeros(M, N, device="cuda", dtype=torch.bfloat16) if epi in (0, 1) else torch.ones(M, N, device="cuda")
+    if epi == 2:
+        ref = ref + 1.0
+    rc = lib.gram_op_gemm(0, 1, 1, epi, C.c_void_p(Ad.data_ptr()), C.c_void_p(Wd.data_ptr()), C.c_void_p(Cd.data_ptr()),
+                          M, N, K, None)
+    assert rc == 0, lib.gram_last_error(None)
+    torch.cuda.synchronize()
+    assert rel_err(Cd, ref) < (8e-3 if epi in (0, 1) else 5e-6)
+
+
 @pytest.mark.parametrize("dtype,impl", [("fp32", 0), ("bf16", 0), ("bf16", 1)])
 @pytest.mark.parametrize("dk,H,K", [(16, 4, 4), (64, 8, 20), (64, 12, 50), (64, 8, 1), (64, 4, 33)])
 def test_cross_attention_op(dtype, impl, dk, H, K):
