@@ -82,31 +82,31 @@ __device__ __forceinline__ uint32_t swz(uint32_t base, int row, int chunk) {
   return base + (uint32_t)(row * 128) + (uint32_t)(((chunk ^ (row & 7)) & 7) << 4);
 }
 
-// One 64-key tile of flash attention for MT 16-row query tiles held by one warp.
+// One tile of flash attention for MT 16-row query tiles held by one warp: NKT*8 keys starting at key row
+// `row_off` of a [64 keys][64 d] swizzled tile.
 //   qf      Q fragments [MT][4 k-steps][4]
-//   kbase   shared address of the K tile  [64 keys][64 d]   (swizzled)
-//   vbase   shared address of the V tile  [64 keys][64 d]   (swizzled)
+//   kbase   shared address of the K tile, vbase of the V tile
 //   BiasFn  additive score term bias(row_in_warp_tile, key_in_tile) (0 for cross-attention)
-//   kmask   bit j set = key j of the tile is visible
-template <int MT, typename BiasFn>
-__device__ __forceinline__ void flash_tile(const uint32_t (&qf)[MT][4][4], uint32_t kbase, uint32_t vbase,
+//   kmask   bit j set = key (row_off + j) of the tile is visible
+template <int MT, int NKT, typename BiasFn>
+__device__ __forceinline__ void flash_tile(const uint32_t (&qf)[MT][4][4], uint32_t kbase, uint32_t vbase, int row_off,
                                            unsigned long long kmask, BiasFn bias, float (&o)[MT][8][4],
                                            float (&m_run)[MT][2], float (&l_run)[MT][2], int lane) {
   const int g = lane >> 2, q = lane & 3;
-  float s[MT][8][4];
+  float s[MT][NKT][4];
 #pragma unroll
   for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
-    for (int nt = 0; nt < 8; ++nt)
+    for (int nt = 0; nt < NKT; ++nt)
 #pragma unroll
       for (int e = 0; e < 4; ++e) s[mt][nt][e] = 0.f;
   // ---- S = Q K^T ----
 #pragma unroll
-  for (int p = 0; p < 4; ++p) {            // pairs of 8-key n-tiles
+  for (int p = 0; p < NKT / 2; ++p) {      // pairs of 8-key n-tiles
 #pragma unroll
     for (int ks = 0; ks < 4; ++ks) {       // 16-wide steps over d
       uint32_t b0, b1, b2, b3;
-      const int row = p * 16 + (lane & 7) + ((lane >> 4) << 3);
+      const int row = row_off + p * 16 + (lane & 7) + ((lane >> 4) << 3);
       const int chunk = ks * 2 + ((lane >> 3) & 1);
       ldsm_x4(swz(kbase, row, chunk), b0, b1, b2, b3);
 #pragma unroll
@@ -121,13 +121,13 @@ __device__ __forceinline__ void flash_tile(const uint32_t (&qf)[MT][4][4], uint3
   for (int mt = 0; mt < MT; ++mt) {
     float mx[2] = {-INFINITY, -INFINITY};
 #pragma unroll
-    for (int nt = 0; nt < 8; ++nt) {
+    for (int nt = 0; nt < NKT; ++nt) {
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         const int col = nt * 8 + 2 * q + (e & 1);
         const int rr = mt * 16 + g + ((e >> 1) << 3);
         const bool vis = (kmask >> col) & 1ull;
-        const float v = vis ? s[mt][nt][e] + bias(rr, col) : -INFINITY;
+        const float v = vis ? s[mt][nt][e] + bias(rr, row_off + col) : -INFINITY;
         s[mt][nt][e] = v;
         mx[e >> 1] = fmaxf(mx[e >> 1], v);
       }
@@ -145,7 +145,7 @@ __device__ __forceinline__ void flash_tile(const uint32_t (&qf)[MT][4][4], uint3
       const float mb = (m_new == -INFINITY) ? 0.f : m_new * LOG2E;
       float psum = 0.f;
 #pragma unroll
-      for (int nt = 0; nt < 8; ++nt) {
+      for (int nt = 0; nt < NKT; ++nt) {
 #pragma unroll
         for (int e2 = 0; e2 < 2; ++e2) {
           const int e = hf * 2 + e2;
@@ -153,6 +153,9 @@ __device__ __forceinline__ void flash_tile(const uint32_t (&qf)[MT][4][4], uint3
           s[mt][nt][e] = p;
           psum += p;
         }
+      }
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
         o[mt][nt][hf * 2] *= corr;
         o[mt][nt][hf * 2 + 1] *= corr;
       }
@@ -161,7 +164,7 @@ __device__ __forceinline__ void flash_tile(const uint32_t (&qf)[MT][4][4], uint3
   }
   // ---- O += P V ----
 #pragma unroll
-  for (int ks = 0; ks < 4; ++ks) {         // 16-key steps
+  for (int ks = 0; ks < NKT / 2; ++ks) {   // 16-key steps
     uint32_t pa[MT][4];
 #pragma unroll
     for (int mt = 0; mt < MT; ++mt) {
@@ -173,7 +176,7 @@ __device__ __forceinline__ void flash_tile(const uint32_t (&qf)[MT][4][4], uint3
 #pragma unroll
     for (int dp = 0; dp < 4; ++dp) {       // pairs of 8-wide d n-tiles
       uint32_t b0, b1, b2, b3;
-      const int row = ks * 16 + (lane & 7) + (((lane >> 3) & 1) << 3);
+      const int row = row_off + ks * 16 + (lane & 7) + (((lane >> 3) & 1) << 3);
       const int chunk = dp * 2 + (lane >> 4);
       ldsm_x4_t(swz(vbase, row, chunk), b0, b1, b2, b3);
 #pragma unroll
@@ -196,18 +199,21 @@ constexpr int XA_WARPS = 4;                                   // consumer warps 
 constexpr int XA_THREADS = (XA_WARPS + 1) * 32;               // + 1 TMA producer warp
 constexpr int XA_STAGE_TARGET = 64 * 1024;
 
-// HEADS heads per CTA, BH beam-halves (32 beams each) per head: HEADS * BH == 4 consumer warps.
-//   K <= 32: <4, 1>  (64 KiB stages, 3 stages)      K <= 64: <2, 2>  (32 KiB stages, 6 stages)
-template <int HEADS, int BH>
-__global__ void __launch_bounds__(XA_THREADS, 1)
+// HEADS heads per CTA, BH beam-halves (32 beams each) and KH key-halves (32 keys of every 64-key tile) per head:
+// HEADS * BH * KH == 4 consumer warps.  Key-halves are merged once at the end through shared memory.
+//   K <= 32: <4, 1, 1, 1>, 64 KiB stages x 3, one CTA per SM      K <= 64: <2, 2, 1, 1>, 32 KiB stages x 6
+//   (<2, 1, 2, 2> -- key-halves, two CTAs per SM -- measured 8 % slower on B200 and is kept only as an option)
+template <int HEADS, int BH, int KH, int MINB>
+__global__ void __launch_bounds__(XA_THREADS, MINB)
 cross_attention_mma_kernel(const __grid_constant__ CUtensorMap map_kv, const bf16* __restrict__ qg,
-                           bf16* __restrict__ out, const int* __restrict__ ustart,
+                           bf16* __restrict__ out, const int* __restrict__ ustart, const int* __restrict__ uorder,
                            const uint8_t* __restrict__ tok_valid, int K, int H, int k_col0, int v_col0) {
   constexpr int MT = 2;
   constexpr int XA_HEADS = HEADS;
   constexpr uint32_t XA_STAGE_BYTES = 2 * HEADS * BOX_BYTES;   // K boxes then V boxes
-  constexpr int XA_STAGES = 3 * XA_STAGE_TARGET / (int)XA_STAGE_BYTES;
-  static_assert(HEADS * BH == XA_WARPS, "four consumer warps");
+  constexpr int XA_STAGES = MINB == 2 ? 3 : 3 * XA_STAGE_TARGET / (int)XA_STAGE_BYTES;
+  constexpr int NKT = 8 / KH;
+  static_assert(HEADS * BH * KH == XA_WARPS, "four consumer warps");
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
@@ -215,7 +221,9 @@ cross_attention_mma_kernel(const __grid_constant__ CUtensorMap map_kv, const bf1
   const uint32_t bars = base + XA_STAGES * XA_STAGE_BYTES;     // full[ST], empty[ST]
   unsigned long long* masks = reinterpret_cast<unsigned long long*>(smem + XA_STAGES * XA_STAGE_BYTES + 128);
 
-  const int u = blockIdx.x, hg = blockIdx.y;
+  // longest-first order: the block scheduler hands out blockIdx.x in order, so heavy users start first and the
+  // short ones fill the tail of the last wave
+  const int u = uorder ? uorder[blockIdx.x] : blockIdx.x, hg = blockIdx.y;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int s_beg = ustart[u], s_end = ustart[u + 1];
   const int n_tiles = (s_end - s_beg + TS - 1) / TS;
@@ -256,8 +264,8 @@ cross_attention_mma_kernel(const __grid_constant__ CUtensorMap map_kv, const bf1
     return;
   }
 
-  // ===================== consumers: warp = (head, beam half) =====================
-  const int hl = warp / BH, b_off = (warp % BH) * 32;
+  // ===================== consumers: warp = (head, beam half, key half) =====================
+  const int hl = warp / (BH * KH), b_off = ((warp / KH) % BH) * 32, kh = warp % KH;
   const int h = hg * XA_HEADS + hl;
   const int g = lane >> 2, q = lane & 3;
   uint32_t qf[MT][4][4];
@@ -291,10 +299,50 @@ cross_attention_mma_kernel(const __grid_constant__ CUtensorMap map_kv, const bf1
     mbar_wait(bars + 8u * stage, phase);
     const unsigned long long kmask = masks[stage];
     const uint32_t sb = base + stage * XA_STAGE_BYTES;
-    flash_tile<MT>(qf, sb + hl * BOX_BYTES, sb + (XA_HEADS + hl) * BOX_BYTES, kmask, NoBias(), o, m_run, l_run, lane);
+    flash_tile<MT, NKT>(qf, sb + hl * BOX_BYTES, sb + (XA_HEADS + hl) * BOX_BYTES, kh * 32, kmask >> (kh * 32), NoBias(), o,
+                        m_run, l_run, lane);
     __syncwarp();
     if (lane == 0) mbar_arrive(bars + 8u * (XA_STAGES + stage));
     if (++stage == XA_STAGES) { stage = 0; phase ^= 1u; }
+  }
+  if (KH == 2) {
+    // ---- merge the two key-halves of every (head, beam half): every tile has been consumed, so the ring is free ----
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+    float* xch = reinterpret_cast<float*>(smem) + (size_t)(warp >> 1) * (32 * 72);   // 72 floats per lane
+    if (kh == 1) {
+      float* dst = xch + lane;
+#pragma unroll
+      for (int mt = 0; mt < MT; ++mt) {
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf) {
+          dst[(mt * 2 + hf) * 32] = m_run[mt][hf];
+          dst[(4 + mt * 2 + hf) * 32] = l_run[mt][hf];
+        }
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+          for (int e = 0; e < 4; ++e) dst[(8 + (mt * 8 + nt) * 4 + e) * 32] = o[mt][nt][e];
+      }
+    }
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+    if (kh == 1) return;
+    const float* src = xch + lane;
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt) {
+#pragma unroll
+      for (int hf = 0; hf < 2; ++hf) {
+        const float m0 = m_run[mt][hf], m1 = src[(mt * 2 + hf) * 32];
+        const float mn = fmaxf(m0, m1);
+        const float c0 = (m0 == -INFINITY) ? 0.f : exp2f((m0 - mn) * LOG2E);
+        const float c1 = (m1 == -INFINITY) ? 0.f : exp2f((m1 - mn) * LOG2E);
+        l_run[mt][hf] = l_run[mt][hf] * c0 + src[(4 + mt * 2 + hf) * 32] * c1;
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+          o[mt][nt][hf * 2] = o[mt][nt][hf * 2] * c0 + src[(8 + (mt * 8 + nt) * 4 + hf * 2) * 32] * c1;
+          o[mt][nt][hf * 2 + 1] = o[mt][nt][hf * 2 + 1] * c0 + src[(8 + (mt * 8 + nt) * 4 + hf * 2 + 1) * 32] * c1;
+        }
+      }
+    }
   }
   // ---- normalise and store ----
 #pragma unroll
@@ -401,7 +449,7 @@ enc_attention_mma_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, c
     }
     for (int t = 0; t < n_tiles; ++t) {
       RelBias rb{lut, t * TS - qb + Lb - 1};
-      flash_tile<EA_MT>(qf, kb + t * BOX_BYTES, vb + t * BOX_BYTES, masks[t], rb, o, m_run, l_run, lane);
+      flash_tile<EA_MT, 8>(qf, kb + t * BOX_BYTES, vb + t * BOX_BYTES, 0, masks[t], rb, o, m_run, l_run, lane);
     }
 #pragma unroll
     for (int mt = 0; mt < EA_MT; ++mt)
@@ -457,35 +505,35 @@ bool get_kv_map(const void* ptr, size_t rows, size_t cols, CUtensorMap* out) {
 
 }  // namespace fa
 
-bool cross_attention_mma_supported(int K, int H, int dk) {
-  return dk == fa::DK && K <= 64 && (K <= 32 ? (H % 4) == 0 : (H % 2) == 0);
-}
+bool cross_attention_mma_supported(int K, int H, int dk) { return dk == fa::DK && K <= 64 && (H % 2) == 0; }
 
 cudaError_t cross_attention_mma(const void* q, const void* kv, size_t kv_rows, size_t kv_stride, int k_off, int v_off,
-                                const int* ustart, const uint8_t* tok_valid, void* out, int users, int K, int H,
-                                cudaStream_t s) {
+                                const int* ustart, const int* uorder, const uint8_t* tok_valid, void* out, int users,
+                                int K, int H, cudaStream_t s) {
   if (users <= 0) return cudaSuccess;
   std::lock_guard<std::mutex> lk(fa::g_mu);
   CUtensorMap map;
   if (!fa::get_kv_map(kv, kv_rows, kv_stride, &map)) return cudaErrorUnknown;
   constexpr size_t smem = (size_t)3 * fa::XA_STAGE_TARGET + 1024 + 256;
   static bool attr[2] = {false, false};
-  if (K <= 32) {
-    auto kern = fa::cross_attention_mma_kernel<4, 1>;
+  if (K <= 32 && (H % 4) == 0) {
+    auto kern = fa::cross_attention_mma_kernel<4, 1, 1, 1>;
     if (!attr[0]) {
       cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       if (e != cudaSuccess) return e;
       attr[0] = true;
     }
-    kern<<<dim3(users, H / 4), fa::XA_THREADS, smem, s>>>(map, (const bf16*)q, (bf16*)out, ustart, tok_valid, K, H, k_off, v_off);
+    kern<<<dim3(users, H / 4), fa::XA_THREADS, smem, s>>>(map, (const bf16*)q, (bf16*)out, ustart, uorder, tok_valid, K, H,
+                                                          k_off, v_off);
   } else {
-    auto kern = fa::cross_attention_mma_kernel<2, 2>;
+    auto kern = fa::cross_attention_mma_kernel<2, 2, 1, 1>;
     if (!attr[1]) {
       cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       if (e != cudaSuccess) return e;
       attr[1] = true;
     }
-    kern<<<dim3(users, H / 2), fa::XA_THREADS, smem, s>>>(map, (const bf16*)q, (bf16*)out, ustart, tok_valid, K, H, k_off, v_off);
+    kern<<<dim3(users, H / 2), fa::XA_THREADS, smem, s>>>(map, (const bf16*)q, (bf16*)out, ustart, uorder, tok_valid, K, H,
+                                                          k_off, v_off);
   }
   return cudaGetLastError();
 }

@@ -91,11 +91,25 @@ __global__ void passage_fill_kernel(const int64_t* __restrict__ ids, const uint8
   }
 }
 
+// uorder[rank] = user, ranked by packed length descending (ties by index): O(B^2 / 1024) per thread, B <= a few thousand
+__global__ void __launch_bounds__(1024) user_order_kernel(const int* __restrict__ ustart, int B, int* __restrict__ uorder) {
+  for (int u = threadIdx.x; u < B; u += blockDim.x) {
+    const int len = ustart[u + 1] - ustart[u];
+    int rank = 0;
+    for (int v = 0; v < B; ++v) {
+      const int lv = ustart[v + 1] - ustart[v];
+      rank += (lv > len) || (lv == len && v < u);
+    }
+    uorder[rank] = u;
+  }
+}
+
 cudaError_t enc_pack(const int64_t* ids, const uint8_t* mask, int B, int N, int L, PackMeta pm, cudaStream_t s) {
   const int P = B * N;
   passage_len_kernel<<<(P * 32 + 255) / 256, 256, 0, s>>>(mask, P, L, pm.plen);
   passage_scan_kernel<<<1, 1024, 0, s>>>(pm.plen, P, N, B, pm.poff, pm.ustart, pm.total);
   passage_fill_kernel<<<P, 128, 0, s>>>(ids, mask, N, L, pm, 0);
+  user_order_kernel<<<1, 1024, 0, s>>>(pm.ustart, B, pm.uorder);
   return cudaGetLastError();
 }
 

@@ -311,7 +311,7 @@ int run_encode(gram_handle* h, const int64_t* ids, const uint8_t* mask, int B, i
   const int* mp = h->pm.total;
   const int D = h->D, HD = h->HD, F = h->F;
   CKL(GRAM_K_OTHER, enc_pack(dids, dmask, B, N, L, h->pm, s));
-  h->launches += 2;   // enc_pack issues three kernels
+  h->launches += 3;   // enc_pack issues four kernels
   CKL(GRAM_K_OTHER, embed_rows(c.dtype, h->shared, h->pm.tok_id, h->x, Mmax, mp, D, s));
   for (int l = 0; l < h->Le; ++l) {
     const LayerW& W = h->enc[l];
@@ -356,7 +356,7 @@ int decoder_step(gram_handle* h, int R, int K, int users, int t, const int* anc,
     RC(gemm(h, GRAM_K_GEMM_DEC, EPI_STORE, h->dxn, W.cq, h->dq, R, nullptr, HD, D, s));
     if (c.dtype == GRAM_DTYPE_BF16 && !(c.flags & GRAM_FLAG_SIMT_ATTN) && cross_attention_mma_supported(K, h->H, h->dk)) {
       CKL(GRAM_K_CROSS_ATTN, cross_attention_mma(h->dq, h->ckv, (size_t)h->Mcap + 256, (size_t)h->Ld * 2 * HD, l * 2 * HD,
-                                                 l * 2 * HD + HD, h->pm.ustart, h->pm.tok_valid, h->dao, users, K, h->H, s));
+                                                 l * 2 * HD + HD, h->pm.ustart, h->pm.uorder, h->pm.tok_valid, h->dao, users, K, h->H, s));
     } else {
       CKL(GRAM_K_CROSS_ATTN, cross_attention(c.dtype, h->dq, h->ckv, (size_t)h->Ld * 2 * HD, l * 2 * HD, l * 2 * HD + HD,
                                              h->pm.ustart, h->pm.tok_valid, h->dao, users, K, h->H, h->dk, s));
@@ -477,6 +477,7 @@ int gram_create(const gram_config* cfg, gram_handle** out) {
   const size_t Mc = (size_t)h->Mcap + 256;     // slack rows so vector loads/TMA boxes never leave the buffer
   const size_t P = (size_t)c.max_users * c.max_passages;
   DAC(h->pm.plen, P * 4); DAC(h->pm.poff, (P + 1) * 4); DAC(h->pm.ustart, ((size_t)c.max_users + 1) * 4);
+  DAC(h->pm.uorder, ((size_t)c.max_users + 1) * 4);
   DAC(h->pm.total, 16);
   DAC(h->pm.tok_id, Mc * 4); DAC(h->pm.tok_pos, Mc * 4); DAC(h->pm.tok_valid, Mc); DAC(h->pm.row_src, Mc * 4);
   DAC(h->d_ids, (size_t)full * 8); DAC(h->d_mask, (size_t)full);
@@ -840,7 +841,7 @@ int gram_op_cross_attention(int32_t device, int32_t dtype, int32_t impl, const v
       g_create_error = "gram_op_cross_attention: tensor-core path needs bf16, d_kv 64, K <= 64 and H % 4 == 0 (K <= 32) or H % 2 == 0";
       return GRAM_ERR_UNSUPPORTED;
     }
-    e = cross_attention_mma(q, kv, (size_t)kv_rows, (size_t)2 * H * dk, 0, H * dk, user_start, tok_valid, out, users, K, H,
+    e = cross_attention_mma(q, kv, (size_t)kv_rows, (size_t)2 * H * dk, 0, H * dk, user_start, nullptr, tok_valid, out, users, K, H,
                             (cudaStream_t)stream);
   } else {
     e = cross_attention(dtype, q, kv, (size_t)2 * H * dk, 0, H * dk, user_start, tok_valid, out, users, K, H, dk,

@@ -26,6 +26,7 @@ struct PackMeta {            // device-resident description of the packed (valid
   int* plen;                 // [P]    valid length of passage p (last valid index + 1)
   int* poff;                 // [P+1]  first packed row of passage p
   int* ustart;               // [B+1]  first packed row of user b
+  int* uorder;               // [B]    users ordered longest-first (launch order of the cross-attention CTAs)
   int* total;                // [1]    number of packed rows (M of every encoder GEMM)
   int* tok_id;               // [Mcap] token id per packed row
   int* tok_pos;              // [Mcap] passage index within the user (row of the position table)
@@ -64,8 +65,8 @@ bool cross_attention_mma_supported(int K, int H, int dk);
 // kv_rows = rows of the allocation behind `kv` (TMA bound); rows past a user's range are masked, so the buffer
 // must only hold finite values.
 cudaError_t cross_attention_mma(const void* q, const void* kv, size_t kv_rows, size_t kv_stride, int k_off, int v_off,
-                                const int* ustart, const uint8_t* tok_valid, void* out, int users, int K, int H,
-                                cudaStream_t s);
+                                const int* ustart, const int* uorder /* nullable: users longest-first */,
+                                const uint8_t* tok_valid, void* out, int users, int K, int H, cudaStream_t s);
 bool enc_attention_mma_supported(int dk, int Lmax);
 cudaError_t enc_attention_mma(const void* qkv, void* out, const int* plen, const int* poff, const uint8_t* tok_valid,
                               const float* bias_lut, int Lb, int P, int H, int Lmax, cudaStream_t s);
