@@ -470,6 +470,107 @@ enc_attention_mma_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, c
   }
 }
 
+// ================================================================================================
+// encoder self-attention, pipelined version: one CTA per passage walks its H heads; Q, K and V of head h+1 are
+// prefetched with cp.async (128B-swizzled, zero-filled past the passage length) while head h is computed, so the
+// global-load latency that dominated the one-(passage, head)-per-CTA kernel is hidden.
+// ================================================================================================
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, bool valid) {
+  const int sz = valid ? 16 : 0;                                  // src-size 0 -> 16 bytes of zeros
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+template <int LT>
+__global__ void __launch_bounds__(EA_THREADS, 2)
+enc_attention_pipe_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, const int* __restrict__ plen,
+                          const int* __restrict__ poff, const uint8_t* __restrict__ tok_valid,
+                          const float* __restrict__ bias_lut, int Lb, int H) {
+  const int p = blockIdx.x;
+  const int len = plen[p];
+  if (len == 0) return;
+  const int row0 = poff[p];
+  const int HD = H * DK;
+  const size_t ld = (size_t)3 * HD;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (base - raw);
+  constexpr uint32_t BUF = 3 * LT * BOX_BYTES;                    // Q | K | V tiles of one head
+  float* lut = reinterpret_cast<float*>(smem + 2 * BUF) + 32;     // [H][2*Lb-1] (+32 floats of slack below index 0)
+  const int lut_n = 2 * Lb - 1;
+  unsigned long long* masks = reinterpret_cast<unsigned long long*>(smem + 2 * BUF + 128 + (((size_t)H * lut_n * 4 + 15) / 16) * 16);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int n_tiles = (len + TS - 1) / TS;
+
+  auto prefetch = [&](int h, int buf) {
+    const uint32_t qb = base + buf * BUF, kb = qb + LT * BOX_BYTES, vb = kb + LT * BOX_BYTES;
+    for (int i = tid; i < n_tiles * TS * 8; i += EA_THREADS) {
+      const int r = i >> 3, c = i & 7;
+      const bool ok = r < len;
+      const bf16* src = qkv + (size_t)(row0 + (ok ? r : 0)) * ld + h * DK + c * 8;
+      const int tile = r >> 6, rr = r & 63;
+      cp_async16(swz(qb + tile * BOX_BYTES, rr, c), src, ok);
+      cp_async16(swz(kb + tile * BOX_BYTES, rr, c), src + HD, ok);
+      cp_async16(swz(vb + tile * BOX_BYTES, rr, c), src + 2 * HD, ok);
+    }
+    cp_async_commit();
+  };
+
+  prefetch(0, 0);
+  for (int i = tid; i < H * lut_n; i += EA_THREADS) lut[i] = bias_lut[i];
+  if (warp < n_tiles) {
+    const int r0 = warp * TS + lane, r1 = r0 + 32;
+    const bool v0 = r0 < len && tok_valid[row0 + r0] != 0;
+    const bool v1 = r1 < len && tok_valid[row0 + r1] != 0;
+    const unsigned lo = __ballot_sync(0xffffffffu, v0), hi = __ballot_sync(0xffffffffu, v1);
+    if (lane == 0) masks[warp] = ((unsigned long long)hi << 32) | lo;
+  }
+  const int g = lane >> 2, q = lane & 3;
+  for (int h = 0; h < H; ++h) {
+    const int buf = h & 1;
+    if (h + 1 < H) { prefetch(h + 1, buf ^ 1); cp_async_wait<1>(); } else { cp_async_wait<0>(); }
+    __syncthreads();                                              // head h's tiles (and lut/masks) are visible
+    const uint32_t qb = base + buf * BUF, kb = qb + LT * BOX_BYTES, vb = kb + LT * BOX_BYTES;
+    for (int q0 = warp * 16; q0 < len; q0 += (EA_THREADS / 32) * 16) {
+      uint32_t qf[1][4][4];
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks) {
+        const int r = q0 + (lane & 7) + (((lane >> 3) & 1) << 3);
+        ldsm_x4(swz(qb + (r >> 6) * BOX_BYTES, r & 63, ks * 2 + (lane >> 4)), qf[0][ks][0], qf[0][ks][1], qf[0][ks][2],
+                qf[0][ks][3]);
+      }
+      float o[1][8][4], m_run[1][2], l_run[1][2];
+      m_run[0][0] = m_run[0][1] = -INFINITY;
+      l_run[0][0] = l_run[0][1] = 0.f;
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) o[0][nt][e] = 0.f;
+      for (int t = 0; t < n_tiles; ++t) {
+        RelBias rb{lut + h * lut_n, t * TS - q0 + Lb - 1};
+        flash_tile<1, 8>(qf, kb + t * BOX_BYTES, vb + t * BOX_BYTES, 0, masks[t], rb, o, m_run, l_run, lane);
+      }
+#pragma unroll
+      for (int hf = 0; hf < 2; ++hf) {
+        float l = l_run[0][hf];
+        l += __shfl_xor_sync(0xffffffffu, l, 1);
+        l += __shfl_xor_sync(0xffffffffu, l, 2);
+        const float inv = l > 0.f ? 1.0f / l : 0.f;
+        const int r = q0 + g + hf * 8;
+        if (r < len) {
+          bf16* orow = out + (size_t)(row0 + r) * HD + h * DK;
+#pragma unroll
+          for (int nt = 0; nt < 8; ++nt)
+            *reinterpret_cast<uint32_t*>(orow + nt * 8 + 2 * q) = pack_bf16(o[0][nt][hf * 2] * inv, o[0][nt][hf * 2 + 1] * inv);
+        }
+      }
+    }
+    __syncthreads();                                              // buffer `buf` may be overwritten by prefetch(h + 2)
+  }
+}
+
 // ---- host side -------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -544,19 +645,18 @@ cudaError_t enc_attention_mma(const void* qkv, void* out, const int* plen, const
                               const float* bias_lut, int Lb, int P, int H, int Lmax, cudaStream_t s) {
   if (P <= 0) return cudaSuccess;
   const int LT = (Lmax + fa::TS - 1) / fa::TS;
-  const size_t lut_bytes = ((size_t)(2 * Lb - 1) * 4 + 15) / 16 * 16;
+  const size_t lut_bytes = ((size_t)H * (2 * Lb - 1) * 4 + 15) / 16 * 16;
   static bool attr[5] = {false, false, false, false, false};
-  dim3 grid(P, H);
 #define GRAM_EA(LTV)                                                                                         \
   {                                                                                                          \
-    const size_t smem = (size_t)2 * LTV * fa::BOX_BYTES + 128 + lut_bytes + LTV * 8 + 1024 + 64;                   \
-    auto kern = fa::enc_attention_mma_kernel<LTV>;                                                           \
+    const size_t smem = (size_t)2 * 3 * LTV * fa::BOX_BYTES + 128 + lut_bytes + LTV * 8 + 1024 + 64;         \
+    auto kern = fa::enc_attention_pipe_kernel<LTV>;                                                          \
     if (!attr[LTV]) {                                                                                        \
       cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);    \
       if (e != cudaSuccess) return e;                                                                        \
       attr[LTV] = true;                                                                                      \
     }                                                                                                        \
-    kern<<<grid, fa::EA_THREADS, smem, s>>>((const bf16*)qkv, (bf16*)out, plen, poff, tok_valid, bias_lut, Lb, H); \
+    kern<<<P, fa::EA_THREADS, smem, s>>>((const bf16*)qkv, (bf16*)out, plen, poff, tok_valid, bias_lut, Lb, H); \
   }
   if (LT <= 1) GRAM_EA(1)
   else if (LT == 2) GRAM_EA(2)
