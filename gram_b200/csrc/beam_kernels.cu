@@ -185,7 +185,8 @@ size_t beam_step_smem(int cand_cap) { return (size_t)cand_cap * sizeof(unsigned 
 
 __global__ void __launch_bounds__(BEAM_THREADS)
 beam_step_kernel(BeamState bs, TrieCSR trie, const float* __restrict__ logits, const bf16* __restrict__ hidden,
-                 const bf16* __restrict__ head, int D, const float* __restrict__ lse, int users, int t, int cand_cap) {
+                 const bf16* __restrict__ head, int D, const float* __restrict__ lse, int users, int t, int cand_cap,
+                 int compact) {
   extern __shared__ __align__(16) unsigned long long keys[];
   __shared__ int pre[BEAM_KMAX + 1];
   __shared__ int sel_parent[BEAM_KMAX], sel_tok[BEAM_KMAX], sel_node[BEAM_KMAX];
@@ -204,7 +205,7 @@ beam_step_kernel(BeamState bs, TrieCSR trie, const float* __restrict__ logits, c
 
   if (bs.tap_lse) {
     for (int b = tid; b < K; b += BEAM_THREADS) {
-      bs.tap_lse[(size_t)t * R + base + b] = lse[base + b];
+      bs.tap_lse[(size_t)t * R + base + b] = lse[compact ? u : base + b];
       bs.tap_score[(size_t)t * R + base + b] = score_c[base + b];
     }
     for (int i = tid; i < K * ML; i += BEAM_THREADS)
@@ -222,7 +223,7 @@ beam_step_kernel(BeamState bs, TrieCSR trie, const float* __restrict__ logits, c
     for (int i = tid; i < K * ML; i += BEAM_THREADS) {
       const int b = i / ML, j = i % ML;
       bs.seq[nxt][(size_t)base * ML + i] = (j == cur_len) ? bs.pad : seq_c[(size_t)base * ML + i];
-      bs.anc[nxt][(size_t)base * ML + i] = (j == t) ? b : anc_c[(size_t)base * ML + i];
+      bs.anc[nxt][(size_t)base * ML + i] = (j == t) ? (compact ? (u - base) : b) : anc_c[(size_t)base * ML + i];
     }
     return;
   }
@@ -254,8 +255,8 @@ beam_step_kernel(BeamState bs, TrieCSR trie, const float* __restrict__ logits, c
         const int nd = node_c[base + b];
         const int e = trie.child_offsets[nd] + (c - pre[b]);
         const int tok = trie.child_tokens[e];
-        const int row = base + b;
-        float s = (logits[(size_t)row * V + tok] - lse[row]) + score_c[row];
+        const int row = base + b, lrow = compact ? u : row;   // compact step: one decoder row per user
+        float s = (logits[(size_t)lrow * V + tok] - lse[lrow]) + score_c[row];
         if (!(s == s)) s = -INFINITY;
         const unsigned int idx = (unsigned int)b * (unsigned int)V + (unsigned int)tok;
         key = ((unsigned long long)float_key(s) << 32) | (unsigned long long)(0xFFFFFFFFu - idx);
@@ -272,8 +273,8 @@ beam_step_kernel(BeamState bs, TrieCSR trie, const float* __restrict__ logits, c
       const int nd = node_c[base + b];
       const int e = trie.child_offsets[nd] + (c - pre[b]);
       const int tok = trie.child_tokens[e];
-      const int row = base + b;
-      const bf16* hr = hidden + (size_t)row * D;
+      const int row = base + b, lrow = compact ? u : row;
+      const bf16* hr = hidden + (size_t)lrow * D;
       const bf16* er = head + (size_t)tok * D;
       float a = 0.f;
       for (int d = lane * 8; d < D; d += 256) {
@@ -290,7 +291,7 @@ beam_step_kernel(BeamState bs, TrieCSR trie, const float* __restrict__ logits, c
       }
       a = warp_sum(a);
       if (lane == 0) {
-        float s = (a - lse[row]) + score_c[row];
+        float s = (a - lse[lrow]) + score_c[row];
         if (!(s == s)) s = -INFINITY;
         const unsigned int idx = (unsigned int)b * (unsigned int)V + (unsigned int)tok;
         keys[c] = ((unsigned long long)float_key(s) << 32) | (unsigned long long)(0xFFFFFFFFu - idx);
@@ -362,13 +363,13 @@ beam_step_kernel(BeamState bs, TrieCSR trie, const float* __restrict__ logits, c
     bs.seq[nxt][(size_t)base * ML + i] = tokv;
     int a = 0;
     if (j < t) a = anc_c[(size_t)(base + par) * ML + j];
-    else if (j == t) a = par;
+    else if (j == t) a = compact ? (u - base) : par;   // compact step 0 wrote ONE cache row per user, at row u
     bs.anc[nxt][(size_t)base * ML + i] = a;
   }
 }
 
 cudaError_t beam_step(BeamState bs, TrieCSR trie, const float* logits, const void* hidden, const void* head, int D,
-                      const float* lse, int users, int t, int cand_cap, cudaStream_t s) {
+                      const float* lse, int users, int t, int cand_cap, int compact, cudaStream_t s) {
   if (users <= 0) return cudaSuccess;
   if (bs.K > BEAM_KMAX) return cudaErrorInvalidValue;
   if (logits == nullptr && (hidden == nullptr || head == nullptr || (D & 7))) return cudaErrorInvalidValue;
@@ -380,7 +381,7 @@ cudaError_t beam_step(BeamState bs, TrieCSR trie, const float* logits, const voi
     configured = smem;
   }
   beam_step_kernel<<<users, BEAM_THREADS, smem, s>>>(bs, trie, logits, (const bf16*)hidden, (const bf16*)head, D, lse, users, t,
-                                                     cand_cap);
+                                                     cand_cap, compact);
   return cudaGetLastError();
 }
 

@@ -676,12 +676,16 @@ int gram_generate(gram_handle* h, const int64_t* ids, const uint8_t* mask, int32
   const bool fused = c.dtype == GRAM_DTYPE_BF16 && !(c.flags & (GRAM_FLAG_SIMT_GEMM | GRAM_FLAG_KEEP_LOGITS)) &&
                      gemm_tc_supported(h->V, h->D) && (h->D % 8) == 0;
   for (int t = 0; t < T; ++t) {
-    RC(decoder_step(h, R, K, users, t, bs.anc[t & 1], fused, s));
+    // step 0: the K beams of a user all hold the start token and attend to the same memory, i.e. K identical rows
+    // (HF computes them K times); one row per user is decoded and shared by the user's beams
+    const int compact = (t == 0 && K > 1) ? 1 : 0;
+    const int Rt = compact ? users : R, Kt = compact ? 1 : K;
+    RC(decoder_step(h, Rt, Kt, users, t, bs.anc[t & 1], fused, s));
     if (fused) {
-      CKL(GRAM_K_BEAM, beam_step(bs, h->trie, nullptr, h->dxn, h->lm_head, h->D, h->lse, users, t, h->cand_cap, s));
+      CKL(GRAM_K_BEAM, beam_step(bs, h->trie, nullptr, h->dxn, h->lm_head, h->D, h->lse, users, t, h->cand_cap, compact, s));
     } else {
-      CKL(GRAM_K_LM_HEAD, lse_rows(h->logits, h->lse, R, h->V, s));
-      CKL(GRAM_K_BEAM, beam_step(bs, h->trie, h->logits, nullptr, nullptr, h->D, h->lse, users, t, h->cand_cap, s));
+      CKL(GRAM_K_LM_HEAD, lse_rows(h->logits, h->lse, Rt, h->V, s));
+      CKL(GRAM_K_BEAM, beam_step(bs, h->trie, h->logits, nullptr, nullptr, h->D, h->lse, users, t, h->cand_cap, compact, s));
     }
   }
   CKL(GRAM_K_BEAM, beam_finalize(bs, users, T, R_ret, h->d_out_seq, h->d_out_scores, h->d_out_width, s));

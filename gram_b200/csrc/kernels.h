@@ -101,7 +101,9 @@ cudaError_t beam_init(BeamState bs, TrieCSR trie, int users, int start_tok, cuda
 // logits == nullptr: recompute them as dot(hidden[row], head[token]) from the bf16 decoder output `hidden` [R,D]
 // and the bf16 vocabulary head `head` [V,D] (fused mode: full-vocab logits are never written)
 cudaError_t beam_step(BeamState bs, TrieCSR trie, const float* logits, const void* hidden, const void* head, int D,
-                      const float* lse, int users, int t, int cand_cap, cudaStream_t s);
+                      const float* lse, int users, int t, int cand_cap, int compact, cudaStream_t s);
+// compact != 0 (only at t == 0): all K beams of a user are identical, so the decoder ran ONE row per user; row u of
+// logits/hidden/lse serves every beam of user u and the step-0 self-attention cache row is recorded in the ancestry
 cudaError_t beam_finalize(BeamState bs, int users, int t_final, int R_ret, int64_t* out_seq, float* out_scores,
                           int* out_width, cudaStream_t s);
 // teacher forcing: tok[r] = ids[r*q + t], anc[r][t'] = 0
