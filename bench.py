@@ -199,6 +199,24 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+def ncu_traffic(name, tag="r1"):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture
+    (profiles/<tag>_<name>_metrics.csv, same command at the default batch); None when no capture is present."""
+    import csv
+    path = os.path.join(ROOT, "profiles", f"{tag}_{name}_metrics.csv")
+    if not os.path.exists(path):
+        return None
+    rows = list(csv.reader(open(path)))
+    hdr, units = rows[0], rows[1]
+    try:
+        ir, iw = hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
+        scale = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}
+        vals = [float(r[ir]) * scale[units[ir]] + float(r[iw]) * scale[units[iw]] for r in rows[2:]]
+        return float(np.mean(vals))
+    except Exception:
+        return None
+
+
 def workload_config(args, data, max_length):
     return dict(workload=f"{DATASET} full test set ({data.n_users} users, {data.n_items}-item trie), T5-small, beam {BEAMS}, "
                          f"return {BEAMS}, max_length {max_length}, max_his {data.max_his} x {data.L} tokens",
@@ -339,8 +357,10 @@ def main():
     total_all = sum(v["ms"] for v in prof_all.values())
     kernels = {c: dict(ms_per_step=v["ms"] / S, launches_per_step=v["launches"] // S,
                        share=v["ms"] / total_all if total_all else 0.0) for c, v in prof_all.items()}
-    roofline_cross = dict(bound="hbm", kernel="cross_attention", achieved=xa_gbs, peak=peaks["hbm"], unit="GB/s",
-                          frac=xa_gbs / peaks["hbm"], traffic=None)
+    roofline_cross = dict(bound="hbm", kernel="cross_attention_mma_kernel", achieved=xa_gbs, peak=peaks["hbm"], unit="GB/s",
+                          frac=xa_gbs / peaks["hbm"], traffic=ncu_traffic("xattn"),
+                          algorithmic_bytes_per_launch=xa_bytes / max(prof_all["cross_attn"]["launches"], 1),
+                          peak_source=f"{peaks['src']} copy bandwidth")
 
     # ---- CPU baseline (bounded sample) -----------------------------------------------------------------
     cpu = None
@@ -355,7 +375,10 @@ def main():
                 clocks=clocks.summary(), e2e=e2e, gpu_launches=int(model.stats()["launches"]) * S,
                 roofline=roofline, roofline_cross_attention=roofline_cross, kernel_classes=kernels,
                 cpu_baseline=cpu, tokens_per_step=float(np.mean(tok_timed)),
-                gemm_impl="simt" if (args.simt or args.dtype == "fp32") else "tcgen05")
+                gemm_impl="simt" if (args.simt or args.dtype == "fp32") else "tcgen05",
+                notes="roofline = all tcgen05 GEMM launches of the timed steps (CUDA events recorded by the library on the "
+                      "launching stream); per-launch DRAM traffic is shape dependent, see profiles/r1_gemm_enc_metrics.csv; "
+                      "kernel_classes come from a second pass over the same steps with every class bracketed")
     print(json.dumps(line), flush=True)
     if dist is not None:
         dist.destroy_process_group()

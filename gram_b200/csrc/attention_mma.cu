@@ -10,9 +10,10 @@
 //   head each) run QK^T and PV on the tensor cores straight out of the swizzled tiles via ldmatrix.
 //   This op is HBM-bound by design: per 2 KB row of K|V it does 2*2*32*512 padded flops, i.e. ~64 flop/B.
 //
-// enc_attention_mma    -- per-(passage, head) bidirectional self-attention of the encoder (reference
-//   src/model/gram_t5_modeling.py:572-621 with the layer-0 relative-position bias :452-477 shared by all
-//   layers :1249 and the key padding mask :1130).  Same tile math; K/V of the passage are staged once.
+// enc_attention_mma    -- bidirectional self-attention of the encoder, one CTA per passage walking its heads
+//   (reference src/model/gram_t5_modeling.py:572-621 with the layer-0 relative-position bias :452-477 shared by
+//   all layers :1249 and the key padding mask :1130).  Same tile math; Q/K/V of head h+1 are prefetched with
+//   cp.async while head h is computed.
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <mutex>
@@ -365,110 +366,15 @@ cross_attention_mma_kernel(const __grid_constant__ CUtensorMap map_kv, const bf1
 }
 
 // ================================================================================================
-// encoder self-attention: one CTA per (passage, head); warp w owns query rows [32w, 32w+32)
+// encoder self-attention: shared definitions
 // ================================================================================================
 constexpr int EA_THREADS = 256;        // 8 warps x 16 query rows: low register count -> more resident CTAs per SM
-constexpr int EA_MT = 1;
 
 struct RelBias {
   const float* lut;   // shared memory, [2*Lb-1]
   int off;            // key_tile_start - query_warp_start + Lb - 1
   __device__ __forceinline__ float operator()(int rr, int col) const { return lut[off + col - rr]; }
 };
-
-template <int LT>     // key tiles of 64 the kernel is sized for (L <= 64*LT)
-__global__ void __launch_bounds__(EA_THREADS, 2)
-enc_attention_mma_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, const int* __restrict__ plen,
-                         const int* __restrict__ poff, const uint8_t* __restrict__ tok_valid,
-                         const float* __restrict__ bias_lut, int Lb, int H) {
-  const int p = blockIdx.x, h = blockIdx.y;
-  const int len = plen[p];
-  if (len == 0) return;
-  const int row0 = poff[p];
-  const int HD = H * DK;
-  const size_t ld = (size_t)3 * HD;
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t raw = smem_u32(smem_raw);
-  const uint32_t base = (raw + 1023u) & ~1023u;
-  uint8_t* smem = smem_raw + (base - raw);
-  // [K tiles LT x 8 KiB][V tiles LT x 8 KiB][lut (2*Lb-1) floats][masks LT x u64]
-  const uint32_t kb = base, vb = base + LT * BOX_BYTES;
-  float* lut = reinterpret_cast<float*>(smem + 2 * LT * BOX_BYTES) + 32;   // 32 floats of slack below index 0 (padding rows)
-  unsigned long long* masks = reinterpret_cast<unsigned long long*>(smem + 2 * LT * BOX_BYTES + 128 + ((2 * Lb - 1) * 4 + 15) / 16 * 16);
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int n_tiles = (len + TS - 1) / TS;
-
-  // stage K and V (16-byte chunks, swizzled like a TMA 128B-swizzle box); rows past `len` are zero-filled
-  for (int i = tid; i < n_tiles * TS * 8; i += EA_THREADS) {
-    const int r = i >> 3, c = i & 7;
-    uint4 kv4 = make_uint4(0, 0, 0, 0), vv4 = kv4;
-    if (r < len) {
-      const bf16* src = qkv + (size_t)(row0 + r) * ld + h * DK + c * 8;
-      kv4 = *reinterpret_cast<const uint4*>(src + HD);
-      vv4 = *reinterpret_cast<const uint4*>(src + 2 * HD);
-    }
-    const int tile = r >> 6, rr = r & 63;
-    *reinterpret_cast<uint4*>(smem + (swz(kb + tile * BOX_BYTES, rr, c) - base)) = kv4;
-    *reinterpret_cast<uint4*>(smem + (swz(vb + tile * BOX_BYTES, rr, c) - base)) = vv4;
-  }
-  for (int i = tid; i < 2 * Lb - 1; i += EA_THREADS) lut[i] = bias_lut[(size_t)h * (2 * Lb - 1) + i];
-  if (warp < n_tiles) {                                        // n_tiles <= 4 < 8 warps
-    const int r0 = warp * TS + lane, r1 = r0 + 32;
-    const bool v0 = r0 < len && tok_valid[row0 + r0] != 0;
-    const bool v1 = r1 < len && tok_valid[row0 + r1] != 0;
-    const unsigned lo = __ballot_sync(0xffffffffu, v0), hi = __ballot_sync(0xffffffffu, v1);
-    if (lane == 0) masks[warp] = ((unsigned long long)hi << 32) | lo;
-  }
-  __syncthreads();
-
-  const int g = lane >> 2, q = lane & 3;
-  constexpr int ROWS = EA_MT * 16;                              // query rows per warp pass
-  for (int qb = warp * ROWS; qb < len; qb += (EA_THREADS / 32) * ROWS) {
-    uint32_t qf[EA_MT][4][4];
-#pragma unroll
-    for (int mt = 0; mt < EA_MT; ++mt)
-#pragma unroll
-      for (int ks = 0; ks < 4; ++ks)
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const int r = qb + mt * 16 + g + ((e & 1) << 3);
-          const int d = ks * 16 + 2 * q + ((e >> 1) << 3);
-          uint32_t v = 0u;
-          if (r < len) v = *reinterpret_cast<const uint32_t*>(qkv + (size_t)(row0 + r) * ld + h * DK + d);
-          qf[mt][ks][e] = v;
-        }
-    float o[EA_MT][8][4], m_run[EA_MT][2], l_run[EA_MT][2];
-#pragma unroll
-    for (int mt = 0; mt < EA_MT; ++mt) {
-      m_run[mt][0] = m_run[mt][1] = -INFINITY;
-      l_run[mt][0] = l_run[mt][1] = 0.f;
-#pragma unroll
-      for (int nt = 0; nt < 8; ++nt)
-#pragma unroll
-        for (int e = 0; e < 4; ++e) o[mt][nt][e] = 0.f;
-    }
-    for (int t = 0; t < n_tiles; ++t) {
-      RelBias rb{lut, t * TS - qb + Lb - 1};
-      flash_tile<EA_MT, 8>(qf, kb + t * BOX_BYTES, vb + t * BOX_BYTES, 0, masks[t], rb, o, m_run, l_run, lane);
-    }
-#pragma unroll
-    for (int mt = 0; mt < EA_MT; ++mt)
-#pragma unroll
-      for (int hf = 0; hf < 2; ++hf) {
-        float l = l_run[mt][hf];
-        l += __shfl_xor_sync(0xffffffffu, l, 1);
-        l += __shfl_xor_sync(0xffffffffu, l, 2);
-        const float inv = l > 0.f ? 1.0f / l : 0.f;
-        const int r = qb + mt * 16 + g + hf * 8;
-        if (r < len) {
-          bf16* orow = out + (size_t)(row0 + r) * HD + h * DK;
-#pragma unroll
-          for (int nt = 0; nt < 8; ++nt)
-            *reinterpret_cast<uint32_t*>(orow + nt * 8 + 2 * q) = pack_bf16(o[mt][nt][hf * 2] * inv, o[mt][nt][hf * 2 + 1] * inv);
-        }
-      }
-  }
-}
 
 // ================================================================================================
 // encoder self-attention, pipelined version: one CTA per passage walks its H heads; Q, K and V of head h+1 are
@@ -646,15 +552,15 @@ cudaError_t enc_attention_mma(const void* qkv, void* out, const int* plen, const
   if (P <= 0) return cudaSuccess;
   const int LT = (Lmax + fa::TS - 1) / fa::TS;
   const size_t lut_bytes = ((size_t)H * (2 * Lb - 1) * 4 + 15) / 16 * 16;
-  static bool attr[5] = {false, false, false, false, false};
+  static size_t attr[5] = {0, 0, 0, 0, 0};     // largest dynamic shared-memory size configured per instantiation
 #define GRAM_EA(LTV)                                                                                         \
   {                                                                                                          \
     const size_t smem = (size_t)2 * 3 * LTV * fa::BOX_BYTES + 128 + lut_bytes + LTV * 8 + 1024 + 64;         \
     auto kern = fa::enc_attention_pipe_kernel<LTV>;                                                          \
-    if (!attr[LTV]) {                                                                                        \
+    if (smem > attr[LTV]) {                                                                                  \
       cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);    \
       if (e != cudaSuccess) return e;                                                                        \
-      attr[LTV] = true;                                                                                      \
+      attr[LTV] = smem;                                                                                      \
     }                                                                                                        \
     kern<<<P, fa::EA_THREADS, smem, s>>>((const bf16*)qkv, (bf16*)out, plen, poff, tok_valid, bias_lut, Lb, H); \
   }

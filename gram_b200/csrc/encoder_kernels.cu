@@ -78,12 +78,16 @@ __global__ void __launch_bounds__(1024) passage_scan_kernel(const int* __restric
 }
 
 __global__ void passage_fill_kernel(const int64_t* __restrict__ ids, const uint8_t* __restrict__ mask, int N, int L,
-                                    PackMeta pm, int vocab_hi) {
+                                    PackMeta pm) {
   const int p = blockIdx.x;
   const int len = pm.plen[p], off = pm.poff[p];
   for (int l = threadIdx.x; l < len; l += blockDim.x) {
     const size_t src = (size_t)p * L + l;
     long long id = ids[src];
+    if (id < 0 || id >= pm.vocab) {              // the reference's nn.Embedding would raise IndexError
+      atomicExch(pm.err, 2);
+      id = 0;
+    }
     pm.tok_id[off + l] = (int)id;
     pm.tok_valid[off + l] = mask[src] ? 1 : 0;
     pm.tok_pos[off + l] = p % N;
@@ -108,7 +112,7 @@ cudaError_t enc_pack(const int64_t* ids, const uint8_t* mask, int B, int N, int 
   const int P = B * N;
   passage_len_kernel<<<(P * 32 + 255) / 256, 256, 0, s>>>(mask, P, L, pm.plen);
   passage_scan_kernel<<<1, 1024, 0, s>>>(pm.plen, P, N, B, pm.poff, pm.ustart, pm.total);
-  passage_fill_kernel<<<P, 128, 0, s>>>(ids, mask, N, L, pm, 0);
+  passage_fill_kernel<<<P, 128, 0, s>>>(ids, mask, N, L, pm);
   user_order_kernel<<<1, 1024, 0, s>>>(pm.ustart, B, pm.uorder);
   return cudaGetLastError();
 }

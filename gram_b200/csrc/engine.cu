@@ -31,11 +31,6 @@ namespace {
 
 thread_local std::string g_create_error;
 
-struct DevBuf {
-  void* p = nullptr;
-  size_t bytes = 0;
-};
-
 struct LayerW {
   void *qkv = nullptr, *o = nullptr, *wi = nullptr, *wo = nullptr;      // self-attn + FF
   void *cq = nullptr, *co = nullptr;                                     // decoder cross-attn q / o
@@ -93,6 +88,7 @@ struct gram_handle {
   BeamState bs{};
   double* d_len_pow = nullptr;
   double* h_len_pow = nullptr;           // pinned
+  cudaEvent_t len_pow_ev = nullptr;       // recorded after the H2D copy of h_len_pow; waited on before it is rewritten
   int64_t* d_out_seq = nullptr;
   float* d_out_scores = nullptr;
   int* d_out_width = nullptr;
@@ -394,6 +390,7 @@ void gram_destroy(gram_handle* h) {
   cudaSetDevice(h->cfg.device);
   for (void* p : h->allocs) cudaFree(p);
   for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
+  if (h->len_pow_ev) cudaEventDestroy(h->len_pow_ev);
   if (h->h_len_pow) cudaFreeHost(h->h_len_pow);
   if (h->h_flags) cudaFreeHost(h->h_flags);
   delete h;
@@ -505,6 +502,8 @@ int gram_create(const gram_config* cfg, gram_handle** out) {
   DAC(bs.hyp_score, U * S * 8); DAC(bs.hyp_len, U * S * 4); DAC(bs.hyp_seqno, U * S * 4); DAC(bs.hyp_tok, U * S * ML * 4);
   DAC(bs.n_hyp, U * 4); DAC(bs.worst, U * 8); DAC(bs.next_seqno, U * 4); DAC(bs.done, U * 4);
   DAC(bs.err, 16);
+  h->pm.err = bs.err;
+  h->pm.vocab = V;
   DAC(h->d_len_pow, ((size_t)ML + 1) * 8);
   bs.len_pow = h->d_len_pow;
   bs.tap_lse = nullptr; bs.tap_score = nullptr; bs.tap_seq = nullptr;
@@ -667,9 +666,12 @@ int gram_generate(gram_handle* h, const int64_t* ids, const uint8_t* mask, int32
   // the candidate buffer was sized for cfg.max_beams; K <= max_beams so it is sufficient
   BeamState bs = h->bs;
   bs.K = K; bs.max_length = c.max_length; bs.gen_len = max_length;
+  if (h->len_pow_ev) CK(cudaEventSynchronize(h->len_pow_ev));
+  else CK(cudaEventCreateWithFlags(&h->len_pow_ev, cudaEventDisableTiming));
   memcpy(h->h_len_pow, len_pow, ((size_t)max_length + 1) * sizeof(double));
   for (int i = max_length + 1; i <= c.max_length; ++i) h->h_len_pow[i] = 1.0;
   CK(cudaMemcpyAsync(h->d_len_pow, h->h_len_pow, ((size_t)c.max_length + 1) * 8, cudaMemcpyHostToDevice, s));
+  CK(cudaEventRecord(h->len_pow_ev, s));
   CKL(GRAM_K_BEAM, beam_init(bs, h->trie, users, c.start_id, s));
   // fused head (bf16 + tcgen05 GEMM): log-softmax statistics come out of the GEMM epilogue and candidate logits are
   // recomputed from the trie children only; otherwise (fp32 parity mode) full logits are materialised
@@ -706,8 +708,10 @@ int gram_generate(gram_handle* h, const int64_t* ids, const uint8_t* mask, int32
   if (host_out || !is_device_ptr(out_scores) || !is_device_ptr(out_width)) {
     CK(cudaStreamSynchronize(s));
     if (h->h_flags[0] != 0) {
+      const int code = h->h_flags[0];
       cudaMemsetAsync(bs.err, 0, 4, s);
-      return fail(h, GRAM_ERR_INVALID, "gram_generate: candidate buffer overflow (trie fan-out larger than declared)");
+      return fail(h, GRAM_ERR_INVALID, code == 2 ? "gram_generate: input token id outside [0, vocab_size)"
+                                                 : "gram_generate: candidate buffer overflow (trie fan-out larger than declared)");
     }
   }
   return GRAM_OK;

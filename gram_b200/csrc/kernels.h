@@ -15,7 +15,6 @@ cudaError_t gemm_simt(int dtype, int epi, const void* A, const void* W, void* C,
                       int N, int K, cudaStream_t s);
 
 // ---- gemm_tc.cu (tcgen05 / TMEM / TMA, bf16) -----------------------------------------------------
-struct TcGemmPlan;   // cached TMA descriptors for one (A, W, shape)
 bool gemm_tc_supported(int N, int K);
 cudaError_t gemm_tc(int epi, const void* A, const void* W, void* C, int M_max, const int* m_ptr, int N, int K,
                     int num_sms, cudaStream_t s);
@@ -32,6 +31,8 @@ struct PackMeta {            // device-resident description of the packed (valid
   int* tok_pos;              // [Mcap] passage index within the user (row of the position table)
   uint8_t* tok_valid;        // [Mcap] attention-mask bit per packed row
   int* row_src;              // [Mcap] flat index b*N*L + n*L + l of the packed row (for unpacking)
+  int* err;                  // [1]    sticky device error flag (2 = token id outside the vocabulary)
+  int vocab;                 // vocabulary size, for the id range check
 };
 cudaError_t enc_pack(const int64_t* ids, const uint8_t* mask, int B, int N, int L, PackMeta pm, cudaStream_t s);
 cudaError_t embed_rows(int dtype, const void* table, const int* tok_id, float* x, int M_max, const int* m_ptr,

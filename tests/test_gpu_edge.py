@@ -102,6 +102,10 @@ def test_capacity_and_argument_errors():
     with pytest.raises(ValueError):
         bad = prefix_allowed_tokens_fn(Trie([[0, cfg.vocab_size + 5, 1]]))                   # token outside the vocabulary
         m.generate(ids, mask, 3, prefix_allowed_tokens_fn=bad, num_beams=2)
+    with pytest.raises(ValueError):                                                          # input id outside the vocabulary
+        bad_ids = ids.clone()
+        bad_ids[0, 0, 3] = cfg.vocab_size + 9
+        m.generate(bad_ids.cpu(), mask.cpu(), 3, prefix_allowed_tokens_fn=fn, num_beams=2)
     # a start token that is not in the trie: every beam is dead, scores are -inf, nothing crashes
     dead = prefix_allowed_tokens_fn(Trie([[7, 5, 1]]))
     out = m.generate(ids, mask, 3, prefix_allowed_tokens_fn=dead, num_beams=2, num_return_sequences=2, return_dict_in_generate=True)
