@@ -69,6 +69,7 @@ class SurrogateTokenizer:
         self.first_free = nxt
         self._id2piece = {int(i): p for i, p in zip(self.piece_id, self.pieces)}
         self._piece2id = None
+        self._decode_cache = {}
 
     def encode(self, text: str) -> List[int]:
         """Lexical-id string ('|piece|piece...' or pieces separated by '|') -> ids + EOS, with the
@@ -97,9 +98,21 @@ class SurrogateTokenizer:
         return "".join(toks).replace("▁", " ").strip()
 
     def batch_decode(self, batch, skip_special_tokens: bool = True) -> List[str]:
+        """Rows are decoded once and memoised: the eval loop decodes K predictions per user, all drawn from the
+        same few thousand item ids."""
         if hasattr(batch, "tolist"):
             batch = batch.tolist()
-        return [self.decode(row, skip_special_tokens) for row in batch]
+        cache = self._decode_cache
+        out = []
+        for row in batch:
+            key = (tuple(row), skip_special_tokens)
+            text = cache.get(key)
+            if text is None:
+                text = self.decode(row, skip_special_tokens)
+                if len(cache) < 1_000_000:
+                    cache[key] = text
+            out.append(text)
+        return out
 
 
 class GramTestData:

@@ -23,6 +23,8 @@ from __future__ import annotations
 
 import logging
 import os
+import queue
+import threading
 import time
 from types import SimpleNamespace
 from typing import List, Optional, Sequence
@@ -112,7 +114,10 @@ class GramRunner:
                               num_return_sequences=self.generate_num, output_scores=True,
                               return_dict_in_generate=True, length_penalty=self.length_penalty)
 
-    def test_dataset_task(self, testloader, mode: str = "test"):
+    def test_dataset_task(self, testloader, mode: str = "test", pipeline: bool = True):
+        """Eval loop.  With `pipeline`, batch collation runs one or two batches ahead in a background thread and
+        decoding / metric bookkeeping of batch i runs while the GPU works on batch i+1 (the C-ABI call releases the
+        GIL), so the loop is bound by `generate`, not by host Python."""
         data = testloader.dataset
         logging.info(f"[{mode}] testing {data.dataset} dataset on {data.task} task")
         G = self.generate_num
@@ -120,22 +125,59 @@ class GramRunner:
         candidate_trie = gt.Trie(encoded)
         prefix_fn = gt.prefix_allowed_tokens_fn(candidate_trie)
         max_length = max(len(c) for c in encoded)
-        total_time = 0.0
         rows = []                                # (user index, gold string, predictions, scores, hit rank)
+
+        def post(batch, seqs, scores):
+            gold = self.tokenizer.batch_decode(batch["target_ids"], skip_special_tokens=True)
+            sents = self.tokenizer.batch_decode(seqs, skip_special_tokens=True)
+            rel = evaluate.rel_results(sents, gold, scores, G)
+            for i, u in enumerate(batch["user_index"]):
+                r = rel[i]
+                rows.append((u, gold[i], sents[i * G:(i + 1) * G], scores[i * G:(i + 1) * G].tolist(),
+                             r.index(1) if 1 in r else -1))
+
+        def batches():
+            if not pipeline:
+                yield from testloader
+                return
+            q = queue.Queue(maxsize=2)
+            stop = object()
+
+            def produce():
+                try:
+                    for b in testloader:
+                        q.put(b)
+                    q.put(stop)
+                except BaseException as e:      # surface loader errors in the consumer
+                    q.put(e)
+
+            threading.Thread(target=produce, daemon=True).start()
+            while True:
+                b = q.get()
+                if b is stop:
+                    return
+                if isinstance(b, BaseException):
+                    raise b
+                yield b
+
+        total_time = 0.0
+        pending = None                           # post-processing thread of the previous batch
         with torch.no_grad():
-            for batch in testloader:
+            for batch in batches():
                 t0 = time.time()
                 pred = self._generate(batch, max_length, prefix_fn)
                 seqs = pred["sequences"].cpu()
                 scores = pred["sequences_scores"].cpu()
                 total_time += time.time() - t0
-                gold = self.tokenizer.batch_decode(batch["target_ids"], skip_special_tokens=True)
-                sents = self.tokenizer.batch_decode(seqs, skip_special_tokens=True)
-                rel = evaluate.rel_results(sents, gold, scores, G)
-                for i, u in enumerate(batch["user_index"]):
-                    r = rel[i]
-                    rank_of_gold = r.index(1) if 1 in r else -1
-                    rows.append((u, gold[i], sents[i * G:(i + 1) * G], scores[i * G:(i + 1) * G].tolist(), rank_of_gold))
+                if pending is not None:
+                    pending.join()
+                if pipeline:
+                    pending = threading.Thread(target=post, args=(batch, seqs, scores))
+                    pending.start()
+                else:
+                    post(batch, seqs, scores)
+        if pending is not None:
+            pending.join()
         # ---- one gather after the loop (reference: all_reduce(metrics), all_reduce(total), TSV merge) ----
         rows = self._gather(rows)
         rows.sort(key=lambda r: r[0])
