@@ -360,6 +360,8 @@ def main():
     roofline_cross = dict(bound="hbm", kernel="cross_attention_mma_kernel", achieved=xa_gbs, peak=peaks["hbm"], unit="GB/s",
                           frac=xa_gbs / peaks["hbm"], traffic=ncu_traffic("xattn"),
                           algorithmic_bytes_per_launch=xa_bytes / max(prof_all["cross_attn"]["launches"], 1),
+                          traffic_note="ncu capture = launches 21-22 of the first generate call (users of step 0): "
+                                       f"algorithmic bytes of that launch = {data.valid_tokens(step_users(data, 0, B, 0, 1)) * 2 * cfg.inner_dim * esz}",
                           peak_source=f"{peaks['src']} copy bandwidth")
 
     # ---- CPU baseline (bounded sample) -----------------------------------------------------------------
