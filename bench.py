@@ -351,6 +351,14 @@ def main():
                     achieved=achieved_tf, peak=peaks["tensor"], unit="TFLOP/s", frac=achieved_tf / peaks["tensor"],
                     traffic=None, peak_source=f"{peaks['src']} sustained bf16", launches=gemm_launches,
                     avg_launch_ms=gemm_ms / max(gemm_launches, 1), share_of_step=gemm_ms / ms)
+    by_class = {}
+    for cname, key in (("gemm_enc", "gemm_enc"), ("gemm_kv", "gemm_kv"), ("gemm_dec", "gemm_dec"), ("lm_head", "gemm_head")):
+        fl = sum(w[key] for w in work)
+        t_ms = prof[cname]["ms"]
+        if t_ms > 0:
+            by_class[cname] = dict(tflops=fl / (t_ms / 1000.0) / 1e12, frac=fl / (t_ms / 1000.0) / 1e12 / peaks["tensor"],
+                                   ms_per_step=t_ms / S)
+    roofline["by_class"] = by_class
     xa_ms = prof_all["cross_attn"]["ms"]
     xa_bytes = sum(w["xattn_bytes"] for w in work)
     xa_gbs = xa_bytes / (xa_ms / 1000.0) / 1e9 if xa_ms > 0 else 0.0
