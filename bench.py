@@ -240,6 +240,8 @@ def main():
     dev = torch.device("cuda", local)
     dist = None
     if world > 1:
+        # NCCL writes its version / debug lines to stdout by default; stdout must carry exactly one JSON line
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
 
