@@ -77,24 +77,35 @@ class ClockSampler:
         self._t = None
 
     def _run(self):
-        while not self._stop.is_set():
-            try:
-                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                      "-i", str(self.index)], capture_output=True, text=True, timeout=5).stdout
-                if out.strip():
-                    self.rows.append([c.strip() for c in out.strip().split(",")])
-            except Exception:
-                pass
-            self._stop.wait(0.2)
+        # one long-running nvidia-smi that prints a row every 100 ms (re-launching it per sample costs ~100 ms each)
+        try:
+            self._proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                           "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE,
+                                          stderr=subprocess.DEVNULL, text=True)
+            for line in self._proc.stdout:
+                if self._stop.is_set():
+                    break
+                if line.strip():
+                    self.rows.append([c.strip() for c in line.strip().split(",")])
+        except Exception:
+            pass
 
     def __enter__(self):
+        self._proc = None
         self._t = threading.Thread(target=self._run, daemon=True)
         self._t.start()
+        time.sleep(0.25)                       # let the first samples arrive before the timed region starts
+        self.rows.clear()
         return self
 
     def __exit__(self, *a):
         self._stop.set()
-        self._t.join(timeout=6)
+        if self._proc is not None:
+            try:
+                self._proc.terminate()         # the exact process this object started
+            except Exception:
+                pass
+        self._t.join(timeout=3)
 
     def summary(self):
         sm, mx, reasons = [], [], set()
