@@ -43,9 +43,9 @@ def parse():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=472,
-                    help="users per step per GPU (472 users x 20 beams = 9440 decoder rows = 74 row tiles of 128: the "
-                         "512-wide decoder GEMMs then have 296 tiles = exactly two waves of the 148 SMs)")
+    ap.add_argument("--batch", type=int, default=944,
+                    help="users per step per GPU (944 users x 20 beams = 18880 decoder rows = 148 row tiles of 128: every "
+                         "decoder GEMM then has a whole number of 148-SM waves of tiles; ~66 GB of workspace)")
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--cpu-users", type=int, default=8, help="users timed for cpu_baseline (0 = skip)")
     ap.add_argument("--simt", action="store_true", help="force the CUDA-core GEMM (A/B timing)")
