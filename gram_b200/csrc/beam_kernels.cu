@@ -258,8 +258,9 @@ beam_step_kernel(BeamState bs, TrieCSR trie, const float* __restrict__ logits, c
         const int row = base + b, lrow = compact ? u : row;   // compact step: one decoder row per user
         float s = (logits[(size_t)lrow * V + tok] - lse[lrow]) + score_c[row];
         if (!(s == s)) s = -INFINITY;
-        const unsigned int idx = (unsigned int)b * (unsigned int)V + (unsigned int)tok;
-        key = ((unsigned long long)float_key(s) << 32) | (unsigned long long)(0xFFFFFFFFu - idx);
+        // children are stored token-ascending, so the enumeration index c orders candidates exactly like the flat
+        // index beam * V + token: it is both the tie-break (smaller first) and the handle back to (beam, edge)
+        key = ((unsigned long long)float_key(s) << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned int)c);
       }
       keys[c] = key;
     }
@@ -293,8 +294,7 @@ beam_step_kernel(BeamState bs, TrieCSR trie, const float* __restrict__ logits, c
       if (lane == 0) {
         float s = (a - lse[lrow]) + score_c[row];
         if (!(s == s)) s = -INFINITY;
-        const unsigned int idx = (unsigned int)b * (unsigned int)V + (unsigned int)tok;
-        keys[c] = ((unsigned long long)float_key(s) << 32) | (unsigned long long)(0xFFFFFFFFu - idx);
+        keys[c] = ((unsigned long long)float_key(s) << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned int)c);
       }
     }
   }
@@ -324,12 +324,11 @@ beam_step_kernel(BeamState bs, TrieCSR trie, const float* __restrict__ logits, c
       if (rank < C) {
         const unsigned long long key = keys[n_sort - 1 - rank];
         s = key_float((unsigned int)(key >> 32));
-        const unsigned int idx = 0xFFFFFFFFu - (unsigned int)(key & 0xFFFFFFFFull);
-        b = (int)(idx / (unsigned int)V);
-        tok = (int)(idx % (unsigned int)V);
-        const int nd = node_c[base + b];
-        for (int e = trie.child_offsets[nd]; e < trie.child_offsets[nd + 1]; ++e)
-          if (trie.child_tokens[e] == tok) { child = trie.child_nodes[e]; break; }
+        const int c = (int)(0xFFFFFFFFu - (unsigned int)(key & 0xFFFFFFFFull));
+        while (pre[b + 1] <= c) ++b;
+        const int e = trie.child_offsets[node_c[base + b]] + (c - pre[b]);
+        tok = trie.child_tokens[e];
+        child = trie.child_nodes[e];
         if (s == -INFINITY) { tok = bs.pad; child = -1; }   // indistinguishable from a filler
       }
       if (rank == 0) best = s;

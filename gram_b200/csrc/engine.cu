@@ -367,7 +367,7 @@ int decoder_step(gram_handle* h, int R, int K, int users, int t, const int* anc,
   if (fused_lse) {
     // kernel (c): vocabulary projection with the log-softmax statistics fused into the epilogue; logits never stored
     RC(gemm(h, GRAM_K_LM_HEAD, EPI_LSE, h->dxn, h->lm_head, h->lse_partial, R, nullptr, h->V, D, s));
-    CKL(GRAM_K_LM_HEAD, lse_combine(h->lse_partial, h->lse, R, (h->V + 127) / 128, s));
+    CKL(GRAM_K_LM_HEAD, lse_combine(h->lse_partial, h->lse, R, gemm_tc_lse_ntiles(R, h->V, h->num_sms), s));
   } else {
     RC(gemm(h, GRAM_K_LM_HEAD, EPI_F32, h->dxn, h->lm_head, h->logits, R, nullptr, h->V, D, s));
   }

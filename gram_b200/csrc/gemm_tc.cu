@@ -422,6 +422,11 @@ bool gemm_tc_supported(int N, int K) { return (K % tc::BLOCK_K) == 0 && (N % 16)
 
 const char* gemm_tc_last_error() { return tc::g_err.c_str(); }
 
+int gemm_tc_lse_ntiles(int M_max, int N, int num_sms) {
+  const int bn = tc::pick_bn(M_max, N, num_sms);
+  return (N + bn - 1) / bn;
+}
+
 cudaError_t gemm_tc(int epi, const void* A, const void* W, void* C, int M_max, const int* m_ptr, int N, int K,
                     int num_sms, cudaStream_t s) {
   if (M_max <= 0) return cudaSuccess;
@@ -429,9 +434,11 @@ cudaError_t gemm_tc(int epi, const void* A, const void* W, void* C, int M_max, c
   std::lock_guard<std::mutex> lk(tc::g_mu);
   CUtensorMap ma, mw, mc;
   const int ckind = (epi == EPI_STORE || epi == EPI_RELU) ? 0 : 1;
-  const int bn = epi == EPI_LSE ? 128 : tc::pick_bn(M_max, N, num_sms);
+  const int bn = tc::pick_bn(M_max, N, num_sms);
   if (!tc::get_map(A, M_max, K, 0, tc::BLOCK_M, &ma) || !tc::get_map(W, N, K, 0, bn, &mw)) return cudaErrorUnknown;
-  if (epi == EPI_LSE) return tc::launch<EPI_LSE, 128>(ma, mw, ma, (float2*)C, M_max, m_ptr, N, K, num_sms, s);
+  if (epi == EPI_LSE)
+    return bn == 256 ? tc::launch<EPI_LSE, 256>(ma, mw, ma, (float2*)C, M_max, m_ptr, N, K, num_sms, s)
+                     : tc::launch<EPI_LSE, 128>(ma, mw, ma, (float2*)C, M_max, m_ptr, N, K, num_sms, s);
   if (!tc::get_map(C, M_max, N, ckind, tc::BLOCK_M, &mc)) return cudaErrorUnknown;
 #define GRAM_TC_LAUNCH(E)                                                                               \
   return bn == 256 ? tc::launch<E, 256>(ma, mw, mc, nullptr, M_max, m_ptr, N, K, num_sms, s)           \

@@ -19,6 +19,8 @@ bool gemm_tc_supported(int N, int K);
 cudaError_t gemm_tc(int epi, const void* A, const void* W, void* C, int M_max, const int* m_ptr, int N, int K,
                     int num_sms, cudaStream_t s);
 const char* gemm_tc_last_error();
+// number of column tiles (= per-row partials) the EPI_LSE epilogue writes for this problem
+int gemm_tc_lse_ntiles(int M_max, int N, int num_sms);
 
 // ---- encoder_kernels.cu --------------------------------------------------------------------------
 struct PackMeta {            // device-resident description of the packed (valid-token) layout

@@ -102,8 +102,10 @@ class Trie(object):
 
     # ---- device form ---------------------------------------------------------------------------
     def to_csr(self, start_token: int = 0):
-        """Flatten to CSR.  Node 0 is the empty prefix; nodes are numbered breadth-first; children
-        keep dict insertion order (the order `get` lists them in).
+        """Flatten to CSR.  Node 0 is the empty prefix; nodes are numbered breadth-first; the children of a
+        node are stored in ascending token order (the SET equals `get(prefix)`; the device enumerates candidates
+        beam-major then token-ascending, which is the order of the flat index beam * V + token that HF's
+        `topk` ranks, so a candidate's enumeration index doubles as its tie-break key).
 
         Returns dict(child_offsets int32[n_nodes+1], child_tokens int32[n_edges],
         child_nodes int32[n_edges], n_nodes, n_edges, root_node, max_fanout) where `root_node` is the
@@ -120,7 +122,7 @@ class Trie(object):
         while head < len(queue):
             node = queue[head]
             head += 1
-            for tok, child in node.items():
+            for tok, child in sorted(node.items()):
                 tokens.append(tok)
                 child_nodes.append(len(queue))
                 queue.append(child)
