@@ -192,6 +192,9 @@ beam_step_kernel(BeamState bs, TrieCSR trie, const float* __restrict__ logits, c
   __shared__ int sel_parent[BEAM_KMAX], sel_tok[BEAM_KMAX], sel_node[BEAM_KMAX];
   __shared__ float sel_score[BEAM_KMAX];
   __shared__ int n_sort_s;
+  __shared__ int cand_off[BEAM_KMAX], cand_cnt[BEAM_KMAX];          // first CSR edge / fan-out of each live beam
+  __shared__ float r_score[2 * BEAM_KMAX];                           // the 2K best candidates, decoded in parallel
+  __shared__ int r_beam[2 * BEAM_KMAX], r_tok[2 * BEAM_KMAX], r_child[2 * BEAM_KMAX];
 
   const int u = blockIdx.x, tid = threadIdx.x;
   const int K = bs.K, V = bs.V, ML = bs.max_length;
@@ -229,13 +232,31 @@ beam_step_kernel(BeamState bs, TrieCSR trie, const float* __restrict__ logits, c
   }
 
   // ---- enumerate candidates: children of every live beam's trie node ----
+  // (the per-beam fan-outs are fetched in parallel: a single thread chasing node -> offsets serially costs
+  //  ~1 us of dependent global-load latency per beam)
+  if (tid < K) {
+    const int nd = node_c[base + tid];
+    const float sc = score_c[base + tid];
+    int cnt = 0;
+    if (nd >= 0 && sc > -INFINITY) {
+      const int o0 = trie.child_offsets[nd];
+      cnt = trie.child_offsets[nd + 1] - o0;
+      cand_off[tid] = o0;
+    } else {
+      cand_off[tid] = 0;
+    }
+    cand_cnt[tid] = cnt;
+  }
+  __syncthreads();
   if (tid == 0) {
+    // step 0: beams 1..K-1 start at -1e9 on the same (root) node as beam 0.  If beam 0 alone offers >= 2K
+    // candidates, theirs (all ~ -1e9) cannot enter the top-2K, so they are not enumerated: same result as HF.
+    const bool first_only = (t == 0) && cand_cnt[0] >= 2 * K && score_c[base] == 0.f;
     int run = 0;
     for (int b = 0; b < K; ++b) {
       pre[b] = run;
-      const int nd = node_c[base + b];
-      const float sc = score_c[base + b];
-      if (nd >= 0 && sc > -INFINITY) run += trie.child_offsets[nd + 1] - trie.child_offsets[nd];
+      if (first_only && b > 0 && score_c[base + b] <= -1e8f) cand_cnt[b] = 0;
+      run += cand_cnt[b];
     }
     pre[K] = run;
     int n = 2;
@@ -252,8 +273,7 @@ beam_step_kernel(BeamState bs, TrieCSR trie, const float* __restrict__ logits, c
       if (c < C) {
         int b = 0;
         while (pre[b + 1] <= c) ++b;                         // K <= 64, linear search
-        const int nd = node_c[base + b];
-        const int e = trie.child_offsets[nd] + (c - pre[b]);
+        const int e = cand_off[b] + (c - pre[b]);
         const int tok = trie.child_tokens[e];
         const int row = base + b, lrow = compact ? u : row;   // compact step: one decoder row per user
         float s = (logits[(size_t)lrow * V + tok] - lse[lrow]) + score_c[row];
@@ -265,36 +285,64 @@ beam_step_kernel(BeamState bs, TrieCSR trie, const float* __restrict__ logits, c
       keys[c] = key;
     }
   } else {
-    // fused mode: one warp per candidate recomputes its logit = hidden[row] . head[token] (bf16 operands, fp32 sum)
+    // fused mode: a warp recomputes the logits of 4 candidates per iteration, logit = hidden[row] . head[token]
+    // (bf16 operands, fp32 sum); the 4 x 2 row loads are in flight together, the chain token -> row -> reduce of a
+    // one-candidate-per-iteration loop is latency-bound
     const int wid = tid >> 5, lane = tid & 31;
+    constexpr int UN = 4;
     for (int c = C + tid; c < n_sort; c += BEAM_THREADS) keys[c] = 0ull;
-    for (int c = wid; c < C; c += BEAM_THREADS / 32) {
-      int b = 0;
-      while (pre[b + 1] <= c) ++b;
-      const int nd = node_c[base + b];
-      const int e = trie.child_offsets[nd] + (c - pre[b]);
-      const int tok = trie.child_tokens[e];
-      const int row = base + b, lrow = compact ? u : row;
-      const bf16* hr = hidden + (size_t)lrow * D;
-      const bf16* er = head + (size_t)tok * D;
-      float a = 0.f;
-      for (int d = lane * 8; d < D; d += 256) {
-        const uint4 hv = *reinterpret_cast<const uint4*>(hr + d);
-        const uint4 ev = *reinterpret_cast<const uint4*>(er + d);
-        const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&hv);
-        const __nv_bfloat162* e2 = reinterpret_cast<const __nv_bfloat162*>(&ev);
+    for (int c0 = wid * UN; c0 < C; c0 += (BEAM_THREADS / 32) * UN) {
+      int bb[UN], tk[UN];
+      const bf16* hr[UN];
+      const bf16* er[UN];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const float2 x = __bfloat1622float2(h2[i]), y = __bfloat1622float2(e2[i]);
-          a = fmaf(x.x, y.x, a);
-          a = fmaf(x.y, y.y, a);
+      for (int j = 0; j < UN; ++j) {
+        const int c = min(c0 + j, C - 1);
+        int b = 0;
+        while (pre[b + 1] <= c) ++b;
+        bb[j] = b;
+        tk[j] = trie.child_tokens[cand_off[b] + (c - pre[b])];
+      }
+#pragma unroll
+      for (int j = 0; j < UN; ++j) {
+        hr[j] = hidden + (size_t)(compact ? u : base + bb[j]) * D;
+        er[j] = head + (size_t)tk[j] * D;
+      }
+      float a[UN];
+#pragma unroll
+      for (int j = 0; j < UN; ++j) a[j] = 0.f;
+      for (int d = lane * 8; d < D; d += 256) {
+        uint4 hv[UN], ev[UN];
+#pragma unroll
+        for (int j = 0; j < UN; ++j) {
+          hv[j] = *reinterpret_cast<const uint4*>(hr[j] + d);
+          ev[j] = *reinterpret_cast<const uint4*>(er[j] + d);
+        }
+#pragma unroll
+        for (int j = 0; j < UN; ++j) {
+          const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&hv[j]);
+          const __nv_bfloat162* e2 = reinterpret_cast<const __nv_bfloat162*>(&ev[j]);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float2 x = __bfloat1622float2(h2[i]), y = __bfloat1622float2(e2[i]);
+            a[j] = fmaf(x.x, y.x, a[j]);
+            a[j] = fmaf(x.y, y.y, a[j]);
+          }
         }
       }
-      a = warp_sum(a);
-      if (lane == 0) {
-        float s = (a - lse[lrow]) + score_c[row];
-        if (!(s == s)) s = -INFINITY;
-        keys[c] = ((unsigned long long)float_key(s) << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned int)c);
+#pragma unroll
+      for (int j = 0; j < UN; ++j) a[j] = warp_sum(a[j]);
+      if (lane < UN && c0 + lane < C) {
+        float av = a[0];
+#pragma unroll
+        for (int j = 1; j < UN; ++j) av = (lane == j) ? a[j] : av;
+        int b = bb[0];
+#pragma unroll
+        for (int j = 1; j < UN; ++j) b = (lane == j) ? bb[j] : b;
+        const int row = base + b, lrow = compact ? u : row;
+        float sc = (av - lse[lrow]) + score_c[row];
+        if (!(sc == sc)) sc = -INFINITY;
+        keys[c0 + lane] = ((unsigned long long)float_key(sc) << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned int)(c0 + lane));
       }
     }
   }
@@ -313,25 +361,31 @@ beam_step_kernel(BeamState bs, TrieCSR trie, const float* __restrict__ logits, c
       __syncthreads();
     }
   }
-  // ---- BeamSearchScorer.process for this user ----
+  // ---- decode the 2K best candidates in parallel (key -> score, beam, token, child node) ----
+  if (tid < 2 * K) {
+    float s = -INFINITY;
+    int b = 0, tok = bs.pad, child = -1;
+    if (tid < C) {
+      const unsigned long long key = keys[n_sort - 1 - tid];
+      s = key_float((unsigned int)(key >> 32));
+      const int c = (int)(0xFFFFFFFFu - (unsigned int)(key & 0xFFFFFFFFull));
+      while (pre[b + 1] <= c) ++b;
+      const int e = cand_off[b] + (c - pre[b]);
+      tok = trie.child_tokens[e];
+      child = trie.child_nodes[e];
+      if (s == -INFINITY) { tok = bs.pad; child = -1; }     // indistinguishable from a filler
+    }
+    r_score[tid] = s; r_beam[tid] = b; r_tok[tid] = tok; r_child[tid] = child;
+  }
+  __syncthreads();
+  // ---- BeamSearchScorer.process for this user (inherently sequential, shared memory only) ----
   if (tid == 0) {
     HypView hv = hyp_view(bs, u);
     int slot = 0;
-    float best = -INFINITY;
+    const float best = r_score[0];
     for (int rank = 0; rank < 2 * K && slot < K; ++rank) {
-      float s = -INFINITY;
-      int b = 0, tok = bs.pad, child = -1;
-      if (rank < C) {
-        const unsigned long long key = keys[n_sort - 1 - rank];
-        s = key_float((unsigned int)(key >> 32));
-        const int c = (int)(0xFFFFFFFFu - (unsigned int)(key & 0xFFFFFFFFull));
-        while (pre[b + 1] <= c) ++b;
-        const int e = trie.child_offsets[node_c[base + b]] + (c - pre[b]);
-        tok = trie.child_tokens[e];
-        child = trie.child_nodes[e];
-        if (s == -INFINITY) { tok = bs.pad; child = -1; }   // indistinguishable from a filler
-      }
-      if (rank == 0) best = s;
+      const float s = r_score[rank];
+      const int b = r_beam[rank], tok = r_tok[rank], child = r_child[rank];
       if (tok == bs.eos && s > -INFINITY) {
         if (rank >= K) continue;
         hyp_add(hv, seq_c + (size_t)(base + b) * ML, cur_len, s, bs.len_pow);
