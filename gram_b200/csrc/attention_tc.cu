@@ -1,0 +1,309 @@
+// tcgen05 / TMEM encoder self-attention for passages of up to 128 tokens (bf16, d_kv = 64).
+//
+// Reference semantics: per-passage bidirectional T5 self-attention, scores = Q K^T (no 1/sqrt(d) scale) + relative
+// position bias (layer-0 table shared by all layers) + key padding mask, fp32 softmax, P V
+// (reference src/model/gram_t5_modeling.py:572-621, bias :452-477 and :1249, mask :1130).
+//
+// One CTA = one (passage, head), 128 threads:
+//   TMA      three 128-row x 64-col boxes (Q, K, V of this head) straight out of the packed qkv activation, 128B swizzle
+//   MMA 1    S[128 q x 128 keys] = Q K^T : 4 x tcgen05.mma (M=128, N=128, K=16), both operands K-major, fp32 in TMEM
+//   softmax  thread r owns query row r (TMEM lane r): tcgen05.ld of its 128 scores, + bias LUT, mask, max, exp2, sum --
+//            a row-wise softmax with no cross-thread traffic -- and writes P (bf16) into shared memory in the K-major
+//            128B-swizzled operand layout, over the dead Q and K tiles
+//   MMA 2    O[128 q x 64 d] = P V : 8 x tcgen05.mma (M=128, N=64, K=16), A = P (K-major), B = V read in place in its
+//            MN-major (d-contiguous) layout; O re-uses the TMEM columns of S
+//   epilogue tcgen05.ld of the 64 outputs, 1/sum, bf16, one 128-byte row store per thread
+// 49 KiB of shared memory and 128 TMEM columns per CTA: four CTAs per SM overlap each other's TMA / MMA / softmax.
+// Rows past the passage length in the boxes belong to the next passage (finite values): masked as keys, and not
+// stored as queries.
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <mutex>
+#include <map>
+#include <tuple>
+
+#include "common.cuh"
+#include "kernels.h"
+
+namespace gram {
+namespace ta {
+
+constexpr int DK = 64, LQ = 128;
+constexpr uint32_t BOX = LQ * DK * 2;      // 16 KiB
+constexpr float LOG2E = 1.4426950408889634f;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "TA_WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra TA_WAIT_DONE;\n"
+      "bra TA_WAIT_LOOP;\n"
+      "TA_WAIT_DONE:\n"
+      "}\n" ::"r"(bar), "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// shared-memory matrix descriptor, 128B swizzle, 8-row (K-major) / 8-k (MN-major) groups 1024 B apart
+__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)1 << 16;                   // leading byte offset: unused (one 64-element block in the leading mode)
+  d |= (uint64_t)(1024 >> 4) << 32;         // stride byte offset = 1024 B
+  d |= (uint64_t)1 << 46;                   // descriptor version 1 (Blackwell)
+  d |= (uint64_t)2 << 61;                   // SWIZZLE_128B
+  return d;
+}
+// D = f32, A = B = bf16, M = 128
+constexpr uint32_t IDESC_QK = (1u << 4) | (1u << 7) | (1u << 10) | ((128u >> 3) << 17) | ((128u >> 4) << 24);              // N=128, B K-major
+constexpr uint32_t IDESC_PV = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 16) | ((64u >> 3) << 17) | ((128u >> 4) << 24);  // N=64, B MN-major
+
+constexpr int THREADS = 128;
+constexpr int TMEM_COLS = 128;
+
+__global__ void __launch_bounds__(THREADS, 4)
+enc_attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, bf16* __restrict__ out,
+                        const int* __restrict__ plen, const int* __restrict__ poff,
+                        const uint8_t* __restrict__ tok_valid, const float* __restrict__ bias_lut, int Lb, int H) {
+  const int p = blockIdx.x, h = blockIdx.y;
+  const int len = plen[p];
+  if (len == 0) return;
+  const int row0 = poff[p];
+  const int HD = H * DK;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (base - raw);
+  const uint32_t sQ = base, sK = base + BOX, sV = base + 2 * BOX;       // P later overwrites Q | K
+  const int lut_n = 2 * Lb - 1;
+  float* lut = reinterpret_cast<float*>(smem + 3 * BOX);                // [lut_n]
+  uint32_t* masks = reinterpret_cast<uint32_t*>(smem + 3 * BOX + ((lut_n * 4 + 15) / 16) * 16);   // [4]
+  const uint32_t bars = base + 3 * BOX + ((lut_n * 4 + 15) / 16) * 16 + 16;                       // tma, mma
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + 3 * BOX + ((lut_n * 4 + 15) / 16) * 16 + 32);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t bar_tma = bars, bar_mma = bars + 8;
+
+  if (tid == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_qkv) : "memory");
+    mbar_init(bar_tma, 1);
+    mbar_init(bar_mma, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  for (int i = tid; i < lut_n; i += THREADS) lut[i] = bias_lut[(size_t)h * lut_n + i];
+  {
+    const int j = warp * 32 + lane;
+    const bool vis = j < len && tok_valid[row0 + j] != 0;
+    const unsigned m = __ballot_sync(0xffffffffu, vis);
+    if (lane == 0) masks[warp] = m;
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (tid == 0) {
+    mbar_arrive_expect_tx(bar_tma, 3 * BOX);
+    tma_load_2d(sQ, &map_qkv, bar_tma, h * DK, row0);
+    tma_load_2d(sK, &map_qkv, bar_tma, HD + h * DK, row0);
+    tma_load_2d(sV, &map_qkv, bar_tma, 2 * HD + h * DK, row0);
+  }
+  mbar_wait(bar_tma, 0);
+  if (tid == 0) {
+    tcgen05_fence_after();
+    const uint64_t dq = make_desc(sQ), dk = make_desc(sK);
+#pragma unroll
+    for (int k = 0; k < DK / 16; ++k) umma_bf16(tmem, dq + (uint64_t)(k * 2), dk + (uint64_t)(k * 2), IDESC_QK, k ? 1u : 0u);
+    umma_commit(bar_mma);
+  }
+  mbar_wait(bar_mma, 0);
+  tcgen05_fence_after();
+
+  // ---- softmax of row r = tid: two passes over the TMEM row (32 scores in registers at a time keeps the kernel at
+  //      <= 128 registers, i.e. four CTAs per SM) ----
+  const int r = tid;
+  const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
+  const float* lrow = lut + (Lb - 1 - r);          // bias of (query r, key j) = lut[j - r + Lb - 1]; only read for j < len <= Lb
+  float mx = -INFINITY;
+#pragma unroll 1
+  for (int c = 0; c < 4; ++c) {
+    uint32_t v[32];
+    tmem_ld32(trow + c * 32, v);
+    tmem_ld_wait();
+    const uint32_t mk = masks[c];
+#pragma unroll
+    for (int j = 0; j < 32; ++j)
+      if ((mk >> j) & 1u) mx = fmaxf(mx, __uint_as_float(v[j]) + lrow[c * 32 + j]);
+  }
+  const float mb = mx * LOG2E;                       // at least one key is visible (len > 0)
+  float sum = 0.f;
+  // P (bf16) in the K-major 128B-swizzled operand layout: box b = keys [64b, 64b+64), row r, 16-byte chunk j ^ (r & 7)
+#pragma unroll 1
+  for (int c = 0; c < 4; ++c) {
+    uint32_t v[32];
+    tmem_ld32(trow + c * 32, v);
+    tmem_ld_wait();
+    const uint32_t mk = masks[c];
+    float pr[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      const float x = ((mk >> j) & 1u) ? (__uint_as_float(v[j]) + lrow[c * 32 + j]) * LOG2E - mb : -INFINITY;
+      pr[j] = exp2f(x);
+      sum += pr[j];
+    }
+#pragma unroll
+    for (int q4 = 0; q4 < 4; ++q4) {
+      uint32_t pk[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        __nv_bfloat162 h2 = __floats2bfloat162_rn(pr[q4 * 8 + 2 * e], pr[q4 * 8 + 2 * e + 1]);
+        pk[e] = *reinterpret_cast<uint32_t*>(&h2);
+      }
+      const int ch = c * 4 + q4;                     // 16-byte chunk of the 128-key row
+      const uint32_t box = (ch >> 3) ? sK : sQ;
+      const uint32_t addr = box + (uint32_t)r * 128u + (uint32_t)((((ch & 7) ^ (r & 7)) & 7) << 4);
+      asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pk[0]), "r"(pk[1]), "r"(pk[2]), "r"(pk[3]) : "memory");
+    }
+  }
+  tcgen05_fence_before();                            // S has been read out of TMEM by this thread
+  fence_async_smem();
+  __syncthreads();
+  if (tid == 0) {
+    tcgen05_fence_after();
+#pragma unroll
+    for (int ks = 0; ks < LQ / 16; ++ks) {
+      const uint64_t dp = make_desc(((ks >> 2) ? sK : sQ) + (uint32_t)(ks & 3) * 32u);
+      const uint64_t dv = make_desc(sV + (uint32_t)ks * 2048u);
+      umma_bf16(tmem, dp, dv, IDESC_PV, ks ? 1u : 0u);       // O re-uses the (fully read) S columns
+    }
+    umma_commit(bar_mma);
+  }
+  mbar_wait(bar_mma, 1);
+  tcgen05_fence_after();
+  uint32_t ov[2][32];
+  tmem_ld32(trow, ov[0]);
+  tmem_ld32(trow + 32, ov[1]);
+  tmem_ld_wait();
+  if (r < len) {
+    const float inv = 1.0f / sum;
+    bf16* orow = out + (size_t)(row0 + r) * HD + h * DK;
+#pragma unroll
+    for (int g = 0; g < 8; ++g) {
+      uint32_t pk[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int i = g * 8 + 2 * e;
+        __nv_bfloat162 h2 = __floats2bfloat162_rn(__uint_as_float(ov[i >> 5][i & 31]) * inv,
+                                                  __uint_as_float(ov[(i + 1) >> 5][(i + 1) & 31]) * inv);
+        pk[e] = *reinterpret_cast<uint32_t*>(&h2);
+      }
+      *reinterpret_cast<uint4*>(orow + g * 8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+    }
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tcgen05_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(TMEM_COLS) : "memory");
+  }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+std::mutex g_mu;
+EncodeTiledFn g_encode = nullptr;
+std::map<std::tuple<const void*, size_t, size_t>, CUtensorMap> g_maps;
+
+bool get_map(const void* ptr, size_t rows, size_t cols, CUtensorMap* out) {
+  auto key = std::make_tuple(ptr, rows, cols);
+  auto it = g_maps.find(key);
+  if (it != g_maps.end()) { *out = it->second; return true; }
+  if (!g_encode) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qr;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qr) != cudaSuccess ||
+        qr != cudaDriverEntryPointSuccess || !fn) { cudaGetLastError(); return false; }
+    g_encode = (EncodeTiledFn)fn;
+  }
+  CUtensorMap m;
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)cols * 2};
+  cuuint32_t box[2] = {(cuuint32_t)DK, (cuuint32_t)LQ};
+  cuuint32_t estr[2] = {1, 1};
+  if (g_encode(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) return false;
+  if (g_maps.size() > 1024) g_maps.clear();
+  g_maps[key] = m;
+  *out = m;
+  return true;
+}
+
+}  // namespace ta
+
+bool enc_attention_tc_supported(int dk, int Lmax, int Lb) { return dk == ta::DK && Lmax <= ta::LQ && Lb <= 1024; }
+
+cudaError_t enc_attention_tc(const void* qkv, size_t qkv_rows, void* out, const int* plen, const int* poff,
+                             const uint8_t* tok_valid, const float* bias_lut, int Lb, int P, int H, cudaStream_t s) {
+  if (P <= 0) return cudaSuccess;
+  std::lock_guard<std::mutex> lk(ta::g_mu);
+  CUtensorMap map;
+  if (!ta::get_map(qkv, qkv_rows, (size_t)3 * H * ta::DK, &map)) return cudaErrorUnknown;
+  const size_t smem = (size_t)3 * ta::BOX + (((size_t)(2 * Lb - 1) * 4 + 15) / 16) * 16 + 64 + 1024;
+  static size_t configured = 0;
+  if (smem > configured) {
+    cudaError_t e = cudaFuncSetAttribute(ta::enc_attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    configured = smem;
+  }
+  ta::enc_attention_tc_kernel<<<dim3(P, H), ta::THREADS, smem, s>>>(map, (bf16*)out, plen, poff, tok_valid, bias_lut, Lb, H);
+  return cudaGetLastError();
+}
+
+}  // namespace gram

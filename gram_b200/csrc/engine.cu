@@ -313,7 +313,11 @@ int run_encode(gram_handle* h, const int64_t* ids, const uint8_t* mask, int B, i
     const LayerW& W = h->enc[l];
     CKL(GRAM_K_NORM_ENC, rmsnorm_rows(c.dtype, h->x, W.ln0, h->xn, Mmax, mp, D, c.ln_eps, 1.f, nullptr, nullptr, s));
     RC(gemm(h, GRAM_K_GEMM_ENC, EPI_STORE, h->xn, W.qkv, h->qkv, Mmax, mp, 3 * HD, D, s));
-    if (c.dtype == GRAM_DTYPE_BF16 && !(c.flags & GRAM_FLAG_SIMT_ATTN) && enc_attention_mma_supported(h->dk, L)) {
+    if (c.dtype == GRAM_DTYPE_BF16 && (c.flags & GRAM_FLAG_TC_ENC_ATTN) && !(c.flags & GRAM_FLAG_SIMT_ATTN) &&
+        enc_attention_tc_supported(h->dk, L, h->Lb)) {
+      CKL(GRAM_K_ENC_ATTN, enc_attention_tc(h->qkv, (size_t)h->Mcap + 256, h->ao, h->pm.plen, h->pm.poff, h->pm.tok_valid,
+                                            h->enc_bias_lut, h->Lb, B * N, h->H, s));
+    } else if (c.dtype == GRAM_DTYPE_BF16 && !(c.flags & GRAM_FLAG_SIMT_ATTN) && enc_attention_mma_supported(h->dk, L)) {
       CKL(GRAM_K_ENC_ATTN, enc_attention_mma(h->qkv, h->ao, h->pm.plen, h->pm.poff, h->pm.tok_valid, h->enc_bias_lut,
                                              h->Lb, B * N, h->H, L, s));
     } else {
@@ -516,6 +520,8 @@ int gram_create(const gram_config* cfg, gram_handle** out) {
 #undef DAC
   // K/V rows past a user's range are read (and masked) by the TMA-fed attention kernel: they must be finite
   if (cudaMemset(h->ckv, 0, Mc * (size_t)h->Ld * 2 * HD * esz) != cudaSuccess ||
+      cudaMemset(h->qkv, 0, Mc * 3 * (size_t)HD * esz) != cudaSuccess ||   // rows past a passage are read (masked) by TMA
+
       cudaMemset(h->d_zero_anc, 0, R * ML * 4) != cudaSuccess || cudaMemset(bs.err, 0, 16) != cudaSuccess ||
       cudaMemset(bs.anc[0], 0, R * ML * 4) != cudaSuccess || cudaMemset(bs.anc[1], 0, R * ML * 4) != cudaSuccess) {
     h->err = "gram_create: cudaMemset failed"; return bail(GRAM_ERR_CUDA);

@@ -55,7 +55,10 @@ typedef struct gram_config {
 enum {
   GRAM_FLAG_SIMT_GEMM = 1,         /* force the CUDA-core GEMM even for bf16 (debug / A-B timing) */
   GRAM_FLAG_KEEP_LOGITS = 2,       /* record per-step taps (lse, beam scores, prefixes) for parity tests */
-  GRAM_FLAG_SIMT_ATTN = 4          /* force the CUDA-core attention kernels even for bf16 (A-B timing)   */
+  GRAM_FLAG_SIMT_ATTN = 4,         /* force the CUDA-core attention kernels even for bf16 (A-B timing)   */
+  GRAM_FLAG_TC_ENC_ATTN = 8        /* encoder attention through the tcgen05/TMEM kernel (attention_tc.cu): numerically
+                                      verified, but one (passage, head) per CTA without cross-item pipelining it is
+                                      ~15 % slower than the pipelined mma.sync kernel, so it is opt-in for now */
 };
 
 /* ---- lifetime -------------------------------------------------------------------------------- */

@@ -265,6 +265,25 @@ def test_generate_bf16_overlap(built, name):
     assert np.abs(sc[:, 0] - gs[:, 0]).max() < 0.05 * np.abs(gs[:, 0]).max()
 
 
+def test_tcgen05_encoder_attention_matches_mma_path(built):
+    """attention_tc.cu (tcgen05.mma with an MN-major V operand, softmax out of TMEM) against the default mma.sync
+    encoder attention: same fused memory within bf16 rounding, and within 2e-2 of the reference golden logits."""
+    from gram_b200 import _cabi
+    b = built["small"]
+    gold = _golden("small")
+    m_tc = _model(b["case"], b["sd"], "bf16", flags=_cabi.GRAM_FLAG_TC_ENC_ATTN)
+    m_mma = _model(b["case"], b["sd"], "bf16")
+    ids, mask = b["ids"].cuda(), b["mask"].cuda()
+    mem_tc, mem_mma = m_tc.encode(ids, mask).cpu(), m_mma.encode(ids, mask).cpu()
+    assert rel_err(mem_tc, mem_mma) < 2e-2
+    dec = torch.from_numpy(gold["dec_ids"]).cuda()
+    logits = m_tc.forward(ids, mask, decoder_input_ids=dec).logits.cpu()
+    vs = torch.from_numpy(gold["vocab_idx"]).long()
+    err = (logits[:, :, vs] - torch.from_numpy(gold["logits"])).abs().max().item() / float(gold["logits_absmax"])
+    print(f"[tcgen05 enc-attn logits] rel_err={err:.3e}")
+    assert err < BF16_TOL
+
+
 def test_generate_errors(built):
     from gram_b200 import Trie, prefix_allowed_tokens_fn
     b = built["tiny"]
