@@ -196,16 +196,18 @@ struct NoBias {
 // ================================================================================================
 // cross attention
 // ================================================================================================
-constexpr int XA_WARPS = 4;                                   // consumer warps per CTA
-constexpr int XA_THREADS = (XA_WARPS + 1) * 32;               // + 1 TMA producer warp
+constexpr int xa_threads(int warps) { return (warps + 1) * 32; }   // consumer warps + 1 TMA producer warp
 constexpr int XA_STAGE_TARGET = 64 * 1024;
 
 // HEADS heads per CTA, BH beam-halves (32 beams each) and KH key-halves (32 keys of every 64-key tile) per head:
 // HEADS * BH * KH == 4 consumer warps.  Key-halves are merged once at the end through shared memory.
-//   K <= 32: <4, 1, 1, 1>, 64 KiB stages x 3, one CTA per SM      K <= 64: <2, 2, 1, 1>, 32 KiB stages x 6
-//   (<2, 1, 2, 2> -- key-halves, two CTAs per SM -- measured 8 % slower on B200 and is kept only as an option)
+//   K <= 32: <4, 1, 1, 1>: one warp per head, 64 KiB stages x 3, one CTA per SM      (5.1-5.3 TB/s on B200)
+//   K <= 64: <2, 2, 1, 1>: 2 heads x 2 beam-halves, 32 KiB stages x 6
+//   Measured alternatives for K <= 32 (kept as template options): <2, 1, 2, 2> (key-halves, two CTAs per SM) 8 % slower;
+//   <4, 1, 2, 1> (8 consumer warps per CTA) 40 % slower -- splitting a 64-key tile between two warps doubles the per-tile
+//   softmax bookkeeping (running max / rescale of the 32 x 64 output tile) and spills.
 template <int HEADS, int BH, int KH, int MINB>
-__global__ void __launch_bounds__(XA_THREADS, MINB)
+__global__ void __launch_bounds__(xa_threads(HEADS * BH * KH), MINB)
 cross_attention_mma_kernel(const __grid_constant__ CUtensorMap map_kv, const bf16* __restrict__ qg,
                            bf16* __restrict__ out, const int* __restrict__ ustart, const int* __restrict__ uorder,
                            const uint8_t* __restrict__ tok_valid, int K, int H, int k_col0, int v_col0) {
@@ -214,7 +216,7 @@ cross_attention_mma_kernel(const __grid_constant__ CUtensorMap map_kv, const bf1
   constexpr uint32_t XA_STAGE_BYTES = 2 * HEADS * BOX_BYTES;   // K boxes then V boxes
   constexpr int XA_STAGES = MINB == 2 ? 3 : 3 * XA_STAGE_TARGET / (int)XA_STAGE_BYTES;
   constexpr int NKT = 8 / KH;
-  static_assert(HEADS * BH * KH == XA_WARPS, "four consumer warps");
+  constexpr int XA_WARPS = HEADS * BH * KH;                     // consumer warps (4 or 8)
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
@@ -308,7 +310,7 @@ cross_attention_mma_kernel(const __grid_constant__ CUtensorMap map_kv, const bf1
   }
   if (KH == 2) {
     // ---- merge the two key-halves of every (head, beam half): every tile has been consumed, so the ring is free ----
-    asm volatile("bar.sync 1, 128;" ::: "memory");
+    asm volatile("bar.sync 1, %0;" ::"n"(XA_WARPS * 32) : "memory");
     float* xch = reinterpret_cast<float*>(smem) + (size_t)(warp >> 1) * (32 * 72);   // 72 floats per lane
     if (kh == 1) {
       float* dst = xch + lane;
@@ -325,7 +327,7 @@ cross_attention_mma_kernel(const __grid_constant__ CUtensorMap map_kv, const bf1
           for (int e = 0; e < 4; ++e) dst[(8 + (mt * 8 + nt) * 4 + e) * 32] = o[mt][nt][e];
       }
     }
-    asm volatile("bar.sync 1, 128;" ::: "memory");
+    asm volatile("bar.sync 1, %0;" ::"n"(XA_WARPS * 32) : "memory");
     if (kh == 1) return;
     const float* src = xch + lane;
 #pragma unroll
@@ -522,24 +524,22 @@ cudaError_t cross_attention_mma(const void* q, const void* kv, size_t kv_rows, s
   CUtensorMap map;
   if (!fa::get_kv_map(kv, kv_rows, kv_stride, &map)) return cudaErrorUnknown;
   constexpr size_t smem = (size_t)3 * fa::XA_STAGE_TARGET + 1024 + 256;
-  static bool attr[2] = {false, false};
+  static SmemAttr attr[2];
   if (K <= 32 && (H % 4) == 0) {
     auto kern = fa::cross_attention_mma_kernel<4, 1, 1, 1>;
-    if (!attr[0]) {
-      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    {
+      cudaError_t e = attr[0].ensure(kern, smem);
       if (e != cudaSuccess) return e;
-      attr[0] = true;
     }
-    kern<<<dim3(users, H / 4), fa::XA_THREADS, smem, s>>>(map, (const bf16*)q, (bf16*)out, ustart, uorder, tok_valid, K, H,
+    kern<<<dim3(users, H / 4), fa::xa_threads(4), smem, s>>>(map, (const bf16*)q, (bf16*)out, ustart, uorder, tok_valid, K, H,
                                                           k_off, v_off);
   } else {
     auto kern = fa::cross_attention_mma_kernel<2, 2, 1, 1>;
-    if (!attr[1]) {
-      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    {
+      cudaError_t e = attr[1].ensure(kern, smem);
       if (e != cudaSuccess) return e;
-      attr[1] = true;
     }
-    kern<<<dim3(users, H / 2), fa::XA_THREADS, smem, s>>>(map, (const bf16*)q, (bf16*)out, ustart, uorder, tok_valid, K, H,
+    kern<<<dim3(users, H / 2), fa::xa_threads(4), smem, s>>>(map, (const bf16*)q, (bf16*)out, ustart, uorder, tok_valid, K, H,
                                                           k_off, v_off);
   }
   return cudaGetLastError();
@@ -552,15 +552,14 @@ cudaError_t enc_attention_mma(const void* qkv, void* out, const int* plen, const
   if (P <= 0) return cudaSuccess;
   const int LT = (Lmax + fa::TS - 1) / fa::TS;
   const size_t lut_bytes = ((size_t)H * (2 * Lb - 1) * 4 + 15) / 16 * 16;
-  static size_t attr[5] = {0, 0, 0, 0, 0};     // largest dynamic shared-memory size configured per instantiation
+  static SmemAttr attr[5];
 #define GRAM_EA(LTV)                                                                                         \
   {                                                                                                          \
     const size_t smem = (size_t)2 * 3 * LTV * fa::BOX_BYTES + 128 + lut_bytes + LTV * 8 + 1024 + 64;         \
     auto kern = fa::enc_attention_pipe_kernel<LTV>;                                                          \
-    if (smem > attr[LTV]) {                                                                                  \
-      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);    \
+    {                                                                                                        \
+      cudaError_t e = attr[LTV].ensure(kern, smem);                                                          \
       if (e != cudaSuccess) return e;                                                                        \
-      attr[LTV] = smem;                                                                                      \
     }                                                                                                        \
     kern<<<P, fa::EA_THREADS, smem, s>>>((const bf16*)qkv, (bf16*)out, plen, poff, tok_valid, bias_lut, Lb, H); \
   }

@@ -296,11 +296,10 @@ cudaError_t enc_attention_tc(const void* qkv, size_t qkv_rows, void* out, const 
   CUtensorMap map;
   if (!ta::get_map(qkv, qkv_rows, (size_t)3 * H * ta::DK, &map)) return cudaErrorUnknown;
   const size_t smem = (size_t)3 * ta::BOX + (((size_t)(2 * Lb - 1) * 4 + 15) / 16) * 16 + 64 + 1024;
-  static size_t configured = 0;
-  if (smem > configured) {
-    cudaError_t e = cudaFuncSetAttribute(ta::enc_attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  static SmemAttr attr;
+  {
+    cudaError_t e = attr.ensure(ta::enc_attention_tc_kernel, smem);
     if (e != cudaSuccess) return e;
-    configured = smem;
   }
   ta::enc_attention_tc_kernel<<<dim3(P, H), ta::THREADS, smem, s>>>(map, (bf16*)out, plen, poff, tok_valid, bias_lut, Lb, H);
   return cudaGetLastError();

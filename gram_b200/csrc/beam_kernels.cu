@@ -427,11 +427,10 @@ cudaError_t beam_step(BeamState bs, TrieCSR trie, const float* logits, const voi
   if (bs.K > BEAM_KMAX) return cudaErrorInvalidValue;
   if (logits == nullptr && (hidden == nullptr || head == nullptr || (D & 7))) return cudaErrorInvalidValue;
   const size_t smem = beam_step_smem(cand_cap);
-  static size_t configured = 0;
-  if (smem > configured) {
-    cudaError_t e = cudaFuncSetAttribute(beam_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  static SmemAttr attr;
+  {
+    cudaError_t e = attr.ensure(beam_step_kernel, smem);
     if (e != cudaSuccess) return e;
-    configured = smem;
   }
   beam_step_kernel<<<users, BEAM_THREADS, smem, s>>>(bs, trie, logits, (const bf16*)hidden, (const bf16*)head, D, lse, users, t,
                                                      cand_cap, compact);

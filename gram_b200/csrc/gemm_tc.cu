@@ -350,7 +350,7 @@ std::mutex g_mu;
 EncodeTiledFn g_encode = nullptr;
 std::string g_err;
 std::map<std::tuple<const void*, int, long long>, CUtensorMap> g_maps;
-bool g_attr_set[10] = {false, false, false, false, false, false, false, false, false, false};
+SmemAttr g_attr[10];
 
 bool get_encode() {
   if (g_encode) return true;
@@ -397,11 +397,9 @@ cudaError_t launch(const CUtensorMap& ma, const CUtensorMap& mw, const CUtensorM
                    const int* m_ptr, int N, int K, int num_sms, cudaStream_t s) {
   auto kern = gemm_tc_kernel<EPI, BN>;
   constexpr size_t smem = Cfg<BN>::SMEM_BYTES;
-  bool& done = g_attr_set[EPI * 2 + (BN == 256)];
-  if (!done) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  {
+    cudaError_t e = g_attr[EPI * 2 + (BN == 256)].ensure(kern, smem);
     if (e != cudaSuccess) return e;
-    done = true;
   }
   const int tiles = ((M_max + BLOCK_M - 1) / BLOCK_M) * ((N + BN - 1) / BN);
   const int grid = tiles < num_sms ? tiles : num_sms;

@@ -6,6 +6,25 @@
 
 namespace gram {
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize is per device: remember, per device, the largest size configured for a
+// kernel and raise it on demand (a process may drive several GPUs).
+struct SmemAttr {
+  size_t configured[64] = {0};
+  template <typename Kern>
+  cudaError_t ensure(Kern kern, size_t bytes) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    dev &= 63;
+    if (bytes > configured[dev]) {
+      e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+      if (e != cudaSuccess) return e;
+      configured[dev] = bytes;
+    }
+    return cudaSuccess;
+  }
+};
+
 enum { EPI_STORE = 0, EPI_RELU = 1, EPI_RESID = 2, EPI_F32 = 3, EPI_LSE = 4 };
 // EPI_LSE (tcgen05 GEMM only): C is float2 [M, ceil(N/128)] of per-tile (max, sum exp(x - max)); no logits are stored
 
