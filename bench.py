@@ -50,6 +50,7 @@ def parse():
     ap.add_argument("--cpu-users", type=int, default=8, help="users timed for cpu_baseline (0 = skip)")
     ap.add_argument("--simt", action="store_true", help="force the CUDA-core GEMM (A/B timing)")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--gemm-1cta", action="store_true", help="keep every tcgen05 GEMM on single-CTA tiles (A/B timing)")
     ap.add_argument("--tc-enc-attn", action="store_true", help="opt into the tcgen05 encoder-attention kernel (A/B timing)")
     return ap.parse_args()
 
@@ -259,7 +260,8 @@ def main():
 
     from gram_b200 import GRAM, _cabi
     data, cfg, sd, cands, max_length, trie, fn = build_workload(args, rank, world)
-    flags = (_cabi.GRAM_FLAG_SIMT_GEMM if args.simt else 0) | (_cabi.GRAM_FLAG_TC_ENC_ATTN if args.tc_enc_attn else 0)
+    flags = (_cabi.GRAM_FLAG_SIMT_GEMM if args.simt else 0) | (_cabi.GRAM_FLAG_TC_ENC_ATTN if args.tc_enc_attn else 0) | \
+        (_cabi.GRAM_FLAG_GEMM_1CTA if args.gemm_1cta else 0)
     model = GRAM(cfg, dtype=args.dtype, device=dev, flags=flags)
     model.load_state_dict(sd)
     B, K, W, S = args.batch, BEAMS, args.warmup, args.steps

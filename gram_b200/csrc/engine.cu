@@ -198,7 +198,7 @@ int gemm(gram_handle* h, int cls, int epi, const void* A, const void* W, void* C
   Scope sc(h, cls, s);
   cudaError_t e;
   if (h->cfg.dtype == GRAM_DTYPE_BF16 && !(h->cfg.flags & GRAM_FLAG_SIMT_GEMM) && gemm_tc_supported(N, K)) {
-    e = gemm_tc(epi, A, W, C, M_max, m_ptr, N, K, h->num_sms, s);
+    e = gemm_tc(epi, A, W, C, M_max, m_ptr, N, K, h->num_sms, (h->cfg.flags & GRAM_FLAG_GEMM_1CTA) ? 1 : 2, s);
     if (e != cudaSuccess) {
       h->err = std::string("tcgen05 gemm launch failed: ") + cudaGetErrorString(e) + " / " + gemm_tc_last_error();
       return GRAM_ERR_CUDA;
@@ -832,11 +832,11 @@ int gram_op_gemm(int32_t device, int32_t dtype, int32_t impl, int32_t epilogue, 
                  int32_t M, int32_t N, int32_t K, void* stream) {
   if (cudaSetDevice(device) != cudaSuccess) return GRAM_ERR_CUDA;
   cudaError_t e;
-  if (impl == 1) {
+  if (impl == 1 || impl == 2) {
     if (dtype != GRAM_DTYPE_BF16 || !gemm_tc_supported(N, K)) { g_create_error = "gram_op_gemm: tcgen05 path needs bf16 and a supported (N,K)"; return GRAM_ERR_UNSUPPORTED; }
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
-    e = gemm_tc(epilogue, A, W, C, M, nullptr, N, K, sms, (cudaStream_t)stream);
+    e = gemm_tc(epilogue, A, W, C, M, nullptr, N, K, sms, impl == 2 ? 1 : 2, (cudaStream_t)stream);
     if (e != cudaSuccess) { g_create_error = std::string("gemm_tc: ") + cudaGetErrorString(e) + " / " + gemm_tc_last_error(); return GRAM_ERR_CUDA; }
     return GRAM_OK;
   }

@@ -16,7 +16,15 @@
 //               ReLU / dtype conversion, staged through a 128B-swizzled shared-memory tile and written with TMA
 //               bulk tensor stores; the residual add (x += A W^T) is a TMA reduce-add performed at the L2, so the
 //               SM never reads the residual stream
-// TMEM holds two 128-column accumulators so the epilogue of tile i overlaps the MMAs of tile i+1.
+// TMEM holds two accumulators so the epilogue of tile i overlaps the MMAs of tile i+1.
+//
+// CTA pairs (CTAS = 2): two CTAs of a (2,1,1) cluster -- the two SMs of a TPC -- compute one 256 x 256 tile with
+// tcgen05.mma.cta_group::2.  Each CTA loads its own 128 rows of A and HALF of the W tile (128 of the 256 output
+// columns), so a CTA moves 32 KiB of operands per 128x256x64 MACs instead of 48 KiB: the single-CTA kernel is paced
+// by the L2 -> SM feed (measured: tensor pipe 67 % busy = 64 of the 96 B/clk it asks for), the pair asks for 64.
+// The leader CTA (cluster rank 0) issues every MMA; the TMA loads of both CTAs complete on the leader's `full`
+// barrier; tcgen05.commit multicasts the `empty` / `accumulator full` arrivals to both CTAs; both epilogues hand
+// the accumulator back on the leader's `accumulator empty` barrier.
 // M may live in device memory (*m_ptr): the packed encoder token count is only known on the device, so the
 // kernel derives its tile loop bound there and the host never synchronises.
 #include <cuda.h>
@@ -41,15 +49,16 @@ constexpr int ACC_STAGES = 2;
 constexpr int THREADS = 192;
 constexpr uint32_t A_BYTES = BLOCK_M * BLOCK_K * 2;        // 16 KiB
 constexpr uint32_t CSTAGE_BYTES = 32 * 1024;               // epilogue staging: two 128-row x 128-byte boxes
-template <int BN> struct Cfg {
-  static constexpr int STAGES = BN == 128 ? 6 : 4;
-  static constexpr uint32_t B_BYTES = BN * BLOCK_K * 2;    // 16 or 32 KiB
+template <int BN, int CTAS> struct Cfg {
+  static constexpr int LOAD_N = BN / CTAS;                 // W rows each CTA loads per stage
+  static constexpr uint32_t B_BYTES = LOAD_N * BLOCK_K * 2;   // 16 or 32 KiB
   static constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = STAGE_BYTES == 32768 ? 6 : 4;
   static constexpr int TMEM_COLS = ACC_STAGES * BN;        // 256 or 512 (power of two)
   static constexpr size_t SMEM_BYTES = (size_t)STAGES * STAGE_BYTES + CSTAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
-  // instruction descriptor: D=f32, A=B=bf16, both K-major, M=128, N=BN
+  // instruction descriptor: D=f32, A=B=bf16, both K-major, M=128 per CTA (256 for a pair), N=BN
   static constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) |
-                                    ((uint32_t)(BLOCK_M >> 4) << 24);
+                                    ((uint32_t)((BLOCK_M * CTAS) >> 4) << 24);
 };
 
 // ---- PTX wrappers --------------------------------------------------------------------------------------
@@ -109,6 +118,58 @@ __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint
       "}\n" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(acc)
       : "memory");
 }
+// ---- CTA-pair (cta_group::2) variants ----
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+// shared::cluster address of the same shared-memory location in the leader CTA (cluster rank 0)
+__device__ __forceinline__ uint32_t leader_addr(uint32_t cta_addr) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, 0;" : "=r"(r) : "r"(cta_addr));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_bar) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP_C:\n"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra WAIT_DONE_C;\n"
+      "bra WAIT_LOOP_C;\n"
+      "WAIT_DONE_C:\n"
+      "}\n" ::"r"(bar), "r"(parity)
+      : "memory");
+}
+// the destination is this CTA's shared memory, the mbarrier is the leader's (shared::cluster address)
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap* map, uint32_t cluster_bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(map), "r"(cluster_bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void umma_bf16_pair(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+// arrive on the barrier at this offset in BOTH CTAs of the pair once all prior MMAs have retired
+__device__ __forceinline__ void umma_commit_pair(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"((uint16_t)3) : "memory");
+}
+
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -133,15 +194,17 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
   d |= (uint64_t)2 << 61;                                // layout type: SWIZZLE_128B              bits [61,64)
   return d;
 }
-template <int EPI, int BLOCK_N>
+template <int EPI, int BLOCK_N, int CTAS>
 __global__ void __launch_bounds__(THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
                const __grid_constant__ CUtensorMap map_c, float2* __restrict__ lse_partial, int M_imm,
                const int* __restrict__ m_ptr, int N, int K) {
-  constexpr int STAGES = Cfg<BLOCK_N>::STAGES;
-  constexpr uint32_t STAGE_BYTES = Cfg<BLOCK_N>::STAGE_BYTES;
-  constexpr int TMEM_COLS = Cfg<BLOCK_N>::TMEM_COLS;
-  constexpr uint32_t kInstrDesc = Cfg<BLOCK_N>::IDESC;
+  using C_ = Cfg<BLOCK_N, CTAS>;
+  constexpr int STAGES = C_::STAGES;
+  constexpr uint32_t STAGE_BYTES = C_::STAGE_BYTES;
+  constexpr int TMEM_COLS = C_::TMEM_COLS;
+  constexpr uint32_t kInstrDesc = C_::IDESC;
+  constexpr int TILE_M = BLOCK_M * CTAS;                   // rows of one (pair) tile
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;           // 1024-byte alignment for the 128B swizzle atoms
@@ -156,50 +219,69 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int M = m_ptr ? *m_ptr : M_imm;
-  const int num_m = (M + BLOCK_M - 1) / BLOCK_M, num_n = (N + BLOCK_N - 1) / BLOCK_N;
+  const int num_m = (M + TILE_M - 1) / TILE_M, num_n = (N + BLOCK_N - 1) / BLOCK_N;
   const int num_tiles = num_m * num_n;
   const int num_kb = K / BLOCK_K;
+  const int rank = CTAS == 2 ? (int)cluster_ctarank() : 0;             // 0 = leader of the pair
+  const int tile0 = CTAS == 2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int tile_step = (int)gridDim.x / CTAS;
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_c) : "memory");
     for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-    for (int s = 0; s < ACC_STAGES; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 4); }
+    for (int s = 0; s < ACC_STAGES; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 4 * CTAS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(TMEM_COLS) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if (CTAS == 2) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(TMEM_COLS) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(TMEM_COLS) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   tcgen05_fence_before();
-  __syncthreads();
+  if (CTAS == 2) cluster_sync_all();      // the peer's barriers are initialised before anything signals them
+  else __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
     // ===================== TMA producer =====================
     int stage = 0; uint32_t phase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    for (int tile = tile0; tile < num_tiles; tile += tile_step) {
       const int m_blk = tile / num_n, n_blk = tile % num_n;
       for (int kb = 0; kb < num_kb; ++kb) {
         mbar_wait(empty_bar(stage), phase ^ 1u);
         if (lane == 0) {
           const uint32_t sa = base + stage * STAGE_BYTES, sb = sa + A_BYTES;
-          mbar_arrive_expect_tx(full_bar(stage), STAGE_BYTES);
-          tma_load_2d(sa, &map_a, full_bar(stage), kb * BLOCK_K, m_blk * BLOCK_M);
-          tma_load_2d(sb, &map_w, full_bar(stage), kb * BLOCK_K, n_blk * BLOCK_N);
+          if (CTAS == 2) {
+            // both CTAs' bytes are counted on the leader's barrier
+            if (rank == 0) mbar_arrive_expect_tx(full_bar(stage), 2 * STAGE_BYTES);
+            const uint32_t fb = leader_addr(full_bar(stage));
+            tma_load_2d_pair(sa, &map_a, fb, kb * BLOCK_K, m_blk * TILE_M + rank * BLOCK_M);
+            tma_load_2d_pair(sb, &map_w, fb, kb * BLOCK_K, n_blk * BLOCK_N + rank * C_::LOAD_N);
+          } else {
+            mbar_arrive_expect_tx(full_bar(stage), STAGE_BYTES);
+            tma_load_2d(sa, &map_a, full_bar(stage), kb * BLOCK_K, m_blk * BLOCK_M);
+            tma_load_2d(sb, &map_w, full_bar(stage), kb * BLOCK_K, n_blk * BLOCK_N);
+          }
         }
         __syncwarp();
         if (++stage == STAGES) { stage = 0; phase ^= 1u; }
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
+    // ===================== MMA issuer (the leader CTA of a pair) =====================
     int stage = 0; uint32_t phase = 0;
     int acc = 0; uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      mbar_wait(tempty_bar(acc), acc_phase ^ 1u);          // epilogue has drained this accumulator
+    for (int tile = tile0; tile < num_tiles && rank == 0; tile += tile_step) {
+      // the epilogue (of both CTAs) has drained this accumulator
+      if (CTAS == 2) mbar_wait_cluster(tempty_bar(acc), acc_phase ^ 1u);
+      else mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
       tcgen05_fence_after();
       const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BLOCK_N);
       for (int kb = 0; kb < num_kb; ++kb) {
@@ -211,10 +293,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 #pragma unroll
           for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
             // advance 16 bf16 = 32 bytes inside the 128-byte swizzle row: +2 in 16-byte address units
-            umma_bf16(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), kInstrDesc, (kb | k) ? 1u : 0u);
+            if (CTAS == 2) umma_bf16_pair(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), kInstrDesc, (kb | k) ? 1u : 0u);
+            else umma_bf16(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), kInstrDesc, (kb | k) ? 1u : 0u);
           }
-          umma_commit(empty_bar(stage));                   // frees the ring slot when these MMAs retire
-          if (kb == num_kb - 1) umma_commit(tfull_bar(acc));   // accumulator complete
+          if (CTAS == 2) {
+            umma_commit_pair(empty_bar(stage));            // frees the ring slot in both CTAs
+            if (kb == num_kb - 1) umma_commit_pair(tfull_bar(acc));
+          } else {
+            umma_commit(empty_bar(stage));                 // frees the ring slot when these MMAs retire
+            if (kb == num_kb - 1) umma_commit(tfull_bar(acc));   // accumulator complete
+          }
         }
         __syncwarp();
         if (++stage == STAGES) { stage = 0; phase ^= 1u; }
@@ -230,15 +318,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     constexpr int CHUNKS_PER_ROUND = kOutBf16 ? 4 : 2;     // 32 KiB of staging = 128 bf16 or 64 fp32 columns
     constexpr int ROUNDS = (BLOCK_N / 32) / CHUNKS_PER_ROUND;
     int acc = 0; uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    auto release_acc = [&](int a) {
+      if (CTAS == 2) mbar_arrive_cluster(leader_addr(tempty_bar(a)));
+      else mbar_arrive(tempty_bar(a));
+    };
+    for (int tile = tile0; tile < num_tiles; tile += tile_step) {
       const int m_blk = tile / num_n, n_blk = tile % num_n;
+      const int row0 = m_blk * TILE_M + rank * BLOCK_M;    // first row of this CTA's half of the tile
       mbar_wait(tfull_bar(acc), acc_phase);
       tcgen05_fence_after();
       if (EPI == EPI_LSE) {
         // fused log-softmax statistics: per row, (max, sum exp(x - max)) over this tile's columns; the logits
         // themselves are never written (reference computes log_softmax over the materialised [rows, V] logits)
         float mx = -INFINITY, sum = 0.f;
-        const int row = m_blk * BLOCK_M + r;
+        const int row = row0 + r;
 #pragma unroll 1
         for (int c = 0; c < BLOCK_N / 32; ++c) {
           uint32_t v[32];
@@ -264,7 +357,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         }
         tcgen05_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(tempty_bar(acc));
+        if (lane == 0) release_acc(acc);
         if (row < M) lse_partial[(size_t)row * num_n + n_blk] = make_float2(mx, sum);
         if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1u; }
         continue;
@@ -312,12 +405,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           // every tcgen05.ld of this accumulator has completed: hand it back to the MMA warp
           tcgen05_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(tempty_bar(acc));
+          if (lane == 0) release_acc(acc);
         }
         fence_async_smem();                                // generic-proxy writes -> visible to the async proxy
         epi_bar();
         if (issuer) {
-          const int row0 = m_blk * BLOCK_M;
 #pragma unroll
           for (int bx = 0; bx < 2; ++bx) {
             const int col0 = n_blk * BLOCK_N + (kOutBf16 ? (rd * 2 + bx) * 64 : (rd * 2 + bx) * 32);
@@ -334,10 +426,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     if (issuer) tma_store_wait_all();
   }
   tcgen05_fence_before();
-  __syncthreads();
+  if (CTAS == 2) cluster_sync_all();      // neither CTA leaves while the pair's MMAs / barrier arrivals are in flight
+  else __syncthreads();
   if (warp == 1) {
     tcgen05_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
+    if (CTAS == 2) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
+    else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
   }
 }
 
@@ -350,7 +444,7 @@ std::mutex g_mu;
 EncodeTiledFn g_encode = nullptr;
 std::string g_err;
 std::map<std::tuple<const void*, int, long long>, CUtensorMap> g_maps;
-SmemAttr g_attr[10];
+SmemAttr g_attr[15];
 
 bool get_encode() {
   if (g_encode) return true;
@@ -392,26 +486,69 @@ bool get_map(const void* ptr, int rows, int cols, int kind, int box_rows, CUtens
   return true;
 }
 
-template <int EPI, int BN>
-cudaError_t launch(const CUtensorMap& ma, const CUtensorMap& mw, const CUtensorMap& mc, float2* lse_partial, int M_max,
-                   const int* m_ptr, int N, int K, int num_sms, cudaStream_t s) {
-  auto kern = gemm_tc_kernel<EPI, BN>;
-  constexpr size_t smem = Cfg<BN>::SMEM_BYTES;
-  {
-    cudaError_t e = g_attr[EPI * 2 + (BN == 256)].ensure(kern, smem);
-    if (e != cudaSuccess) return e;
+// resident CTA pairs the device can hold for one instantiation (cached per device)
+template <typename Kern>
+int max_pairs(Kern kern, size_t smem, int num_sms, int* cache) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  dev &= 63;
+  if (cache[dev] == 0) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(num_sms & ~1);
+    cfg.blockDim = dim3(THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess || n <= 0) { cudaGetLastError(); n = -1; }
+    cache[dev] = n;
   }
-  const int tiles = ((M_max + BLOCK_M - 1) / BLOCK_M) * ((N + BN - 1) / BN);
-  const int grid = tiles < num_sms ? tiles : num_sms;
-  kern<<<grid, THREADS, smem, s>>>(ma, mw, mc, lse_partial, M_max, m_ptr, N, K);
-  return cudaGetLastError();
+  return cache[dev];
 }
 
-// wide tiles only when they still give every SM at least two tiles
-inline int pick_bn(int M_max, int N, int num_sms) {
-  if (N < 256) return 128;
+int g_pairs[15][64];
+
+template <int EPI, int BN, int CTAS>
+cudaError_t launch(const CUtensorMap& ma, const CUtensorMap& mw, const CUtensorMap& mc, float2* lse_partial, int M_max,
+                   const int* m_ptr, int N, int K, int num_sms, cudaStream_t s) {
+  auto kern = gemm_tc_kernel<EPI, BN, CTAS>;
+  constexpr size_t smem = Cfg<BN, CTAS>::SMEM_BYTES;
+  constexpr int slot = EPI * 3 + (BN == 256) + (CTAS == 2);
+  {
+    cudaError_t e = g_attr[slot].ensure(kern, smem);
+    if (e != cudaSuccess) return e;
+  }
+  const int tiles = ((M_max + BLOCK_M * CTAS - 1) / (BLOCK_M * CTAS)) * ((N + BN - 1) / BN);
+  if (CTAS == 1) {
+    const int grid = tiles < num_sms ? tiles : num_sms;
+    kern<<<grid, THREADS, smem, s>>>(ma, mw, mc, lse_partial, M_max, m_ptr, N, K);
+    return cudaGetLastError();
+  }
+  const int pairs = max_pairs(kern, smem, num_sms, g_pairs[slot]);
+  if (pairs <= 0) return cudaErrorLaunchOutOfResources;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(2 * (tiles < pairs ? tiles : pairs));
+  cfg.blockDim = dim3(THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kern, ma, mw, mc, lse_partial, M_max, m_ptr, N, K);
+}
+
+// Tile shape: 128 x 128 for small problems; 128 x 256 when that still gives every SM at least two tiles; a CTA pair
+// (256 x 256) when pairs are allowed (max_ctas >= 2) and every SM gets at least 16 tiles -- below that the cluster
+// launch + cluster barriers cost more than the pair saves (measured: M = 18880, N = 2048: 39.2 us vs 37.2 us).
+struct Shape { int bn, ctas; };
+inline Shape pick_shape(int M_max, int N, int num_sms, int max_ctas) {
+  if (N < 256) return {128, 1};
   const long long tiles256 = (long long)((M_max + BLOCK_M - 1) / BLOCK_M) * ((N + 255) / 256);
-  return tiles256 >= 2LL * num_sms ? 256 : 128;
+  if (tiles256 < 2LL * num_sms) return {128, 1};
+  return {256, (max_ctas >= 2 && tiles256 >= 16LL * num_sms) ? 2 : 1};
 }
 
 }  // namespace tc
@@ -421,31 +558,33 @@ bool gemm_tc_supported(int N, int K) { return (K % tc::BLOCK_K) == 0 && (N % 16)
 const char* gemm_tc_last_error() { return tc::g_err.c_str(); }
 
 int gemm_tc_lse_ntiles(int M_max, int N, int num_sms) {
-  const int bn = tc::pick_bn(M_max, N, num_sms);
+  const int bn = tc::pick_shape(M_max, N, num_sms, 1).bn;
   return (N + bn - 1) / bn;
 }
 
 cudaError_t gemm_tc(int epi, const void* A, const void* W, void* C, int M_max, const int* m_ptr, int N, int K,
-                    int num_sms, cudaStream_t s) {
+                    int num_sms, int max_ctas, cudaStream_t s) {
   if (M_max <= 0) return cudaSuccess;
   if (!gemm_tc_supported(N, K)) return cudaErrorInvalidValue;
   std::lock_guard<std::mutex> lk(tc::g_mu);
   CUtensorMap ma, mw, mc;
   const int ckind = (epi == EPI_STORE || epi == EPI_RELU) ? 0 : 1;
-  const int bn = tc::pick_bn(M_max, N, num_sms);
-  if (!tc::get_map(A, M_max, K, 0, tc::BLOCK_M, &ma) || !tc::get_map(W, N, K, 0, bn, &mw)) return cudaErrorUnknown;
-  if (epi == EPI_LSE)
-    return bn == 256 ? tc::launch<EPI_LSE, 256>(ma, mw, ma, (float2*)C, M_max, m_ptr, N, K, num_sms, s)
-                     : tc::launch<EPI_LSE, 128>(ma, mw, ma, (float2*)C, M_max, m_ptr, N, K, num_sms, s);
+  // the fused log-softmax epilogue stays on single-CTA tiles: it is exp2-bound, and making the leader wait for the
+  // slower of two epilogues cost 11 % on the vocabulary head (measured)
+  const tc::Shape sh = tc::pick_shape(M_max, N, num_sms, epi == EPI_LSE ? 1 : max_ctas);
+  // the W box is the rows ONE CTA loads per stage
+  if (!tc::get_map(A, M_max, K, 0, tc::BLOCK_M, &ma) || !tc::get_map(W, N, K, 0, sh.bn / sh.ctas, &mw)) return cudaErrorUnknown;
+#define GRAM_TC_LAUNCH(E, MC, LP)                                                                              \
+  return sh.ctas == 2 ? tc::launch<E, 256, 2>(ma, mw, MC, LP, M_max, m_ptr, N, K, num_sms, s)                  \
+         : sh.bn == 256 ? tc::launch<E, 256, 1>(ma, mw, MC, LP, M_max, m_ptr, N, K, num_sms, s)                \
+                        : tc::launch<E, 128, 1>(ma, mw, MC, LP, M_max, m_ptr, N, K, num_sms, s)
+  if (epi == EPI_LSE) { GRAM_TC_LAUNCH(EPI_LSE, ma, (float2*)C); }
   if (!tc::get_map(C, M_max, N, ckind, tc::BLOCK_M, &mc)) return cudaErrorUnknown;
-#define GRAM_TC_LAUNCH(E)                                                                               \
-  return bn == 256 ? tc::launch<E, 256>(ma, mw, mc, nullptr, M_max, m_ptr, N, K, num_sms, s)           \
-                   : tc::launch<E, 128>(ma, mw, mc, nullptr, M_max, m_ptr, N, K, num_sms, s)
   switch (epi) {
-    case EPI_STORE: GRAM_TC_LAUNCH(EPI_STORE);
-    case EPI_RELU: GRAM_TC_LAUNCH(EPI_RELU);
-    case EPI_RESID: GRAM_TC_LAUNCH(EPI_RESID);
-    case EPI_F32: GRAM_TC_LAUNCH(EPI_F32);
+    case EPI_STORE: GRAM_TC_LAUNCH(EPI_STORE, mc, nullptr);
+    case EPI_RELU: GRAM_TC_LAUNCH(EPI_RELU, mc, nullptr);
+    case EPI_RESID: GRAM_TC_LAUNCH(EPI_RESID, mc, nullptr);
+    case EPI_F32: GRAM_TC_LAUNCH(EPI_F32, mc, nullptr);
     default: return cudaErrorInvalidValue;
   }
 #undef GRAM_TC_LAUNCH

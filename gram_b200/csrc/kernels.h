@@ -35,8 +35,9 @@ cudaError_t gemm_simt(int dtype, int epi, const void* A, const void* W, void* C,
 
 // ---- gemm_tc.cu (tcgen05 / TMEM / TMA, bf16) -----------------------------------------------------
 bool gemm_tc_supported(int N, int K);
+// max_ctas: 2 = large problems run on CTA pairs (tcgen05 cta_group::2, 256x256 tiles), 1 = single-CTA tiles only
 cudaError_t gemm_tc(int epi, const void* A, const void* W, void* C, int M_max, const int* m_ptr, int N, int K,
-                    int num_sms, cudaStream_t s);
+                    int num_sms, int max_ctas, cudaStream_t s);
 const char* gemm_tc_last_error();
 // number of column tiles (= per-row partials) the EPI_LSE epilogue writes for this problem
 int gemm_tc_lse_ntiles(int M_max, int N, int num_sms);

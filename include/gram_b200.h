@@ -56,9 +56,10 @@ enum {
   GRAM_FLAG_SIMT_GEMM = 1,         /* force the CUDA-core GEMM even for bf16 (debug / A-B timing) */
   GRAM_FLAG_KEEP_LOGITS = 2,       /* record per-step taps (lse, beam scores, prefixes) for parity tests */
   GRAM_FLAG_SIMT_ATTN = 4,         /* force the CUDA-core attention kernels even for bf16 (A-B timing)   */
-  GRAM_FLAG_TC_ENC_ATTN = 8        /* encoder attention through the tcgen05/TMEM kernel (attention_tc.cu): numerically
+  GRAM_FLAG_TC_ENC_ATTN = 8,       /* encoder attention through the tcgen05/TMEM kernel (attention_tc.cu): numerically
                                       verified, but one (passage, head) per CTA without cross-item pipelining it is
                                       ~15 % slower than the pipelined mma.sync kernel, so it is opt-in for now */
+  GRAM_FLAG_GEMM_1CTA = 16         /* keep every tcgen05 GEMM on single-CTA tiles (no cta_group::2 pairs; A-B timing) */
 };
 
 /* ---- lifetime -------------------------------------------------------------------------------- */
@@ -148,7 +149,7 @@ int gram_profile_end(gram_handle* h, float* ms_per_class /*[GRAM_K_COUNT]*/, int
 
 /* ---- single-operator entry points (unit parity tests and roofline measurement) ------------------ */
 /* C[M,N] = A[M,K] * W[N,K]^T on device pointers.  dtype as in gram_config; impl 0 = SIMT fp32-accumulate,
- * 1 = tcgen05 (bf16 only).  epilogue: 0 store (dtype), 1 relu+store (dtype), 2 C_f32 += acc, 3 store fp32. */
+ * 1 = tcgen05 (bf16 only; CTA pairs on large problems), 2 = tcgen05 single-CTA tiles only.  epilogue: 0 store (dtype), 1 relu+store (dtype), 2 C_f32 += acc, 3 store fp32. */
 int gram_op_gemm(int32_t device, int32_t dtype, int32_t impl, int32_t epilogue, const void* A, const void* W,
                  void* C, int32_t M, int32_t N, int32_t K, void* stream);
 /* decoder cross-attention over an in-place K/V memory: q [users*K, H*dk], kv [kv_rows, 2*H*dk] (K|V),

@@ -60,12 +60,20 @@ if __name__ == "__main__":
                       (38000, 512, 512), (38001, 784, 128), (20000, 32128, 64)]:   # the last three take the 128x256 tile
         for epi in (0, 1, 2, 3):
             allok &= run(M, N, K, epi)
+    print("CTA pairs (impl 1) against single-CTA tiles (impl 2) on shapes large enough for 256x256 pair tiles")
+    for (M, N, K) in [(38000, 512, 512), (38001, 784, 128), (20000, 32128, 64), (37889, 1536, 512), (75776, 2048, 512),
+                      (40000, 512, 2048), (18880, 512, 512), (18880, 2048, 512)]:
+        for epi in (0, 1, 2, 3):
+            allok &= run(M, N, K, epi, impl=1)
+            allok &= run(M, N, K, epi, impl=2)
     print("ALL OK" if allok else "SOME FAILED")
     if "--time" in sys.argv:
         print("timing")
         for (M, N, K, epi) in [(262144, 1536, 512, 0), (262144, 512, 512, 2), (262144, 2048, 512, 1), (262144, 512, 2048, 2),
-                               (262144, 6144, 512, 0), (5120, 1536, 512, 0), (5120, 512, 512, 2), (5120, 2048, 512, 1),
+                               (262144, 6144, 512, 0), (1048576, 1536, 512, 0), (1048576, 2048, 512, 1), (18880, 32128, 512, 3), (18880, 512, 512, 2), (18880, 2048, 512, 1), (5120, 1536, 512, 0), (5120, 512, 512, 2), (5120, 2048, 512, 1),
                                (5120, 512, 2048, 2), (5120, 32128, 512, 3)]:
             run(M, N, K, epi, impl=1, check=False, iters=10)
-            run(M, N, K, epi, impl=0, check=False, iters=2)
+            run(M, N, K, epi, impl=2, check=False, iters=10)
+            if "--simt" in sys.argv:
+                run(M, N, K, epi, impl=0, check=False, iters=2)
     sys.exit(0 if allok else 1)

@@ -104,6 +104,36 @@ def test_gemm_tcgen05(shape, epi):
     assert rel_err(Cd, ref) < (8e-3 if epi in (0, 1) else 5e-6)
 
 
+@pytest.mark.parametrize("shape", [(151553, 1024, 64), (76000, 784, 128), (40000, 2048, 512)])
+@pytest.mark.parametrize("epi", [0, 1, 2, 3])
+def test_gemm_tcgen05_cta_pairs(shape, epi):
+    """Problems with >= 16 tiles per SM run on CTA pairs (tcgen05 cta_group::2, 256x256 tiles; impl 1); impl 2 keeps
+    single-CTA tiles.  Both against fp64, and bit-identical to each other (same accumulation order per element).
+    Shapes: an odd number of 128-row blocks (the second CTA of the last pair is entirely out of range), a ragged N."""
+    from gram_b200 import _cabi
+    lib = _cabi.load_library()
+    M, N, K = shape
+    g = torch.Generator(device="cpu").manual_seed(M + 3 * N + K + epi)
+    Ad = torch.randn(M, K, generator=g).cuda().to(torch.bfloat16)
+    Wd = (torch.randn(N, K, generator=g) * (K ** -0.5)).cuda().to(torch.bfloat16)
+    ref = Ad.float() @ Wd.float().t()                       # fp32 matmul of bf16 operands (TF32 is off in conftest)
+    if epi == 1:
+        ref = ref.clamp_min(0)
+    if epi == 2:
+        ref = ref + 1.0
+    outs = []
+    for impl in (1, 2):
+        Cd = torch.zeros(M, N, device="cuda", dtype=torch.bfloat16) if epi in (0, 1) else torch.ones(M, N, device="cuda")
+        rc = lib.gram_op_gemm(0, 1, impl, epi, C.c_void_p(Ad.data_ptr()), C.c_void_p(Wd.data_ptr()),
+                              C.c_void_p(Cd.data_ptr()), M, N, K, None)
+        assert rc == 0, lib.gram_last_error(None)
+        torch.cuda.synchronize()
+        err = float((Cd.float() - ref).abs().max() / ref.abs().max())        # on the device: these are 100M+ elements
+        assert err < (8e-3 if epi in (0, 1) else 2e-5)
+        outs.append(Cd)
+    assert torch.equal(outs[0], outs[1])
+
+
 @pytest.mark.parametrize("dtype,impl", [("fp32", 0), ("bf16", 0), ("bf16", 1)])
 @pytest.mark.parametrize("dk,H,K", [(16, 4, 4), (64, 8, 20), (64, 12, 50), (64, 8, 1), (64, 4, 33)])
 def test_cross_attention_op(dtype, impl, dk, H, K):
