@@ -23,6 +23,7 @@ EXPORTED_SYMBOLS = [
     "gram_set_rel_buckets", "gram_finalize_weights", "gram_set_trie", "gram_encode", "gram_generate",
     "gram_get_memory", "gram_decoder_logits", "gram_get_step_taps", "gram_get_stats",
     "gram_profile_begin", "gram_profile_end", "gram_op_gemm", "gram_op_cross_attention",
+    "gram_cache_items", "gram_encode_cached", "gram_check_errors",
 ]
 
 
@@ -89,6 +90,12 @@ def load_library():
     lib.gram_set_trie.restype = C.c_int
     lib.gram_encode.argtypes = [vp, i64p, u8p, i32, i32, i32, vp]
     lib.gram_encode.restype = C.c_int
+    lib.gram_cache_items.argtypes = [vp, i64p, u8p, i32, i32, vp]
+    lib.gram_cache_items.restype = C.c_int
+    lib.gram_encode_cached.argtypes = [vp, i64p, u8p, i32p, i32, i32, i32, vp]
+    lib.gram_encode_cached.restype = C.c_int
+    lib.gram_check_errors.argtypes = [vp, vp]
+    lib.gram_check_errors.restype = C.c_int
     lib.gram_generate.argtypes = [vp, i64p, u8p, i32, i32, i32, i32, i32, i32, C.c_void_p, i64p, i32p, f32p, vp]
     lib.gram_generate.restype = C.c_int
     lib.gram_get_memory.argtypes = [vp, f32p, vp]

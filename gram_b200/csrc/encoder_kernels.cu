@@ -118,6 +118,111 @@ cudaError_t enc_pack(const int64_t* ids, const uint8_t* mask, int B, int N, int 
 }
 
 // ------------------------------------------------------------------------------------------------
+// per-item encoder-state cache.  Every passage except the user prompt is a function
+// of the ITEM only (reference src/utils/indexing.py:209-211,315-320), passages are encoded independently
+// (src/model/gram.py:206-216) and the passage-position row is added AFTER the encoder (src/model/gram.py:238-249):
+// the final-normed encoder rows of an item passage are therefore identical for every user and are kept, as fp32
+// before the position add, in a table [n_items][L][D].  A cached encode runs the encoder stack on the user prompts
+// only and assembles each user's memory from prompt rows + cached item rows + position rows -- bit-identical to
+// encoding all passages (same kernels per passage, same separately-rounded position add).
+// ------------------------------------------------------------------------------------------------
+// packed fp32 rows of a chunk of items ([B, N, L] layout, item = item0 + passage) -> table rows item*L + l
+__global__ void cache_scatter_kernel(const float* __restrict__ src, const int* __restrict__ row_src,
+                                     const uint8_t* __restrict__ tok_valid, const int* __restrict__ m_ptr, int D,
+                                     long long row0, float* __restrict__ item_mem, uint8_t* __restrict__ item_valid) {
+  const int M = *m_ptr;
+  const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (row >= M) return;
+  const long long dst = row0 + row_src[row];
+  const float* s = src + (size_t)row * D;
+  float* d = item_mem + (size_t)dst * D;
+  for (int c = lane * 4; c < D; c += 128) store4(d + c, load4(s + c));
+  if (lane == 0) item_valid[dst] = tok_valid[row];
+}
+
+cudaError_t cache_scatter(const float* src, const PackMeta& pm, int M_max, int D, long long row0, float* item_mem,
+                          uint8_t* item_valid, cudaStream_t s) {
+  if (M_max <= 0) return cudaSuccess;
+  cache_scatter_kernel<<<(M_max + 7) / 8, 256, 0, s>>>(src, pm.row_src, pm.tok_valid, pm.total, D, row0, item_mem, item_valid);
+  return cudaGetLastError();
+}
+
+// passage lengths of the full user layout [B][1 + NI]: passage 0 = the prompt, passage 1 + j = item items[b][j]
+__global__ void cached_plen_kernel(const int* __restrict__ prompt_len, const int* __restrict__ items,
+                                   const int* __restrict__ item_len, int n_items, int B, int NI, int* __restrict__ plen,
+                                   int* __restrict__ err) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * (NI + 1)) return;
+  const int b = i / (NI + 1), n = i % (NI + 1);
+  int len = 0;
+  if (n == 0) {
+    len = prompt_len[b];
+  } else {
+    const int it = items[b * NI + n - 1];
+    if (it >= n_items) atomicExch(err, 3);
+    else if (it >= 0) len = item_len[it];
+  }
+  plen[i] = len;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(128)
+cached_assemble_kernel(PackMeta pm, const int* __restrict__ prompt_off, const uint8_t* __restrict__ prompt_valid,
+                       const float* __restrict__ prompt_rows, const int* __restrict__ items,
+                       const float* __restrict__ item_mem, const uint8_t* __restrict__ item_valid,
+                       const float* __restrict__ pos_table, int NI, int L, int D, T* __restrict__ mem) {
+  const int p = blockIdx.x;
+  const int len = pm.plen[p];
+  if (len == 0) return;
+  const int off = pm.poff[p];
+  const int b = p / (NI + 1), n = p % (NI + 1);
+  const float* src;
+  const uint8_t* vsrc;
+  if (n == 0) {
+    src = prompt_rows + (size_t)prompt_off[b] * D;
+    vsrc = prompt_valid + prompt_off[b];
+  } else {
+    const size_t r0 = (size_t)items[b * NI + n - 1] * L;
+    src = item_mem + r0 * D;
+    vsrc = item_valid + r0;
+  }
+  const float* pe = pos_table ? pos_table + (size_t)n * D : nullptr;
+  const int q = D / 4;
+  for (int i = threadIdx.x; i < len * q; i += blockDim.x) {
+    const int l = i / q, c = (i % q) * 4;
+    float4 v = load4(src + (size_t)l * D + c);
+    if (pe) {
+      const float4 e = load4(pe + c);
+      v.x = __fadd_rn(v.x, e.x); v.y = __fadd_rn(v.y, e.y); v.z = __fadd_rn(v.z, e.z); v.w = __fadd_rn(v.w, e.w);
+    }
+    store4(mem + (size_t)(off + l) * D + c, v);
+  }
+  for (int l = threadIdx.x; l < len; l += blockDim.x) {
+    pm.tok_valid[off + l] = vsrc[l];
+    pm.tok_pos[off + l] = n;
+    pm.row_src[off + l] = p * L + l;
+    pm.tok_id[off + l] = 0;
+  }
+}
+
+cudaError_t cached_pack_assemble(int dtype, const PackMeta& pm, const PackMeta& prompt_pm, const float* prompt_rows,
+                                 const int* items, const float* item_mem, const uint8_t* item_valid, const int* item_len,
+                                 int n_items, const float* pos_table, int B, int NI, int L, int D, void* mem,
+                                 cudaStream_t s) {
+  const int P = B * (NI + 1);
+  cached_plen_kernel<<<(P + 255) / 256, 256, 0, s>>>(prompt_pm.plen, items, item_len, n_items, B, NI, pm.plen, pm.err);
+  passage_scan_kernel<<<1, 1024, 0, s>>>(pm.plen, P, NI + 1, B, pm.poff, pm.ustart, pm.total);
+  if (dtype == 0)
+    cached_assemble_kernel<float><<<P, 128, 0, s>>>(pm, prompt_pm.poff, prompt_pm.tok_valid, prompt_rows, items, item_mem,
+                                                    item_valid, pos_table, NI, L, D, (float*)mem);
+  else
+    cached_assemble_kernel<bf16><<<P, 128, 0, s>>>(pm, prompt_pm.poff, prompt_pm.tok_valid, prompt_rows, items, item_mem,
+                                                   item_valid, pos_table, NI, L, D, (bf16*)mem);
+  user_order_kernel<<<1, 1024, 0, s>>>(pm.ustart, B, pm.uorder);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
 // embedding gather: x[row] = table[tok_id[row]]   (fp32 residual stream)
 // ------------------------------------------------------------------------------------------------
 template <typename T>
@@ -164,11 +269,14 @@ __global__ void rmsnorm_rows_kernel(const float* __restrict__ x, const float* __
     const float4 v = load4(xr + c);
     const float4 g = load4(w + c);
     float4 o;
-    o.x = g.x * (v.x * r); o.y = g.y * (v.y * r); o.z = g.z * (v.z * r); o.w = g.w * (v.w * r);
+    // separately rounded multiply / add, as the reference computes them (weight * normed, then + position row); no
+    // FMA contraction, so the cached-item path (cached_assemble_kernel) reproduces these bits exactly
+    o.x = __fmul_rn(g.x, __fmul_rn(v.x, r)); o.y = __fmul_rn(g.y, __fmul_rn(v.y, r));
+    o.z = __fmul_rn(g.z, __fmul_rn(v.z, r)); o.w = __fmul_rn(g.w, __fmul_rn(v.w, r));
     if (scale != 1.0f) { o.x *= scale; o.y *= scale; o.z *= scale; o.w *= scale; }
     if (pe) {
       const float4 q = load4(pe + c);
-      o.x += q.x; o.y += q.y; o.z += q.z; o.w += q.w;
+      o.x = __fadd_rn(o.x, q.x); o.y = __fadd_rn(o.y, q.y); o.z = __fadd_rn(o.z, q.z); o.w = __fadd_rn(o.w, q.w);
     }
     store4(yr + c, o);
   }

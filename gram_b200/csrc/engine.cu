@@ -78,6 +78,14 @@ struct gram_handle {
   int enc_B = 0, enc_N = 0, enc_L = 0;
   bool encoded = false;
 
+  // per-item encoder-state cache: fp32 final-normed rows before the position add
+  float* item_mem = nullptr;             // [n_items * item_L, D]
+  uint8_t* item_valid = nullptr;         // [n_items * item_L]
+  int* item_len = nullptr;               // [n_items]
+  int n_items = 0, item_L = 0;
+  PackMeta pm_prompt{};                  // packed layout of the user prompts alone (P = B passages)
+  int* d_items = nullptr;                // staging for the item-index matrix [max_users, max_passages]
+
   // decoder workspace
   int Rcap = 0;
   float* dx = nullptr;
@@ -123,6 +131,14 @@ namespace {
 int fail(gram_handle* h, int code, const std::string& msg) {
   h->err = msg;
   return code;
+}
+
+void free_item_cache(gram_handle* h) {
+  if (h->item_mem) cudaFree(h->item_mem);
+  if (h->item_valid) cudaFree(h->item_valid);
+  if (h->item_len) cudaFree(h->item_len);
+  h->item_mem = nullptr; h->item_valid = nullptr; h->item_len = nullptr;
+  h->n_items = 0; h->item_L = 0;
 }
 
 template <typename P>
@@ -287,6 +303,36 @@ std::vector<std::string> required_weights(const gram_handle* h) {
 int next_pow2(int v) { int n = 1; while (n < v) n <<= 1; return n; }
 
 // ---- encoder --------------------------------------------------------------------------------------
+// embedding + all encoder blocks over the packed rows described by `pm` (P passages of at most L tokens); leaves the
+// residual stream in h->x, ready for the final norm
+int encoder_stack(gram_handle* h, const PackMeta& pm, int P, int L, int Mmax, cudaStream_t s) {
+  const gram_config& c = h->cfg;
+  const int* mp = pm.total;
+  const int D = h->D, HD = h->HD, F = h->F;
+  CKL(GRAM_K_OTHER, embed_rows(c.dtype, h->shared, pm.tok_id, h->x, Mmax, mp, D, s));
+  for (int l = 0; l < h->Le; ++l) {
+    const LayerW& W = h->enc[l];
+    CKL(GRAM_K_NORM_ENC, rmsnorm_rows(c.dtype, h->x, W.ln0, h->xn, Mmax, mp, D, c.ln_eps, 1.f, nullptr, nullptr, s));
+    RC(gemm(h, GRAM_K_GEMM_ENC, EPI_STORE, h->xn, W.qkv, h->qkv, Mmax, mp, 3 * HD, D, s));
+    if (c.dtype == GRAM_DTYPE_BF16 && (c.flags & GRAM_FLAG_TC_ENC_ATTN) && !(c.flags & GRAM_FLAG_SIMT_ATTN) &&
+        enc_attention_tc_supported(h->dk, L, h->Lb)) {
+      CKL(GRAM_K_ENC_ATTN, enc_attention_tc(h->qkv, (size_t)h->Mcap + 256, h->ao, pm.plen, pm.poff, pm.tok_valid,
+                                            h->enc_bias_lut, h->Lb, P, h->H, s));
+    } else if (c.dtype == GRAM_DTYPE_BF16 && !(c.flags & GRAM_FLAG_SIMT_ATTN) && enc_attention_mma_supported(h->dk, L)) {
+      CKL(GRAM_K_ENC_ATTN, enc_attention_mma(h->qkv, h->ao, pm.plen, pm.poff, pm.tok_valid, h->enc_bias_lut,
+                                             h->Lb, P, h->H, L, s));
+    } else {
+      CKL(GRAM_K_ENC_ATTN, enc_attention(c.dtype, h->qkv, h->ao, pm.plen, pm.poff, pm.tok_valid,
+                                         h->enc_bias_lut, h->Lb, P, h->H, h->dk, L, s));
+    }
+    RC(gemm(h, GRAM_K_GEMM_ENC, EPI_RESID, h->ao, W.o, h->x, Mmax, mp, D, HD, s));
+    CKL(GRAM_K_NORM_ENC, rmsnorm_rows(c.dtype, h->x, W.ln1, h->xn, Mmax, mp, D, c.ln_eps, 1.f, nullptr, nullptr, s));
+    RC(gemm(h, GRAM_K_GEMM_ENC, EPI_RELU, h->xn, W.wi, h->ff, Mmax, mp, F, D, s));
+    RC(gemm(h, GRAM_K_GEMM_ENC, EPI_RESID, h->ff, W.wo, h->x, Mmax, mp, D, F, s));
+  }
+  return GRAM_OK;
+}
+
 int run_encode(gram_handle* h, const int64_t* ids, const uint8_t* mask, int B, int N, int L, cudaStream_t s) {
   const gram_config& c = h->cfg;
   if (!h->weights_ready) return fail(h, GRAM_ERR_STATE, "gram_encode: weights not finalised");
@@ -304,35 +350,13 @@ int run_encode(gram_handle* h, const int64_t* ids, const uint8_t* mask, int B, i
   h->encoded = false;
   h->enc_B = B; h->enc_N = N; h->enc_L = L;
   const int Mmax = (int)n;
-  const int* mp = h->pm.total;
-  const int D = h->D, HD = h->HD, F = h->F;
   CKL(GRAM_K_OTHER, enc_pack(dids, dmask, B, N, L, h->pm, s));
   h->launches += 3;   // enc_pack issues four kernels
-  CKL(GRAM_K_OTHER, embed_rows(c.dtype, h->shared, h->pm.tok_id, h->x, Mmax, mp, D, s));
-  for (int l = 0; l < h->Le; ++l) {
-    const LayerW& W = h->enc[l];
-    CKL(GRAM_K_NORM_ENC, rmsnorm_rows(c.dtype, h->x, W.ln0, h->xn, Mmax, mp, D, c.ln_eps, 1.f, nullptr, nullptr, s));
-    RC(gemm(h, GRAM_K_GEMM_ENC, EPI_STORE, h->xn, W.qkv, h->qkv, Mmax, mp, 3 * HD, D, s));
-    if (c.dtype == GRAM_DTYPE_BF16 && (c.flags & GRAM_FLAG_TC_ENC_ATTN) && !(c.flags & GRAM_FLAG_SIMT_ATTN) &&
-        enc_attention_tc_supported(h->dk, L, h->Lb)) {
-      CKL(GRAM_K_ENC_ATTN, enc_attention_tc(h->qkv, (size_t)h->Mcap + 256, h->ao, h->pm.plen, h->pm.poff, h->pm.tok_valid,
-                                            h->enc_bias_lut, h->Lb, B * N, h->H, s));
-    } else if (c.dtype == GRAM_DTYPE_BF16 && !(c.flags & GRAM_FLAG_SIMT_ATTN) && enc_attention_mma_supported(h->dk, L)) {
-      CKL(GRAM_K_ENC_ATTN, enc_attention_mma(h->qkv, h->ao, h->pm.plen, h->pm.poff, h->pm.tok_valid, h->enc_bias_lut,
-                                             h->Lb, B * N, h->H, L, s));
-    } else {
-      CKL(GRAM_K_ENC_ATTN, enc_attention(c.dtype, h->qkv, h->ao, h->pm.plen, h->pm.poff, h->pm.tok_valid,
-                                         h->enc_bias_lut, h->Lb, B * N, h->H, h->dk, L, s));
-    }
-    RC(gemm(h, GRAM_K_GEMM_ENC, EPI_RESID, h->ao, W.o, h->x, Mmax, mp, D, HD, s));
-    CKL(GRAM_K_NORM_ENC, rmsnorm_rows(c.dtype, h->x, W.ln1, h->xn, Mmax, mp, D, c.ln_eps, 1.f, nullptr, nullptr, s));
-    RC(gemm(h, GRAM_K_GEMM_ENC, EPI_RELU, h->xn, W.wi, h->ff, Mmax, mp, F, D, s));
-    RC(gemm(h, GRAM_K_GEMM_ENC, EPI_RESID, h->ff, W.wo, h->x, Mmax, mp, D, F, s));
-  }
-  CKL(GRAM_K_NORM_ENC, rmsnorm_rows(c.dtype, h->x, h->enc_final_ln, h->mem, Mmax, mp, D, c.ln_eps, 1.f,
+  RC(encoder_stack(h, h->pm, B * N, L, Mmax, s));
+  CKL(GRAM_K_NORM_ENC, rmsnorm_rows(c.dtype, h->x, h->enc_final_ln, h->mem, Mmax, h->pm.total, h->D, c.ln_eps, 1.f,
                                  h->pos_emb, h->pos_emb ? h->pm.tok_pos : nullptr, s));
   // cross-attention K/V of every decoder layer, written in place in the layout kernel (b) reads
-  RC(gemm(h, GRAM_K_GEMM_KV, EPI_STORE, h->mem, h->ckv_w, h->ckv, Mmax, mp, h->Ld * 2 * HD, D, s));
+  RC(gemm(h, GRAM_K_GEMM_KV, EPI_STORE, h->mem, h->ckv_w, h->ckv, Mmax, h->pm.total, h->Ld * 2 * h->HD, h->D, s));
   h->encoded = true;
   return GRAM_OK;
 }
@@ -392,6 +416,7 @@ const char* gram_last_error(const gram_handle* h) { return h ? h->err.c_str() : 
 void gram_destroy(gram_handle* h) {
   if (!h) return;
   cudaSetDevice(h->cfg.device);
+  free_item_cache(h);
   for (void* p : h->allocs) cudaFree(p);
   for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
   if (h->len_pow_ev) cudaEventDestroy(h->len_pow_ev);
@@ -649,6 +674,117 @@ int gram_encode(gram_handle* h, const int64_t* ids, const uint8_t* mask, int32_t
   return run_encode(h, ids, mask, B, N, L, (cudaStream_t)stream);
 }
 
+// ---- per-item encoder-state cache ((f)-1) ---------------------------------------------------------------------
+int gram_cache_items(gram_handle* h, const int64_t* ids, const uint8_t* mask, int32_t n_items, int32_t L, void* stream) {
+  if (!h || !ids || !mask) return GRAM_ERR_INVALID;
+  CK(cudaSetDevice(h->cfg.device));
+  cudaStream_t s = (cudaStream_t)stream;
+  const gram_config& c = h->cfg;
+  if (!h->weights_ready) return fail(h, GRAM_ERR_STATE, "gram_cache_items: weights not finalised");
+  if (n_items <= 0 || L <= 0 || L > c.max_seq_len) return fail(h, GRAM_ERR_INVALID, "gram_cache_items: bad n_items / L");
+  CK(cudaStreamSynchronize(s));
+  free_item_cache(h);
+  h->encoded = false;
+  const size_t rows = (size_t)n_items * L;
+  {
+    cudaError_t e1 = cudaMalloc(&h->item_mem, rows * h->D * 4), e2 = cudaMalloc(&h->item_valid, rows),
+                e3 = cudaMalloc(&h->item_len, (size_t)n_items * 4);
+    if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess) {
+      cudaGetLastError();
+      free_item_cache(h);
+      return fail(h, GRAM_ERR_CUDA, "gram_cache_items: cudaMalloc of the item table failed");
+    }
+  }
+  CK(cudaMemsetAsync(h->item_valid, 0, rows, s));
+  if (!h->pm_prompt.plen) {
+    // layout arrays of the prompt-only encoder pass (one passage per user)
+    const size_t U = (size_t)c.max_users, Mp = U * c.max_seq_len + 256;
+    int rc;
+#define DAC2(ptr, bytes) do { rc = dalloc(h, &(ptr), (bytes)); if (rc) return rc; } while (0)
+    DAC2(h->pm_prompt.plen, U * 4); DAC2(h->pm_prompt.poff, (U + 1) * 4); DAC2(h->pm_prompt.ustart, (U + 1) * 4);
+    DAC2(h->pm_prompt.uorder, (U + 1) * 4); DAC2(h->pm_prompt.total, 16);
+    DAC2(h->pm_prompt.tok_id, Mp * 4); DAC2(h->pm_prompt.tok_pos, Mp * 4); DAC2(h->pm_prompt.tok_valid, Mp);
+    DAC2(h->pm_prompt.row_src, Mp * 4);
+    DAC2(h->d_items, U * c.max_passages * 4);
+#undef DAC2
+    h->pm_prompt.err = h->pm.err;
+    h->pm_prompt.vocab = h->V;
+  }
+  // encode the items in chunks shaped like an ordinary batch [Bc, N, L] (item = first + b*N + n)
+  const int N = c.max_passages;
+  int64_t per_chunk = (int64_t)c.max_users * N;
+  if (per_chunk * L > h->Mcap) per_chunk = h->Mcap / L;
+  if (per_chunk <= 0) return fail(h, GRAM_ERR_INVALID, "gram_cache_items: token capacity below one passage");
+  const bool dev_in = is_device_ptr(ids), dev_mask = is_device_ptr(mask);
+  for (int64_t first = 0; first < n_items; first += per_chunk) {
+    const int64_t cnt = std::min<int64_t>(per_chunk, n_items - first);
+    const int Bc = (int)((cnt + N - 1) / N);
+    const size_t full = (size_t)Bc * N * L, have = (size_t)cnt * L;
+    CK(cudaMemsetAsync(h->d_mask, 0, full, s));
+    CK(cudaMemsetAsync(h->d_ids, 0, full * 8, s));
+    CK(cudaMemcpyAsync(h->d_ids, ids + first * L, have * 8, dev_in ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(h->d_mask, mask + first * L, have, dev_mask ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, s));
+    const int Mmax = (int)full;
+    CKL(GRAM_K_OTHER, enc_pack(h->d_ids, h->d_mask, Bc, N, L, h->pm, s));
+    RC(encoder_stack(h, h->pm, Bc * N, L, Mmax, s));
+    // final norm in fp32, WITHOUT the position row (h->ff is free after the last block and holds >= Mcap*D floats)
+    CKL(GRAM_K_NORM_ENC, rmsnorm_rows(GRAM_DTYPE_F32, h->x, h->enc_final_ln, h->ff, Mmax, h->pm.total, h->D, c.ln_eps, 1.f,
+                                   nullptr, nullptr, s));
+    CKL(GRAM_K_OTHER, cache_scatter((const float*)h->ff, h->pm, Mmax, h->D, first * L, h->item_mem, h->item_valid, s));
+    CK(cudaMemcpyAsync(h->item_len + first, h->pm.plen, (size_t)cnt * 4, cudaMemcpyDeviceToDevice, s));
+    if (!dev_in || !dev_mask) CK(cudaStreamSynchronize(s));     // the caller's host buffers are consumed per chunk
+  }
+  CK(cudaMemcpyAsync(&h->h_flags[0], h->pm.err, 4, cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  if (h->h_flags[0] != 0) {
+    cudaMemsetAsync(h->pm.err, 0, 4, s);
+    free_item_cache(h);
+    return fail(h, GRAM_ERR_INVALID, "gram_cache_items: input token id outside [0, vocab_size)");
+  }
+  h->n_items = n_items; h->item_L = L;
+  return GRAM_OK;
+}
+
+int gram_encode_cached(gram_handle* h, const int64_t* prompt_ids, const uint8_t* prompt_mask, const int32_t* items,
+                       int32_t B, int32_t NI, int32_t L, void* stream) {
+  if (!h || !prompt_ids || !prompt_mask || (NI > 0 && !items)) return GRAM_ERR_INVALID;
+  CK(cudaSetDevice(h->cfg.device));
+  cudaStream_t s = (cudaStream_t)stream;
+  const gram_config& c = h->cfg;
+  if (!h->item_mem) return fail(h, GRAM_ERR_STATE, "gram_encode_cached: no item table (gram_cache_items)");
+  if (L != h->item_L) return fail(h, GRAM_ERR_INVALID, "gram_encode_cached: L differs from the L the item table was built with");
+  const int N = NI + 1;
+  if (B <= 0 || NI < 0) return fail(h, GRAM_ERR_INVALID, "gram_encode_cached: empty batch");
+  if (B > c.max_users || N > c.max_passages) return fail(h, GRAM_ERR_INVALID, "gram_encode_cached: B/N exceed the capacities given to gram_create");
+  if ((int64_t)B * N * L > h->Mcap) return fail(h, GRAM_ERR_INVALID, "gram_encode_cached: B*N*L exceeds max_tokens");
+  if (c.n_positions > 0 && N > c.n_positions) return fail(h, GRAM_ERR_INVALID, "gram_encode_cached: more passages than rows in the position table");
+  h->launches = 0;
+  const size_t n = (size_t)B * L;
+  const int64_t* dids = prompt_ids;
+  const uint8_t* dmask = prompt_mask;
+  const int* ditems = items;
+  if (!is_device_ptr(prompt_ids)) { CK(cudaMemcpyAsync(h->d_ids, prompt_ids, n * 8, cudaMemcpyHostToDevice, s)); dids = h->d_ids; }
+  if (!is_device_ptr(prompt_mask)) { CK(cudaMemcpyAsync(h->d_mask, prompt_mask, n, cudaMemcpyHostToDevice, s)); dmask = h->d_mask; }
+  if (NI > 0 && !is_device_ptr(items)) { CK(cudaMemcpyAsync(h->d_items, items, (size_t)B * NI * 4, cudaMemcpyHostToDevice, s)); ditems = h->d_items; }
+  h->encoded = false;
+  h->enc_B = B; h->enc_N = N; h->enc_L = L;
+  // 1. the encoder stack on the prompts alone
+  CKL(GRAM_K_OTHER, enc_pack(dids, dmask, B, 1, L, h->pm_prompt, s));
+  h->launches += 3;
+  RC(encoder_stack(h, h->pm_prompt, B, L, (int)n, s));
+  CKL(GRAM_K_NORM_ENC, rmsnorm_rows(GRAM_DTYPE_F32, h->x, h->enc_final_ln, h->ff, (int)n, h->pm_prompt.total, h->D, c.ln_eps,
+                                 1.f, nullptr, nullptr, s));
+  // 2. user layout + memory = prompt rows / cached item rows + position rows
+  const int Mmax = (int)((size_t)B * N * L);
+  CKL(GRAM_K_OTHER, cached_pack_assemble(c.dtype, h->pm, h->pm_prompt, (const float*)h->ff, ditems, h->item_mem, h->item_valid,
+                                         h->item_len, h->n_items, h->pos_emb, B, NI, L, h->D, h->mem, s));
+  h->launches += 3;
+  // 3. cross-attention K/V, as in the uncached path
+  RC(gemm(h, GRAM_K_GEMM_KV, EPI_STORE, h->mem, h->ckv_w, h->ckv, Mmax, h->pm.total, h->Ld * 2 * h->HD, h->D, s));
+  h->encoded = true;
+  return GRAM_OK;
+}
+
 int gram_generate(gram_handle* h, const int64_t* ids, const uint8_t* mask, int32_t B, int32_t N, int32_t L, int32_t K,
                   int32_t R_ret, int32_t max_length, const double* len_pow, int64_t* out_seq, int32_t* out_width,
                   float* out_scores, void* stream) {
@@ -660,9 +796,9 @@ int gram_generate(gram_handle* h, const int64_t* ids, const uint8_t* mask, int32
   if (K <= 0 || K > c.max_beams) return fail(h, GRAM_ERR_INVALID, "gram_generate: num_beams exceeds max_beams");
   if (R_ret <= 0 || R_ret > K) return fail(h, GRAM_ERR_INVALID, "`num_return_sequences` has to be smaller or equal to `num_beams`.");
   if (max_length < 2 || max_length > c.max_length) return fail(h, GRAM_ERR_INVALID, "gram_generate: max_length outside [2, cfg.max_length]");
-  h->launches = 0;
   if (ids) {
     if (!mask) return GRAM_ERR_INVALID;
+    h->launches = 0;
     RC(run_encode(h, ids, mask, B, N, L, s));
   } else {
     if (!h->encoded) return fail(h, GRAM_ERR_STATE, "gram_generate: ids == NULL but nothing has been encoded");
@@ -716,8 +852,9 @@ int gram_generate(gram_handle* h, const int64_t* ids, const uint8_t* mask, int32
     if (h->h_flags[0] != 0) {
       const int code = h->h_flags[0];
       cudaMemsetAsync(bs.err, 0, 4, s);
-      return fail(h, GRAM_ERR_INVALID, code == 2 ? "gram_generate: input token id outside [0, vocab_size)"
-                                                 : "gram_generate: candidate buffer overflow (trie fan-out larger than declared)");
+      return fail(h, GRAM_ERR_INVALID, code == 2   ? "gram_generate: input token id outside [0, vocab_size)"
+                                       : code == 3 ? "gram_generate: item index outside the cached item table"
+                                                   : "gram_generate: candidate buffer overflow (trie fan-out larger than declared)");
     }
   }
   return GRAM_OK;
@@ -782,6 +919,20 @@ int gram_get_step_taps(gram_handle* h, float* lse, float* beam_scores, int32_t* 
   if (beam_tokens) CK(cudaMemcpy(beam_tokens, h->bs.tap_seq, n * h->cfg.max_length * 4, cudaMemcpyDefault));
   if (n_steps) *n_steps = h->last_steps;
   return GRAM_OK;
+}
+
+int gram_check_errors(gram_handle* h, void* stream) {
+  if (!h) return GRAM_ERR_INVALID;
+  CK(cudaSetDevice(h->cfg.device));
+  cudaStream_t s = (cudaStream_t)stream;
+  CK(cudaMemcpyAsync(&h->h_flags[0], h->pm.err, 4, cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  const int code = h->h_flags[0];
+  if (code == 0) return GRAM_OK;
+  CK(cudaMemsetAsync(h->pm.err, 0, 4, s));
+  return fail(h, GRAM_ERR_INVALID, code == 2   ? "input token id outside [0, vocab_size)"
+                                   : code == 3 ? "item index outside the cached item table"
+                                               : "candidate buffer overflow (trie fan-out larger than declared)");
 }
 
 int gram_get_stats(gram_handle* h, gram_stats* out) {

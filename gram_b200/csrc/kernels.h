@@ -57,6 +57,14 @@ struct PackMeta {            // device-resident description of the packed (valid
   int vocab;                 // vocabulary size, for the id range check
 };
 cudaError_t enc_pack(const int64_t* ids, const uint8_t* mask, int B, int N, int L, PackMeta pm, cudaStream_t s);
+// per-item encoder-state cache (see encoder_kernels.cu): scatter a chunk's packed fp32 rows into the item table, and
+// build a user layout + memory from prompt rows and cached item rows (4 launches)
+cudaError_t cache_scatter(const float* src, const PackMeta& pm, int M_max, int D, long long row0, float* item_mem,
+                          uint8_t* item_valid, cudaStream_t s);
+cudaError_t cached_pack_assemble(int dtype, const PackMeta& pm, const PackMeta& prompt_pm, const float* prompt_rows,
+                                 const int* items /*[B,NI], -1 = none*/, const float* item_mem, const uint8_t* item_valid,
+                                 const int* item_len, int n_items, const float* pos_table, int B, int NI, int L, int D,
+                                 void* mem, cudaStream_t s);
 cudaError_t embed_rows(int dtype, const void* table, const int* tok_id, float* x, int M_max, const int* m_ptr,
                        int D, cudaStream_t s);
 // y = w * (x * rsqrt(mean(x^2)+eps)) * scale  [+ pos_table[tok_pos[row]]]   (x fp32 -> y dtype)

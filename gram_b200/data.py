@@ -248,6 +248,33 @@ class GramTestData:
         return dict(item_text_ids=ids, item_text_masks=mask, target_ids=tgt, target_items=list(targets),
                     user_ids=[f"u{u}" for u in users])
 
+    # ---- cached-item path: the item passages once, users as (prompt, item indices) ----------
+    def item_table(self):
+        """(ids int64 [n_items, L], mask bool [n_items, L]): every item passage, for `GRAM.cache_items`."""
+        tab, lens = self.item_passages()
+        return tab, np.arange(self.L)[None, :] < lens[:, None]
+
+    def collate_cached(self, users: Sequence[int]):
+        """The same batch as `collate`, factored for `GRAM.generate_cached`: prompt_ids / prompt_masks [B, L]
+        (passage 0, padded to the table's L) and item_index int32 [B, N-1] (passage 1+j = item, -1 = the empty
+        passages `collate` pads with)."""
+        hists, targets = zip(*(self.split(u) for u in users))
+        max_in_batch = max(len(h) for h in hists) + 1
+        N = min(max_in_batch, self.max_his) + 1
+        B, L = len(users), self.L
+        ids = np.zeros((B, L), dtype=np.int64)
+        mask = np.zeros((B, L), dtype=bool)
+        items = np.full((B, N - 1), -1, dtype=np.int32)
+        for b, h in enumerate(hists):
+            up = self.user_prompt(h)
+            ids[b, :len(up)] = up
+            mask[b, :len(up)] = True
+            k = min(len(h), N - 1)
+            items[b, :k] = h[:k]
+        tgt = [[0] + self.item_tok[t].tolist() + [1] for t in targets]
+        return dict(prompt_ids=ids, prompt_masks=mask, item_index=items, target_ids=tgt, target_items=list(targets),
+                    user_ids=[f"u{u}" for u in users])
+
     def valid_tokens(self, users: Sequence[int]) -> int:
         """Packed (valid) encoder tokens of these users: the S_valid of SURVEY 8(d)."""
         total = 0

@@ -267,6 +267,7 @@ class GRAM:
             score_parts.append(out_scores)
             widths.append(out_width)
         width = max(int(w.item()) for w in widths)
+        _cabi.check(self._lib.gram_check_errors(self._handle, self._stream()), self._handle, "gram_generate")
         sequences = torch.cat(seq_parts, 0)[:, :width].contiguous()
         scores = torch.cat(score_parts, 0)
         if not return_dict_in_generate:
@@ -292,6 +293,105 @@ class GRAM:
         _cabi.check(self._lib.gram_generate(
             self._handle, _ptr(ids), _ptr(mask), B, N, L, K, R, int(max_length), self._len_pow,
             _ptr(out_seq), _ptr(out_width), _ptr(out_scores), self._stream()), self._handle, "gram_generate")
+
+    # ---- per-item encoder-state cache (no counterpart in the reference) -------------------
+    @torch.no_grad()
+    def cache_items(self, item_ids, item_mask):
+        """Encode every item passage once (`item_ids` int64 / `item_mask` bool `[n_items, L]`) and keep the encoder
+        states on the device; `generate_cached` then only encodes the user prompts.  Exact: item passages do not
+        depend on the user (src/utils/indexing.py:209-211,315-320) and the position row is added after the encoder
+        (src/model/gram.py:238-249)."""
+        ids = torch.as_tensor(item_ids).to(torch.int64).contiguous()
+        mask = torch.as_tensor(item_mask)
+        if ids.dim() != 2 or mask.shape != ids.shape:
+            raise ValueError("item_ids / item_mask must both be [n_items, L]")
+        if mask.dtype != torch.bool:
+            mask = mask != 0
+        self._item_table = (ids, mask.contiguous().view(torch.uint8))
+        self._item_table_handle = None
+
+    def _ensure_items(self):
+        if getattr(self, "_item_table", None) is None:
+            raise RuntimeError("generate_cached: no item table (call cache_items first)")
+        if self._item_table_handle is not self._handle:          # first use, or the engine was re-created
+            ids, mask = self._item_table
+            _cabi.check(self._lib.gram_cache_items(self._handle, _ptr(ids), _ptr(mask), ids.shape[0], ids.shape[1],
+                                                   self._stream()), self._handle, "gram_cache_items")
+            self._item_table_handle = self._handle
+
+    @torch.no_grad()
+    def generate_cached(self, prompt_ids, prompt_mask, item_index, max_length, prefix_allowed_tokens_fn=None,
+                        num_beams: int = 1, num_return_sequences: int = 1, return_dict_in_generate: bool = False,
+                        length_penalty: float = 1.0, **kwargs):
+        """`generate` for users given as (prompt passage `[B, L]`, history item indices `[B, NI]`, -1 = none) over
+        the table built by `cache_items`.  Same outputs, bit for bit, as `generate` on the `[B, 1+NI, L]` tensors
+        whose passage 1+j is the cached passage of `item_index[b][j]`."""
+        trie = getattr(prefix_allowed_tokens_fn, "candidate_trie", None)
+        if trie is None:
+            raise NotImplementedError("generate_cached needs `prefix_allowed_tokens_fn` built by "
+                                      "gram_b200.generation_trie.prefix_allowed_tokens_fn(trie)")
+        if num_return_sequences > num_beams:
+            raise ValueError("`num_return_sequences` has to be smaller or equal to `num_beams`.")
+        ids = torch.as_tensor(prompt_ids).to(torch.int64).contiguous()
+        mask = torch.as_tensor(prompt_mask)
+        if mask.dtype != torch.bool:
+            mask = mask != 0
+        mask = mask.contiguous().view(torch.uint8)
+        items = torch.as_tensor(item_index).to(torch.int32).contiguous()
+        if ids.dim() != 2 or mask.shape != ids.shape or items.dim() != 2 or items.shape[0] != ids.shape[0]:
+            raise ValueError("prompt_ids / prompt_mask must be [B, L] and item_index [B, NI]")
+        B, L = ids.shape
+        NI = items.shape[1]
+        K, R = int(num_beams), int(num_return_sequences)
+        max_length = int(max_length)
+        self.encoder.n_passages = NI + 1
+        self._ensure(min(B, max(self._cap["max_users"], self.user_limit)), NI + 1, L, K, max_length)
+        self._set_trie(trie)
+        self._ensure_items()
+        len_pow = (C.c_double * (max_length + 1))(*[float(c) ** float(length_penalty) if c > 0 else 1.0
+                                                    for c in range(max_length + 1)])
+        dev = ids.device if ids.is_cuda else self.device
+        cap_u = self._cap["max_users"]
+        seq_parts, score_parts, widths = [], [], []
+        for b0 in range(0, B, cap_u):
+            b1 = min(B, b0 + cap_u)
+            nb = b1 - b0
+            out_seq = torch.zeros((nb * R, max_length), dtype=torch.int64, device=dev)
+            out_scores = torch.zeros((nb * R,), dtype=torch.float32, device=dev)
+            out_width = torch.zeros((1,), dtype=torch.int32, device=dev)
+            _cabi.check(self._lib.gram_encode_cached(self._handle, _ptr(ids[b0:b1]), _ptr(mask[b0:b1]), _ptr(items[b0:b1]),
+                                                     nb, NI, L, self._stream()), self._handle, "gram_encode_cached")
+            _cabi.check(self._lib.gram_generate(
+                self._handle, None, None, nb, NI + 1, L, K, R, max_length, len_pow,
+                _ptr(out_seq), _ptr(out_width), _ptr(out_scores), self._stream()), self._handle, "gram_generate")
+            seq_parts.append(out_seq)
+            score_parts.append(out_scores)
+            widths.append(out_width)
+        width = max(int(w.item()) for w in widths)
+        _cabi.check(self._lib.gram_check_errors(self._handle, self._stream()), self._handle, "gram_generate_cached")
+        sequences = torch.cat(seq_parts, 0)[:, :width].contiguous().to(ids.device)
+        scores = torch.cat(score_parts, 0).to(ids.device)
+        if not return_dict_in_generate:
+            return sequences
+        return GenerateOutput(sequences=sequences, sequences_scores=scores, scores=None, beam_indices=None)
+
+    @torch.no_grad()
+    def encode_cached(self, prompt_ids, prompt_mask, item_index):
+        """Fused memory `[B, (1+NI)*L, d_model]` fp32 of the cached path -- parity tap, compare with `encode`."""
+        ids = torch.as_tensor(prompt_ids).to(torch.int64).contiguous()
+        mask = torch.as_tensor(prompt_mask)
+        mask = (mask if mask.dtype == torch.bool else mask != 0).contiguous().view(torch.uint8)
+        items = torch.as_tensor(item_index).to(torch.int32).contiguous()
+        B, L = ids.shape
+        NI = items.shape[1]
+        self._ensure(B, NI + 1, L, 1, 2)
+        self._ensure_items()
+        _cabi.check(self._lib.gram_encode_cached(self._handle, _ptr(ids), _ptr(mask), _ptr(items), B, NI, L, self._stream()),
+                    self._handle, "gram_encode_cached")
+        dev = ids.device if ids.is_cuda else self.device
+        out = torch.empty((B, (NI + 1) * L, self.gcfg.d_model), dtype=torch.float32, device=dev)
+        _cabi.check(self._lib.gram_get_memory(self._handle, _ptr(out), self._stream()), self._handle, "gram_get_memory")
+        return out.to(ids.device)
 
     @torch.no_grad()
     def encode(self, input_ids, attention_mask):

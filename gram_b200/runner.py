@@ -49,9 +49,12 @@ class GramEvalLoader:
     users and exposes `.dataset` (with `.all_items`, `.dataset`, `.task`) like the reference's."""
 
     def __init__(self, data, batch_size: int, rank: int = 0, world: int = 1, users: Optional[Sequence[int]] = None,
-                 sort_by_length: bool = True):
+                 sort_by_length: bool = True, item_cache: bool = False):
         self.dataset = data
         self.batch_size = batch_size
+        # item_cache: batches are (prompt, history item indices) for GRAM.generate_cached -- every item passage is
+        # encoded once per eval instead of once per occurrence (SURVEY.md 8(f)-1); same predictions bit for bit
+        self.item_cache = item_cache
         all_users = list(users) if users is not None else list(range(data.n_users))
         lo, hi = shard_range(len(all_users), rank, world)
         mine = all_users[lo:hi]
@@ -66,10 +69,15 @@ class GramEvalLoader:
     def __iter__(self):
         for i in range(0, len(self.users), self.batch_size):
             idx = self.users[i:i + self.batch_size]
-            b = self.dataset.collate(idx)
+            if self.item_cache:
+                b = self.dataset.collate_cached(idx)
+                for k in ("prompt_ids", "prompt_masks", "item_index"):
+                    b[k] = torch.from_numpy(b[k])
+            else:
+                b = self.dataset.collate(idx)
+                b["item_text_ids"] = torch.from_numpy(b["item_text_ids"])
+                b["item_text_masks"] = torch.from_numpy(b["item_text_masks"])
             b["user_index"] = idx
-            b["item_text_ids"] = torch.from_numpy(b["item_text_ids"])
-            b["item_text_masks"] = torch.from_numpy(b["item_text_masks"])
             yield b
 
 
@@ -105,6 +113,13 @@ class GramRunner:
 
     def _generate(self, batch, max_length, prefix_fn):
         model = getattr(self.model_rec, "module", self.model_rec)
+        on_gpu = self.device is not None and torch.device(self.device).type == "cuda"
+        if "prompt_ids" in batch:
+            args = [batch[k].to(self.device, non_blocking=True) if on_gpu else batch[k]
+                    for k in ("prompt_ids", "prompt_masks", "item_index")]
+            return model.generate_cached(*args, max_length=max_length, prefix_allowed_tokens_fn=prefix_fn,
+                                         num_beams=self.generate_num, num_return_sequences=self.generate_num,
+                                         return_dict_in_generate=True, length_penalty=self.length_penalty)
         ids = batch["item_text_ids"]
         mask = batch["item_text_masks"]
         if self.device is not None and torch.device(self.device).type == "cuda":
@@ -125,6 +140,11 @@ class GramRunner:
         candidate_trie = gt.Trie(encoded)
         prefix_fn = gt.prefix_allowed_tokens_fn(candidate_trie)
         max_length = max(len(c) for c in encoded)
+        if getattr(testloader, "item_cache", False):
+            model = getattr(self.model_rec, "module", self.model_rec)
+            if getattr(model, "_item_table_owner", None) is not data:
+                model.cache_items(*data.item_table())
+                model._item_table_owner = data
         rows = []                                # (user index, gold string, predictions, scores, hit rank)
 
         def post(batch, seqs, scores):

@@ -128,6 +128,12 @@ int gram_decoder_logits(gram_handle* h, const int64_t* dec_ids, int32_t q, float
 int gram_get_step_taps(gram_handle* h, float* lse, float* beam_scores, int32_t* beam_tokens, int32_t* n_steps);
 
 /* ---- measurement ------------------------------------------------------------------------------- */
+/* Calls whose outputs are all device pointers never synchronise, so input errors the kernels detect (token id
+ * outside the vocabulary -- the reference's nn.Embedding raises IndexError, src/model/gram_t5_modeling.py:1091 --,
+ * item index outside the cached table, candidate overflow) stay in a sticky device flag.  This synchronises the
+ * stream, returns GRAM_ERR_INVALID with the message if the flag is set, and clears it. */
+int gram_check_errors(gram_handle* h, void* stream);
+
 typedef struct gram_stats {
   int64_t launches;          /* kernels launched by the last encode/generate call            */
   int64_t packed_tokens;     /* valid encoder tokens of the last encode (needs a sync to read) */
@@ -146,6 +152,19 @@ enum {
 int gram_profile_begin(gram_handle* h, uint32_t class_mask);
 /* synchronises the stream, returns per-class total milliseconds and launch counts, clears the log */
 int gram_profile_end(gram_handle* h, float* ms_per_class /*[GRAM_K_COUNT]*/, int64_t* launches_per_class);
+
+/* ---- per-item encoder-state cache (no counterpart in the reference) ------------
+ * Every passage except the user prompt depends on the ITEM only (reference src/utils/indexing.py:209-211,315-320),
+ * passages are encoded independently (src/model/gram.py:206-216) and the passage-position row is added after the
+ * encoder (src/model/gram.py:238-249).  gram_cache_items encodes each item passage once -- ids int64 / mask uint8
+ * [n_items, L], host or device -- and keeps its final-normed encoder rows (fp32, before the position add) in the
+ * handle.  gram_encode_cached then encodes only the user prompts [B, L] and assembles every user's memory from the
+ * prompt rows and the cached rows of items[b][0..NI) (int32, -1 = no passage), passage index 1 + j; L must equal
+ * the L of the table.  The result is bit-identical to gram_encode on the equivalent [B, 1+NI, L] input; follow it
+ * with gram_generate(h, NULL, NULL, ...) to decode.  The table is dropped by gram_destroy / a new gram_cache_items. */
+int gram_cache_items(gram_handle* h, const int64_t* ids, const uint8_t* mask, int32_t n_items, int32_t L, void* stream);
+int gram_encode_cached(gram_handle* h, const int64_t* prompt_ids, const uint8_t* prompt_mask, const int32_t* items,
+                       int32_t B, int32_t NI, int32_t L, void* stream);
 
 /* ---- single-operator entry points (unit parity tests and roofline measurement) ------------------ */
 /* C[M,N] = A[M,K] * W[N,K]^T on device pointers.  dtype as in gram_config; impl 0 = SIMT fp32-accumulate,

@@ -29,6 +29,7 @@ def main():
     ap.add_argument("--dtype", default="bf16")
     ap.add_argument("--users", type=int, default=0, help="evaluate only the first N users (0 = all)")
     ap.add_argument("--no-pipeline", action="store_true")
+    ap.add_argument("--item-cache", action="store_true", help="encode every item passage once (GRAM.generate_cached)")
     args = ap.parse_args()
     rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -52,9 +53,9 @@ def main():
 
     users = list(range(args.users or data.n_users))
     runner = GramRunner(model, data.tokenizer, f"cuda:{local}", Args(), rank, world)
-    loader = GramEvalLoader(data, args.batch, rank, world, users=users)
+    loader = GramEvalLoader(data, args.batch, rank, world, users=users, item_cache=args.item_cache)
     # warm-up (engine creation, weight upload, trie upload) on one batch, outside the clock
-    warm = GramEvalLoader(data, args.batch, 0, 1, users=users[:args.batch])
+    warm = GramEvalLoader(data, args.batch, 0, 1, users=users[:args.batch], item_cache=args.item_cache)
     runner.world_size = 1
     runner.test_dataset_task(warm, "warmup", pipeline=False)
     runner.world_size = world
@@ -63,7 +64,7 @@ def main():
     res = runner.test_dataset_task(loader, "test", pipeline=not args.no_pipeline)
     dt = time.time() - t0
     if rank == 0:
-        print(json.dumps(dict(dataset=args.dataset, users=res["test_total"], n_gpus=world, batch=args.batch, dtype=args.dtype,
+        print(json.dumps(dict(dataset=args.dataset, users=res["test_total"], n_gpus=world, item_cache=args.item_cache, batch=args.batch, dtype=args.dtype,
                               seconds=dt, users_per_sec=res["test_total"] / dt, generate_seconds_rank0=res["generate_seconds"],
                               metrics=res["metrics"], inputs="surrogate tokenizer, synthetic metadata, random-init weights")))
     if world > 1:

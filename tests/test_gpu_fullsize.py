@@ -121,6 +121,11 @@ def test_eval_loop_batch_size_independent(beauty):
     p0 = [r[2] for r in res[0]["rows"]]
     p1 = [r[2] for r in res[1]["rows"]]
     assert p0 == p1                                                        # identical decoded rankings
+    # the cached-item loader (every item passage encoded once per eval) gives the same rows, scores included
+    loader = GramEvalLoader(b["data"], batch_size=16, users=users, item_cache=True)
+    cached = GramRunner(model, b["data"].tokenizer, "cuda:0", Args()).test_dataset_task(loader)
+    assert cached["metrics"] == res[1]["metrics"]
+    assert [r[2:] for r in cached["rows"]] == [r[2:] for r in res[1]["rows"]]
 
 
 @pytest.mark.parametrize("dataset", ["Toys", "Sports", "Yelp"])
