@@ -376,6 +376,31 @@ class GRAM:
         return GenerateOutput(sequences=sequences, sequences_scores=scores, scores=None, beam_indices=None)
 
     @torch.no_grad()
+    def generate_cached_into(self, prompt_ids, prompt_mask, item_index, max_length, trie, num_beams, num_return_sequences,
+                             length_penalty, out_seq, out_scores, out_width):
+        """`generate_cached` without the Python-side post-processing (see `generate_into`): two C-ABI calls, no
+        synchronisation with device tensors."""
+        ids = prompt_ids.to(torch.int64).contiguous()
+        mask = (prompt_mask if prompt_mask.dtype == torch.bool else prompt_mask != 0).contiguous().view(torch.uint8)
+        items = item_index.to(torch.int32).contiguous()
+        B, L = ids.shape
+        NI = items.shape[1]
+        K, R = int(num_beams), int(num_return_sequences)
+        self._ensure(B, NI + 1, L, K, int(max_length))
+        self._set_trie(trie)
+        self._ensure_items()
+        key = (int(max_length), float(length_penalty))
+        if getattr(self, "_len_pow_key", None) != key:
+            self._len_pow = (C.c_double * (max_length + 1))(*[float(c) ** float(length_penalty) if c > 0 else 1.0
+                                                              for c in range(max_length + 1)])
+            self._len_pow_key = key
+        _cabi.check(self._lib.gram_encode_cached(self._handle, _ptr(ids), _ptr(mask), _ptr(items), B, NI, L, self._stream()),
+                    self._handle, "gram_encode_cached")
+        _cabi.check(self._lib.gram_generate(
+            self._handle, None, None, B, NI + 1, L, K, R, int(max_length), self._len_pow,
+            _ptr(out_seq), _ptr(out_width), _ptr(out_scores), self._stream()), self._handle, "gram_generate")
+
+    @torch.no_grad()
     def encode_cached(self, prompt_ids, prompt_mask, item_index):
         """Fused memory `[B, (1+NI)*L, d_model]` fp32 of the cached path -- parity tap, compare with `encode`."""
         ids = torch.as_tensor(prompt_ids).to(torch.int64).contiguous()

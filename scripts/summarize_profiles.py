@@ -28,7 +28,9 @@ METRICS = [
     "sm__inst_executed_pipe_tensor_subpipe_hmma.avg.pct_of_peak_sustained_active",
     "sm__warps_active.avg.pct_of_peak_sustained_active", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
     "launch__registers_per_thread", "launch__grid_size", "launch__block_size", "launch__shared_mem_per_block_dynamic",
-    "lts__t_bytes.sum", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "smsp__cycles_active.avg",
+    "lts__t_bytes.sum", "lts__throughput.avg.pct_of_peak_sustained_elapsed", "lts__t_sector_hit_rate.pct",
+    "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "smsp__cycles_active.avg", "sm__cycles_elapsed.avg.per_second",
+    "launch__cluster_size",
     "sm__ops_path_tensor_op_hmma_src_bf16_dst_fp32_sparsity_off.avg.pct_of_peak_sustained_elapsed",
 ]
 
@@ -46,6 +48,14 @@ def launches(tag):
         if hdr and len(r) == len(hdr):
             data.append(r)
     ki, vi, gi, bi = hdr.index("Kernel Name"), hdr.index("Metric Value"), hdr.index("Grid Size"), hdr.index("Block Size")
+    # keep exactly one step: from the last passage_len_kernel (first launch of a generate call) that is followed by a
+    # beam_finalize_kernel (its last launch) through that launch
+    starts = [i for i, r in enumerate(data) if "passage_len_kernel" in r[ki]]
+    ends = [i for i, r in enumerate(data) if "beam_finalize_kernel" in r[ki]]
+    whole = [(a, min(e for e in ends if e > a)) for a in starts if any(e > a for e in ends)]
+    if whole:
+        a, e = whole[-1]
+        data = data[a:e + 1]
     with open(os.path.join(OUT, f"{tag}_launches.csv"), "w", newline="") as f:
         w = csv.writer(f)
         w.writerow(["id", "kernel", "grid", "block", "gpu__time_duration_ns"])
@@ -58,7 +68,7 @@ def launches(tag):
         agg[name][1] += float(r[vi]) / 1e3
     tot = sum(v[1] for v in agg.values())
     with open(os.path.join(OUT, f"{tag}_launch_summary.txt"), "w") as f:
-        f.write(f"# ncu --metrics gpu__time_duration.sum --clock-control none ; {len(data)} consecutive launches of bench.py\n")
+        f.write(f"# ncu --metrics gpu__time_duration.sum --clock-control none ; {len(data)} consecutive launches of bench.py = one whole step (generate call)\n")
         f.write("# cold-cache, serialised per-launch times: compare SHARES with bench.py's kernel_classes, not absolutes\n")
         f.write(f"# total {tot:.1f} us\n")
         for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1]):
