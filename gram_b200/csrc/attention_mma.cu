@@ -20,6 +20,7 @@
 #include <map>
 #include <tuple>
 #include <string>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "kernels.h"
@@ -205,13 +206,16 @@ constexpr int XA_STAGE_TARGET = 64 * 1024;
 //   K <= 64: <2, 2, 1, 1>: 2 heads x 2 beam-halves, 32 KiB stages x 6
 //   Measured alternatives for K <= 32 (kept as template options): <2, 1, 2, 2> (key-halves, two CTAs per SM) 8 % slower;
 //   <4, 1, 2, 1> (8 consumer warps per CTA) 40 % slower -- splitting a 64-key tile between two warps doubles the per-tile
-//   softmax bookkeeping (running max / rescale of the 32 x 64 output tile) and spills.
-template <int HEADS, int BH, int KH, int MINB>
+//   softmax bookkeeping (running max / rescale of the 32 x 64 output tile) and spills; <4, 2, 1, 1, MT = 1> (8 warps,
+//   16 beams each, no merge, 168 registers) within 0.6 % of <4, 1, 1, 1> -- the consumers are not what paces it.
+//   Timed alone (scripts/exp_xattn_context.py) the kernel streams 6.3 TB/s back to back = 0.96 of the measured copy
+//   bandwidth (6.0 with a sync between launches); inside a step, after the encoder phase has driven the chip into its
+//   power cap, the same launches run at 4.9-5.3 TB/s.
+template <int HEADS, int BH, int KH, int MINB, int MT = 2>
 __global__ void __launch_bounds__(xa_threads(HEADS * BH * KH), MINB)
 cross_attention_mma_kernel(const __grid_constant__ CUtensorMap map_kv, const bf16* __restrict__ qg,
                            bf16* __restrict__ out, const int* __restrict__ ustart, const int* __restrict__ uorder,
                            const uint8_t* __restrict__ tok_valid, int K, int H, int k_col0, int v_col0) {
-  constexpr int MT = 2;
   constexpr int XA_HEADS = HEADS;
   constexpr uint32_t XA_STAGE_BYTES = 2 * HEADS * BOX_BYTES;   // K boxes then V boxes
   constexpr int XA_STAGES = MINB == 2 ? 3 : 3 * XA_STAGE_TARGET / (int)XA_STAGE_BYTES;
@@ -268,7 +272,7 @@ cross_attention_mma_kernel(const __grid_constant__ CUtensorMap map_kv, const bf1
   }
 
   // ===================== consumers: warp = (head, beam half, key half) =====================
-  const int hl = warp / (BH * KH), b_off = ((warp / KH) % BH) * 32, kh = warp % KH;
+  const int hl = warp / (BH * KH), b_off = ((warp / KH) % BH) * (MT * 16), kh = warp % KH;
   const int h = hg * XA_HEADS + hl;
   const int g = lane >> 2, q = lane & 3;
   uint32_t qf[MT][4][4];
