@@ -120,8 +120,9 @@ class GramTestData:
 
     def __init__(self, dataset: str = "Beauty", mode: str = "test", max_his: int = None,
                  item_prompt_max_len: int = None, top_k_similar: int = None, vocab_size: int = 32128,
-                 synthetic_users: int = 0, synthetic_history: int = 10, seed: int = 2023):
-        path = os.path.join(ASSET_DIR, f"{dataset}.npz")
+                 synthetic_users: int = 0, synthetic_history: int = 10, seed: int = 2023, packed_path: str = None):
+        # packed_path: a cache written by gram_b200.formats.save_packed(pack_dataset(...)) from the reference's text files
+        path = packed_path or os.path.join(ASSET_DIR, f"{dataset}.npz")
         if not os.path.exists(path):
             raise FileNotFoundError(f"{path}: run scripts/make_dataset_fixture.py in the build container")
         z = np.load(path)

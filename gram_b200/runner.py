@@ -32,7 +32,7 @@ from typing import List, Optional, Sequence
 import numpy as np
 import torch
 
-from . import evaluate
+from . import evaluate, formats
 from . import generation_trie as gt
 from .data import SEPARATOR_IDS
 
@@ -230,15 +230,8 @@ class GramRunner:
         os.makedirs(self.pred_dir, exist_ok=True)
         stamp = time.strftime("%Y%m%d_%H%M%S")
         path = os.path.join(self.pred_dir, f"{stamp}_{data.dataset}_{data.task}_pred_{mode}.tsv")
-        names = ["H@5", "H@10", "NDCG@5", "NDCG@10"]
-        with open(path, "w") as f:
-            f.write("idx\t" + "\t".join(names) + "\tgold\tpred\tscores\n")
-            for u, gold, preds, scores, rank in rows:
-                per_user = evaluate.metric_sums_from_ranks(np.array([rank]), self.metrics)
-                f.write("\t".join([f"u{u}", "\t".join(str(x) for x in per_user), gold, "||".join(preds),
-                                   "||".join(str(s) for s in scores)]) + "\n")
-            for m, v in metrics.items():
-                f.write(f"{m}: {v}\n")
+        per_user = [evaluate.metric_sums_from_ranks(np.array([r[4]]), self.metrics) for r in rows]
+        formats.write_predictions_tsv(path, rows, metrics, per_user, self.metrics)
         return path
 
     # reference entry points (single:370-408): checkpoints are state dicts

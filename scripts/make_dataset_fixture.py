@@ -18,7 +18,10 @@ similar int32 [n_items, 10] (-1 padded).
 import os
 import sys
 
-import numpy as np
+import numpy as np  # noqa: F401
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from gram_b200 import formats  # noqa: E402
 
 SRC = os.environ.get("GRAM_REFERENCE_ROOT", "/root/reference") + "/rec_datasets"
 DST = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gram_b200", "assets")
@@ -33,58 +36,12 @@ ID_FILES = {
 
 def pack(name):
     d = os.path.join(SRC, name)
-    pieces, piece_idx = [], {}
-    asins, lex = [], []
-    with open(os.path.join(d, ID_FILES[name]), encoding="utf-8") as f:
-        for line in f:
-            line = line.rstrip("\n")
-            if not line:
-                continue
-            asin, rest = line.split(" ", 1)
-            ps = [p for p in rest.split("|") if p != ""]
-            row = []
-            for p in ps:
-                if p not in piece_idx:
-                    piece_idx[p] = len(pieces)
-                    pieces.append(p)
-                row.append(piece_idx[p])
-            asins.append(asin)
-            lex.append(row)
-    item_idx = {a: i for i, a in enumerate(asins)}
-    width = max(len(r) for r in lex)
-    item_lex = np.full((len(lex), width), -1, dtype=np.int32)
-    for i, r in enumerate(lex):
-        item_lex[i, :len(r)] = r
-    out = dict(pieces=np.array(pieces), item_asin=np.array(asins), item_lex=item_lex)
-    up = os.path.join(d, "user_sequence.txt")
-    if os.path.exists(up):
-        off, items = [0], []
-        with open(up) as f:
-            for line in f:
-                parts = line.split()
-                if len(parts) < 2:
-                    continue
-                items.extend(item_idx[a] for a in parts[1:])
-                off.append(len(items))
-        out["user_off"] = np.asarray(off, dtype=np.int32)
-        out["user_items"] = np.asarray(items, dtype=np.int32)
-    sp = os.path.join(d, "similar_item_sasrec.txt")
-    if os.path.exists(sp):
-        sim = np.full((len(asins), 10), -1, dtype=np.int32)
-        with open(sp) as f:
-            for line in f:
-                if line.startswith("anchor"):
-                    continue
-                parts = line.split()
-                if not parts or parts[0] not in item_idx:
-                    continue
-                row = [item_idx[a] for a in parts[1:11] if a in item_idx]
-                sim[item_idx[parts[0]], :len(row)] = row
-        out["similar"] = sim
+    out = formats.pack_dataset(os.path.join(d, ID_FILES[name]), os.path.join(d, "user_sequence.txt"),
+                               os.path.join(d, "similar_item_sasrec.txt"), top_k=10)
     os.makedirs(DST, exist_ok=True)
     path = os.path.join(DST, f"{name}.npz")
-    np.savez_compressed(path, **out)
-    print(f"{name}: {len(asins)} items, {len(pieces)} pieces, id width {width}, "
+    formats.save_packed(path, out)
+    print(f"{name}: {len(out['item_asin'])} items, {len(out['pieces'])} pieces, id width {out['item_lex'].shape[1]}, "
           f"{len(out.get('user_off', [0])) - 1} users -> {path} ({os.path.getsize(path)} bytes)")
 
 

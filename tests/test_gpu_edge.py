@@ -4,7 +4,7 @@ import numpy as np
 import pytest
 import torch
 
-from helpers import ROOT  # noqa: F401
+from helpers import CASES, ROOT  # noqa: F401
 from gram_b200 import GRAM, GramConfig, Trie, prefix_allowed_tokens_fn, synth
 
 pytestmark = pytest.mark.gpu
@@ -136,3 +136,21 @@ def test_large_synthetic_trie_beam50():
         rows = [tuple(r[:list(r).index(1) + 1]) for r in seq[u * K:(u + 1) * K]]
         assert all(r in items for r in rows) and len(set(rows)) == K
     assert np.all(sc[:, :-1] >= sc[:, 1:]) and np.isfinite(sc).all()
+
+
+def test_generate_from_a_csr_trie_file(tmp_path):
+    """A trie loaded from its CSR file (gram_b200.formats) drives `generate` exactly like the nested-dict Trie."""
+    from gram_b200 import formats
+    case = CASES["tiny_lp"]
+    sd, ids, mask, seqs, ml = case.build()
+    m = GRAM(case.cfg, dtype="fp32", device="cuda:0")
+    m.load_state_dict(sd)
+    t = Trie(seqs)
+    path = str(tmp_path / "trie.npz")
+    formats.save_trie_csr(path, t)
+    K = case.num_beams
+    a = m.generate(ids.cuda(), mask.cuda(), ml, prefix_allowed_tokens_fn=prefix_allowed_tokens_fn(t), num_beams=K,
+                   num_return_sequences=K, return_dict_in_generate=True, length_penalty=case.length_penalty)
+    b = m.generate(ids.cuda(), mask.cuda(), ml, prefix_allowed_tokens_fn=prefix_allowed_tokens_fn(formats.load_trie_csr(path)),
+                   num_beams=K, num_return_sequences=K, return_dict_in_generate=True, length_penalty=case.length_penalty)
+    assert torch.equal(a["sequences"], b["sequences"]) and torch.equal(a["sequences_scores"], b["sequences_scores"])
