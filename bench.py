@@ -43,13 +43,15 @@ def parse():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=944,
-                    help="users per step per GPU (944 users x 20 beams = 18880 decoder rows = 148 row tiles of 128: every "
-                         "decoder GEMM then has a whole number of 148-SM waves of tiles; ~66 GB of workspace)")
+    ap.add_argument("--batch", type=int, default=1888,
+                    help="users per step per GPU (1888 users x 20 beams = 37760 decoder rows = 295 row tiles of 128: two "
+                         "148-SM waves for every decoder GEMM; ~65 GB of workspace with the token-sized max_tokens)")
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--cpu-users", type=int, default=8, help="users timed for cpu_baseline (0 = skip)")
     ap.add_argument("--simt", action="store_true", help="force the CUDA-core GEMM (A/B timing)")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--max-tokens", type=int, default=0,
+                    help="workspace rows (valid encoder tokens per step); 0 = the largest step of this run + 2 %%")
     ap.add_argument("--no-item-cache", action="store_true", help="skip the extra (non-headline) cached-item measurement")
     ap.add_argument("--gemm-1cta", action="store_true", help="keep every tcgen05 GEMM on single-CTA tiles (A/B timing)")
     ap.add_argument("--tc-enc-attn", action="store_true", help="opt into the tcgen05 encoder-attention kernel (A/B timing)")
@@ -210,7 +212,7 @@ def run_reference(args, rank, world):
                 config=workload_config(args, data, max_length),
                 cpu_baseline=dict(value=value, unit="users/s", cores=os.cpu_count(), kind="port", sample=sample),
                 e2e=dict(value=value, unit="users/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def ncu_traffic(name, tag="r1"):
@@ -234,14 +236,36 @@ def ncu_traffic(name, tag="r1"):
 def workload_config(args, data, max_length):
     return dict(workload=f"{DATASET} full test set ({data.n_users} users, {data.n_items}-item trie), T5-small, beam {BEAMS}, "
                          f"return {BEAMS}, max_length {max_length}, max_his {data.max_his} x {data.L} tokens",
-                users_per_step_per_gpu=args.batch, parallelism=f"user-sharded dp{args.gpus}",
+                users_per_step_per_gpu=args.batch, workspace="sized by the valid tokens of the largest step (max_tokens), not by users x 21 full passages", parallelism=f"user-sharded dp{args.gpus}",
                 inputs="surrogate tokenizer + synthetic metadata tokens + random-init tied weights (seed 0)",
                 cache="per-step working set (K/V memory + activations, > 8 GB) exceeds the 126 MB L2; every step uses different users")
 
 
 # --------------------------------------------------------------------------------------------------
+_REAL_STDOUT = None
+
+
+def capture_stdout():
+    """stdout must carry exactly ONE JSON line, but C libraries write there too (NCCL prints its version line on
+    stdout whatever NCCL_DEBUG_FILE says): point fd 1 at stderr for the whole run and keep the real stdout aside."""
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def main():
     args = parse()
+    capture_stdout()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -266,7 +290,6 @@ def main():
     model = GRAM(cfg, dtype=args.dtype, device=dev, flags=flags)
     model.load_state_dict(sd)
     B, K, W, S = args.batch, BEAMS, args.warmup, args.steps
-    model.configure(max_users=B, max_beams=K, max_length=max_length, max_passages=data.max_his + 1, max_seq_len=data.L)
     model.user_limit = B
 
     # ---- inputs: host (pinned) and device copies for every step -----------------------------------
@@ -281,6 +304,12 @@ def main():
     out_seq = torch.zeros((B * K, max_length), dtype=torch.int64, device=dev)
     out_scores = torch.zeros((B * K,), dtype=torch.float32, device=dev)
     out_width = torch.zeros((1,), dtype=torch.int32, device=dev)
+    # workspace sized by the VALID tokens of the largest step (+2 %), not by users x 21 full passages: that is what
+    # lets 1,888 users share a step (the library checks the count on the device and reports a batch that exceeds it)
+    max_tokens = args.max_tokens if args.max_tokens > 0 else int(max(tokens) * 1.02) + 1024
+    max_tokens = min(max_tokens, B * (data.max_his + 1) * data.L)
+    model.configure(max_users=B, max_beams=K, max_length=max_length, max_passages=data.max_his + 1, max_seq_len=data.L,
+                    max_tokens=max_tokens)
 
     def barrier():
         if dist is not None:
@@ -467,7 +496,7 @@ def main():
                 notes="roofline = all tcgen05 GEMM launches of the timed steps (CUDA events recorded by the library on the "
                       "launching stream); per-launch DRAM traffic is shape dependent, see profiles/r1_gemm_enc_metrics.csv; "
                       "kernel_classes come from a second pass over the same steps with every class bracketed")
-    print(json.dumps(line), flush=True)
+    emit(line)
     if dist is not None:
         dist.destroy_process_group()
 

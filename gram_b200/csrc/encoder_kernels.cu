@@ -33,9 +33,11 @@ __global__ void passage_len_kernel(const uint8_t* __restrict__ mask, int P, int 
 }
 
 // single-CTA exclusive scan (P is at most a few hundred thousand)
-__global__ void __launch_bounds__(1024) passage_scan_kernel(const int* __restrict__ plen, int P, int N, int B,
+// If the batch holds more valid tokens than the workspace (`cap` rows) the whole batch is emptied (every passage
+// length 0) and the sticky error flag is set: capacity is checked where the count is known, on the device.
+__global__ void __launch_bounds__(1024) passage_scan_kernel(int* __restrict__ plen, int P, int N, int B,
                                                             int* __restrict__ poff, int* __restrict__ ustart,
-                                                            int* __restrict__ total) {
+                                                            int* __restrict__ total, long long cap, int* __restrict__ err) {
   __shared__ int warp_sums[32];
   __shared__ int carry_s;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -64,16 +66,20 @@ __global__ void __launch_bounds__(1024) passage_scan_kernel(const int* __restric
     if (lane == 31) carry_s = wi;
   }
   __syncthreads();
+  const bool over = (long long)carry_s > cap;
   int run = warp_sums[wid] + incl - sum;
   for (int i = beg; i < end; ++i) {
-    poff[i] = run;
-    if (i % N == 0) ustart[i / N] = run;
+    poff[i] = over ? 0 : run;
+    if (i % N == 0) ustart[i / N] = over ? 0 : run;
     run += plen[i];
+    if (over) plen[i] = 0;
   }
   if (tid == 0) {
-    poff[P] = carry_s;
-    ustart[B] = carry_s;
-    *total = carry_s;
+    const int tot = over ? 0 : carry_s;
+    poff[P] = tot;
+    ustart[B] = tot;
+    *total = tot;
+    if (over) atomicExch(err, 4);
   }
 }
 
@@ -111,7 +117,7 @@ __global__ void __launch_bounds__(1024) user_order_kernel(const int* __restrict_
 cudaError_t enc_pack(const int64_t* ids, const uint8_t* mask, int B, int N, int L, PackMeta pm, cudaStream_t s) {
   const int P = B * N;
   passage_len_kernel<<<(P * 32 + 255) / 256, 256, 0, s>>>(mask, P, L, pm.plen);
-  passage_scan_kernel<<<1, 1024, 0, s>>>(pm.plen, P, N, B, pm.poff, pm.ustart, pm.total);
+  passage_scan_kernel<<<1, 1024, 0, s>>>(pm.plen, P, N, B, pm.poff, pm.ustart, pm.total, pm.cap, pm.err);
   passage_fill_kernel<<<P, 128, 0, s>>>(ids, mask, N, L, pm);
   user_order_kernel<<<1, 1024, 0, s>>>(pm.ustart, B, pm.uorder);
   return cudaGetLastError();
@@ -211,7 +217,7 @@ cudaError_t cached_pack_assemble(int dtype, const PackMeta& pm, const PackMeta& 
                                  cudaStream_t s) {
   const int P = B * (NI + 1);
   cached_plen_kernel<<<(P + 255) / 256, 256, 0, s>>>(prompt_pm.plen, items, item_len, n_items, B, NI, pm.plen, pm.err);
-  passage_scan_kernel<<<1, 1024, 0, s>>>(pm.plen, P, NI + 1, B, pm.poff, pm.ustart, pm.total);
+  passage_scan_kernel<<<1, 1024, 0, s>>>(pm.plen, P, NI + 1, B, pm.poff, pm.ustart, pm.total, pm.cap, pm.err);
   if (dtype == 0)
     cached_assemble_kernel<float><<<P, 128, 0, s>>>(pm, prompt_pm.poff, prompt_pm.tok_valid, prompt_rows, items, item_mem,
                                                     item_valid, pos_table, NI, L, D, (float*)mem);

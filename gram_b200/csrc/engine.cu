@@ -339,7 +339,7 @@ int run_encode(gram_handle* h, const int64_t* ids, const uint8_t* mask, int B, i
   if (B <= 0 || N <= 0 || L <= 0) return fail(h, GRAM_ERR_INVALID, "gram_encode: empty batch");
   if (B > c.max_users || N > c.max_passages || L > c.max_seq_len)
     return fail(h, GRAM_ERR_INVALID, "gram_encode: B/N/L exceed the capacities given to gram_create");
-  if ((int64_t)B * N * L > h->Mcap) return fail(h, GRAM_ERR_INVALID, "gram_encode: B*N*L exceeds max_tokens");
+  if ((int64_t)B * N * L > 0x7fffffff) return fail(h, GRAM_ERR_INVALID, "gram_encode: B*N*L exceeds 2^31");
   if (c.n_positions > 0 && N > c.n_positions)
     return fail(h, GRAM_ERR_INVALID, "gram_encode: more passages than rows in the position table");
   const size_t n = (size_t)B * N * L;
@@ -349,7 +349,9 @@ int run_encode(gram_handle* h, const int64_t* ids, const uint8_t* mask, int B, i
   if (!is_device_ptr(mask)) { CK(cudaMemcpyAsync(h->d_mask, mask, n, cudaMemcpyHostToDevice, s)); dmask = h->d_mask; }
   h->encoded = false;
   h->enc_B = B; h->enc_N = N; h->enc_L = L;
-  const int Mmax = (int)n;
+  // rows the batch can occupy: its padded size, or the workspace when max_tokens caps it below that (the VALID
+  // token count is checked against the workspace on the device, by the packing scan)
+  const int Mmax = (int)std::min<int64_t>((int64_t)n, h->Mcap);
   CKL(GRAM_K_OTHER, enc_pack(dids, dmask, B, N, L, h->pm, s));
   h->launches += 3;   // enc_pack issues four kernels
   RC(encoder_stack(h, h->pm, B * N, L, Mmax, s));
@@ -533,6 +535,7 @@ int gram_create(const gram_config* cfg, gram_handle** out) {
   DAC(bs.err, 16);
   h->pm.err = bs.err;
   h->pm.vocab = V;
+  h->pm.cap = h->Mcap;
   DAC(h->d_len_pow, ((size_t)ML + 1) * 8);
   bs.len_pow = h->d_len_pow;
   bs.tap_lse = nullptr; bs.tap_score = nullptr; bs.tap_seq = nullptr;
@@ -709,6 +712,7 @@ int gram_cache_items(gram_handle* h, const int64_t* ids, const uint8_t* mask, in
 #undef DAC2
     h->pm_prompt.err = h->pm.err;
     h->pm_prompt.vocab = h->V;
+    h->pm_prompt.cap = (long long)U * c.max_seq_len;
   }
   // encode the items in chunks shaped like an ordinary batch [Bc, N, L] (item = first + b*N + n)
   const int N = c.max_passages;
@@ -756,7 +760,7 @@ int gram_encode_cached(gram_handle* h, const int64_t* prompt_ids, const uint8_t*
   const int N = NI + 1;
   if (B <= 0 || NI < 0) return fail(h, GRAM_ERR_INVALID, "gram_encode_cached: empty batch");
   if (B > c.max_users || N > c.max_passages) return fail(h, GRAM_ERR_INVALID, "gram_encode_cached: B/N exceed the capacities given to gram_create");
-  if ((int64_t)B * N * L > h->Mcap) return fail(h, GRAM_ERR_INVALID, "gram_encode_cached: B*N*L exceeds max_tokens");
+  if ((int64_t)B * N * L > 0x7fffffff) return fail(h, GRAM_ERR_INVALID, "gram_encode_cached: B*N*L exceeds 2^31");
   if (c.n_positions > 0 && N > c.n_positions) return fail(h, GRAM_ERR_INVALID, "gram_encode_cached: more passages than rows in the position table");
   h->launches = 0;
   const size_t n = (size_t)B * L;
@@ -775,7 +779,7 @@ int gram_encode_cached(gram_handle* h, const int64_t* prompt_ids, const uint8_t*
   CKL(GRAM_K_NORM_ENC, rmsnorm_rows(GRAM_DTYPE_F32, h->x, h->enc_final_ln, h->ff, (int)n, h->pm_prompt.total, h->D, c.ln_eps,
                                  1.f, nullptr, nullptr, s));
   // 2. user layout + memory = prompt rows / cached item rows + position rows
-  const int Mmax = (int)((size_t)B * N * L);
+  const int Mmax = (int)std::min<int64_t>((int64_t)B * N * L, h->Mcap);
   CKL(GRAM_K_OTHER, cached_pack_assemble(c.dtype, h->pm, h->pm_prompt, (const float*)h->ff, ditems, h->item_mem, h->item_valid,
                                          h->item_len, h->n_items, h->pos_emb, B, NI, L, h->D, h->mem, s));
   h->launches += 3;
@@ -854,6 +858,7 @@ int gram_generate(gram_handle* h, const int64_t* ids, const uint8_t* mask, int32
       cudaMemsetAsync(bs.err, 0, 4, s);
       return fail(h, GRAM_ERR_INVALID, code == 2   ? "gram_generate: input token id outside [0, vocab_size)"
                                        : code == 3 ? "gram_generate: item index outside the cached item table"
+                                       : code == 4 ? "gram_generate: the batch holds more valid tokens than max_tokens"
                                                    : "gram_generate: candidate buffer overflow (trie fan-out larger than declared)");
     }
   }
@@ -932,6 +937,7 @@ int gram_check_errors(gram_handle* h, void* stream) {
   CK(cudaMemsetAsync(h->pm.err, 0, 4, s));
   return fail(h, GRAM_ERR_INVALID, code == 2   ? "input token id outside [0, vocab_size)"
                                    : code == 3 ? "item index outside the cached item table"
+                                   : code == 4 ? "the batch holds more valid tokens than max_tokens"
                                                : "candidate buffer overflow (trie fan-out larger than declared)");
 }
 

@@ -55,6 +55,7 @@ struct PackMeta {            // device-resident description of the packed (valid
   int* row_src;              // [Mcap] flat index b*N*L + n*L + l of the packed row (for unpacking)
   int* err;                  // [1]    sticky device error flag (2 = token id outside the vocabulary)
   int vocab;                 // vocabulary size, for the id range check
+  long long cap;             // rows the packed buffers hold; a batch with more valid tokens is emptied and err = 4
 };
 cudaError_t enc_pack(const int64_t* ids, const uint8_t* mask, int B, int N, int L, PackMeta pm, cudaStream_t s);
 // per-item encoder-state cache (see encoder_kernels.cu): scatter a chunk's packed fp32 rows into the item table, and

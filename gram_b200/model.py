@@ -69,7 +69,7 @@ class GRAM:
         self._device = torch.device(device) if device is not None else None
         self._cap = dict(max_users=max_users, max_beams=max_beams or 1, max_length=max_length,
                          max_passages=max_passages or (g.max_item_num + 1),
-                         max_seq_len=max_seq_len or g.max_seq_len)
+                         max_seq_len=max_seq_len or g.max_seq_len, max_tokens=0)
         self._weights = None            # canonical name -> fp32 ndarray (host copy, reloaded on regrow)
         self._handle = None
         self._trie_key = None
@@ -150,8 +150,9 @@ class GRAM:
             pass
 
     def configure(self, **caps):
-        """Set capacities (max_users, max_beams, max_length, max_passages, max_seq_len) up front so the
-        engine is created once with the right workspace."""
+        """Set capacities (max_users, max_beams, max_length, max_passages, max_seq_len, max_tokens) up front so the
+        engine is created once with the right workspace.  max_tokens (0 = every passage full) sizes the encoder /
+        K-V workspace by VALID tokens per call, so a larger user batch fits when histories are short."""
         changed = False
         for k, v in caps.items():
             if k not in self._cap:
@@ -189,7 +190,7 @@ class GRAM:
             dtype=_cabi.GRAM_DTYPE_F32 if self.dtype == "fp32" else _cabi.GRAM_DTYPE_BF16,
             device=self.device.index or 0,
             max_users=cap["max_users"], max_passages=cap["max_passages"], max_seq_len=cap["max_seq_len"],
-            max_beams=cap["max_beams"], max_length=cap["max_length"], max_tokens=0, flags=self.flags)
+            max_beams=cap["max_beams"], max_length=cap["max_length"], max_tokens=cap["max_tokens"], flags=self.flags)
         hp = C.c_void_p()
         _cabi.check(lib.gram_create(C.byref(cc), C.byref(hp)), None, "gram_create")
         self._handle = hp

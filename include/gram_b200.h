@@ -48,7 +48,10 @@ typedef struct gram_config {
   int32_t max_seq_len;             /* L */
   int32_t max_beams;               /* K */
   int32_t max_length;              /* decoder max_length (start token included) */
-  int64_t max_tokens;              /* cap on packed valid encoder tokens per call; 0 = B*N*L */
+  int64_t max_tokens;              /* workspace rows = cap on VALID encoder tokens per call; 0 = max_users*max_passages*
+                                      max_seq_len (every passage full).  A smaller value lets a bigger user batch fit:
+                                      the valid-token count is checked on the device, a batch above it is emptied and
+                                      reported (gram_generate with host outputs / gram_check_errors)               */
   int32_t flags;                   /* GRAM_FLAG_* */
 } gram_config;
 

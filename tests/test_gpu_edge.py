@@ -154,3 +154,29 @@ def test_generate_from_a_csr_trie_file(tmp_path):
     b = m.generate(ids.cuda(), mask.cuda(), ml, prefix_allowed_tokens_fn=prefix_allowed_tokens_fn(formats.load_trie_csr(path)),
                    num_beams=K, num_return_sequences=K, return_dict_in_generate=True, length_penalty=case.length_penalty)
     assert torch.equal(a["sequences"], b["sequences"]) and torch.equal(a["sequences_scores"], b["sequences_scores"])
+
+
+def test_max_tokens_capacity_is_checked_on_the_device():
+    """max_tokens sizes the workspace by VALID tokens: a batch below it runs (identical results to the uncapped
+    engine), a batch above it is reported, not silently truncated."""
+    case = CASES["tiny"]
+    sd, ids, mask, seqs, ml = case.build()
+    fn = prefix_allowed_tokens_fn(Trie(seqs))
+    K = case.num_beams
+    valid = int(mask.sum())
+    ref = GRAM(case.cfg, dtype="fp32", device="cuda:0")
+    ref.load_state_dict(sd)
+    want = ref.generate(ids.cuda(), mask.cuda(), ml, prefix_allowed_tokens_fn=fn, num_beams=K, num_return_sequences=K)
+    m = GRAM(case.cfg, dtype="fp32", device="cuda:0")
+    m.load_state_dict(sd)
+    m.configure(max_users=ids.shape[0], max_passages=ids.shape[1], max_seq_len=ids.shape[2], max_tokens=valid + 1)
+    assert valid + 1 < ids.numel() // 1                       # the padded size would not fit
+    got = m.generate(ids.cuda(), mask.cuda(), ml, prefix_allowed_tokens_fn=fn, num_beams=K, num_return_sequences=K)
+    assert torch.equal(got, want)
+    m.configure(max_tokens=valid - 1)
+    with pytest.raises(ValueError, match="max_tokens"):
+        m.generate(ids.cuda(), mask.cuda(), ml, prefix_allowed_tokens_fn=fn, num_beams=K, num_return_sequences=K)
+    with pytest.raises(ValueError, match="max_tokens"):      # host tensors: reported by gram_generate itself
+        m.generate(ids, mask, ml, prefix_allowed_tokens_fn=fn, num_beams=K, num_return_sequences=K)
+    m.configure(max_tokens=0)
+    assert torch.equal(m.generate(ids.cuda(), mask.cuda(), ml, prefix_allowed_tokens_fn=fn, num_beams=K, num_return_sequences=K), want)
