@@ -9,7 +9,9 @@ from __future__ import annotations
 import ctypes as C
 import os
 
-_LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libgram_b200.so")
+# GRAM_B200_LIB selects another build of the same library (A/B timing of two builds inside one process launch each)
+_LIB_PATH = os.environ.get("GRAM_B200_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib",
+                                                            "libgram_b200.so")
 
 GRAM_DTYPE_F32, GRAM_DTYPE_BF16 = 0, 1
 GRAM_FLAG_SIMT_GEMM, GRAM_FLAG_KEEP_LOGITS, GRAM_FLAG_SIMT_ATTN, GRAM_FLAG_TC_ENC_ATTN, GRAM_FLAG_GEMM_1CTA = 1, 2, 4, 8, 16

@@ -141,7 +141,7 @@ __device__ __forceinline__ void flash_tile(const uint32_t (&qf)[MT][4][4], uint3
       t = fmaxf(t, __shfl_xor_sync(0xffffffffu, t, 2));
       const float m_old = m_run[mt][hf];
       const float m_new = fmaxf(m_old, t);
-      const float corr = (m_old == -INFINITY) ? 0.f : exp2f((m_old - m_new) * LOG2E);
+      const float corr = (m_old == -INFINITY) ? 0.f : ex2_ftz((m_old - m_new) * LOG2E);
       m_run[mt][hf] = m_new;
       l_run[mt][hf] *= corr;
       const float mb = (m_new == -INFINITY) ? 0.f : m_new * LOG2E;
@@ -151,7 +151,7 @@ __device__ __forceinline__ void flash_tile(const uint32_t (&qf)[MT][4][4], uint3
 #pragma unroll
         for (int e2 = 0; e2 < 2; ++e2) {
           const int e = hf * 2 + e2;
-          const float p = exp2f(s[mt][nt][e] * LOG2E - mb);     // exp2(-inf) = 0 for masked keys
+          const float p = ex2_ftz(s[mt][nt][e] * LOG2E - mb);     // exp2(-inf) = 0 for masked keys
           s[mt][nt][e] = p;
           psum += p;
         }
@@ -340,8 +340,8 @@ cross_attention_mma_kernel(const __grid_constant__ CUtensorMap map_kv, const bf1
       for (int hf = 0; hf < 2; ++hf) {
         const float m0 = m_run[mt][hf], m1 = src[(mt * 2 + hf) * 32];
         const float mn = fmaxf(m0, m1);
-        const float c0 = (m0 == -INFINITY) ? 0.f : exp2f((m0 - mn) * LOG2E);
-        const float c1 = (m1 == -INFINITY) ? 0.f : exp2f((m1 - mn) * LOG2E);
+        const float c0 = (m0 == -INFINITY) ? 0.f : ex2_ftz((m0 - mn) * LOG2E);
+        const float c1 = (m1 == -INFINITY) ? 0.f : ex2_ftz((m1 - mn) * LOG2E);
         l_run[mt][hf] = l_run[mt][hf] * c0 + src[(4 + mt * 2 + hf) * 32] * c1;
 #pragma unroll
         for (int nt = 0; nt < 8; ++nt) {

@@ -44,6 +44,15 @@ __device__ __forceinline__ void store4(bf16* p, float4 v) {
   *reinterpret_cast<uint2*>(p) = u;
 }
 
+// 2^x as ONE instruction (MUFU.EX2 with flush-to-zero).  exp2f() brackets the same MUFU with a range test and two
+// scalings so that results below 2^-126 come out denormal instead of 0 -- four instructions per softmax element for a
+// distinction a softmax weight cannot use.  Identical bits whenever the result is a normal number.
+__device__ __forceinline__ float ex2_ftz(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 // ---- warp reductions --------------------------------------------------------------------------
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

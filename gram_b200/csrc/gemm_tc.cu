@@ -350,8 +350,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           if (nm > -INFINITY) {
             float cs = 0.f;
 #pragma unroll
-            for (int e = 0; e < 32; ++e) cs += exp2f((__uint_as_float(v[e]) - nm) * 1.4426950408889634f);
-            sum = sum * exp2f((mx - nm) * 1.4426950408889634f) + cs;
+            for (int e = 0; e < 32; ++e) cs += ex2_ftz((__uint_as_float(v[e]) - nm) * 1.4426950408889634f);
+            sum = sum * ex2_ftz((mx - nm) * 1.4426950408889634f) + cs;
             mx = nm;
           }
         }
