@@ -35,9 +35,10 @@ def test_library_exports_every_declared_symbol():
 def test_config_struct_layout_matches_header():
     header = open(os.path.join(ROOT, "include", "gram_b200.h")).read()
     body = header[header.index("typedef struct gram_config {"):header.index("} gram_config;")]
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)      # comments may span lines
     fields = []
     for line in body.splitlines()[1:]:
-        line = line.split("/*")[0].strip().rstrip(";")
+        line = line.strip().rstrip(";")
         if not line:
             continue
         typ, names = line.split(None, 1)
