@@ -55,6 +55,8 @@ def parse():
     ap.add_argument("--no-item-cache", action="store_true", help="skip the extra (non-headline) cached-item measurement")
     ap.add_argument("--gemm-1cta", action="store_true", help="keep every tcgen05 GEMM on single-CTA tiles (A/B timing)")
     ap.add_argument("--tc-enc-attn", action="store_true", help="opt into the tcgen05 encoder-attention kernel (A/B timing)")
+    ap.add_argument("--all-rows", action="store_true",
+                    help="decode dead beams / finished users too, as the reference does (A/B timing of live-row compaction)")
     return ap.parse_args()
 
 
@@ -238,6 +240,8 @@ def workload_config(args, data, max_length):
                          f"return {BEAMS}, max_length {max_length}, max_his {data.max_his} x {data.L} tokens",
                 users_per_step_per_gpu=args.batch, workspace="sized by the valid tokens of the largest step (max_tokens), not by users x 21 full passages", parallelism=f"user-sharded dp{args.gpus}",
                 inputs="surrogate tokenizer + synthetic metadata tokens + random-init tied weights (seed 0)",
+                decode_rows="every beam row (reference behaviour)" if args.all_rows else
+                "live beams only: dead (-inf) beams and finished users are compacted away on the device before each decode step; rankings and scores bit-identical (tests/test_gpu_live_rows.py)",
                 cache="per-step working set (K/V memory + activations, > 8 GB) exceeds the 126 MB L2; every step uses different users")
 
 
@@ -286,7 +290,7 @@ def main():
     from gram_b200 import GRAM, _cabi
     data, cfg, sd, cands, max_length, trie, fn = build_workload(args, rank, world)
     flags = (_cabi.GRAM_FLAG_SIMT_GEMM if args.simt else 0) | (_cabi.GRAM_FLAG_TC_ENC_ATTN if args.tc_enc_attn else 0) | \
-        (_cabi.GRAM_FLAG_GEMM_1CTA if args.gemm_1cta else 0)
+        (_cabi.GRAM_FLAG_GEMM_1CTA if args.gemm_1cta else 0) | (_cabi.GRAM_FLAG_ALL_ROWS if args.all_rows else 0)
     model = GRAM(cfg, dtype=args.dtype, device=dev, flags=flags)
     model.load_state_dict(sd)
     B, K, W, S = args.batch, BEAMS, args.warmup, args.steps

@@ -292,7 +292,8 @@ template <int HEADS, int BH, int KH, int MINB, int MT = 2>
 __global__ void __launch_bounds__(xa_threads(HEADS * BH * KH), MINB)
 cross_attention_mma_kernel(const __grid_constant__ CUtensorMap map_kv, const bf16* __restrict__ qg,
                            bf16* __restrict__ out, const int* __restrict__ ustart, const int* __restrict__ uorder,
-                           const uint8_t* __restrict__ tok_valid, int K, int H, int k_col0, int v_col0) {
+                           const uint8_t* __restrict__ tok_valid, int K_all, int H, int k_col0, int v_col0,
+                           const int* __restrict__ live_start, const int* __restrict__ live_count) {
   constexpr int XA_HEADS = HEADS;
   constexpr uint32_t XA_STAGE_BYTES = 2 * HEADS * BOX_BYTES;   // K boxes then V boxes
   constexpr int XA_STAGES = MINB == 2 ? 3 : 3 * XA_STAGE_TARGET / (int)XA_STAGE_BYTES;
@@ -309,6 +310,11 @@ cross_attention_mma_kernel(const __grid_constant__ CUtensorMap map_kv, const bf1
   // short ones fill the tail of the last wave
   const int u = uorder ? uorder[blockIdx.x] : blockIdx.x, hg = blockIdx.y;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // query rows: the user's K beams, or (live-row compaction) its live beams only; a user whose beams are all dead or
+  // whose hypotheses are final does not stream its K/V at all
+  const int K = live_start ? live_count[u] : K_all;
+  if (K == 0) return;
+  const int qrow0 = live_start ? live_start[u] : u * K_all;
   const int s_beg = ustart[u], s_end = ustart[u + 1];
   const int n_tiles = (s_end - s_beg + TS - 1) / TS;
   const int HD = H * DK;
@@ -362,7 +368,7 @@ cross_attention_mma_kernel(const __grid_constant__ CUtensorMap map_kv, const bf1
         const int b = b_off + mt * 16 + g + ((e & 1) << 3);
         const int d = ks * 16 + 2 * q + ((e >> 1) << 3);
         uint32_t v = 0u;
-        if (b < K) v = *reinterpret_cast<const uint32_t*>(qg + (size_t)(u * K + b) * HD + h * DK + d);
+        if (b < K) v = *reinterpret_cast<const uint32_t*>(qg + (size_t)(qrow0 + b) * HD + h * DK + d);
         qf[mt][ks][e] = v;
       }
     }
@@ -439,7 +445,7 @@ cross_attention_mma_kernel(const __grid_constant__ CUtensorMap map_kv, const bf1
       const float inv = l > 0.f ? 1.0f / l : 0.f;
       const int b = b_off + mt * 16 + g + hf * 8;
       if (b < K) {
-        bf16* orow = out + (size_t)(u * K + b) * HD + h * DK;
+        bf16* orow = out + (size_t)(qrow0 + b) * HD + h * DK;
 #pragma unroll
         for (int nt = 0; nt < 8; ++nt)
           *reinterpret_cast<uint32_t*>(orow + nt * 8 + 2 * q) = pack_bf16(o[mt][nt][hf * 2] * inv, o[mt][nt][hf * 2 + 1] * inv);
@@ -600,7 +606,7 @@ bool cross_attention_mma_supported(int K, int H, int dk) { return dk == fa::DK &
 
 cudaError_t cross_attention_mma(const void* q, const void* kv, size_t kv_rows, size_t kv_stride, int k_off, int v_off,
                                 const int* ustart, const int* uorder, const uint8_t* tok_valid, void* out, int users,
-                                int K, int H, cudaStream_t s) {
+                                int K, int H, const int* live_start, const int* live_count, cudaStream_t s) {
   if (users <= 0) return cudaSuccess;
   std::lock_guard<std::mutex> lk(fa::g_mu);
   CUtensorMap map;
@@ -614,7 +620,7 @@ cudaError_t cross_attention_mma(const void* q, const void* kv, size_t kv_rows, s
       if (e != cudaSuccess) return e;
     }
     kern<<<dim3(users, H / 4), fa::xa_threads(4), smem, s>>>(map, (const bf16*)q, (bf16*)out, ustart, uorder, tok_valid, K, H,
-                                                          k_off, v_off);
+                                                          k_off, v_off, live_start, live_count);
   } else {
     auto kern = fa::cross_attention_mma_kernel<2, 2, 1, 1>;
     {
@@ -622,7 +628,7 @@ cudaError_t cross_attention_mma(const void* q, const void* kv, size_t kv_rows, s
       if (e != cudaSuccess) return e;
     }
     kern<<<dim3(users, H / 2), fa::xa_threads(4), smem, s>>>(map, (const bf16*)q, (bf16*)out, ustart, uorder, tok_valid, K, H,
-                                                          k_off, v_off);
+                                                          k_off, v_off, live_start, live_count);
   }
   return cudaGetLastError();
 }

@@ -28,9 +28,11 @@ namespace gram {
 // ------------------------------------------------------------------------------------------------
 // lse[row] = log(sum(exp(logits[row, :])))  computed as max + log(sum(exp(x - max)))
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) lse_rows_kernel(const float* __restrict__ logits, float* __restrict__ lse, int V) {
+__global__ void __launch_bounds__(256) lse_rows_kernel(const float* __restrict__ logits, float* __restrict__ lse, int V,
+                                                       const int* __restrict__ n_rows) {
   __shared__ float red[8];
   __shared__ float bcast;
+  if (n_rows && (int)blockIdx.x >= *n_rows) return;
   const float* x = logits + (size_t)blockIdx.x * V;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   float mx = -INFINITY;
@@ -64,16 +66,17 @@ __global__ void __launch_bounds__(256) lse_rows_kernel(const float* __restrict__
   }
 }
 
-cudaError_t lse_rows(const float* logits, float* lse, int R, int V, cudaStream_t s) {
+cudaError_t lse_rows(const float* logits, float* lse, int R, int V, const int* n_rows, cudaStream_t s) {
   if (R <= 0) return cudaSuccess;
   if (V & 3) return cudaErrorInvalidValue;
-  lse_rows_kernel<<<R, 256, 0, s>>>(logits, lse, V);
+  lse_rows_kernel<<<R, 256, 0, s>>>(logits, lse, V, n_rows);
   return cudaGetLastError();
 }
 
-__global__ void lse_combine_kernel(const float2* __restrict__ partial, float* __restrict__ lse, int R, int n_tiles) {
+__global__ void lse_combine_kernel(const float2* __restrict__ partial, float* __restrict__ lse, int R, int n_tiles,
+                                   const int* __restrict__ n_rows) {
   const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  if (row >= R) return;
+  if (row >= (n_rows ? *n_rows : R)) return;
   const float2* p = partial + (size_t)row * n_tiles;
   float mx = -INFINITY;
   for (int i = lane; i < n_tiles; i += 32) mx = fmaxf(mx, p[i].x);
@@ -87,9 +90,9 @@ __global__ void lse_combine_kernel(const float2* __restrict__ partial, float* __
   if (lane == 0) lse[row] = mx + logf(sum);
 }
 
-cudaError_t lse_combine(const void* partial, float* lse, int R, int n_tiles, cudaStream_t s) {
+cudaError_t lse_combine(const void* partial, float* lse, int R, int n_tiles, const int* n_rows, cudaStream_t s) {
   if (R <= 0) return cudaSuccess;
-  lse_combine_kernel<<<(R + 7) / 8, 256, 0, s>>>((const float2*)partial, lse, R, n_tiles);
+  lse_combine_kernel<<<(R + 7) / 8, 256, 0, s>>>((const float2*)partial, lse, R, n_tiles, n_rows);
   return cudaGetLastError();
 }
 
@@ -108,6 +111,7 @@ __global__ void beam_init_kernel(BeamState bs, int root, int users, int start_to
     bs.worst[r] = 1e9;
     bs.next_seqno[r] = 0;
     bs.done[r] = 0;
+    bs.live_cnt[r] = bs.K;
   }
 }
 
@@ -186,7 +190,7 @@ size_t beam_step_smem(int cand_cap) { return (size_t)cand_cap * sizeof(unsigned 
 __global__ void __launch_bounds__(BEAM_THREADS)
 beam_step_kernel(BeamState bs, TrieCSR trie, const float* __restrict__ logits, const bf16* __restrict__ hidden,
                  const bf16* __restrict__ head, int D, const float* __restrict__ lse, int users, int t, int cand_cap,
-                 int compact) {
+                 int compact, const int* __restrict__ row_slot) {
   extern __shared__ __align__(16) unsigned long long keys[];
   __shared__ int pre[BEAM_KMAX + 1];
   __shared__ int sel_parent[BEAM_KMAX], sel_tok[BEAM_KMAX], sel_node[BEAM_KMAX];
@@ -205,10 +209,14 @@ beam_step_kernel(BeamState bs, TrieCSR trie, const float* __restrict__ logits, c
   const int* node_c = bs.node[cur];
   const int* seq_c = bs.seq[cur];
   const int* anc_c = bs.anc[cur];
+  // decoder row (of logits / hidden / lse) that served beam row `row`: the user's single row at the compact step 0,
+  // the beam's compact slot under live-row compaction (dead beams have none and offer no candidates), else the row
+  auto dec_row = [&](int row) { return compact ? u : (row_slot ? row_slot[row] : row); };
 
   if (bs.tap_lse) {
     for (int b = tid; b < K; b += BEAM_THREADS) {
-      bs.tap_lse[(size_t)t * R + base + b] = lse[compact ? u : base + b];
+      const int lr = dec_row(base + b);
+      bs.tap_lse[(size_t)t * R + base + b] = lr >= 0 ? lse[lr] : 0.f;
       bs.tap_score[(size_t)t * R + base + b] = score_c[base + b];
     }
     for (int i = tid; i < K * ML; i += BEAM_THREADS)
@@ -223,6 +231,7 @@ beam_step_kernel(BeamState bs, TrieCSR trie, const float* __restrict__ logits, c
       bs.node[nxt][base + b] = -1;
       bs.tok[base + b] = bs.pad;
     }
+    if (tid == 0) bs.live_cnt[u] = 0;
     for (int i = tid; i < K * ML; i += BEAM_THREADS) {
       const int b = i / ML, j = i % ML;
       bs.seq[nxt][(size_t)base * ML + i] = (j == cur_len) ? bs.pad : seq_c[(size_t)base * ML + i];
@@ -275,7 +284,7 @@ beam_step_kernel(BeamState bs, TrieCSR trie, const float* __restrict__ logits, c
         while (pre[b + 1] <= c) ++b;                         // K <= 64, linear search
         const int e = cand_off[b] + (c - pre[b]);
         const int tok = trie.child_tokens[e];
-        const int row = base + b, lrow = compact ? u : row;   // compact step: one decoder row per user
+        const int row = base + b, lrow = dec_row(row);
         float s = (logits[(size_t)lrow * V + tok] - lse[lrow]) + score_c[row];
         if (!(s == s)) s = -INFINITY;
         // children are stored token-ascending, so the enumeration index c orders candidates exactly like the flat
@@ -305,7 +314,7 @@ beam_step_kernel(BeamState bs, TrieCSR trie, const float* __restrict__ logits, c
       }
 #pragma unroll
       for (int j = 0; j < UN; ++j) {
-        hr[j] = hidden + (size_t)(compact ? u : base + bb[j]) * D;
+        hr[j] = hidden + (size_t)dec_row(base + bb[j]) * D;
         er[j] = head + (size_t)tk[j] * D;
       }
       float a[UN];
@@ -339,7 +348,7 @@ beam_step_kernel(BeamState bs, TrieCSR trie, const float* __restrict__ logits, c
         int b = bb[0];
 #pragma unroll
         for (int j = 1; j < UN; ++j) b = (lane == j) ? bb[j] : b;
-        const int row = base + b, lrow = compact ? u : row;
+        const int row = base + b, lrow = dec_row(row);
         float sc = (av - lse[lrow]) + score_c[row];
         if (!(sc == sc)) sc = -INFINITY;
         keys[c0 + lane] = ((unsigned long long)float_key(sc) << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned int)(c0 + lane));
@@ -396,10 +405,16 @@ beam_step_kernel(BeamState bs, TrieCSR trie, const float* __restrict__ logits, c
     }
     for (; slot < K; ++slot) { sel_parent[slot] = 0; sel_tok[slot] = bs.pad; sel_node[slot] = -1; sel_score[slot] = -INFINITY; }
     // BeamHypotheses.is_done(best_sum_logprobs = max of the 2K candidate scores, cur_len)
+    bool done = false;
     if (*hv.n >= K) {
       const double cur_score = (double)best / bs.len_pow[cur_len];
-      if (*hv.worst >= cur_score) bs.done[u] = 1;
+      if (*hv.worst >= cur_score) { bs.done[u] = 1; done = true; }
     }
+    // beams the next step has to decode: candidates were taken best-first, so the live ones (finite score, a trie
+    // node to continue from) are the first `live` slots
+    int live = 0;
+    while (live < K && sel_node[live] >= 0 && sel_score[live] > -INFINITY) ++live;
+    bs.live_cnt[u] = done ? 0 : live;
   }
   __syncthreads();
   for (int b = tid; b < K; b += BEAM_THREADS) {
@@ -422,7 +437,7 @@ beam_step_kernel(BeamState bs, TrieCSR trie, const float* __restrict__ logits, c
 }
 
 cudaError_t beam_step(BeamState bs, TrieCSR trie, const float* logits, const void* hidden, const void* head, int D,
-                      const float* lse, int users, int t, int cand_cap, int compact, cudaStream_t s) {
+                      const float* lse, int users, int t, int cand_cap, int compact, const int* row_slot, cudaStream_t s) {
   if (users <= 0) return cudaSuccess;
   if (bs.K > BEAM_KMAX) return cudaErrorInvalidValue;
   if (logits == nullptr && (hidden == nullptr || head == nullptr || (D & 7))) return cudaErrorInvalidValue;
@@ -433,7 +448,7 @@ cudaError_t beam_step(BeamState bs, TrieCSR trie, const float* logits, const voi
     if (e != cudaSuccess) return e;
   }
   beam_step_kernel<<<users, BEAM_THREADS, smem, s>>>(bs, trie, logits, (const bf16*)hidden, (const bf16*)head, D, lse, users, t,
-                                                     cand_cap, compact);
+                                                     cand_cap, compact, row_slot);
   return cudaGetLastError();
 }
 
@@ -486,6 +501,74 @@ cudaError_t beam_finalize(BeamState bs, int users, int t_final, int R_ret, int64
   cudaError_t e = cudaMemsetAsync(out_width, 0, sizeof(int), s);
   if (e != cudaSuccess) return e;
   beam_finalize_kernel<<<(users + 63) / 64, 64, 0, s>>>(bs, users, t_final, R_ret, (long long*)out_seq, out_scores, out_width);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+// live-row compaction: slot ranges per user (one CTA, chunked block scan), then the row <-> slot maps
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) live_scan_kernel(const int* __restrict__ live_cnt, int users, int* __restrict__ start,
+                                                         int* __restrict__ n_live) {
+  __shared__ int warp_tot[32];
+  __shared__ int carry_s;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  if (tid == 0) carry_s = 0;
+  __syncthreads();
+  for (int u0 = 0; u0 < users; u0 += 1024) {
+    const int u = u0 + tid;
+    const int c = u < users ? live_cnt[u] : 0;
+    int x = c;                                              // inclusive scan within the warp
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int y = __shfl_up_sync(0xffffffffu, x, o);
+      if (lane >= o) x += y;
+    }
+    if (lane == 31) warp_tot[wid] = x;
+    __syncthreads();
+    if (wid == 0) {
+      int w = warp_tot[lane];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int y = __shfl_up_sync(0xffffffffu, w, o);
+        if (lane >= o) w += y;
+      }
+      warp_tot[lane] = w;                                   // inclusive totals of warps 0..lane
+    }
+    __syncthreads();
+    const int carry = carry_s;
+    if (u < users) start[u] = carry + (wid ? warp_tot[wid - 1] : 0) + x - c;
+    __syncthreads();
+    if (tid == 0) carry_s = carry + warp_tot[31];
+    __syncthreads();
+  }
+  if (tid == 0) { start[users] = carry_s; *n_live = carry_s; }
+}
+
+__global__ void live_fill_kernel(BeamState bs, int users, int cur, LiveMap lm) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  const int K = bs.K;
+  if (r >= users * K) return;
+  const int u = r / K, b = r - u * K;
+  const int c = bs.live_cnt[u];
+  // cross-check of the "live beams are the first live_cnt beams" contract against the beam state itself
+  const bool alive = bs.done[u] == 0 && bs.node[cur][r] >= 0 && bs.beam_score[cur][r] > -INFINITY;
+  if (alive != (b < c)) atomicExch(bs.err, 5);
+  int slot = -1;
+  if (b < c) {
+    slot = lm.start[u] + b;
+    lm.slot_row[slot] = r;
+    lm.tok[slot] = bs.tok[r];
+  }
+  lm.row_slot[r] = slot;
+}
+
+cudaError_t live_compact(BeamState bs, int users, int cur, LiveMap lm, cudaStream_t s) {
+  if (users <= 0) return cudaSuccess;
+  live_scan_kernel<<<1, 1024, 0, s>>>(bs.live_cnt, users, lm.start, lm.n_live);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  const int R = users * bs.K;
+  live_fill_kernel<<<(R + 255) / 256, 256, 0, s>>>(bs, users, cur, lm);
   return cudaGetLastError();
 }
 

@@ -25,13 +25,15 @@ template <typename T, int DK>
 __global__ void __launch_bounds__(128)
 dec_self_attention_kernel(const T* __restrict__ qkv, T* __restrict__ cache_k, T* __restrict__ cache_v,
                           const int* __restrict__ anc, int Tmax, const float* __restrict__ dec_bias, int n_dec,
-                          T* __restrict__ out, int R, int K, int H, int t) {
+                          T* __restrict__ out, int R, int K, int H, int t, const int* __restrict__ slot_row,
+                          const int* __restrict__ n_rows) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  if (warp >= R * H) return;
-  const int r = warp / H, h = warp % H;
+  if (warp >= (n_rows ? *n_rows : R) * H) return;
+  const int slot = warp / H, h = warp % H;                  // qkv / out row
+  const int r = slot_row ? slot_row[slot] : slot;           // beam row: cache row, ancestry, user membership
   const int HD = H * DK;
   const int ubase = (r / K) * K;
-  const T* qrow = qkv + (size_t)r * 3 * HD + h * DK;
+  const T* qrow = qkv + (size_t)slot * 3 * HD + h * DK;
   // append this step's key/value (slot t, own row)
   T* kslot = cache_k + ((size_t)t * R + r) * HD + h * DK;
   T* vslot = cache_v + ((size_t)t * R + r) * HD + h * DK;
@@ -96,7 +98,7 @@ dec_self_attention_kernel(const T* __restrict__ qkv, T* __restrict__ cache_k, T*
       if (d < DK) o[e] = fmaf(pj, to_f32(vr[d]), o[e]);
     }
   }
-  T* orow = out + (size_t)r * HD + h * DK;
+  T* orow = out + (size_t)slot * HD + h * DK;
 #pragma unroll
   for (int e = 0; e < (DK + 31) / 32; ++e) {
     const int d = lane + 32 * e;
@@ -135,19 +137,21 @@ template <typename T>
 __global__ void __launch_bounds__(128)
 dec_self_attention64_kernel(const T* __restrict__ qkv, T* __restrict__ cache_k, T* __restrict__ cache_v,
                             const int* __restrict__ anc, int Tmax, const float* __restrict__ dec_bias, int n_dec,
-                            T* __restrict__ out, int R, int K, int H, int t) {
+                            T* __restrict__ out, int R, int K, int H, int t, const int* __restrict__ slot_row,
+                            const int* __restrict__ n_rows) {
   constexpr int DK = 64;
   const int HQ = H >> 2;                                 // head quads per row
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  if (warp >= R * HQ) return;
-  const int r = warp / HQ, h = (warp % HQ) * 4 + (lane >> 3), c = lane & 7;
+  if (warp >= (n_rows ? *n_rows : R) * HQ) return;
+  const int slot = warp / HQ, h = (warp % HQ) * 4 + (lane >> 3), c = lane & 7;
+  const int r = slot_row ? slot_row[slot] : slot;        // beam row: cache row, ancestry, user membership
   const int HD = H * DK;
   const int ubase = (r / K) * K;
   const size_t col = (size_t)h * DK + c * 8;
   // ancestry of this row: lane j holds position j (and j + 32)
   const int a0 = (lane < t) ? anc[(size_t)r * Tmax + lane] : 0;
   const int a1 = (lane + 32 < t) ? anc[(size_t)r * Tmax + lane + 32] : 0;
-  const T* qrow = qkv + (size_t)r * 3 * HD + col;
+  const T* qrow = qkv + (size_t)slot * 3 * HD + col;
   float qv[8], kc[8], vc[8];
   load8(qrow, qv);
   load8(qrow + HD, kc);
@@ -196,23 +200,23 @@ dec_self_attention64_kernel(const T* __restrict__ qkv, T* __restrict__ cache_k, 
   const float inv = 1.0f / l;
 #pragma unroll
   for (int e = 0; e < 8; ++e) acc[e] *= inv;
-  store8(out + (size_t)r * HD + col, acc);
+  store8(out + (size_t)slot * HD + col, acc);
 }
 
 template <typename T>
 static cudaError_t launch_dec_self(const void* qkv, void* ck, void* cv, const int* anc, int Tmax,
                                    const float* dec_bias, int n_dec, void* out, int R, int K, int H, int dk, int t,
-                                   cudaStream_t s) {
+                                   const int* slot_row, const int* n_rows, cudaStream_t s) {
   const int warps = (dk == 64 && (H & 3) == 0) ? R * (H / 4) : R * H;
   const int grid = (warps + 3) / 4;
   if (dk == 64 && (H & 3)) {
-    dec_self_attention_kernel<T, 64><<<grid, 128, 0, s>>>((const T*)qkv, (T*)ck, (T*)cv, anc, Tmax, dec_bias, n_dec, (T*)out, R, K, H, t);
+    dec_self_attention_kernel<T, 64><<<grid, 128, 0, s>>>((const T*)qkv, (T*)ck, (T*)cv, anc, Tmax, dec_bias, n_dec, (T*)out, R, K, H, t, slot_row, n_rows);
     return cudaGetLastError();
   }
   switch (dk) {
-    case 16: dec_self_attention_kernel<T, 16><<<grid, 128, 0, s>>>((const T*)qkv, (T*)ck, (T*)cv, anc, Tmax, dec_bias, n_dec, (T*)out, R, K, H, t); break;
-    case 32: dec_self_attention_kernel<T, 32><<<grid, 128, 0, s>>>((const T*)qkv, (T*)ck, (T*)cv, anc, Tmax, dec_bias, n_dec, (T*)out, R, K, H, t); break;
-    case 64: dec_self_attention64_kernel<T><<<grid, 128, 0, s>>>((const T*)qkv, (T*)ck, (T*)cv, anc, Tmax, dec_bias, n_dec, (T*)out, R, K, H, t); break;
+    case 16: dec_self_attention_kernel<T, 16><<<grid, 128, 0, s>>>((const T*)qkv, (T*)ck, (T*)cv, anc, Tmax, dec_bias, n_dec, (T*)out, R, K, H, t, slot_row, n_rows); break;
+    case 32: dec_self_attention_kernel<T, 32><<<grid, 128, 0, s>>>((const T*)qkv, (T*)ck, (T*)cv, anc, Tmax, dec_bias, n_dec, (T*)out, R, K, H, t, slot_row, n_rows); break;
+    case 64: dec_self_attention64_kernel<T><<<grid, 128, 0, s>>>((const T*)qkv, (T*)ck, (T*)cv, anc, Tmax, dec_bias, n_dec, (T*)out, R, K, H, t, slot_row, n_rows); break;
     default: return cudaErrorInvalidValue;
   }
   return cudaGetLastError();
@@ -220,11 +224,12 @@ static cudaError_t launch_dec_self(const void* qkv, void* ck, void* cv, const in
 
 cudaError_t dec_self_attention(int dtype, const void* qkv, void* cache_k, void* cache_v, const int* anc, int Tmax,
                                const float* dec_bias, int n_dec, void* out, int R, int K, int H, int dk, int t,
-                               cudaStream_t s) {
+                               const int* slot_row, const int* n_rows, cudaStream_t s) {
   if (R <= 0) return cudaSuccess;
   if (t + 1 > 64) return cudaErrorInvalidValue;
-  if (dtype == 0) return launch_dec_self<float>(qkv, cache_k, cache_v, anc, Tmax, dec_bias, n_dec, out, R, K, H, dk, t, s);
-  return launch_dec_self<bf16>(qkv, cache_k, cache_v, anc, Tmax, dec_bias, n_dec, out, R, K, H, dk, t, s);
+  if (dtype == 0)
+    return launch_dec_self<float>(qkv, cache_k, cache_v, anc, Tmax, dec_bias, n_dec, out, R, K, H, dk, t, slot_row, n_rows, s);
+  return launch_dec_self<bf16>(qkv, cache_k, cache_v, anc, Tmax, dec_bias, n_dec, out, R, K, H, dk, t, slot_row, n_rows, s);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -240,12 +245,16 @@ template <typename T, int DK>
 __global__ void __launch_bounds__(XA_THREADS)
 cross_attention_kernel(const T* __restrict__ q, const T* __restrict__ kv, size_t kv_stride, int k_off, int v_off,
                        const int* __restrict__ ustart, const uint8_t* __restrict__ tok_valid, T* __restrict__ out,
-                       int K, int H) {
+                       int K_all, int H, const int* __restrict__ live_start, const int* __restrict__ live_count) {
   constexpr int KS = DK + 4;                 // padded, keeps 16B alignment and conflict-free LDS.128
   constexpr int G = XA_THREADS / DK;         // beam groups in the PV phase
   constexpr int NBT = (XA_KMAX + G - 1) / G; // beams per thread in the PV phase
   constexpr int NBS = XA_KMAX / 4;           // beams per thread in the score phase (4 groups of 32 rows)
   const int u = blockIdx.x, h = blockIdx.y;
+  // query rows of this user: its K beams, or (live-row compaction) its live beams only
+  const int K = live_start ? live_count[u] : K_all;
+  if (K == 0) return;
+  const int qrow0 = live_start ? live_start[u] : u * K_all;
   const int s_beg = ustart[u], s_end = ustart[u + 1];
   const int HD = H * DK;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -261,7 +270,7 @@ cross_attention_kernel(const T* __restrict__ q, const T* __restrict__ kv, size_t
 
   for (int i = tid; i < K * DK; i += XA_THREADS) {
     const int b = i / DK, d = i % DK;
-    qs[b * DK + d] = to_f32(q[(size_t)(u * K + b) * HD + h * DK + d]);
+    qs[b * DK + d] = to_f32(q[(size_t)(qrow0 + b) * HD + h * DK + d]);
   }
   for (int i = tid; i < XA_KMAX; i += XA_THREADS) { m_s[i] = -INFINITY; l_s[i] = 0.f; c_s[i] = 0.f; }
 
@@ -352,7 +361,7 @@ cross_attention_kernel(const T* __restrict__ q, const T* __restrict__ kv, size_t
     const int b = pv_g + G * i;
     if (b < K) {
       const float l = l_s[b];
-      out[(size_t)(u * K + b) * HD + h * DK + pv_d] = from_f32<T>(l > 0.f ? acc[i] / l : 0.f);
+      out[(size_t)(qrow0 + b) * HD + h * DK + pv_d] = from_f32<T>(l > 0.f ? acc[i] / l : 0.f);
     }
   }
 }
@@ -360,27 +369,30 @@ cross_attention_kernel(const T* __restrict__ q, const T* __restrict__ kv, size_t
 template <typename T, int DK>
 static cudaError_t launch_cross(const void* q, const void* kv, size_t kv_stride, int k_off, int v_off,
                                 const int* ustart, const uint8_t* tok_valid, void* out, int users, int K, int H,
-                                cudaStream_t s) {
+                                const int* live_start, const int* live_count, cudaStream_t s) {
   constexpr int KS = DK + 4;
   const size_t smem = sizeof(float) * ((size_t)XA_KMAX * DK + XA_TS * KS + XA_TS * DK + XA_KMAX * XA_TS + 3 * XA_KMAX);
   auto kern = cross_attention_kernel<T, DK>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   kern<<<dim3(users, H), XA_THREADS, smem, s>>>((const T*)q, (const T*)kv, kv_stride, k_off, v_off, ustart,
-                                                 tok_valid, (T*)out, K, H);
+                                                 tok_valid, (T*)out, K, H, live_start, live_count);
   return cudaGetLastError();
 }
 
 cudaError_t cross_attention(int dtype, const void* q, const void* kv, size_t kv_stride, int k_off, int v_off,
                             const int* ustart, const uint8_t* tok_valid, void* out, int users, int K, int H, int dk,
-                            cudaStream_t s) {
+                            const int* live_start, const int* live_count, cudaStream_t s) {
   if (users <= 0) return cudaSuccess;
   if (K > XA_KMAX) return cudaErrorInvalidValue;
 #define GRAM_XA(TT)                                                                                              \
   switch (dk) {                                                                                                  \
-    case 16: return launch_cross<TT, 16>(q, kv, kv_stride, k_off, v_off, ustart, tok_valid, out, users, K, H, s); \
-    case 32: return launch_cross<TT, 32>(q, kv, kv_stride, k_off, v_off, ustart, tok_valid, out, users, K, H, s); \
-    case 64: return launch_cross<TT, 64>(q, kv, kv_stride, k_off, v_off, ustart, tok_valid, out, users, K, H, s); \
+    case 16: return launch_cross<TT, 16>(q, kv, kv_stride, k_off, v_off, ustart, tok_valid, out, users, K, H,  \
+                                            live_start, live_count, s);                                             \
+    case 32: return launch_cross<TT, 32>(q, kv, kv_stride, k_off, v_off, ustart, tok_valid, out, users, K, H,  \
+                                            live_start, live_count, s);                                             \
+    case 64: return launch_cross<TT, 64>(q, kv, kv_stride, k_off, v_off, ustart, tok_valid, out, users, K, H,  \
+                                            live_start, live_count, s);                                             \
     default: return cudaErrorInvalidValue;                                                                       \
   }
   if (dtype == 0) { GRAM_XA(float) }

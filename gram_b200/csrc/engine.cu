@@ -94,6 +94,7 @@ struct gram_handle {
   float *logits = nullptr, *lse = nullptr;
   void* lse_partial = nullptr;           // float2 [Rcap][ceil(V/128)]
   BeamState bs{};
+  LiveMap live{};                        // live-row compaction of the decode steps (beam_kernels.cu:live_compact)
   double* d_len_pow = nullptr;
   double* h_len_pow = nullptr;           // pinned
   cudaEvent_t len_pow_ev = nullptr;       // recorded after the H2D copy of h_len_pow; waited on before it is rewritten
@@ -364,42 +365,50 @@ int run_encode(gram_handle* h, const int64_t* ids, const uint8_t* mask, int B, i
 }
 
 // ---- one decoder step (all layers + lm_head) for R rows ---------------------------------------------
-int decoder_step(gram_handle* h, int R, int K, int users, int t, const int* anc, bool fused_lse, cudaStream_t s) {
+// live: the step decodes only the compact slots of h->live (their count *mp is known on the device alone; every launch
+// is sized for R and bounded by *mp, like the encoder's packed token count)
+int decoder_step(gram_handle* h, int R, int K, int users, int t, const int* anc, bool fused_lse, bool live, cudaStream_t s) {
   const gram_config& c = h->cfg;
   const int D = h->D, HD = h->HD, F = h->F;
   const size_t esz = h->esz;
   const size_t layer_cache = (size_t)c.max_length * h->Rcap * HD * esz;
-  CKL(GRAM_K_OTHER, embed_rows(c.dtype, h->shared, h->bs.tok, h->dx, R, nullptr, D, s));
+  const LiveMap& lm = h->live;
+  const int* mp = live ? lm.n_live : nullptr;
+  const int* slot_row = live ? lm.slot_row : nullptr;
+  const int *lstart = live ? lm.start : nullptr, *lcount = live ? h->bs.live_cnt : nullptr;
+  CKL(GRAM_K_OTHER, embed_rows(c.dtype, h->shared, live ? lm.tok : h->bs.tok, h->dx, R, mp, D, s));
   for (int l = 0; l < h->Ld; ++l) {
     const LayerW& W = h->dec[l];
-    CKL(GRAM_K_NORM_DEC, rmsnorm_rows(c.dtype, h->dx, W.ln0, h->dxn, R, nullptr, D, c.ln_eps, 1.f, nullptr, nullptr, s));
-    RC(gemm(h, GRAM_K_GEMM_DEC, EPI_STORE, h->dxn, W.qkv, h->dqkv, R, nullptr, 3 * HD, D, s));
+    CKL(GRAM_K_NORM_DEC, rmsnorm_rows(c.dtype, h->dx, W.ln0, h->dxn, R, mp, D, c.ln_eps, 1.f, nullptr, nullptr, s));
+    RC(gemm(h, GRAM_K_GEMM_DEC, EPI_STORE, h->dxn, W.qkv, h->dqkv, R, mp, 3 * HD, D, s));
     // cache slices are indexed [t][R][HD] with the *current* R as the row pitch
     CKL(GRAM_K_SELF_ATTN, dec_self_attention(c.dtype, h->dqkv, (char*)h->sk + l * layer_cache, (char*)h->sv + l * layer_cache,
-                                         anc, c.max_length, h->dec_bias_lut, h->n_dec_lut, h->dao, R, K, h->H, h->dk, t, s));
-    RC(gemm(h, GRAM_K_GEMM_DEC, EPI_RESID, h->dao, W.o, h->dx, R, nullptr, D, HD, s));
-    CKL(GRAM_K_NORM_DEC, rmsnorm_rows(c.dtype, h->dx, W.ln1, h->dxn, R, nullptr, D, c.ln_eps, 1.f, nullptr, nullptr, s));
-    RC(gemm(h, GRAM_K_GEMM_DEC, EPI_STORE, h->dxn, W.cq, h->dq, R, nullptr, HD, D, s));
+                                         anc, c.max_length, h->dec_bias_lut, h->n_dec_lut, h->dao, R, K, h->H, h->dk, t,
+                                         slot_row, mp, s));
+    RC(gemm(h, GRAM_K_GEMM_DEC, EPI_RESID, h->dao, W.o, h->dx, R, mp, D, HD, s));
+    CKL(GRAM_K_NORM_DEC, rmsnorm_rows(c.dtype, h->dx, W.ln1, h->dxn, R, mp, D, c.ln_eps, 1.f, nullptr, nullptr, s));
+    RC(gemm(h, GRAM_K_GEMM_DEC, EPI_STORE, h->dxn, W.cq, h->dq, R, mp, HD, D, s));
     if (c.dtype == GRAM_DTYPE_BF16 && !(c.flags & GRAM_FLAG_SIMT_ATTN) && cross_attention_mma_supported(K, h->H, h->dk)) {
       CKL(GRAM_K_CROSS_ATTN, cross_attention_mma(h->dq, h->ckv, (size_t)h->Mcap + 256, (size_t)h->Ld * 2 * HD, l * 2 * HD,
-                                                 l * 2 * HD + HD, h->pm.ustart, h->pm.uorder, h->pm.tok_valid, h->dao, users, K, h->H, s));
+                                                 l * 2 * HD + HD, h->pm.ustart, h->pm.uorder, h->pm.tok_valid, h->dao, users, K, h->H,
+                                                 lstart, lcount, s));
     } else {
       CKL(GRAM_K_CROSS_ATTN, cross_attention(c.dtype, h->dq, h->ckv, (size_t)h->Ld * 2 * HD, l * 2 * HD, l * 2 * HD + HD,
-                                             h->pm.ustart, h->pm.tok_valid, h->dao, users, K, h->H, h->dk, s));
+                                             h->pm.ustart, h->pm.tok_valid, h->dao, users, K, h->H, h->dk, lstart, lcount, s));
     }
-    RC(gemm(h, GRAM_K_GEMM_DEC, EPI_RESID, h->dao, W.co, h->dx, R, nullptr, D, HD, s));
-    CKL(GRAM_K_NORM_DEC, rmsnorm_rows(c.dtype, h->dx, W.ln2, h->dxn, R, nullptr, D, c.ln_eps, 1.f, nullptr, nullptr, s));
-    RC(gemm(h, GRAM_K_GEMM_DEC, EPI_RELU, h->dxn, W.wi, h->dff, R, nullptr, F, D, s));
-    RC(gemm(h, GRAM_K_GEMM_DEC, EPI_RESID, h->dff, W.wo, h->dx, R, nullptr, D, F, s));
+    RC(gemm(h, GRAM_K_GEMM_DEC, EPI_RESID, h->dao, W.co, h->dx, R, mp, D, HD, s));
+    CKL(GRAM_K_NORM_DEC, rmsnorm_rows(c.dtype, h->dx, W.ln2, h->dxn, R, mp, D, c.ln_eps, 1.f, nullptr, nullptr, s));
+    RC(gemm(h, GRAM_K_GEMM_DEC, EPI_RELU, h->dxn, W.wi, h->dff, R, mp, F, D, s));
+    RC(gemm(h, GRAM_K_GEMM_DEC, EPI_RESID, h->dff, W.wo, h->dx, R, mp, D, F, s));
   }
   const float scale = c.tie_word_embeddings ? 1.0f / sqrtf((float)D) : 1.0f;
-  CKL(GRAM_K_NORM_DEC, rmsnorm_rows(c.dtype, h->dx, h->dec_final_ln, h->dxn, R, nullptr, D, c.ln_eps, scale, nullptr, nullptr, s));
+  CKL(GRAM_K_NORM_DEC, rmsnorm_rows(c.dtype, h->dx, h->dec_final_ln, h->dxn, R, mp, D, c.ln_eps, scale, nullptr, nullptr, s));
   if (fused_lse) {
     // kernel (c): vocabulary projection with the log-softmax statistics fused into the epilogue; logits never stored
-    RC(gemm(h, GRAM_K_LM_HEAD, EPI_LSE, h->dxn, h->lm_head, h->lse_partial, R, nullptr, h->V, D, s));
-    CKL(GRAM_K_LM_HEAD, lse_combine(h->lse_partial, h->lse, R, gemm_tc_lse_ntiles(R, h->V, h->num_sms), s));
+    RC(gemm(h, GRAM_K_LM_HEAD, EPI_LSE, h->dxn, h->lm_head, h->lse_partial, R, mp, h->V, D, s));
+    CKL(GRAM_K_LM_HEAD, lse_combine(h->lse_partial, h->lse, R, gemm_tc_lse_ntiles(R, h->V, h->num_sms), mp, s));
   } else {
-    RC(gemm(h, GRAM_K_LM_HEAD, EPI_F32, h->dxn, h->lm_head, h->logits, R, nullptr, h->V, D, s));
+    RC(gemm(h, GRAM_K_LM_HEAD, EPI_F32, h->dxn, h->lm_head, h->logits, R, mp, h->V, D, s));
   }
   return GRAM_OK;
 }
@@ -532,6 +541,9 @@ int gram_create(const gram_config* cfg, gram_handle** out) {
   const size_t U = c.max_users, S = (size_t)c.max_beams + 1;
   DAC(bs.hyp_score, U * S * 8); DAC(bs.hyp_len, U * S * 4); DAC(bs.hyp_seqno, U * S * 4); DAC(bs.hyp_tok, U * S * ML * 4);
   DAC(bs.n_hyp, U * 4); DAC(bs.worst, U * 8); DAC(bs.next_seqno, U * 4); DAC(bs.done, U * 4);
+  DAC(bs.live_cnt, U * 4);
+  DAC(h->live.start, (U + 1) * 4); DAC(h->live.slot_row, R * 4); DAC(h->live.row_slot, R * 4); DAC(h->live.tok, R * 4);
+  DAC(h->live.n_live, 16);
   DAC(bs.err, 16);
   h->pm.err = bs.err;
   h->pm.vocab = V;
@@ -828,12 +840,20 @@ int gram_generate(gram_handle* h, const int64_t* ids, const uint8_t* mask, int32
     // (HF computes them K times); one row per user is decoded and shared by the user's beams
     const int compact = (t == 0 && K > 1) ? 1 : 0;
     const int Rt = compact ? users : R, Kt = compact ? 1 : K;
-    RC(decoder_step(h, Rt, Kt, users, t, bs.anc[t & 1], fused, s));
+    // later steps: only beams that can still reach an output are decoded (dead beams and finished users are compacted
+    // away on the device; the reference decodes them and discards the result)
+    const bool live = t > 0 && !(c.flags & GRAM_FLAG_ALL_ROWS);
+    if (live) {
+      CKL(GRAM_K_BEAM, live_compact(bs, users, t & 1, h->live, s));
+      h->launches += 1;   // live_compact issues two kernels
+    }
+    const int* row_slot = live ? h->live.row_slot : nullptr;
+    RC(decoder_step(h, Rt, Kt, users, t, bs.anc[t & 1], fused, live, s));
     if (fused) {
-      CKL(GRAM_K_BEAM, beam_step(bs, h->trie, nullptr, h->dxn, h->lm_head, h->D, h->lse, users, t, h->cand_cap, compact, s));
+      CKL(GRAM_K_BEAM, beam_step(bs, h->trie, nullptr, h->dxn, h->lm_head, h->D, h->lse, users, t, h->cand_cap, compact, row_slot, s));
     } else {
-      CKL(GRAM_K_LM_HEAD, lse_rows(h->logits, h->lse, Rt, h->V, s));
-      CKL(GRAM_K_BEAM, beam_step(bs, h->trie, h->logits, nullptr, nullptr, h->D, h->lse, users, t, h->cand_cap, compact, s));
+      CKL(GRAM_K_LM_HEAD, lse_rows(h->logits, h->lse, Rt, h->V, live ? h->live.n_live : nullptr, s));
+      CKL(GRAM_K_BEAM, beam_step(bs, h->trie, h->logits, nullptr, nullptr, h->D, h->lse, users, t, h->cand_cap, compact, row_slot, s));
     }
   }
   CKL(GRAM_K_BEAM, beam_finalize(bs, users, T, R_ret, h->d_out_seq, h->d_out_scores, h->d_out_width, s));
@@ -859,6 +879,7 @@ int gram_generate(gram_handle* h, const int64_t* ids, const uint8_t* mask, int32
       return fail(h, GRAM_ERR_INVALID, code == 2   ? "gram_generate: input token id outside [0, vocab_size)"
                                        : code == 3 ? "gram_generate: item index outside the cached item table"
                                        : code == 4 ? "gram_generate: the batch holds more valid tokens than max_tokens"
+                                       : code == 5 ? "gram_generate: internal error, live beams are not a prefix of the user's beams"
                                                    : "gram_generate: candidate buffer overflow (trie fan-out larger than declared)");
     }
   }
@@ -904,7 +925,7 @@ int gram_decoder_logits(gram_handle* h, const int64_t* dec_ids, int32_t q, float
   const size_t V = h->V;
   for (int t = 0; t < q; ++t) {
     CKL(GRAM_K_OTHER, forced_step(bs, dids, q, t, R, s));
-    RC(decoder_step(h, R, 1, B, t, h->d_zero_anc, false, s));
+    RC(decoder_step(h, R, 1, B, t, h->d_zero_anc, false, false, s));
     // logits [R, V] -> out[b][t][:]
     CK(cudaMemcpy2DAsync(out_logits + (size_t)t * V, (size_t)q * V * 4, h->logits, V * 4, V * 4, R,
                          dev ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, s));
@@ -938,6 +959,7 @@ int gram_check_errors(gram_handle* h, void* stream) {
   return fail(h, GRAM_ERR_INVALID, code == 2   ? "input token id outside [0, vocab_size)"
                                    : code == 3 ? "item index outside the cached item table"
                                    : code == 4 ? "the batch holds more valid tokens than max_tokens"
+                                   : code == 5 ? "internal error, live beams are not a prefix of the user's beams"
                                                : "candidate buffer overflow (trie fan-out larger than declared)");
 }
 
@@ -1013,10 +1035,10 @@ int gram_op_cross_attention(int32_t device, int32_t dtype, int32_t impl, const v
       return GRAM_ERR_UNSUPPORTED;
     }
     e = cross_attention_mma(q, kv, (size_t)kv_rows, (size_t)2 * H * dk, 0, H * dk, user_start, nullptr, tok_valid, out, users, K, H,
-                            (cudaStream_t)stream);
+                            nullptr, nullptr, (cudaStream_t)stream);
   } else {
     e = cross_attention(dtype, q, kv, (size_t)2 * H * dk, 0, H * dk, user_start, tok_valid, out, users, K, H, dk,
-                        (cudaStream_t)stream);
+                        nullptr, nullptr, (cudaStream_t)stream);
   }
   if (e != cudaSuccess) { g_create_error = std::string("cross_attention: ") + cudaGetErrorString(e); return GRAM_ERR_CUDA; }
   return GRAM_OK;

@@ -82,15 +82,18 @@ cudaError_t unpack_memory(int dtype, const void* mem, const int* row_src, float*
 // single-token causal self-attention with an ancestry-indirected KV cache.
 //   qkv [R, 3*HD]; cache_k/v [Tmax][R][HD]; anc [R][Tmax] (row *within the user* holding position j);
 //   dec_bias [H][n_dec]; t = current position.  Writes this step's k/v into slot t.
+// Live-row compaction (slot_row != nullptr): the step decodes only *n_rows compact slots; slot s stands for beam row
+// slot_row[s] (cache rows, ancestry and user membership follow the beam row, qkv/out rows follow the slot).
 cudaError_t dec_self_attention(int dtype, const void* qkv, void* cache_k, void* cache_v, const int* anc, int Tmax,
                                const float* dec_bias, int n_dec, void* out, int R, int K, int H, int dk, int t,
-                               cudaStream_t s);
+                               const int* slot_row, const int* n_rows, cudaStream_t s);
 // cross-attention over the in-place packed K/V memory (kernel (b)).
 //   q [R, HD]; kv rows of `kv_stride` elements with K at column k_off and V at column v_off (+ h*dk);
-//   user u owns packed rows [ustart[u], ustart[u+1]); beams of user u are rows u*K .. u*K+K-1.
+//   user u owns packed rows [ustart[u], ustart[u+1]); beams of user u are rows u*K .. u*K+K-1, or -- with live-row
+//   compaction (live_start != nullptr) -- the live_count[u] rows from live_start[u] (a user without live beams is skipped).
 cudaError_t cross_attention(int dtype, const void* q, const void* kv, size_t kv_stride, int k_off, int v_off,
                             const int* ustart, const uint8_t* tok_valid, void* out, int users, int K, int H, int dk,
-                            cudaStream_t s);
+                            const int* live_start, const int* live_count, cudaStream_t s);
 
 // ---- attention_mma.cu (bf16, tensor cores) --------------------------------------------------------------
 bool cross_attention_mma_supported(int K, int H, int dk);
@@ -98,7 +101,9 @@ bool cross_attention_mma_supported(int K, int H, int dk);
 // must only hold finite values.
 cudaError_t cross_attention_mma(const void* q, const void* kv, size_t kv_rows, size_t kv_stride, int k_off, int v_off,
                                 const int* ustart, const int* uorder /* nullable: users longest-first */,
-                                const uint8_t* tok_valid, void* out, int users, int K, int H, cudaStream_t s);
+                                const uint8_t* tok_valid, void* out, int users, int K, int H,
+                                const int* live_start, const int* live_count /* nullable, see cross_attention */,
+                                cudaStream_t s);
 bool enc_attention_mma_supported(int dk, int Lmax);
 cudaError_t enc_attention_mma(const void* qkv, void* out, const int* plen, const int* poff, const uint8_t* tok_valid,
                               const float* bias_lut, int Lb, int P, int H, int Lmax, cudaStream_t s);
@@ -125,21 +130,38 @@ struct BeamState {           // all device pointers; rows R = users*K
   // hypotheses (per user, K+1 slots)
   double* hyp_score; int* hyp_len; int* hyp_seqno; int* hyp_tok;   // [U][K+1], ..., [U][K+1][max_length]
   int* n_hyp; double* worst; int* next_seqno; int* done;            // [U]
+  int* live_cnt;             // [U]   beams of the user that are still alive after the step (0 once the user is done);
+                             //       they are the user's FIRST live_cnt beams (candidates are ranked best-first)
   int* err;                  // [1] sticky device-side error flag
   const double* len_pow;     // [max_length+1]
   // optional taps
   float* tap_lse; float* tap_score; int* tap_seq;                   // [steps][R](...)
 };
-cudaError_t lse_rows(const float* logits, float* lse, int R, int V, cudaStream_t s);
+// n_rows (nullable, device): only the first *n_rows rows are computed
+cudaError_t lse_rows(const float* logits, float* lse, int R, int V, const int* n_rows, cudaStream_t s);
 // lse[row] from the per-tile (max, sumexp) partials of the EPI_LSE GEMM epilogue
-cudaError_t lse_combine(const void* partial, float* lse, int R, int n_tiles, cudaStream_t s);
+cudaError_t lse_combine(const void* partial, float* lse, int R, int n_tiles, const int* n_rows, cudaStream_t s);
 cudaError_t beam_init(BeamState bs, TrieCSR trie, int users, int start_tok, cudaStream_t s);
 // one beam-search step: PrefixConstrainedLogitsProcessor + topk(2K) + BeamSearchScorer.process
 // logits != nullptr: gather candidate logits from the materialised [R,V] matrix (fp32 parity mode);
 // logits == nullptr: recompute them as dot(hidden[row], head[token]) from the bf16 decoder output `hidden` [R,D]
 // and the bf16 vocabulary head `head` [V,D] (fused mode: full-vocab logits are never written)
+// row_slot (nullable): live-row compaction of this step -- beam row r was decoded as row row_slot[r] of
+// logits/hidden/lse (-1 = dead beam, not decoded)
 cudaError_t beam_step(BeamState bs, TrieCSR trie, const float* logits, const void* hidden, const void* head, int D,
-                      const float* lse, int users, int t, int cand_cap, int compact, cudaStream_t s);
+                      const float* lse, int users, int t, int cand_cap, int compact, const int* row_slot, cudaStream_t s);
+// Live-row compaction for the step that follows a beam_step (two launches): an exclusive scan of bs.live_cnt gives
+// every user its slot range, then slot_row / row_slot / the slots' input tokens are filled.  `cur` = index of the
+// beam buffers the coming step reads.  Dead beams (-inf score: fewer finite candidates than K, typically item ids
+// that ended one token earlier) and finished users cannot influence any output, so they are not decoded.
+struct LiveMap {
+  int* start;                // [U+1] first compact slot of user u
+  int* slot_row;             // [R]   beam row of slot s
+  int* row_slot;             // [R]   slot of beam row r, -1 = dead
+  int* tok;                  // [R]   input token of slot s
+  int* n_live;               // [1]   number of slots = M of the step's GEMMs
+};
+cudaError_t live_compact(BeamState bs, int users, int cur, LiveMap lm, cudaStream_t s);
 // compact != 0 (only at t == 0): all K beams of a user are identical, so the decoder ran ONE row per user; row u of
 // logits/hidden/lse serves every beam of user u and the step-0 self-attention cache row is recorded in the ancestry
 cudaError_t beam_finalize(BeamState bs, int users, int t_final, int R_ret, int64_t* out_seq, float* out_scores,

@@ -62,7 +62,12 @@ enum {
   GRAM_FLAG_TC_ENC_ATTN = 8,       /* encoder attention through the tcgen05/TMEM kernel (attention_tc.cu): numerically
                                       verified, but one (passage, head) per CTA without cross-item pipelining it is
                                       ~15 % slower than the pipelined mma.sync kernel, so it is opt-in for now */
-  GRAM_FLAG_GEMM_1CTA = 16         /* keep every tcgen05 GEMM on single-CTA tiles (no cta_group::2 pairs; A-B timing) */
+  GRAM_FLAG_GEMM_1CTA = 16,        /* keep every tcgen05 GEMM on single-CTA tiles (no cta_group::2 pairs; A-B timing) */
+  GRAM_FLAG_ALL_ROWS = 32          /* decode every beam row at every step, as the reference does (A-B timing).  Default:
+                                      beams that are dead (-inf score: the user had fewer than K finite continuations,
+                                      typically item ids that ended a token earlier) and the beams of users whose
+                                      hypotheses are final are compacted away on the device before each step; they
+                                      cannot reach any output, so results are bit-identical                          */
 };
 
 /* ---- lifetime -------------------------------------------------------------------------------- */

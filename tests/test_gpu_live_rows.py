@@ -1,0 +1,51 @@
+"""Live-row compaction (engine.cu: live_compact before every decode step t >= 1) against GRAM_FLAG_ALL_ROWS, which decodes
+every beam row at every step as the reference does (HF beam_search runs dead -inf beams and finished batches through
+the decoder and discards them).  Skipping them must not change a single output bit."""
+import numpy as np
+import pytest
+import torch
+
+from helpers import CASES
+
+pytestmark = pytest.mark.gpu
+
+
+def _run(case, sd, ids, mask, seqs, max_length, dtype, flags, K=None, lp=None):
+    from gram_b200 import GRAM, Trie, prefix_allowed_tokens_fn
+    K = K or case.num_beams
+    m = GRAM(case.cfg, dtype=dtype, device="cuda:0", flags=flags)
+    m.load_state_dict(sd)
+    fn = prefix_allowed_tokens_fn(Trie(seqs))
+    out = m.generate(input_ids=ids.cuda(), attention_mask=mask.cuda(), max_length=max_length, prefix_allowed_tokens_fn=fn,
+                     num_beams=K, num_return_sequences=K, output_scores=True, return_dict_in_generate=True,
+                     length_penalty=case.length_penalty if lp is None else lp)
+    torch.cuda.synchronize()
+    return out["sequences"].cpu().numpy(), out["sequences_scores"].cpu().numpy(), m.stats()["launches"]
+
+
+@pytest.mark.parametrize("dtype", ["fp32", "bf16"])
+@pytest.mark.parametrize("name", list(CASES))
+def test_live_rows_bit_identical_to_all_rows(name, dtype):
+    from gram_b200 import _cabi
+    case = CASES[name]
+    built = case.build()
+    seq_a, sc_a, _ = _run(case, *built, dtype, _cabi.GRAM_FLAG_ALL_ROWS)
+    seq_l, sc_l, _ = _run(case, *built, dtype, 0)
+    assert seq_a.shape == seq_l.shape and np.array_equal(seq_a, seq_l)
+    assert np.array_equal(sc_a.view(np.uint32), sc_l.view(np.uint32)), "sequence scores differ bitwise"
+
+
+@pytest.mark.parametrize("dtype", ["fp32", "bf16"])
+def test_live_rows_with_many_dead_beams(dtype):
+    """A trie with FEWER items than beams under some prefixes and two id lengths: most beams of the late steps are dead,
+    some users finish early, and a wide beam (K > root fan-out) starts with dead beams at step 1."""
+    from gram_b200 import _cabi, synth
+    case = CASES["small"]
+    sd, ids, mask, _, _ = case.build()
+    seqs = synth.make_item_sequences(40, [5, 3, 2, 2], case.cfg.vocab_size, seed=21, variable_tail=True)
+    max_length = max(len(s) for s in seqs)
+    for K in (4, 20):
+        a = _run(case, sd, ids, mask, seqs, max_length, dtype, _cabi.GRAM_FLAG_ALL_ROWS, K=K)
+        b = _run(case, sd, ids, mask, seqs, max_length, dtype, 0, K=K)
+        assert np.array_equal(a[0], b[0])
+        assert np.array_equal(a[1].view(np.uint32), b[1].view(np.uint32))
