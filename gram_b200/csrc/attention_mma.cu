@@ -315,6 +315,10 @@ cross_attention_mma_kernel(const __grid_constant__ CUtensorMap map_kv, const bf1
   const int K = live_start ? live_count[u] : K_all;
   if (K == 0) return;
   const int qrow0 = live_start ? live_start[u] : u * K_all;
+  // the kernel sits at the 255-register limit: the row range is parked in shared memory for the epilogue instead of
+  // staying live across the key loop (two more live registers spill 24 bytes)
+  __shared__ int s_rows[2];
+  if (threadIdx.x == 0) { s_rows[0] = qrow0; s_rows[1] = K; }
   const int s_beg = ustart[u], s_end = ustart[u + 1];
   const int n_tiles = (s_end - s_beg + TS - 1) / TS;
   const int HD = H * DK;
@@ -435,6 +439,7 @@ cross_attention_mma_kernel(const __grid_constant__ CUtensorMap map_kv, const bf1
     }
   }
   // ---- normalise and store ----
+  const int out_row0 = s_rows[0], out_rows = s_rows[1];
 #pragma unroll
   for (int mt = 0; mt < MT; ++mt) {
 #pragma unroll
@@ -444,8 +449,8 @@ cross_attention_mma_kernel(const __grid_constant__ CUtensorMap map_kv, const bf1
       l += __shfl_xor_sync(0xffffffffu, l, 2);
       const float inv = l > 0.f ? 1.0f / l : 0.f;
       const int b = b_off + mt * 16 + g + hf * 8;
-      if (b < K) {
-        bf16* orow = out + (size_t)(qrow0 + b) * HD + h * DK;
+      if (b < out_rows) {
+        bf16* orow = out + (size_t)(out_row0 + b) * HD + h * DK;
 #pragma unroll
         for (int nt = 0; nt < 8; ++nt)
           *reinterpret_cast<uint32_t*>(orow + nt * 8 + 2 * q) = pack_bf16(o[mt][nt][hf * 2] * inv, o[mt][nt][hf * 2 + 1] * inv);

@@ -13,6 +13,7 @@
 //    the user's K/V -- written in place by the projection GEMM in packed [token][layer][K|V][head][dk]
 //    order, no concat copy -- is read once.  This file holds the CUDA-core version used by the fp32
 //    parity mode; cross_attention_mma.cu holds the bf16 tensor-core version.
+#include <stdlib.h>
 #include "common.cuh"
 #include "kernels.h"
 
@@ -131,10 +132,37 @@ __device__ __forceinline__ void store8(bf16* p, const float (&v)[8]) {
   *reinterpret_cast<uint4*>(p) = u;
 }
 
+// 8 consecutive elements of a cache row as they sit in memory: K/V chunks wait in registers in storage form (4
+// registers per 8 bf16) and are widened only when they are consumed, so a warp keeps more positions in flight and
+// more warps fit on an SM (the kernel is bound by memory latency: ncu, 127 registers, 16 warps per SM, 2.4 TB/s)
+template <typename T> struct Raw8;
+template <> struct Raw8<bf16> {
+  uint4 u;
+  __device__ __forceinline__ void load(const bf16* p) { u = *reinterpret_cast<const uint4*>(p); }
+  __device__ __forceinline__ void store(bf16* p) const { *reinterpret_cast<uint4*>(p) = u; }
+  __device__ __forceinline__ void unpack(float (&v)[8]) const {
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { const float2 f = __bfloat1622float2(h[i]); v[2 * i] = f.x; v[2 * i + 1] = f.y; }
+  }
+};
+template <> struct Raw8<float> {
+  float4 a, b;
+  __device__ __forceinline__ void load(const float* p) {
+    a = *reinterpret_cast<const float4*>(p); b = *reinterpret_cast<const float4*>(p + 4);
+  }
+  __device__ __forceinline__ void store(float* p) const {
+    *reinterpret_cast<float4*>(p) = a; *reinterpret_cast<float4*>(p + 4) = b;
+  }
+  __device__ __forceinline__ void unpack(float (&v)[8]) const {
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+  }
+};
+
 // One warp = (row, 4 heads): lane = (head hq = lane/8, 16-byte chunk c = lane%8), positions are walked with an
-// online softmax, four positions' K and V chunks requested per iteration.  Work is proportional to t+1.
-template <typename T>
-__global__ void __launch_bounds__(128)
+// online softmax, UN positions' K and V chunks requested per iteration.  Work is proportional to t+1.
+template <typename T, int UN, int MINB>
+__global__ void __launch_bounds__(128, MINB)
 dec_self_attention64_kernel(const T* __restrict__ qkv, T* __restrict__ cache_k, T* __restrict__ cache_v,
                             const int* __restrict__ anc, int Tmax, const float* __restrict__ dec_bias, int n_dec,
                             T* __restrict__ out, int R, int K, int H, int t, const int* __restrict__ slot_row,
@@ -152,18 +180,22 @@ dec_self_attention64_kernel(const T* __restrict__ qkv, T* __restrict__ cache_k, 
   const int a0 = (lane < t) ? anc[(size_t)r * Tmax + lane] : 0;
   const int a1 = (lane + 32 < t) ? anc[(size_t)r * Tmax + lane + 32] : 0;
   const T* qrow = qkv + (size_t)slot * 3 * HD + col;
-  float qv[8], kc[8], vc[8];
-  load8(qrow, qv);
-  load8(qrow + HD, kc);
-  load8(qrow + 2 * HD, vc);
-  store8(cache_k + ((size_t)t * R + r) * HD + col, kc);  // append this step's key/value (slot t, own row)
-  store8(cache_v + ((size_t)t * R + r) * HD + col, vc);
+  Raw8<T> qr, kc, vc;
+  qr.load(qrow);
+  kc.load(qrow + HD);
+  vc.load(qrow + 2 * HD);
+  kc.store(cache_k + ((size_t)t * R + r) * HD + col);    // append this step's key/value (slot t, own row)
+  vc.store(cache_v + ((size_t)t * R + r) * HD + col);
+  float qv[8];
+  qr.unpack(qv);
   const float* bias = dec_bias + h * n_dec;
   float m = -INFINITY, l = 0.f;
   float acc[8];
 #pragma unroll
   for (int e = 0; e < 8; ++e) acc[e] = 0.f;
-  auto absorb = [&](const float (&kx)[8], const float (&vx)[8], int j) {
+  auto absorb = [&](const Raw8<T>& kraw, const Raw8<T>& vraw, int j) {
+    float kx[8];
+    kraw.unpack(kx);
     float a = 0.f;
 #pragma unroll
     for (int e = 0; e < 8; ++e) a = fmaf(qv[e], kx[e], a);
@@ -176,24 +208,26 @@ dec_self_attention64_kernel(const T* __restrict__ qkv, T* __restrict__ cache_k, 
     const float corr = expf(m - mn);                     // exp(-inf) = 0 on the first position
     const float p = expf(a - mn);
     l = l * corr + p;
+    float vx[8];
+    vraw.unpack(vx);
 #pragma unroll
     for (int e = 0; e < 8; ++e) acc[e] = fmaf(p, vx[e], acc[e] * corr);
     m = mn;
   };
-  for (int j0 = 0; j0 < t; j0 += 4) {
-    float kx[4][8], vx[4][8];
+  for (int j0 = 0; j0 < t; j0 += UN) {
+    Raw8<T> kx[UN], vx[UN];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
+    for (int u = 0; u < UN; ++u) {
       const int j = j0 + u;                              // warp-uniform
       if (j < t) {
         const int sj = ubase + __shfl_sync(0xffffffffu, j < 32 ? a0 : a1, j & 31);
         const size_t off = ((size_t)j * R + sj) * HD + col;
-        load8(cache_k + off, kx[u]);
-        load8(cache_v + off, vx[u]);
+        kx[u].load(cache_k + off);
+        vx[u].load(cache_v + off);
       }
     }
 #pragma unroll
-    for (int u = 0; u < 4; ++u)
+    for (int u = 0; u < UN; ++u)
       if (j0 + u < t) absorb(kx[u], vx[u], j0 + u);
   }
   absorb(kc, vc, t);
@@ -201,6 +235,14 @@ dec_self_attention64_kernel(const T* __restrict__ qkv, T* __restrict__ cache_k, 
 #pragma unroll
   for (int e = 0; e < 8; ++e) acc[e] *= inv;
   store8(out + (size_t)slot * HD + col, acc);
+}
+
+static int self_attn_un() {
+  static const int un = [] {
+    const char* e = getenv("GRAM_SELF_ATTN_UN");
+    return (e && atoi(e) == 4) ? 4 : 8;
+  }();
+  return un;
 }
 
 template <typename T>
@@ -216,7 +258,18 @@ static cudaError_t launch_dec_self(const void* qkv, void* ck, void* cv, const in
   switch (dk) {
     case 16: dec_self_attention_kernel<T, 16><<<grid, 128, 0, s>>>((const T*)qkv, (T*)ck, (T*)cv, anc, Tmax, dec_bias, n_dec, (T*)out, R, K, H, t, slot_row, n_rows); break;
     case 32: dec_self_attention_kernel<T, 32><<<grid, 128, 0, s>>>((const T*)qkv, (T*)ck, (T*)cv, anc, Tmax, dec_bias, n_dec, (T*)out, R, K, H, t, slot_row, n_rows); break;
-    case 64: dec_self_attention64_kernel<T><<<grid, 128, 0, s>>>((const T*)qkv, (T*)ck, (T*)cv, anc, Tmax, dec_bias, n_dec, (T*)out, R, K, H, t, slot_row, n_rows); break;
+    case 64:
+      // bf16: 8 positions in flight per warp (117 registers, 16 warps per SM) or, GRAM_SELF_ATTN_UN=4, 4 positions
+      // (80 registers, 24 warps per SM); fp32 rows are twice as wide in registers
+      if constexpr (sizeof(T) == 2) {
+        if (self_attn_un() == 8)
+          dec_self_attention64_kernel<T, 8, 4><<<grid, 128, 0, s>>>((const T*)qkv, (T*)ck, (T*)cv, anc, Tmax, dec_bias, n_dec, (T*)out, R, K, H, t, slot_row, n_rows);
+        else
+          dec_self_attention64_kernel<T, 4, 6><<<grid, 128, 0, s>>>((const T*)qkv, (T*)ck, (T*)cv, anc, Tmax, dec_bias, n_dec, (T*)out, R, K, H, t, slot_row, n_rows);
+      } else {
+        dec_self_attention64_kernel<T, 4, 4><<<grid, 128, 0, s>>>((const T*)qkv, (T*)ck, (T*)cv, anc, Tmax, dec_bias, n_dec, (T*)out, R, K, H, t, slot_row, n_rows);
+      }
+      break;
     default: return cudaErrorInvalidValue;
   }
   return cudaGetLastError();
@@ -255,6 +308,8 @@ cross_attention_kernel(const T* __restrict__ q, const T* __restrict__ kv, size_t
   const int K = live_start ? live_count[u] : K_all;
   if (K == 0) return;
   const int qrow0 = live_start ? live_start[u] : u * K_all;
+  __shared__ int s_qrow0;                    // re-read by the epilogue instead of staying live across the key loop
+  if (threadIdx.x == 0) s_qrow0 = qrow0;
   const int s_beg = ustart[u], s_end = ustart[u + 1];
   const int HD = H * DK;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -356,12 +411,13 @@ cross_attention_kernel(const T* __restrict__ q, const T* __restrict__ kv, size_t
     }
     __syncthreads();
   }
+  const int out_row0 = s_qrow0;
 #pragma unroll
   for (int i = 0; i < NBT; ++i) {
     const int b = pv_g + G * i;
     if (b < K) {
       const float l = l_s[b];
-      out[(size_t)(qrow0 + b) * HD + h * DK + pv_d] = from_f32<T>(l > 0.f ? acc[i] / l : 0.f);
+      out[(size_t)(out_row0 + b) * HD + h * DK + pv_d] = from_f32<T>(l > 0.f ? acc[i] / l : 0.f);
     }
   }
 }
