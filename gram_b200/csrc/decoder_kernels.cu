@@ -13,7 +13,6 @@
 //    the user's K/V -- written in place by the projection GEMM in packed [token][layer][K|V][head][dk]
 //    order, no concat copy -- is read once.  This file holds the CUDA-core version used by the fp32
 //    parity mode; cross_attention_mma.cu holds the bf16 tensor-core version.
-#include <stdlib.h>
 #include "common.cuh"
 #include "kernels.h"
 
@@ -237,14 +236,6 @@ dec_self_attention64_kernel(const T* __restrict__ qkv, T* __restrict__ cache_k, 
   store8(out + (size_t)slot * HD + col, acc);
 }
 
-static int self_attn_un() {
-  static const int un = [] {
-    const char* e = getenv("GRAM_SELF_ATTN_UN");
-    return (e && atoi(e) == 4) ? 4 : 8;
-  }();
-  return un;
-}
-
 template <typename T>
 static cudaError_t launch_dec_self(const void* qkv, void* ck, void* cv, const int* anc, int Tmax,
                                    const float* dec_bias, int n_dec, void* out, int R, int K, int H, int dk, int t,
@@ -259,13 +250,12 @@ static cudaError_t launch_dec_self(const void* qkv, void* ck, void* cv, const in
     case 16: dec_self_attention_kernel<T, 16><<<grid, 128, 0, s>>>((const T*)qkv, (T*)ck, (T*)cv, anc, Tmax, dec_bias, n_dec, (T*)out, R, K, H, t, slot_row, n_rows); break;
     case 32: dec_self_attention_kernel<T, 32><<<grid, 128, 0, s>>>((const T*)qkv, (T*)ck, (T*)cv, anc, Tmax, dec_bias, n_dec, (T*)out, R, K, H, t, slot_row, n_rows); break;
     case 64:
-      // bf16: 8 positions in flight per warp (117 registers, 16 warps per SM) or, GRAM_SELF_ATTN_UN=4, 4 positions
-      // (80 registers, 24 warps per SM); fp32 rows are twice as wide in registers
+      // bf16, per 1,888-user step on one B200 (A/B in one gpurun call): K/V widened to fp32 on load, 127 registers,
+      // 16 warps per SM: 8.2 ms; storage-form chunks with 8 positions in flight, 117 registers, 16 warps: 8.0 ms;
+      // 4 positions, 80 registers, 24 warps: 6.1 ms; 4 positions, 64 registers (32 bytes spilled), 32 warps: 5.5 ms;
+      // 8-byte lanes (2 heads per warp), 8 positions, 32 warps: 8.4 ms.  Occupancy beats batch depth.
       if constexpr (sizeof(T) == 2) {
-        if (self_attn_un() == 8)
-          dec_self_attention64_kernel<T, 8, 4><<<grid, 128, 0, s>>>((const T*)qkv, (T*)ck, (T*)cv, anc, Tmax, dec_bias, n_dec, (T*)out, R, K, H, t, slot_row, n_rows);
-        else
-          dec_self_attention64_kernel<T, 4, 6><<<grid, 128, 0, s>>>((const T*)qkv, (T*)ck, (T*)cv, anc, Tmax, dec_bias, n_dec, (T*)out, R, K, H, t, slot_row, n_rows);
+        dec_self_attention64_kernel<T, 4, 8><<<grid, 128, 0, s>>>((const T*)qkv, (T*)ck, (T*)cv, anc, Tmax, dec_bias, n_dec, (T*)out, R, K, H, t, slot_row, n_rows);
       } else {
         dec_self_attention64_kernel<T, 4, 4><<<grid, 128, 0, s>>>((const T*)qkv, (T*)ck, (T*)cv, anc, Tmax, dec_bias, n_dec, (T*)out, R, K, H, t, slot_row, n_rows);
       }
