@@ -122,6 +122,7 @@ enc_attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, bf16* __res
   uint32_t* masks = reinterpret_cast<uint32_t*>(smem + 3 * BOX + ((lut_n * 4 + 15) / 16) * 16);   // [4]
   const uint32_t bars = base + 3 * BOX + ((lut_n * 4 + 15) / 16) * 16 + 16;                       // tma, mma
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + 3 * BOX + ((lut_n * 4 + 15) / 16) * 16 + 32);
+  float* brange = reinterpret_cast<float*>(smem + 3 * BOX + ((lut_n * 4 + 15) / 16) * 16 + 48);   // [4] max, [4] min
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t bar_tma = bars, bar_mma = bars + 8;
 
@@ -135,7 +136,18 @@ enc_attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, bf16* __res
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(TMEM_COLS) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
-  for (int i = tid; i < lut_n; i += THREADS) lut[i] = bias_lut[(size_t)h * lut_n + i];
+  // bias LUT in log2 units (the softmax runs on exp2), and its range: a row's maximum is bounded by
+  // max(raw score) * log2e + max(bias), which lets the first pass skip the bias (see below)
+  float bmax = -INFINITY, bmin = INFINITY;
+  for (int i = tid; i < lut_n; i += THREADS) {
+    const float b = bias_lut[(size_t)h * lut_n + i] * LOG2E;
+    lut[i] = b;
+    bmax = fmaxf(bmax, b);
+    bmin = fminf(bmin, b);
+  }
+  bmax = warp_max(bmax);
+  bmin = -warp_max(-bmin);
+  if (lane == 0) { brange[warp] = bmax; brange[4 + warp] = bmin; }
   {
     const int j = warp * 32 + lane;
     const bool vis = j < len && tok_valid[row0 + j] != 0;
@@ -165,36 +177,63 @@ enc_attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, bf16* __res
   tcgen05_fence_after();
 
   // ---- softmax of row r = tid: two passes over the TMEM row (32 scores in registers at a time keeps the kernel at
-  //      <= 128 registers, i.e. four CTAs per SM) ----
+  //      <= 128 registers, i.e. four CTAs per SM).  Everything is in log2 units: p = 2^(s*log2e + bias2 - m).
+  //      Softmax is invariant to the shift m as long as nothing overflows, so pass 1 does not need the exact row
+  //      maximum: for chunks whose 32 keys are all visible it takes max(raw s) -- one FMNMX per score -- and bounds the
+  //      bias by the largest LUT entry; the exact bias + mask walk is kept for the passage's tail chunk, and for every
+  //      chunk when the bias table spans more than 2^64 (then the bound could push small terms into underflow). ----
   const int r = tid;
   const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
-  const float* lrow = lut + (Lb - 1 - r);          // bias of (query r, key j) = lut[j - r + Lb - 1]; only read for j < len <= Lb
-  float mx = -INFINITY;
+  const float* lrow = lut + (Lb - 1 - r);          // bias2 of (query r, key j) = lut[j - r + Lb - 1]; only read for j < len <= Lb
+  const float bias_hi = fmaxf(fmaxf(brange[0], brange[1]), fmaxf(brange[2], brange[3]));
+  const float bias_lo = fminf(fminf(brange[4], brange[5]), fminf(brange[6], brange[7]));
+  const bool exact = !(bias_hi - bias_lo <= 64.f);
+  float mraw = -INFINITY, mex = -INFINITY;
 #pragma unroll 1
   for (int c = 0; c < 4; ++c) {
+    const uint32_t mk = masks[c];
+    if (mk == 0u) continue;                          // chunk past the passage (uniform across the CTA)
     uint32_t v[32];
     tmem_ld32(trow + c * 32, v);
     tmem_ld_wait();
-    const uint32_t mk = masks[c];
+    if (mk == 0xffffffffu && !exact) {
 #pragma unroll
-    for (int j = 0; j < 32; ++j)
-      if ((mk >> j) & 1u) mx = fmaxf(mx, __uint_as_float(v[j]) + lrow[c * 32 + j]);
+      for (int j = 0; j < 32; ++j) mraw = fmaxf(mraw, __uint_as_float(v[j]));
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if ((mk >> j) & 1u) mex = fmaxf(mex, fmaf(__uint_as_float(v[j]), LOG2E, lrow[c * 32 + j]));
+    }
   }
-  const float mb = mx * LOG2E;                       // at least one key is visible (len > 0)
+  const float mb = fmaxf(fmaf(mraw, LOG2E, bias_hi), mex);    // at least one key is visible (len > 0)
   float sum = 0.f;
   // P (bf16) in the K-major 128B-swizzled operand layout: box b = keys [64b, 64b+64), row r, 16-byte chunk j ^ (r & 7)
 #pragma unroll 1
   for (int c = 0; c < 4; ++c) {
-    uint32_t v[32];
-    tmem_ld32(trow + c * 32, v);
-    tmem_ld_wait();
     const uint32_t mk = masks[c];
     float pr[32];
+    if (mk == 0u) {
 #pragma unroll
-    for (int j = 0; j < 32; ++j) {
-      const float x = ((mk >> j) & 1u) ? (__uint_as_float(v[j]) + lrow[c * 32 + j]) * LOG2E - mb : -INFINITY;
-      pr[j] = exp2f(x);
-      sum += pr[j];
+      for (int j = 0; j < 32; ++j) pr[j] = 0.f;
+    } else {
+      uint32_t v[32];
+      tmem_ld32(trow + c * 32, v);
+      tmem_ld_wait();
+      if (mk == 0xffffffffu) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          pr[j] = ex2_ftz(fmaf(__uint_as_float(v[j]), LOG2E, lrow[c * 32 + j] - mb));
+          sum += pr[j];
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          float pj = 0.f;
+          if ((mk >> j) & 1u) pj = ex2_ftz(fmaf(__uint_as_float(v[j]), LOG2E, lrow[c * 32 + j] - mb));
+          pr[j] = pj;
+          sum += pj;
+        }
+      }
     }
 #pragma unroll
     for (int q4 = 0; q4 < 4; ++q4) {
@@ -295,7 +334,7 @@ cudaError_t enc_attention_tc(const void* qkv, size_t qkv_rows, void* out, const 
   std::lock_guard<std::mutex> lk(ta::g_mu);
   CUtensorMap map;
   if (!ta::get_map(qkv, qkv_rows, (size_t)3 * H * ta::DK, &map)) return cudaErrorUnknown;
-  const size_t smem = (size_t)3 * ta::BOX + (((size_t)(2 * Lb - 1) * 4 + 15) / 16) * 16 + 64 + 1024;
+  const size_t smem = (size_t)3 * ta::BOX + (((size_t)(2 * Lb - 1) * 4 + 15) / 16) * 16 + 96 + 1024;
   static SmemAttr attr;
   {
     cudaError_t e = attr.ensure(ta::enc_attention_tc_kernel, smem);
