@@ -100,193 +100,280 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
 constexpr uint32_t IDESC_QK = (1u << 4) | (1u << 7) | (1u << 10) | ((128u >> 3) << 17) | ((128u >> 4) << 24);              // N=128, B K-major
 constexpr uint32_t IDESC_PV = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 16) | ((64u >> 3) << 17) | ((128u >> 4) << 24);  // N=64, B MN-major
 
-constexpr int THREADS = 128;
-constexpr int TMEM_COLS = 128;
+constexpr int CONSUMERS = 128;            // warps 0-3: softmax + epilogue, thread r = query row r = TMEM lane r
+constexpr int THREADS = CONSUMERS + 32;   // warp 4: one elected thread issues every TMA load and every tcgen05.mma
+constexpr int TMEM_COLS = 256;            // two S/O accumulators of 128 columns
+constexpr uint32_t STAGE = 3 * BOX;       // Q | K | V of one (passage, head); P later overwrites Q | K
+constexpr int NSTAGE = 2;
+enum { B_FULL = 0, B_EMPTY = 2, B_SFULL = 4, B_SFREE = 6, B_PREADY = 8, B_OFULL = 10, B_COUNT = 12 };
 
-__global__ void __launch_bounds__(THREADS, 4)
+__device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void consumer_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
+// Persistent, warp-specialised kernel: CTA b walks passages b, b + grid, ... and the H heads of each; two CTAs per SM.
+// Work item k of a CTA (the k-th (passage, head) it processes) uses shared-memory stage k & 1 and TMEM accumulator
+// k & 1; its barrier parity is (k >> 1) & 1.
+//   producer thread     TMA(k) when stage free (EMPTY: MMA 2 of item k-2 retired)            -> FULL
+//                       MMA 1(k) when FULL and the accumulator is drained (SFREE, item k-2)  -> SFULL
+//                       MMA 2(k) when the softmax warps have written P (PREADY)              -> OFULL, EMPTY
+//                       the three are polled (mbarrier.test_wait) so that whichever becomes possible first is issued:
+//                       the loads and S = Q K^T of item k+1 run under the softmax of item k
+//   softmax warps       wait SFULL, softmax out of TMEM, P -> shared, arrive PREADY, wait OFULL, read O, arrive SFREE,
+//                       scale and store
+// The non-persistent version (one CTA per item, four CTAs per SM) spent 5.9 us per item on a serial chain of CTA start,
+// TMEM allocation, LUT load, TMA latency, MMA, softmax, MMA, store for 0.4 us of issue work (ncu: 28 % issue
+// utilisation, long-scoreboard stalls).
+__global__ void __launch_bounds__(THREADS, 2)
 enc_attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, bf16* __restrict__ out,
                         const int* __restrict__ plen, const int* __restrict__ poff,
-                        const uint8_t* __restrict__ tok_valid, const float* __restrict__ bias_lut, int Lb, int H) {
-  const int p = blockIdx.x, h = blockIdx.y;
-  const int len = plen[p];
-  if (len == 0) return;
-  const int row0 = poff[p];
+                        const uint8_t* __restrict__ tok_valid, const float* __restrict__ bias_lut, int Lb, int H, int P) {
   const int HD = H * DK;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
   uint8_t* smem = smem_raw + (base - raw);
-  const uint32_t sQ = base, sK = base + BOX, sV = base + 2 * BOX;       // P later overwrites Q | K
   const int lut_n = 2 * Lb - 1;
-  float* lut = reinterpret_cast<float*>(smem + 3 * BOX);                // [lut_n]
-  uint32_t* masks = reinterpret_cast<uint32_t*>(smem + 3 * BOX + ((lut_n * 4 + 15) / 16) * 16);   // [4]
-  const uint32_t bars = base + 3 * BOX + ((lut_n * 4 + 15) / 16) * 16 + 16;                       // tma, mma
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + 3 * BOX + ((lut_n * 4 + 15) / 16) * 16 + 32);
-  float* brange = reinterpret_cast<float*>(smem + 3 * BOX + ((lut_n * 4 + 15) / 16) * 16 + 48);   // [4] max, [4] min
+  const uint32_t lut_bytes = (uint32_t)(((size_t)H * lut_n * 4 + 15) / 16 * 16);
+  uint8_t* aux = smem + NSTAGE * STAGE;
+  float* lut = reinterpret_cast<float*>(aux);                                  // [H][lut_n], log2 units
+  float* bhi = reinterpret_cast<float*>(aux + lut_bytes);                      // [H] largest LUT entry of the head
+  float* blo = bhi + 32;                                                       // [H] smallest
+  uint32_t* masks = reinterpret_cast<uint32_t*>(aux + lut_bytes + 256);        // [4] key visibility of the current passage
+  const uint32_t bars = base + NSTAGE * STAGE + lut_bytes + 256 + 16;          // B_COUNT mbarriers
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aux + lut_bytes + 256 + 16 + 8 * B_COUNT);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const uint32_t bar_tma = bars, bar_mma = bars + 8;
+  auto bar = [&](int i) { return bars + 8u * (uint32_t)i; };
 
   if (tid == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_qkv) : "memory");
-    mbar_init(bar_tma, 1);
-    mbar_init(bar_mma, 1);
+    for (int i = 0; i < B_COUNT; ++i) mbar_init(bar(i), (i >= B_SFREE && i < B_OFULL) ? CONSUMERS : 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 0) {
+  if (warp == 4) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(TMEM_COLS) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
-  // bias LUT in log2 units (the softmax runs on exp2), and its range: a row's maximum is bounded by
-  // max(raw score) * log2e + max(bias), which lets the first pass skip the bias (see below)
-  float bmax = -INFINITY, bmin = INFINITY;
-  for (int i = tid; i < lut_n; i += THREADS) {
-    const float b = bias_lut[(size_t)h * lut_n + i] * LOG2E;
-    lut[i] = b;
-    bmax = fmaxf(bmax, b);
-    bmin = fminf(bmin, b);
-  }
-  bmax = warp_max(bmax);
-  bmin = -warp_max(-bmin);
-  if (lane == 0) { brange[warp] = bmax; brange[4 + warp] = bmin; }
-  {
-    const int j = warp * 32 + lane;
-    const bool vis = j < len && tok_valid[row0 + j] != 0;
-    const unsigned m = __ballot_sync(0xffffffffu, vis);
-    if (lane == 0) masks[warp] = m;
+  // bias LUTs of every head in log2 units (the softmax runs on exp2), and each head's range
+  for (int i = tid; i < H * lut_n; i += THREADS) lut[i] = bias_lut[i] * LOG2E;
+  __syncthreads();
+  for (int hh = warp; hh < H; hh += THREADS / 32) {
+    float bmax = -INFINITY, bmin = INFINITY;
+    for (int i = lane; i < lut_n; i += 32) {
+      const float b = lut[hh * lut_n + i];
+      bmax = fmaxf(bmax, b);
+      bmin = fminf(bmin, b);
+    }
+    bmax = warp_max(bmax);
+    bmin = -warp_max(-bmin);
+    if (lane == 0) { bhi[hh] = bmax; blo[hh] = bmin; }
   }
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem = *tmem_slot;
 
-  if (tid == 0) {
-    mbar_arrive_expect_tx(bar_tma, 3 * BOX);
-    tma_load_2d(sQ, &map_qkv, bar_tma, h * DK, row0);
-    tma_load_2d(sK, &map_qkv, bar_tma, HD + h * DK, row0);
-    tma_load_2d(sV, &map_qkv, bar_tma, 2 * HD + h * DK, row0);
-  }
-  mbar_wait(bar_tma, 0);
-  if (tid == 0) {
-    tcgen05_fence_after();
-    const uint64_t dq = make_desc(sQ), dk = make_desc(sK);
-#pragma unroll
-    for (int k = 0; k < DK / 16; ++k) umma_bf16(tmem, dq + (uint64_t)(k * 2), dk + (uint64_t)(k * 2), IDESC_QK, k ? 1u : 0u);
-    umma_commit(bar_mma);
-  }
-  mbar_wait(bar_mma, 0);
-  tcgen05_fence_after();
-
-  // ---- softmax of row r = tid: two passes over the TMEM row (32 scores in registers at a time keeps the kernel at
-  //      <= 128 registers, i.e. four CTAs per SM).  Everything is in log2 units: p = 2^(s*log2e + bias2 - m).
-  //      Softmax is invariant to the shift m as long as nothing overflows, so pass 1 does not need the exact row
-  //      maximum: for chunks whose 32 keys are all visible it takes max(raw s) -- one FMNMX per score -- and bounds the
-  //      bias by the largest LUT entry; the exact bias + mask walk is kept for the passage's tail chunk, and for every
-  //      chunk when the bias table spans more than 2^64 (then the bound could push small terms into underflow). ----
-  const int r = tid;
-  const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
-  const float* lrow = lut + (Lb - 1 - r);          // bias2 of (query r, key j) = lut[j - r + Lb - 1]; only read for j < len <= Lb
-  const float bias_hi = fmaxf(fmaxf(brange[0], brange[1]), fmaxf(brange[2], brange[3]));
-  const float bias_lo = fminf(fminf(brange[4], brange[5]), fminf(brange[6], brange[7]));
-  const bool exact = !(bias_hi - bias_lo <= 64.f);
-  float mraw = -INFINITY, mex = -INFINITY;
-#pragma unroll 1
-  for (int c = 0; c < 4; ++c) {
-    const uint32_t mk = masks[c];
-    if (mk == 0u) continue;                          // chunk past the passage (uniform across the CTA)
-    uint32_t v[32];
-    tmem_ld32(trow + c * 32, v);
-    tmem_ld_wait();
-    if (mk == 0xffffffffu && !exact) {
-#pragma unroll
-      for (int j = 0; j < 32; ++j) mraw = fmaxf(mraw, __uint_as_float(v[j]));
-    } else {
-#pragma unroll
-      for (int j = 0; j < 32; ++j)
-        if ((mk >> j) & 1u) mex = fmaxf(mex, fmaf(__uint_as_float(v[j]), LOG2E, lrow[c * 32 + j]));
-    }
-  }
-  const float mb = fmaxf(fmaf(mraw, LOG2E, bias_hi), mex);    // at least one key is visible (len > 0)
-  float sum = 0.f;
-  // P (bf16) in the K-major 128B-swizzled operand layout: box b = keys [64b, 64b+64), row r, 16-byte chunk j ^ (r & 7)
-#pragma unroll 1
-  for (int c = 0; c < 4; ++c) {
-    const uint32_t mk = masks[c];
-    float pr[32];
-    if (mk == 0u) {
-#pragma unroll
-      for (int j = 0; j < 32; ++j) pr[j] = 0.f;
-    } else {
-      uint32_t v[32];
-      tmem_ld32(trow + c * 32, v);
-      tmem_ld_wait();
-      if (mk == 0xffffffffu) {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          pr[j] = ex2_ftz(fmaf(__uint_as_float(v[j]), LOG2E, lrow[c * 32 + j] - mb));
-          sum += pr[j];
+  if (warp == 4) {
+    // ===================== producer: TMA + MMA issue =====================
+    if (lane == 0) {
+      int p_it = (int)blockIdx.x - (int)gridDim.x, h_it = H - 1, row0_it = 0;
+      bool tma_done = false;
+      auto advance = [&]() {                               // next (passage, head) of this CTA, skipping empty passages
+        if (++h_it < H) return;
+        h_it = 0;
+        for (;;) {
+          p_it += (int)gridDim.x;
+          if (p_it >= P) { tma_done = true; return; }
+          if (plen[p_it] > 0) { row0_it = poff[p_it]; return; }
         }
-      } else {
+      };
+      advance();
+      uint32_t k_tma = 0, k_m1 = 0, k_m2 = 0;              // items loaded / S issued / O issued
+      while (!(tma_done && k_m2 == k_tma)) {
+        if (!tma_done && k_tma < k_m2 + NSTAGE) {
+          const uint32_t st = k_tma & 1u, ph = (k_tma >> 1) & 1u;
+          if (mbar_test(bar(B_EMPTY + st), ph ^ 1u)) {
+            const uint32_t sb = base + st * STAGE;
+            mbar_arrive_expect_tx(bar(B_FULL + st), STAGE);
+            tma_load_2d(sb, &map_qkv, bar(B_FULL + st), h_it * DK, row0_it);
+            tma_load_2d(sb + BOX, &map_qkv, bar(B_FULL + st), HD + h_it * DK, row0_it);
+            tma_load_2d(sb + 2 * BOX, &map_qkv, bar(B_FULL + st), 2 * HD + h_it * DK, row0_it);
+            ++k_tma;
+            advance();
+          }
+        }
+        if (k_m1 < k_tma) {
+          const uint32_t st = k_m1 & 1u, ph = (k_m1 >> 1) & 1u;
+          if (mbar_test(bar(B_FULL + st), ph) && mbar_test(bar(B_SFREE + st), ph ^ 1u)) {
+            tcgen05_fence_after();
+            const uint32_t sb = base + st * STAGE;
+            const uint64_t dq = make_desc(sb), dk = make_desc(sb + BOX);
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          float pj = 0.f;
-          if ((mk >> j) & 1u) pj = ex2_ftz(fmaf(__uint_as_float(v[j]), LOG2E, lrow[c * 32 + j] - mb));
-          pr[j] = pj;
-          sum += pj;
+            for (int kk = 0; kk < DK / 16; ++kk)
+              umma_bf16(tmem + st * 128u, dq + (uint64_t)(kk * 2), dk + (uint64_t)(kk * 2), IDESC_QK, kk ? 1u : 0u);
+            umma_commit(bar(B_SFULL + st));
+            ++k_m1;
+          }
+        }
+        if (k_m2 < k_m1) {
+          const uint32_t st = k_m2 & 1u, ph = (k_m2 >> 1) & 1u;
+          if (mbar_test(bar(B_PREADY + st), ph)) {
+            tcgen05_fence_after();
+            const uint32_t sb = base + st * STAGE;
+#pragma unroll
+            for (int ks = 0; ks < LQ / 16; ++ks) {
+              const uint64_t dp = make_desc(sb + ((ks >> 2) ? BOX : 0u) + (uint32_t)(ks & 3) * 32u);
+              const uint64_t dv = make_desc(sb + 2 * BOX + (uint32_t)ks * 2048u);
+              umma_bf16(tmem + st * 128u, dp, dv, IDESC_PV, ks ? 1u : 0u);     // O re-uses the (fully read) S columns
+            }
+            umma_commit(bar(B_OFULL + st));
+            umma_commit(bar(B_EMPTY + st));                 // Q|K (= P) and V of the stage are no longer read
+            ++k_m2;
+          }
         }
       }
     }
-#pragma unroll
-    for (int q4 = 0; q4 < 4; ++q4) {
-      uint32_t pk[4];
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        __nv_bfloat162 h2 = __floats2bfloat162_rn(pr[q4 * 8 + 2 * e], pr[q4 * 8 + 2 * e + 1]);
-        pk[e] = *reinterpret_cast<uint32_t*>(&h2);
+    __syncwarp();
+  } else {
+    // ===================== softmax + epilogue: thread r owns query row r =====================
+    const int r = tid;
+    const uint32_t tlane = (uint32_t)(warp * 32) << 16;
+    uint32_t k = 0;
+    for (int p = blockIdx.x; p < P; p += gridDim.x) {
+      const int len = plen[p];
+      if (len == 0) continue;
+      const int row0 = poff[p];
+      {
+        const bool vis = r < len && tok_valid[row0 + r] != 0;
+        const unsigned m = __ballot_sync(0xffffffffu, vis);
+        consumer_bar();                                  // every warp is done with the previous passage's masks
+        if (lane == 0) masks[warp] = m;
+        consumer_bar();
       }
-      const int ch = c * 4 + q4;                     // 16-byte chunk of the 128-key row
-      const uint32_t box = (ch >> 3) ? sK : sQ;
-      const uint32_t addr = box + (uint32_t)r * 128u + (uint32_t)((((ch & 7) ^ (r & 7)) & 7) << 4);
-      asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pk[0]), "r"(pk[1]), "r"(pk[2]), "r"(pk[3]) : "memory");
-    }
-  }
-  tcgen05_fence_before();                            // S has been read out of TMEM by this thread
-  fence_async_smem();
-  __syncthreads();
-  if (tid == 0) {
-    tcgen05_fence_after();
+      uint32_t mkc[4];
 #pragma unroll
-    for (int ks = 0; ks < LQ / 16; ++ks) {
-      const uint64_t dp = make_desc(((ks >> 2) ? sK : sQ) + (uint32_t)(ks & 3) * 32u);
-      const uint64_t dv = make_desc(sV + (uint32_t)ks * 2048u);
-      umma_bf16(tmem, dp, dv, IDESC_PV, ks ? 1u : 0u);       // O re-uses the (fully read) S columns
-    }
-    umma_commit(bar_mma);
-  }
-  mbar_wait(bar_mma, 1);
-  tcgen05_fence_after();
-  uint32_t ov[2][32];
-  tmem_ld32(trow, ov[0]);
-  tmem_ld32(trow + 32, ov[1]);
-  tmem_ld_wait();
-  if (r < len) {
-    const float inv = 1.0f / sum;
-    bf16* orow = out + (size_t)(row0 + r) * HD + h * DK;
+      for (int c = 0; c < 4; ++c) mkc[c] = masks[c];
+      for (int h = 0; h < H; ++h, ++k) {
+        const uint32_t st = k & 1u, ph = (k >> 1) & 1u;
+        const uint32_t trow = tmem + st * 128u + tlane;
+        const uint32_t sQ = base + st * STAGE, sK = sQ + BOX;
+        // bias2 of (query r, key j) = lut[h][j - r + Lb - 1]; only read for j < len <= Lb
+        const float* lrow = lut + h * lut_n + (Lb - 1 - r);
+        const float bias_hi = bhi[h];
+        const bool exact = !(bias_hi - blo[h] <= 64.f);
+        mbar_wait(bar(B_SFULL + st), ph);
+        tcgen05_fence_after();
+        // Two passes over the TMEM row, 32 scores in registers at a time, everything in log2 units:
+        // p = 2^(s*log2e + bias2 - m).  Softmax is invariant to the shift m as long as nothing overflows, so pass 1
+        // does not need the exact row maximum: for chunks whose 32 keys are all visible it takes max(raw s) -- one
+        // FMNMX per score -- and bounds the bias by the head's largest LUT entry; the exact bias + mask walk is kept
+        // for the passage's tail chunk, and for every chunk when the bias table spans more than 2^64 (then the bound
+        // could push small terms into underflow).
+        float mraw = -INFINITY, mex = -INFINITY;
 #pragma unroll
-    for (int g = 0; g < 8; ++g) {
-      uint32_t pk[4];
+        for (int c = 0; c < 4; ++c) {
+          const uint32_t mk = mkc[c];
+          if (mk == 0u) continue;                        // chunk past the passage (uniform across the CTA)
+          uint32_t v[32];
+          tmem_ld32(trow + c * 32, v);
+          tmem_ld_wait();
+          if (mk == 0xffffffffu && !exact) {
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const int i = g * 8 + 2 * e;
-        __nv_bfloat162 h2 = __floats2bfloat162_rn(__uint_as_float(ov[i >> 5][i & 31]) * inv,
-                                                  __uint_as_float(ov[(i + 1) >> 5][(i + 1) & 31]) * inv);
-        pk[e] = *reinterpret_cast<uint32_t*>(&h2);
+            for (int j = 0; j < 32; ++j) mraw = fmaxf(mraw, __uint_as_float(v[j]));
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if ((mk >> j) & 1u) mex = fmaxf(mex, fmaf(__uint_as_float(v[j]), LOG2E, lrow[c * 32 + j]));
+          }
+        }
+        const float mb = fmaxf(fmaf(mraw, LOG2E, bias_hi), mex);    // at least one key is visible (len > 0)
+        float sum = 0.f;
+        // P (bf16) in the K-major 128B-swizzled operand layout: box b = keys [64b, 64b+64), row r, chunk j ^ (r & 7)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const uint32_t mk = mkc[c];
+          float pr[32];
+          if (mk == 0u) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) pr[j] = 0.f;
+          } else {
+            uint32_t v[32];
+            tmem_ld32(trow + c * 32, v);
+            tmem_ld_wait();
+            if (mk == 0xffffffffu) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                pr[j] = ex2_ftz(fmaf(__uint_as_float(v[j]), LOG2E, lrow[c * 32 + j] - mb));
+                sum += pr[j];
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                float pj = 0.f;
+                if ((mk >> j) & 1u) pj = ex2_ftz(fmaf(__uint_as_float(v[j]), LOG2E, lrow[c * 32 + j] - mb));
+                pr[j] = pj;
+                sum += pj;
+              }
+            }
+          }
+#pragma unroll
+          for (int q4 = 0; q4 < 4; ++q4) {
+            uint32_t pk[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              __nv_bfloat162 h2 = __floats2bfloat162_rn(pr[q4 * 8 + 2 * e], pr[q4 * 8 + 2 * e + 1]);
+              pk[e] = *reinterpret_cast<uint32_t*>(&h2);
+            }
+            const int ch = c * 4 + q4;                   // 16-byte chunk of the 128-key row
+            const uint32_t box = (ch >> 3) ? sK : sQ;
+            const uint32_t addr = box + (uint32_t)r * 128u + (uint32_t)((((ch & 7) ^ (r & 7)) & 7) << 4);
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pk[0]), "r"(pk[1]), "r"(pk[2]), "r"(pk[3]) : "memory");
+          }
+        }
+        tcgen05_fence_before();                          // S has been read out of TMEM by this thread
+        fence_async_smem();                              // P is visible to the tensor core's (async) proxy
+        mbar_arrive(bar(B_PREADY + st));
+        mbar_wait(bar(B_OFULL + st), ph);
+        tcgen05_fence_after();
+        uint32_t ov[2][32];
+        tmem_ld32(trow, ov[0]);
+        tmem_ld32(trow + 32, ov[1]);
+        tmem_ld_wait();
+        tcgen05_fence_before();
+        mbar_arrive(bar(B_SFREE + st));                  // the accumulator may be overwritten by item k + 2
+        if (r < len) {
+          const float inv = 1.0f / sum;
+          bf16* orow = out + (size_t)(row0 + r) * HD + h * DK;
+#pragma unroll
+          for (int g = 0; g < 8; ++g) {
+            uint32_t pk[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const int i = g * 8 + 2 * e;
+              __nv_bfloat162 h2 = __floats2bfloat162_rn(__uint_as_float(ov[i >> 5][i & 31]) * inv,
+                                                        __uint_as_float(ov[(i + 1) >> 5][(i + 1) & 31]) * inv);
+              pk[e] = *reinterpret_cast<uint32_t*>(&h2);
+            }
+            *reinterpret_cast<uint4*>(orow + g * 8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+          }
+        }
       }
-      *reinterpret_cast<uint4*>(orow + g * 8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
     }
   }
   tcgen05_fence_before();
   __syncthreads();
-  if (warp == 0) {
+  if (warp == 4) {
     tcgen05_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(TMEM_COLS) : "memory");
   }
@@ -326,21 +413,29 @@ bool get_map(const void* ptr, size_t rows, size_t cols, CUtensorMap* out) {
 
 }  // namespace ta
 
-bool enc_attention_tc_supported(int dk, int Lmax, int Lb) { return dk == ta::DK && Lmax <= ta::LQ && Lb <= 1024; }
+bool enc_attention_tc_supported(int dk, int Lmax, int Lb) { return dk == ta::DK && Lmax <= ta::LQ && Lb <= 256; }
 
 cudaError_t enc_attention_tc(const void* qkv, size_t qkv_rows, void* out, const int* plen, const int* poff,
                              const uint8_t* tok_valid, const float* bias_lut, int Lb, int P, int H, cudaStream_t s) {
   if (P <= 0) return cudaSuccess;
+  if (H > 32) return cudaErrorInvalidValue;
   std::lock_guard<std::mutex> lk(ta::g_mu);
   CUtensorMap map;
   if (!ta::get_map(qkv, qkv_rows, (size_t)3 * H * ta::DK, &map)) return cudaErrorUnknown;
-  const size_t smem = (size_t)3 * ta::BOX + (((size_t)(2 * Lb - 1) * 4 + 15) / 16) * 16 + 96 + 1024;
+  const size_t smem = (size_t)ta::NSTAGE * ta::STAGE + (((size_t)H * (2 * Lb - 1) * 4 + 15) / 16) * 16 + 256 + 16 +
+                      8 * ta::B_COUNT + 16 + 1024;
   static SmemAttr attr;
   {
     cudaError_t e = attr.ensure(ta::enc_attention_tc_kernel, smem);
     if (e != cudaSuccess) return e;
   }
-  ta::enc_attention_tc_kernel<<<dim3(P, H), ta::THREADS, smem, s>>>(map, (bf16*)out, plen, poff, tok_valid, bias_lut, Lb, H);
+  static int sms[64];
+  int dev = 0;
+  cudaGetDevice(&dev);
+  dev &= 63;
+  if (sms[dev] == 0 && cudaDeviceGetAttribute(&sms[dev], cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return cudaGetLastError();
+  const int grid = P < 2 * sms[dev] ? P : 2 * sms[dev];            // two persistent CTAs per SM
+  ta::enc_attention_tc_kernel<<<grid, ta::THREADS, smem, s>>>(map, (bf16*)out, plen, poff, tok_valid, bias_lut, Lb, H, P);
   return cudaGetLastError();
 }
 

@@ -314,6 +314,33 @@ def test_tcgen05_encoder_attention_matches_mma_path(built):
     assert err < BF16_TOL
 
 
+def test_tcgen05_encoder_attention_many_passages():
+    """The persistent tcgen05 kernel at a batch where every CTA walks several passages (more passages than 2 CTAs per
+    SM), with ragged lengths from 2 to 128 tokens, all-masked passages and masked holes inside a passage: fused memory
+    against the mma.sync path, which the reference-driven goldens pin."""
+    from gram_b200 import _cabi, synth
+    from gram_b200.config import GramConfig
+    cfg = GramConfig.t5_small(max_seq_len=128, max_item_num=8)
+    sd = synth.make_state_dict(cfg, seed=2)
+    ids, mask = synth.make_user_batch(cfg, 96, (1, 8), 128, seed=31, min_len=2)
+    mask = mask.copy()
+    mask[3, 0, 5:9] = False          # holes: masked keys inside the valid prefix
+    mask[40, 1, 0] = False
+    ids, mask = torch.from_numpy(ids).cuda(), torch.from_numpy(mask).cuda()
+    outs = []
+    for flags in (_cabi.GRAM_FLAG_TC_ENC_ATTN, 0):
+        from gram_b200 import GRAM
+        m = GRAM(cfg, dtype="bf16", device="cuda:0", flags=flags)
+        m.load_state_dict(sd)
+        outs.append(m.encode(ids, mask).cpu())
+        del m
+    assert ids.shape[0] * ids.shape[1] > 2 * 148
+    assert torch.isfinite(outs[0]).all()
+    err = rel_err(outs[0], outs[1])
+    print(f"[tcgen05 enc-attn, {ids.shape[0] * ids.shape[1]} passages] memory rel_err vs mma.sync path = {err:.3e}")
+    assert err < 2e-2
+
+
 def test_generate_errors(built):
     from gram_b200 import Trie, prefix_allowed_tokens_fn
     b = built["tiny"]
