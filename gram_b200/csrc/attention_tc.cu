@@ -125,13 +125,14 @@ __device__ __forceinline__ void consumer_bar() { asm volatile("bar.sync 1, 128;"
 // Persistent, warp-specialised kernel: CTA b walks passages b, b + grid, ... and the H heads of each; two CTAs per SM.
 // Work item k of a CTA (the k-th (passage, head) it processes) uses shared-memory stage k & 1 and TMEM accumulator
 // k & 1; its barrier parity is (k >> 1) & 1.
-//   producer thread     TMA(k) when stage free (EMPTY: MMA 2 of item k-2 retired)            -> FULL
-//                       MMA 1(k) when FULL and the accumulator is drained (SFREE, item k-2)  -> SFULL
-//                       MMA 2(k) when the softmax warps have written P (PREADY)              -> OFULL, EMPTY
+//   producer thread     TMA(k) when stage free (EMPTY: epilogue of item k-2 has left the stage)  -> FULL
+//                       MMA 1(k) when FULL and the accumulator is drained (SFREE, item k-2)      -> SFULL
+//                       MMA 2(k) when the softmax warps have written P (PREADY)                  -> OFULL
 //                       the three are polled (mbarrier.test_wait) so that whichever becomes possible first is issued:
 //                       the loads and S = Q K^T of item k+1 run under the softmax of item k
-//   softmax warps       wait SFULL, softmax out of TMEM, P -> shared, arrive PREADY, wait OFULL, read O, arrive SFREE,
-//                       scale and store
+//   softmax warps       pass 2 of item k (exp2, row sum, P -> shared), arrive PREADY; pass 1 (row maximum) of item
+//                       k+1 while the tensor core computes O(k); wait OFULL, read O, arrive SFREE; O rows through the
+//                       dead P rows of the stage to coalesced 128-byte stores; arrive EMPTY
 // The non-persistent version (one CTA per item, four CTAs per SM) spent 5.9 us per item on a serial chain of CTA start,
 // TMEM allocation, LUT load, TMA latency, MMA, softmax, MMA, store for 0.4 us of issue work (ncu: 28 % issue
 // utilisation, long-scoreboard stalls).
@@ -158,7 +159,8 @@ enc_attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, bf16* __res
 
   if (tid == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_qkv) : "memory");
-    for (int i = 0; i < B_COUNT; ++i) mbar_init(bar(i), (i >= B_SFREE && i < B_OFULL) ? CONSUMERS : 1);
+    for (int i = 0; i < B_COUNT; ++i)
+      mbar_init(bar(i), ((i >= B_SFREE && i < B_OFULL) || (i >= B_EMPTY && i < B_SFULL)) ? CONSUMERS : 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 4) {
@@ -238,7 +240,6 @@ enc_attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, bf16* __res
               umma_bf16(tmem + st * 128u, dp, dv, IDESC_PV, ks ? 1u : 0u);     // O re-uses the (fully read) S columns
             }
             umma_commit(bar(B_OFULL + st));
-            umma_commit(bar(B_EMPTY + st));                 // Q|K (= P) and V of the stage are no longer read
             ++k_m2;
           }
         }
@@ -249,126 +250,164 @@ enc_attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, bf16* __res
     // ===================== softmax + epilogue: thread r owns query row r =====================
     const int r = tid;
     const uint32_t tlane = (uint32_t)(warp * 32) << 16;
-    uint32_t k = 0;
-    for (int p = blockIdx.x; p < P; p += gridDim.x) {
-      const int len = plen[p];
-      if (len == 0) continue;
-      const int row0 = poff[p];
-      {
-        const bool vis = r < len && tok_valid[row0 + r] != 0;
-        const unsigned m = __ballot_sync(0xffffffffu, vis);
-        consumer_bar();                                  // every warp is done with the previous passage's masks
-        if (lane == 0) masks[warp] = m;
-        consumer_bar();
+    // ---- iteration over this CTA's items; the key-visibility masks are rebuilt when the passage changes ----
+    int p = (int)blockIdx.x - (int)gridDim.x, h = H - 1, len = 0, row0 = 0;
+    uint32_t mkc[4] = {0u, 0u, 0u, 0u};
+    auto next_item = [&]() -> bool {
+      if (++h < H) return true;
+      h = 0;
+      for (;;) {
+        p += (int)gridDim.x;
+        if (p >= P) return false;
+        len = plen[p];
+        if (len > 0) break;
       }
-      uint32_t mkc[4];
+      row0 = poff[p];
+      const bool vis = r < len && tok_valid[row0 + r] != 0;
+      const unsigned m = __ballot_sync(0xffffffffu, vis);
+      consumer_bar();                                    // every warp is done with the previous passage's masks
+      if (lane == 0) masks[warp] = m;
+      consumer_bar();
 #pragma unroll
       for (int c = 0; c < 4; ++c) mkc[c] = masks[c];
-      for (int h = 0; h < H; ++h, ++k) {
-        const uint32_t st = k & 1u, ph = (k >> 1) & 1u;
-        const uint32_t trow = tmem + st * 128u + tlane;
-        const uint32_t sQ = base + st * STAGE, sK = sQ + BOX;
-        // bias2 of (query r, key j) = lut[h][j - r + Lb - 1]; only read for j < len <= Lb
-        const float* lrow = lut + h * lut_n + (Lb - 1 - r);
-        const float bias_hi = bhi[h];
-        const bool exact = !(bias_hi - blo[h] <= 64.f);
-        mbar_wait(bar(B_SFULL + st), ph);
-        tcgen05_fence_after();
-        // Two passes over the TMEM row, 32 scores in registers at a time, everything in log2 units:
-        // p = 2^(s*log2e + bias2 - m).  Softmax is invariant to the shift m as long as nothing overflows, so pass 1
-        // does not need the exact row maximum: for chunks whose 32 keys are all visible it takes max(raw s) -- one
-        // FMNMX per score -- and bounds the bias by the head's largest LUT entry; the exact bias + mask walk is kept
-        // for the passage's tail chunk, and for every chunk when the bias table spans more than 2^64 (then the bound
-        // could push small terms into underflow).
-        float mraw = -INFINITY, mex = -INFINITY;
+      return true;
+    };
+    // Pass 1 of item k (head hh): an upper bound of the row maximum in log2 units.  Softmax is invariant to the shift
+    // as long as nothing overflows, so the exact maximum is not needed: for chunks whose 32 keys are all visible it
+    // takes max(raw s) -- one FMNMX per score -- and bounds the bias by the head's largest LUT entry; the exact
+    // bias + mask walk is kept for the passage's tail chunk, and for every chunk when the bias table spans more than
+    // 2^64 (then the bound could push small terms into underflow).
+    auto pass1 = [&](uint32_t k, int hh) -> float {
+      const uint32_t st = k & 1u, ph = (k >> 1) & 1u;
+      const uint32_t trow = tmem + st * 128u + tlane;
+      const float* lrow = lut + hh * lut_n + (Lb - 1 - r);
+      const float bias_hi = bhi[hh];
+      const bool exact = !(bias_hi - blo[hh] <= 64.f);
+      mbar_wait(bar(B_SFULL + st), ph);
+      tcgen05_fence_after();
+      float mraw = -INFINITY, mex = -INFINITY;
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          const uint32_t mk = mkc[c];
-          if (mk == 0u) continue;                        // chunk past the passage (uniform across the CTA)
+      for (int c = 0; c < 4; ++c) {
+        const uint32_t mk = mkc[c];
+        if (mk == 0u) continue;                          // chunk past the passage (uniform across the CTA)
+        uint32_t v[32];
+        tmem_ld32(trow + c * 32, v);
+        tmem_ld_wait();
+        if (mk == 0xffffffffu && !exact) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) mraw = fmaxf(mraw, __uint_as_float(v[j]));
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if ((mk >> j) & 1u) mex = fmaxf(mex, fmaf(__uint_as_float(v[j]), LOG2E, lrow[c * 32 + j]));
+        }
+      }
+      return fmaxf(fmaf(mraw, LOG2E, bias_hi), mex);     // at least one key is visible (len > 0)
+    };
+
+    uint32_t k = 0;
+    bool have = next_item();
+    float mb = have ? pass1(0u, h) : 0.f;
+    while (have) {
+      const uint32_t st = k & 1u, ph = (k >> 1) & 1u;
+      const uint32_t trow = tmem + st * 128u + tlane;
+      const uint32_t sQ = base + st * STAGE, sK = sQ + BOX;
+      // bias2 of (query r, key j) = lut[h][j - r + Lb - 1]; only read for j < len <= Lb
+      const float* lrow = lut + h * lut_n + (Lb - 1 - r);
+      // ---- pass 2: p = 2^(s*log2e + bias2 - mb), row sum, P (bf16) into the K-major 128B-swizzled operand layout:
+      //      box b = keys [64b, 64b+64), row r, 16-byte chunk j ^ (r & 7) ----
+      float sum = 0.f;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const uint32_t mk = mkc[c];
+        float pr[32];
+        if (mk == 0u) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) pr[j] = 0.f;
+        } else {
           uint32_t v[32];
           tmem_ld32(trow + c * 32, v);
           tmem_ld_wait();
-          if (mk == 0xffffffffu && !exact) {
+          if (mk == 0xffffffffu) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) mraw = fmaxf(mraw, __uint_as_float(v[j]));
+            for (int j = 0; j < 32; ++j) {
+              pr[j] = ex2_ftz(fmaf(__uint_as_float(v[j]), LOG2E, lrow[c * 32 + j] - mb));
+              sum += pr[j];
+            }
           } else {
 #pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if ((mk >> j) & 1u) mex = fmaxf(mex, fmaf(__uint_as_float(v[j]), LOG2E, lrow[c * 32 + j]));
+            for (int j = 0; j < 32; ++j) {
+              float pj = 0.f;
+              if ((mk >> j) & 1u) pj = ex2_ftz(fmaf(__uint_as_float(v[j]), LOG2E, lrow[c * 32 + j] - mb));
+              pr[j] = pj;
+              sum += pj;
+            }
           }
         }
-        const float mb = fmaxf(fmaf(mraw, LOG2E, bias_hi), mex);    // at least one key is visible (len > 0)
-        float sum = 0.f;
-        // P (bf16) in the K-major 128B-swizzled operand layout: box b = keys [64b, 64b+64), row r, chunk j ^ (r & 7)
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          const uint32_t mk = mkc[c];
-          float pr[32];
-          if (mk == 0u) {
+        for (int q4 = 0; q4 < 4; ++q4) {
+          uint32_t pk[4];
 #pragma unroll
-            for (int j = 0; j < 32; ++j) pr[j] = 0.f;
-          } else {
-            uint32_t v[32];
-            tmem_ld32(trow + c * 32, v);
-            tmem_ld_wait();
-            if (mk == 0xffffffffu) {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) {
-                pr[j] = ex2_ftz(fmaf(__uint_as_float(v[j]), LOG2E, lrow[c * 32 + j] - mb));
-                sum += pr[j];
-              }
-            } else {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) {
-                float pj = 0.f;
-                if ((mk >> j) & 1u) pj = ex2_ftz(fmaf(__uint_as_float(v[j]), LOG2E, lrow[c * 32 + j] - mb));
-                pr[j] = pj;
-                sum += pj;
-              }
-            }
+          for (int e = 0; e < 4; ++e) {
+            __nv_bfloat162 h2 = __floats2bfloat162_rn(pr[q4 * 8 + 2 * e], pr[q4 * 8 + 2 * e + 1]);
+            pk[e] = *reinterpret_cast<uint32_t*>(&h2);
           }
-#pragma unroll
-          for (int q4 = 0; q4 < 4; ++q4) {
-            uint32_t pk[4];
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              __nv_bfloat162 h2 = __floats2bfloat162_rn(pr[q4 * 8 + 2 * e], pr[q4 * 8 + 2 * e + 1]);
-              pk[e] = *reinterpret_cast<uint32_t*>(&h2);
-            }
-            const int ch = c * 4 + q4;                   // 16-byte chunk of the 128-key row
-            const uint32_t box = (ch >> 3) ? sK : sQ;
-            const uint32_t addr = box + (uint32_t)r * 128u + (uint32_t)((((ch & 7) ^ (r & 7)) & 7) << 4);
-            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pk[0]), "r"(pk[1]), "r"(pk[2]), "r"(pk[3]) : "memory");
-          }
-        }
-        tcgen05_fence_before();                          // S has been read out of TMEM by this thread
-        fence_async_smem();                              // P is visible to the tensor core's (async) proxy
-        mbar_arrive(bar(B_PREADY + st));
-        mbar_wait(bar(B_OFULL + st), ph);
-        tcgen05_fence_after();
-        uint32_t ov[2][32];
-        tmem_ld32(trow, ov[0]);
-        tmem_ld32(trow + 32, ov[1]);
-        tmem_ld_wait();
-        tcgen05_fence_before();
-        mbar_arrive(bar(B_SFREE + st));                  // the accumulator may be overwritten by item k + 2
-        if (r < len) {
-          const float inv = 1.0f / sum;
-          bf16* orow = out + (size_t)(row0 + r) * HD + h * DK;
-#pragma unroll
-          for (int g = 0; g < 8; ++g) {
-            uint32_t pk[4];
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const int i = g * 8 + 2 * e;
-              __nv_bfloat162 h2 = __floats2bfloat162_rn(__uint_as_float(ov[i >> 5][i & 31]) * inv,
-                                                        __uint_as_float(ov[(i + 1) >> 5][(i + 1) & 31]) * inv);
-              pk[e] = *reinterpret_cast<uint32_t*>(&h2);
-            }
-            *reinterpret_cast<uint4*>(orow + g * 8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-          }
+          const int ch = c * 4 + q4;                     // 16-byte chunk of the 128-key row
+          const uint32_t box = (ch >> 3) ? sK : sQ;
+          const uint32_t addr = box + (uint32_t)r * 128u + (uint32_t)((((ch & 7) ^ (r & 7)) & 7) << 4);
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pk[0]), "r"(pk[1]), "r"(pk[2]), "r"(pk[3]) : "memory");
         }
       }
+      tcgen05_fence_before();                            // S has been read out of TMEM by this thread
+      fence_async_smem();                                // P is visible to the tensor core's (async) proxy
+      mbar_arrive(bar(B_PREADY + st));
+      // ---- while the tensor core computes O = P V: move on to the next item and run its pass 1 ----
+      const int cur_h = h, cur_len = len, cur_row0 = row0;
+      have = next_item();
+      float mb_next = 0.f;
+      if (have) mb_next = pass1(k + 1u, h);
+      // ---- epilogue of the current item ----
+      mbar_wait(bar(B_OFULL + st), ph);
+      tcgen05_fence_after();
+      uint32_t ov[2][32];
+      tmem_ld32(trow, ov[0]);
+      tmem_ld32(trow + 32, ov[1]);
+      tmem_ld_wait();
+      tcgen05_fence_before();
+      mbar_arrive(bar(B_SFREE + st));                    // the accumulator may be overwritten by item k + 2
+      // O rows go through the (dead) P rows of this warp in the stage -- row r, 16-byte chunk g ^ (r & 7) -- and leave as
+      // full 128-byte lines: a row-per-thread store writes 32 half sectors per instruction and its slow drain held the
+      // registers of the next item (ncu: 12.7 % of the samples on that write-after-read)
+      {
+        const float inv = 1.0f / sum;
+        const uint32_t srow = sQ + (uint32_t)r * 128u;
+#pragma unroll
+        for (int g = 0; g < 8; ++g) {
+          uint32_t pk[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int i = g * 8 + 2 * e;
+            __nv_bfloat162 h2 = __floats2bfloat162_rn(__uint_as_float(ov[i >> 5][i & 31]) * inv,
+                                                      __uint_as_float(ov[(i + 1) >> 5][(i + 1) & 31]) * inv);
+            pk[e] = *reinterpret_cast<uint32_t*>(&h2);
+          }
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(srow + (uint32_t)(((g ^ (r & 7)) & 7) << 4)),
+                       "r"(pk[0]), "r"(pk[1]), "r"(pk[2]), "r"(pk[3]) : "memory");
+        }
+        __syncwarp();
+        const int chunk = lane & 7;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int rr = warp * 32 + i * 4 + (lane >> 3);        // row of the tile
+          uint4 val;
+          asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(val.x), "=r"(val.y), "=r"(val.z), "=r"(val.w)
+                       : "r"(sQ + (uint32_t)rr * 128u + (uint32_t)(((chunk ^ (rr & 7)) & 7) << 4)) : "memory");
+          if (rr < cur_len) *reinterpret_cast<uint4*>(out + (size_t)(cur_row0 + rr) * HD + cur_h * DK + chunk * 8) = val;
+        }
+      }
+      mbar_arrive(bar(B_EMPTY + st));                    // the stage (P/O staging rows and V) may be reloaded
+      ++k;
+      mb = mb_next;
     }
   }
   tcgen05_fence_before();
