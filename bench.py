@@ -54,7 +54,7 @@ def parse():
                     help="workspace rows (valid encoder tokens per step); 0 = the largest step of this run + 2 %%")
     ap.add_argument("--no-item-cache", action="store_true", help="skip the extra (non-headline) cached-item measurement")
     ap.add_argument("--gemm-1cta", action="store_true", help="keep every tcgen05 GEMM on single-CTA tiles (A/B timing)")
-    ap.add_argument("--tc-enc-attn", action="store_true", help="opt into the tcgen05 encoder-attention kernel (A/B timing)")
+    ap.add_argument("--mma-enc-attn", action="store_true", help="encoder attention through the mma.sync kernel instead of the tcgen05 one (A/B timing)")
     ap.add_argument("--all-rows", action="store_true",
                     help="decode dead beams / finished users too, as the reference does (A/B timing of live-row compaction)")
     return ap.parse_args()
@@ -289,7 +289,7 @@ def main():
 
     from gram_b200 import GRAM, _cabi
     data, cfg, sd, cands, max_length, trie, fn = build_workload(args, rank, world)
-    flags = (_cabi.GRAM_FLAG_SIMT_GEMM if args.simt else 0) | (_cabi.GRAM_FLAG_TC_ENC_ATTN if args.tc_enc_attn else 0) | \
+    flags = (_cabi.GRAM_FLAG_SIMT_GEMM if args.simt else 0) | (_cabi.GRAM_FLAG_MMA_ENC_ATTN if args.mma_enc_attn else 0) | \
         (_cabi.GRAM_FLAG_GEMM_1CTA if args.gemm_1cta else 0) | (_cabi.GRAM_FLAG_ALL_ROWS if args.all_rows else 0)
     model = GRAM(cfg, dtype=args.dtype, device=dev, flags=flags)
     model.load_state_dict(sd)

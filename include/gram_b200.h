@@ -59,9 +59,9 @@ enum {
   GRAM_FLAG_SIMT_GEMM = 1,         /* force the CUDA-core GEMM even for bf16 (debug / A-B timing) */
   GRAM_FLAG_KEEP_LOGITS = 2,       /* record per-step taps (lse, beam scores, prefixes) for parity tests */
   GRAM_FLAG_SIMT_ATTN = 4,         /* force the CUDA-core attention kernels even for bf16 (A-B timing)   */
-  GRAM_FLAG_TC_ENC_ATTN = 8,       /* encoder attention through the tcgen05/TMEM kernel (attention_tc.cu): numerically
-                                      verified, but one (passage, head) per CTA without cross-item pipelining it is
-                                      ~15 % slower than the pipelined mma.sync kernel, so it is opt-in for now */
+  GRAM_FLAG_MMA_ENC_ATTN = 8,      /* encoder attention through the mma.sync kernel (attention_mma.cu) instead of the
+                                      persistent tcgen05/TMEM kernel (attention_tc.cu), which is the default for bf16,
+                                      d_kv = 64 and passages of at most 128 tokens (A-B timing, cross-check)          */
   GRAM_FLAG_GEMM_1CTA = 16,        /* keep every tcgen05 GEMM on single-CTA tiles (no cta_group::2 pairs; A-B timing) */
   GRAM_FLAG_ALL_ROWS = 32          /* decode every beam row at every step, as the reference does (A-B timing).  Default:
                                       beams that are dead (-inf score: the user had fewer than K finite continuations,

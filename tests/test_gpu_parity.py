@@ -296,13 +296,13 @@ def test_generate_bf16_overlap(built, name):
 
 
 def test_tcgen05_encoder_attention_matches_mma_path(built):
-    """attention_tc.cu (tcgen05.mma with an MN-major V operand, softmax out of TMEM) against the default mma.sync
+    """attention_tc.cu (the default: tcgen05.mma with an MN-major V operand, softmax out of TMEM) against the mma.sync
     encoder attention: same fused memory within bf16 rounding, and within 2e-2 of the reference golden logits."""
     from gram_b200 import _cabi
     b = built["small"]
     gold = _golden("small")
-    m_tc = _model(b["case"], b["sd"], "bf16", flags=_cabi.GRAM_FLAG_TC_ENC_ATTN)
-    m_mma = _model(b["case"], b["sd"], "bf16")
+    m_tc = _model(b["case"], b["sd"], "bf16")
+    m_mma = _model(b["case"], b["sd"], "bf16", flags=_cabi.GRAM_FLAG_MMA_ENC_ATTN)
     ids, mask = b["ids"].cuda(), b["mask"].cuda()
     mem_tc, mem_mma = m_tc.encode(ids, mask).cpu(), m_mma.encode(ids, mask).cpu()
     assert rel_err(mem_tc, mem_mma) < 2e-2
@@ -328,7 +328,7 @@ def test_tcgen05_encoder_attention_many_passages():
     mask[40, 1, 0] = False
     ids, mask = torch.from_numpy(ids).cuda(), torch.from_numpy(mask).cuda()
     outs = []
-    for flags in (_cabi.GRAM_FLAG_TC_ENC_ATTN, 0):
+    for flags in (0, _cabi.GRAM_FLAG_MMA_ENC_ATTN):
         from gram_b200 import GRAM
         m = GRAM(cfg, dtype="bf16", device="cuda:0", flags=flags)
         m.load_state_dict(sd)
