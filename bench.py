@@ -47,7 +47,7 @@ def parse():
                     help="users per step per GPU (1888 users x 20 beams = 37760 decoder rows = 295 row tiles of 128: two "
                          "148-SM waves for every decoder GEMM; ~65 GB of workspace with the token-sized max_tokens)")
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp32"])
-    ap.add_argument("--cpu-users", type=int, default=8, help="users timed for cpu_baseline (0 = skip)")
+    ap.add_argument("--cpu-users", type=int, default=24, help="users timed for cpu_baseline (0 = skip)")
     ap.add_argument("--simt", action="store_true", help="force the CUDA-core GEMM (A/B timing)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--max-tokens", type=int, default=0,
@@ -55,6 +55,7 @@ def parse():
     ap.add_argument("--no-item-cache", action="store_true", help="skip the extra (non-headline) cached-item measurement")
     ap.add_argument("--gemm-1cta", action="store_true", help="keep every tcgen05 GEMM on single-CTA tiles (A/B timing)")
     ap.add_argument("--mma-enc-attn", action="store_true", help="encoder attention through the mma.sync kernel instead of the tcgen05 one (A/B timing)")
+    ap.add_argument("--fused-norm", action="store_true", help="fold the encoder RMSNorms into the tcgen05 GEMMs (A/B timing)")
     ap.add_argument("--all-rows", action="store_true",
                     help="decode dead beams / finished users too, as the reference does (A/B timing of live-row compaction)")
     return ap.parse_args()
@@ -290,7 +291,8 @@ def main():
     from gram_b200 import GRAM, _cabi
     data, cfg, sd, cands, max_length, trie, fn = build_workload(args, rank, world)
     flags = (_cabi.GRAM_FLAG_SIMT_GEMM if args.simt else 0) | (_cabi.GRAM_FLAG_MMA_ENC_ATTN if args.mma_enc_attn else 0) | \
-        (_cabi.GRAM_FLAG_GEMM_1CTA if args.gemm_1cta else 0) | (_cabi.GRAM_FLAG_ALL_ROWS if args.all_rows else 0)
+        (_cabi.GRAM_FLAG_GEMM_1CTA if args.gemm_1cta else 0) | (_cabi.GRAM_FLAG_ALL_ROWS if args.all_rows else 0) | \
+        (_cabi.GRAM_FLAG_FUSED_NORM if args.fused_norm else 0)
     model = GRAM(cfg, dtype=args.dtype, device=dev, flags=flags)
     model.load_state_dict(sd)
     B, K, W, S = args.batch, BEAMS, args.warmup, args.steps

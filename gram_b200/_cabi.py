@@ -16,6 +16,7 @@ _LIB_PATH = os.environ.get("GRAM_B200_LIB") or os.path.join(os.path.dirname(os.p
 GRAM_DTYPE_F32, GRAM_DTYPE_BF16 = 0, 1
 GRAM_FLAG_SIMT_GEMM, GRAM_FLAG_KEEP_LOGITS, GRAM_FLAG_SIMT_ATTN, GRAM_FLAG_MMA_ENC_ATTN, GRAM_FLAG_GEMM_1CTA = 1, 2, 4, 8, 16
 GRAM_FLAG_ALL_ROWS = 32
+GRAM_FLAG_FUSED_NORM = 64
 K_CLASSES = ["gemm_enc", "enc_attn", "gemm_kv", "gemm_dec", "cross_attn", "lm_head", "beam", "other", "self_attn",
              "norm_enc", "norm_dec"]
 GRAM_K_COUNT = len(K_CLASSES)
@@ -25,7 +26,7 @@ EXPORTED_SYMBOLS = [
     "gram_create", "gram_destroy", "gram_last_error", "gram_version", "gram_load_weight",
     "gram_set_rel_buckets", "gram_finalize_weights", "gram_set_trie", "gram_encode", "gram_generate",
     "gram_get_memory", "gram_decoder_logits", "gram_get_step_taps", "gram_get_stats",
-    "gram_profile_begin", "gram_profile_end", "gram_op_gemm", "gram_op_cross_attention",
+    "gram_profile_begin", "gram_profile_end", "gram_op_gemm", "gram_op_gemm_norm", "gram_op_cross_attention",
     "gram_cache_items", "gram_encode_cached", "gram_check_errors",
 ]
 
@@ -115,6 +116,8 @@ def load_library():
     lib.gram_profile_end.restype = C.c_int
     lib.gram_op_gemm.argtypes = [i32, i32, i32, i32, vp, vp, vp, i32, i32, i32, vp]
     lib.gram_op_gemm.restype = C.c_int
+    lib.gram_op_gemm_norm.argtypes = [i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, C.c_float, i32, i32, i32, vp]
+    lib.gram_op_gemm_norm.restype = C.c_int
     lib.gram_op_cross_attention.argtypes = [i32, i32, i32, vp, vp, i32, i32p, u8p, vp, i32, i32, i32, i32, vp]
     lib.gram_op_cross_attention.restype = C.c_int
     _lib = lib

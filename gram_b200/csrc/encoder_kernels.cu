@@ -242,6 +242,36 @@ __global__ void embed_rows_kernel(const T* __restrict__ table, const int* __rest
   for (int c = lane * 4; c < D; c += 128) store4(dst + c, load4(src + c));
 }
 
+// embedding + the first RMSNorm's input in the folded form the tcgen05 GEMMs consume (kernels.h: GemmNormAux):
+// x fp32, xb = bf16(x * w), and the row's sum of squares per 128-column block.  One warp per row; D % 128 == 0.
+__global__ void embed_rows_norm_kernel(const bf16* __restrict__ table, const int* __restrict__ tok_id, float* __restrict__ x,
+                                       bf16* __restrict__ xb, float* __restrict__ ss, const float* __restrict__ w,
+                                       int M_imm, const int* __restrict__ m_ptr, int D) {
+  const int M = m_ptr ? *m_ptr : M_imm;
+  const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (row >= M) return;
+  const bf16* src = table + (size_t)tok_id[row] * D;
+  for (int c0 = 0; c0 < D; c0 += 128) {
+    const int c = c0 + lane * 4;
+    const float4 v = load4(src + c);
+    const float4 g = load4(w + c);
+    store4(x + (size_t)row * D + c, v);
+    store4(xb + (size_t)row * D + c, make_float4(v.x * g.x, v.y * g.y, v.z * g.z, v.w * g.w));
+    float t = v.x * v.x;
+    t = fmaf(v.y, v.y, t); t = fmaf(v.z, v.z, t); t = fmaf(v.w, v.w, t);
+    t = warp_sum(t);
+    if (lane == 0) ss[(size_t)row * (D >> 7) + (c0 >> 7)] = t;
+  }
+}
+
+cudaError_t embed_rows_norm(const void* table, const int* tok_id, float* x, void* xb, float* ss, const float* w, int M_max,
+                            const int* m_ptr, int D, cudaStream_t s) {
+  if (M_max <= 0) return cudaSuccess;
+  if (D & 127) return cudaErrorInvalidValue;
+  embed_rows_norm_kernel<<<(M_max + 7) / 8, 256, 0, s>>>((const bf16*)table, tok_id, x, (bf16*)xb, ss, w, M_max, m_ptr, D);
+  return cudaGetLastError();
+}
+
 cudaError_t embed_rows(int dtype, const void* table, const int* tok_id, float* x, int M_max, const int* m_ptr, int D,
                        cudaStream_t s) {
   if (M_max <= 0) return cudaSuccess;

@@ -75,6 +75,7 @@ struct gram_handle {
   uint8_t* d_mask = nullptr;
   float* x = nullptr;
   void *xn = nullptr, *qkv = nullptr, *ao = nullptr, *ff = nullptr, *mem = nullptr, *ckv = nullptr;
+  float* ss = nullptr;        // [Mcap][D/128] row sums of squares of the residual stream (RMSNorm folded into the GEMMs)
   int enc_B = 0, enc_N = 0, enc_L = 0;
   bool encoded = false;
 
@@ -211,18 +212,18 @@ __global__ void build_lut_kernel(const float* __restrict__ rel, const int* __res
 }
 
 int gemm(gram_handle* h, int cls, int epi, const void* A, const void* W, void* C, int M_max, const int* m_ptr, int N,
-         int K, cudaStream_t s) {
+         int K, cudaStream_t s, const GemmNormAux* aux = nullptr) {
   Scope sc(h, cls, s);
   cudaError_t e;
   if (h->cfg.dtype == GRAM_DTYPE_BF16 && !(h->cfg.flags & GRAM_FLAG_SIMT_GEMM) && gemm_tc_supported(N, K)) {
-    e = gemm_tc(epi, A, W, C, M_max, m_ptr, N, K, h->num_sms, (h->cfg.flags & GRAM_FLAG_GEMM_1CTA) ? 1 : 2, s);
+    e = gemm_tc(epi, A, W, C, M_max, m_ptr, N, K, h->num_sms, (h->cfg.flags & GRAM_FLAG_GEMM_1CTA) ? 1 : 2, s, aux);
     if (e != cudaSuccess) {
       h->err = std::string("tcgen05 gemm launch failed: ") + cudaGetErrorString(e) + " / " + gemm_tc_last_error();
       return GRAM_ERR_CUDA;
     }
     return GRAM_OK;
   }
-  if (epi == EPI_LSE) { h->err = "EPI_LSE needs the tcgen05 GEMM"; return GRAM_ERR_STATE; }
+  if (epi == EPI_LSE || epi == EPI_RESID_NORM || aux) { h->err = "this epilogue needs the tcgen05 GEMM"; return GRAM_ERR_STATE; }
   e = gemm_simt(h->cfg.dtype, epi, A, W, C, M_max, m_ptr, N, K, s);
   if (e != cudaSuccess) {
     h->err = std::string("simt gemm launch failed: ") + cudaGetErrorString(e);
@@ -310,11 +311,20 @@ int encoder_stack(gram_handle* h, const PackMeta& pm, int P, int L, int Mmax, cu
   const gram_config& c = h->cfg;
   const int* mp = pm.total;
   const int D = h->D, HD = h->HD, F = h->F;
-  CKL(GRAM_K_OTHER, embed_rows(c.dtype, h->shared, pm.tok_id, h->x, Mmax, mp, D, s));
+  // RMSNorm folded into the GEMMs (kernels.h: GemmNormAux): the producer of the residual stream (embedding, o and wo
+  // projections) emits xn = bf16(x * ln_w) and the row sums of squares, the consumer (q|k|v, wi) scales its output rows
+  const bool fused = c.dtype == GRAM_DTYPE_BF16 && (c.flags & GRAM_FLAG_FUSED_NORM) && !(c.flags & GRAM_FLAG_SIMT_GEMM) &&
+                     (D % 128) == 0 && gemm_tc_supported(3 * HD, D) && gemm_tc_supported(D, HD) &&
+                     gemm_tc_supported(F, D) && gemm_tc_supported(D, F);
+  GemmNormAux scaled;                  // consumer side
+  scaled.row_ss = h->ss; scaled.eps = c.ln_eps;
+  auto produce = [&](const float* ln_w) { GemmNormAux a; a.xb = h->xn; a.ss_out = h->ss; a.ln_w = ln_w; return a; };
+  if (fused) CKL(GRAM_K_OTHER, embed_rows_norm(h->shared, pm.tok_id, h->x, h->xn, h->ss, h->enc[0].ln0, Mmax, mp, D, s));
+  else CKL(GRAM_K_OTHER, embed_rows(c.dtype, h->shared, pm.tok_id, h->x, Mmax, mp, D, s));
   for (int l = 0; l < h->Le; ++l) {
     const LayerW& W = h->enc[l];
-    CKL(GRAM_K_NORM_ENC, rmsnorm_rows(c.dtype, h->x, W.ln0, h->xn, Mmax, mp, D, c.ln_eps, 1.f, nullptr, nullptr, s));
-    RC(gemm(h, GRAM_K_GEMM_ENC, EPI_STORE, h->xn, W.qkv, h->qkv, Mmax, mp, 3 * HD, D, s));
+    if (!fused) CKL(GRAM_K_NORM_ENC, rmsnorm_rows(c.dtype, h->x, W.ln0, h->xn, Mmax, mp, D, c.ln_eps, 1.f, nullptr, nullptr, s));
+    RC(gemm(h, GRAM_K_GEMM_ENC, EPI_STORE, h->xn, W.qkv, h->qkv, Mmax, mp, 3 * HD, D, s, fused ? &scaled : nullptr));
     if (c.dtype == GRAM_DTYPE_BF16 && !(c.flags & (GRAM_FLAG_MMA_ENC_ATTN | GRAM_FLAG_SIMT_ATTN)) &&
         enc_attention_tc_supported(h->dk, L, h->Lb)) {
       CKL(GRAM_K_ENC_ATTN, enc_attention_tc(h->qkv, (size_t)h->Mcap + 256, h->ao, pm.plen, pm.poff, pm.tok_valid,
@@ -326,10 +336,22 @@ int encoder_stack(gram_handle* h, const PackMeta& pm, int P, int L, int Mmax, cu
       CKL(GRAM_K_ENC_ATTN, enc_attention(c.dtype, h->qkv, h->ao, pm.plen, pm.poff, pm.tok_valid,
                                          h->enc_bias_lut, h->Lb, P, h->H, h->dk, L, s));
     }
-    RC(gemm(h, GRAM_K_GEMM_ENC, EPI_RESID, h->ao, W.o, h->x, Mmax, mp, D, HD, s));
-    CKL(GRAM_K_NORM_ENC, rmsnorm_rows(c.dtype, h->x, W.ln1, h->xn, Mmax, mp, D, c.ln_eps, 1.f, nullptr, nullptr, s));
-    RC(gemm(h, GRAM_K_GEMM_ENC, EPI_RELU, h->xn, W.wi, h->ff, Mmax, mp, F, D, s));
-    RC(gemm(h, GRAM_K_GEMM_ENC, EPI_RESID, h->ff, W.wo, h->x, Mmax, mp, D, F, s));
+    if (fused) {
+      const GemmNormAux a1 = produce(W.ln1);
+      RC(gemm(h, GRAM_K_GEMM_ENC, EPI_RESID_NORM, h->ao, W.o, h->x, Mmax, mp, D, HD, s, &a1));
+      RC(gemm(h, GRAM_K_GEMM_ENC, EPI_RELU, h->xn, W.wi, h->ff, Mmax, mp, F, D, s, &scaled));
+      if (l + 1 < h->Le) {
+        const GemmNormAux a0 = produce(h->enc[l + 1].ln0);
+        RC(gemm(h, GRAM_K_GEMM_ENC, EPI_RESID_NORM, h->ff, W.wo, h->x, Mmax, mp, D, F, s, &a0));
+      } else {
+        RC(gemm(h, GRAM_K_GEMM_ENC, EPI_RESID, h->ff, W.wo, h->x, Mmax, mp, D, F, s));   // the final norm is a kernel
+      }
+    } else {
+      RC(gemm(h, GRAM_K_GEMM_ENC, EPI_RESID, h->ao, W.o, h->x, Mmax, mp, D, HD, s));
+      CKL(GRAM_K_NORM_ENC, rmsnorm_rows(c.dtype, h->x, W.ln1, h->xn, Mmax, mp, D, c.ln_eps, 1.f, nullptr, nullptr, s));
+      RC(gemm(h, GRAM_K_GEMM_ENC, EPI_RELU, h->xn, W.wi, h->ff, Mmax, mp, F, D, s));
+      RC(gemm(h, GRAM_K_GEMM_ENC, EPI_RESID, h->ff, W.wo, h->x, Mmax, mp, D, F, s));
+    }
   }
   return GRAM_OK;
 }
@@ -522,6 +544,7 @@ int gram_create(const gram_config* cfg, gram_handle** out) {
   DAC(h->xn, Mc * D * esz); DAC(h->qkv, Mc * 3 * HD * esz); DAC(h->ao, Mc * HD * esz);
   DAC(h->ff, Mc * F * esz); DAC(h->mem, Mc * D * esz);
   DAC(h->ckv, Mc * (size_t)h->Ld * 2 * HD * esz);
+  DAC(h->ss, Mc * (size_t)((D + 127) / 128) * 4);
   // ---- decoder workspace ----
   h->Rcap = c.max_users * c.max_beams;
   const size_t R = (size_t)h->Rcap + 128;
@@ -1021,6 +1044,20 @@ int gram_op_gemm(int32_t device, int32_t dtype, int32_t impl, int32_t epilogue, 
   }
   e = gemm_simt(dtype, epilogue, A, W, C, M, nullptr, N, K, (cudaStream_t)stream);
   if (e != cudaSuccess) { g_create_error = std::string("gemm_simt: ") + cudaGetErrorString(e); return GRAM_ERR_CUDA; }
+  return GRAM_OK;
+}
+
+int gram_op_gemm_norm(int32_t device, int32_t impl, int32_t epilogue, const void* A, const void* W, void* C, void* xb,
+                      float* ss, const float* ln_w, const float* row_ss, float eps, int32_t M, int32_t N, int32_t K,
+                      void* stream) {
+  if (cudaSetDevice(device) != cudaSuccess) return GRAM_ERR_CUDA;
+  if (!gemm_tc_supported(N, K)) { g_create_error = "gram_op_gemm_norm: unsupported (N,K)"; return GRAM_ERR_UNSUPPORTED; }
+  int sms = 148;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+  GemmNormAux aux;
+  aux.row_ss = row_ss; aux.xb = xb; aux.ss_out = ss; aux.ln_w = ln_w; aux.eps = eps;
+  cudaError_t e = gemm_tc(epilogue, A, W, C, M, nullptr, N, K, sms, impl == 2 ? 1 : 2, (cudaStream_t)stream, &aux);
+  if (e != cudaSuccess) { g_create_error = std::string("gemm_tc: ") + cudaGetErrorString(e) + " / " + gemm_tc_last_error(); return GRAM_ERR_CUDA; }
   return GRAM_OK;
 }
 

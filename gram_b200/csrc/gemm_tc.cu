@@ -49,13 +49,19 @@ constexpr int ACC_STAGES = 2;
 constexpr int THREADS = 192;
 constexpr uint32_t A_BYTES = BLOCK_M * BLOCK_K * 2;        // 16 KiB
 constexpr uint32_t CSTAGE_BYTES = 32 * 1024;               // epilogue staging: two 128-row x 128-byte boxes
-template <int BN, int CTAS> struct Cfg {
+// EPI_RESID_NORM stages the residual stream through the SM: two 32 KiB buffers (x of the next round is prefetched
+// while the current round is updated in place).  The bf16 copy leaves straight from registers: a staging box for it
+// would cost the operand ring a stage, and with four stages the K = 2048 GEMM starves (ncu: tensor pipe 65 % busy
+// against 90 % with six)
+constexpr uint32_t NORM_EPI_BYTES = 2 * CSTAGE_BYTES;
+template <int BN, int CTAS, bool NORM = false> struct Cfg {
   static constexpr int LOAD_N = BN / CTAS;                 // W rows each CTA loads per stage
   static constexpr uint32_t B_BYTES = LOAD_N * BLOCK_K * 2;   // 16 or 32 KiB
   static constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = STAGE_BYTES == 32768 ? 6 : 4;
+  static constexpr uint32_t EPI_BYTES = NORM ? NORM_EPI_BYTES : CSTAGE_BYTES;
+  static constexpr int STAGES = NORM ? (STAGE_BYTES == 32768 ? 5 : 3) : (STAGE_BYTES == 32768 ? 6 : 4);
   static constexpr int TMEM_COLS = ACC_STAGES * BN;        // 256 or 512 (power of two)
-  static constexpr size_t SMEM_BYTES = (size_t)STAGES * STAGE_BYTES + CSTAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr size_t SMEM_BYTES = (size_t)STAGES * STAGE_BYTES + EPI_BYTES + 1024 /*align*/ + 256 /*barriers*/;
   // instruction descriptor: D=f32, A=B=bf16, both K-major, M=128 per CTA (256 for a pair), N=BN
   static constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) |
                                     ((uint32_t)((BLOCK_M * CTAS) >> 4) << 24);
@@ -194,12 +200,21 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
   d |= (uint64_t)2 << 61;                                // layout type: SWIZZLE_128B              bits [61,64)
   return d;
 }
+// RMSNorm folded into the GEMMs around it (see kernels.h: GemmNormAux)
+struct NormArgs {
+  const float* row_ss;    // consumer: [M][ss_blocks] sums of squares of the A rows; nullptr = no row scale
+  float* ss_out;          // producer (EPI_RESID_NORM): [M][N/128]
+  bf16* xb;               // producer: [M][N] bf16
+  const float* ln_w;      // producer: [N] weight of the next RMSNorm
+  int ss_blocks;          // consumer: K / 128
+  float inv_d, eps;       // consumer: 1 / K, epsilon
+};
+
 template <int EPI, int BLOCK_N, int CTAS>
 __global__ void __launch_bounds__(THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
-               const __grid_constant__ CUtensorMap map_c, float2* __restrict__ lse_partial, int M_imm,
-               const int* __restrict__ m_ptr, int N, int K) {
-  using C_ = Cfg<BLOCK_N, CTAS>;
+               const __grid_constant__ CUtensorMap map_c, float2* __restrict__ lse_partial, int M_imm, const int* __restrict__ m_ptr, int N, int K, NormArgs na) {
+  using C_ = Cfg<BLOCK_N, CTAS, EPI == EPI_RESID_NORM>;
   constexpr int STAGES = C_::STAGES;
   constexpr uint32_t STAGE_BYTES = C_::STAGE_BYTES;
   constexpr int TMEM_COLS = C_::TMEM_COLS;
@@ -210,12 +225,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   const uint32_t base = (raw + 1023u) & ~1023u;           // 1024-byte alignment for the 128B swizzle atoms
   uint8_t* smem = smem_raw + (base - raw);
   const uint32_t cstage = base + STAGES * STAGE_BYTES;    // epilogue staging (1024-aligned)
-  const uint32_t bars = cstage + CSTAGE_BYTES;            // full[STAGES], empty[STAGES], tfull[2], tempty[2], tmem ptr
+  const uint32_t bars = cstage + C_::EPI_BYTES;           // full[STAGES], empty[STAGES], tfull[2], tempty[2], xfull[2], tmem ptr
   auto full_bar = [&](int s) { return bars + 8u * s; };
   auto empty_bar = [&](int s) { return bars + 8u * (STAGES + s); };
   auto tfull_bar = [&](int s) { return bars + 8u * (2 * STAGES + s); };
   auto tempty_bar = [&](int s) { return bars + 8u * (2 * STAGES + ACC_STAGES + s); };
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + STAGES * STAGE_BYTES + CSTAGE_BYTES + 8 * (2 * STAGES + 2 * ACC_STAGES));
+  auto xfull_bar = [&](int s) { return bars + 8u * (2 * STAGES + 2 * ACC_STAGES + s); };
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + STAGES * STAGE_BYTES + C_::EPI_BYTES + 8 * (2 * STAGES + 2 * ACC_STAGES + 2));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int M = m_ptr ? *m_ptr : M_imm;
@@ -232,6 +248,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_c) : "memory");
     for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
     for (int s = 0; s < ACC_STAGES; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 4 * CTAS); }
+    for (int s = 0; s < 2; ++s) mbar_init(xfull_bar(s), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -322,9 +339,27 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       if (CTAS == 2) mbar_arrive_cluster(leader_addr(tempty_bar(a)));
       else mbar_arrive(tempty_bar(a));
     };
+    uint32_t xround = 0;                                   // EPI_RESID_NORM: rounds processed so far (buffer = parity)
+    if constexpr (EPI == EPI_RESID_NORM) {
+      if (issuer && tile0 < num_tiles) {                   // x of the very first round
+        mbar_arrive_expect_tx(xfull_bar(0), CSTAGE_BYTES);
+        tma_load_2d(cstage, &map_c, xfull_bar(0), (tile0 % num_n) * BLOCK_N, (tile0 / num_n) * TILE_M + rank * BLOCK_M);
+        tma_load_2d(cstage + 16384u, &map_c, xfull_bar(0), (tile0 % num_n) * BLOCK_N + 32, (tile0 / num_n) * TILE_M + rank * BLOCK_M);
+      }
+    }
     for (int tile = tile0; tile < num_tiles; tile += tile_step) {
       const int m_blk = tile / num_n, n_blk = tile % num_n;
       const int row0 = m_blk * TILE_M + rank * BLOCK_M;    // first row of this CTA's half of the tile
+      // RMSNorm folded in from the producer side: this row of the output is scaled by rsqrt(mean(x^2) + eps) of its
+      // input row (fetched while the accumulator is still being computed)
+      float rs = 1.f;
+      if (kOutBf16 && na.row_ss != nullptr) {
+        const int row = row0 + r;
+        float t = 0.f;
+        if (row < M)
+          for (int b = 0; b < na.ss_blocks; ++b) t += na.row_ss[(size_t)row * na.ss_blocks + b];
+        rs = 1.0f / sqrtf(t * na.inv_d + na.eps);
+      }
       mbar_wait(tfull_bar(acc), acc_phase);
       tcgen05_fence_after();
       if (EPI == EPI_LSE) {
@@ -362,6 +397,82 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1u; }
         continue;
       }
+      if constexpr (EPI == EPI_RESID_NORM) {
+        // x += A W^T with the next RMSNorm's input produced on the way: per round (64 columns) the old x tile arrives
+        // by TMA (prefetched one round ahead into the other buffer), every thread updates its row in place, and
+        // x (fp32), bf16(x * ln_w) and the row's sum of squares per 128-column block leave the SM.  The consumer GEMM
+        // multiplies its output rows by rsqrt(mean x^2 + eps): y = ((x*w) W^T) * r = (w * x * r) W^T.
+        float ssq = 0.f;
+        const int row = row0 + r;
+#pragma unroll 1
+        for (int rd = 0; rd < ROUNDS; ++rd, ++xround) {
+          const uint32_t xb_cur = cstage + (xround & 1u) * CSTAGE_BYTES, xb_nxt = cstage + ((xround & 1u) ^ 1u) * CSTAGE_BYTES;
+          if (issuer) {
+            tma_store_wait_read();                         // every earlier store has read its staging buffer
+            int nt = tile, nrd = rd + 1;                   // (tile, round) after this one
+            if (nrd == ROUNDS) { nt = tile + tile_step; nrd = 0; }
+            if (nt < num_tiles) {
+              const int ncol = (nt % num_n) * BLOCK_N + nrd * 64, nrow = (nt / num_n) * TILE_M + rank * BLOCK_M;
+              mbar_arrive_expect_tx(xfull_bar((xround & 1u) ^ 1u), CSTAGE_BYTES);
+              tma_load_2d(xb_nxt, &map_c, xfull_bar((xround & 1u) ^ 1u), ncol, nrow);
+              tma_load_2d(xb_nxt + 16384u, &map_c, xfull_bar((xround & 1u) ^ 1u), ncol + 32, nrow);
+            }
+          }
+          mbar_wait(xfull_bar(xround & 1u), (xround >> 1) & 1u);
+#pragma unroll 1
+          for (int cc = 0; cc < 2; ++cc) {
+            const int c = rd * 2 + cc;
+            uint32_t v[32];
+            const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BLOCK_N + c * 32);
+            tmem_ld32(taddr, v);
+            tmem_ld_wait();
+            const uint32_t xrow = xb_cur + (uint32_t)cc * 16384u + (uint32_t)r * 128u;
+            const float* gw = na.ln_w + n_blk * BLOCK_N + c * 32;
+            bf16* xbrow = na.xb + (size_t)row * N + n_blk * BLOCK_N + c * 32;
+#pragma unroll
+            for (int g2 = 0; g2 < 4; ++g2) {
+              uint32_t pk[4];
+#pragma unroll
+              for (int hh = 0; hh < 2; ++hh) {
+                const int g = g2 * 2 + hh;
+                const uint32_t addr = xrow + (uint32_t)((g ^ (r & 7)) << 4);
+                float4 xo;
+                asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(xo.x), "=f"(xo.y), "=f"(xo.z), "=f"(xo.w) : "r"(addr) : "memory");
+                xo.x += __uint_as_float(v[g * 4]); xo.y += __uint_as_float(v[g * 4 + 1]);
+                xo.z += __uint_as_float(v[g * 4 + 2]); xo.w += __uint_as_float(v[g * 4 + 3]);
+                asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(xo.x), "f"(xo.y), "f"(xo.z), "f"(xo.w) : "memory");
+                ssq = fmaf(xo.x, xo.x, ssq); ssq = fmaf(xo.y, xo.y, ssq); ssq = fmaf(xo.z, xo.z, ssq); ssq = fmaf(xo.w, xo.w, ssq);
+                const float4 w4 = __ldg(reinterpret_cast<const float4*>(gw + g * 4));
+                __nv_bfloat162 h0 = __floats2bfloat162_rn(xo.x * w4.x, xo.y * w4.y), h1 = __floats2bfloat162_rn(xo.z * w4.z, xo.w * w4.w);
+                pk[hh * 2] = *reinterpret_cast<uint32_t*>(&h0);
+                pk[hh * 2 + 1] = *reinterpret_cast<uint32_t*>(&h1);
+              }
+              if (row < M) *reinterpret_cast<uint4*>(xbrow + g2 * 8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+            }
+          }
+          if ((rd & 1) == 1) {
+            // rounds 2b and 2b+1 cover 128-column block b of the tile: one partial per (row, block), owned by this
+            // thread alone -- no atomics, and the same summation order whatever the tile shape
+            if (row < M) na.ss_out[(size_t)row * (N >> 7) + n_blk * (BLOCK_N >> 7) + (rd >> 1)] = ssq;
+            ssq = 0.f;
+          }
+          if (rd == ROUNDS - 1) {
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) release_acc(acc);
+          }
+          fence_async_smem();
+          epi_bar();
+          if (issuer) {
+            const int col0 = n_blk * BLOCK_N + rd * 64;
+            if (col0 < N) tma_store_2d(&map_c, xb_cur, col0, row0);
+            if (col0 + 32 < N) tma_store_2d(&map_c, xb_cur + 16384u, col0 + 32, row0);
+            tma_store_commit();
+          }
+        }
+        if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1u; }
+        continue;
+      }
 #pragma unroll 1
       for (int rd = 0; rd < ROUNDS; ++rd) {
         if (issuer) tma_store_wait_read();                 // previous bulk store has finished reading the staging tile
@@ -381,7 +492,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
               uint32_t pk[4];
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
-                float a = __uint_as_float(v[g * 8 + 2 * e]), b = __uint_as_float(v[g * 8 + 2 * e + 1]);
+                float a = __uint_as_float(v[g * 8 + 2 * e]) * rs, b = __uint_as_float(v[g * 8 + 2 * e + 1]) * rs;
                 if (EPI == EPI_RELU) { a = fmaxf(a, 0.f); b = fmaxf(b, 0.f); }
                 __nv_bfloat162 h2 = __floats2bfloat162_rn(a, b);
                 pk[e] = *reinterpret_cast<uint32_t*>(&h2);
@@ -444,7 +555,7 @@ std::mutex g_mu;
 EncodeTiledFn g_encode = nullptr;
 std::string g_err;
 std::map<std::tuple<const void*, int, long long>, CUtensorMap> g_maps;
-SmemAttr g_attr[15];
+SmemAttr g_attr[18];
 
 bool get_encode() {
   if (g_encode) return true;
@@ -508,13 +619,13 @@ int max_pairs(Kern kern, size_t smem, int num_sms, int* cache) {
   return cache[dev];
 }
 
-int g_pairs[15][64];
+int g_pairs[18][64];
 
 template <int EPI, int BN, int CTAS>
-cudaError_t launch(const CUtensorMap& ma, const CUtensorMap& mw, const CUtensorMap& mc, float2* lse_partial, int M_max,
-                   const int* m_ptr, int N, int K, int num_sms, cudaStream_t s) {
+cudaError_t launch(const CUtensorMap& ma, const CUtensorMap& mw, const CUtensorMap& mc, float2* lse_partial, int M_max, const int* m_ptr, int N, int K, const NormArgs& na, int num_sms,
+                   cudaStream_t s) {
   auto kern = gemm_tc_kernel<EPI, BN, CTAS>;
-  constexpr size_t smem = Cfg<BN, CTAS>::SMEM_BYTES;
+  constexpr size_t smem = Cfg<BN, CTAS, EPI == EPI_RESID_NORM>::SMEM_BYTES;
   constexpr int slot = EPI * 3 + (BN == 256) + (CTAS == 2);
   {
     cudaError_t e = g_attr[slot].ensure(kern, smem);
@@ -523,7 +634,7 @@ cudaError_t launch(const CUtensorMap& ma, const CUtensorMap& mw, const CUtensorM
   const int tiles = ((M_max + BLOCK_M * CTAS - 1) / (BLOCK_M * CTAS)) * ((N + BN - 1) / BN);
   if (CTAS == 1) {
     const int grid = tiles < num_sms ? tiles : num_sms;
-    kern<<<grid, THREADS, smem, s>>>(ma, mw, mc, lse_partial, M_max, m_ptr, N, K);
+    kern<<<grid, THREADS, smem, s>>>(ma, mw, mc, lse_partial, M_max, m_ptr, N, K, na);
     return cudaGetLastError();
   }
   const int pairs = max_pairs(kern, smem, num_sms, g_pairs[slot]);
@@ -537,7 +648,7 @@ cudaError_t launch(const CUtensorMap& ma, const CUtensorMap& mw, const CUtensorM
   at[0].id = cudaLaunchAttributeClusterDimension;
   at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
   cfg.attrs = at; cfg.numAttrs = 1;
-  return cudaLaunchKernelEx(&cfg, kern, ma, mw, mc, lse_partial, M_max, m_ptr, N, K);
+  return cudaLaunchKernelEx(&cfg, kern, ma, mw, mc, lse_partial, M_max, m_ptr, N, K, na);
 }
 
 // Tile shape: 128 x 128 for small problems; 128 x 256 when that still gives every SM at least two tiles; a CTA pair
@@ -563,21 +674,37 @@ int gemm_tc_lse_ntiles(int M_max, int N, int num_sms) {
 }
 
 cudaError_t gemm_tc(int epi, const void* A, const void* W, void* C, int M_max, const int* m_ptr, int N, int K,
-                    int num_sms, int max_ctas, cudaStream_t s) {
+                    int num_sms, int max_ctas, cudaStream_t s, const GemmNormAux* aux) {
   if (M_max <= 0) return cudaSuccess;
   if (!gemm_tc_supported(N, K)) return cudaErrorInvalidValue;
   std::lock_guard<std::mutex> lk(tc::g_mu);
   CUtensorMap ma, mw, mc;
   const int ckind = (epi == EPI_STORE || epi == EPI_RELU) ? 0 : 1;
+  tc::NormArgs na = {};
+  if (aux && aux->row_ss) {
+    if ((epi != EPI_STORE && epi != EPI_RELU) || (K & 127)) return cudaErrorInvalidValue;
+    na.row_ss = aux->row_ss; na.ss_blocks = K >> 7; na.inv_d = 1.0f / (float)K; na.eps = aux->eps;
+  }
+  if (epi == EPI_RESID_NORM) {
+    // x += A W^T, plus bf16((x) * ln_w) and per-128-column sums of squares: 128-column single-CTA tiles, or CTA pairs
+    if (!aux || !aux->xb || !aux->ss_out || !aux->ln_w || (N & 127)) return cudaErrorInvalidValue;
+    na.ss_out = aux->ss_out; na.ln_w = aux->ln_w; na.xb = (bf16*)aux->xb;
+    const bool pairs = tc::pick_shape(M_max, N, num_sms, max_ctas).ctas == 2;
+    if (!tc::get_map(A, M_max, K, 0, tc::BLOCK_M, &ma) || !tc::get_map(W, N, K, 0, 128, &mw) ||
+        !tc::get_map(C, M_max, N, 1, tc::BLOCK_M, &mc))
+      return cudaErrorUnknown;
+    return pairs ? tc::launch<EPI_RESID_NORM, 256, 2>(ma, mw, mc, nullptr, M_max, m_ptr, N, K, na, num_sms, s)
+                 : tc::launch<EPI_RESID_NORM, 128, 1>(ma, mw, mc, nullptr, M_max, m_ptr, N, K, na, num_sms, s);
+  }
   // the fused log-softmax epilogue stays on single-CTA tiles: it is exp2-bound, and making the leader wait for the
   // slower of two epilogues cost 11 % on the vocabulary head (measured)
   const tc::Shape sh = tc::pick_shape(M_max, N, num_sms, epi == EPI_LSE ? 1 : max_ctas);
   // the W box is the rows ONE CTA loads per stage
   if (!tc::get_map(A, M_max, K, 0, tc::BLOCK_M, &ma) || !tc::get_map(W, N, K, 0, sh.bn / sh.ctas, &mw)) return cudaErrorUnknown;
 #define GRAM_TC_LAUNCH(E, MC, LP)                                                                              \
-  return sh.ctas == 2 ? tc::launch<E, 256, 2>(ma, mw, MC, LP, M_max, m_ptr, N, K, num_sms, s)                  \
-         : sh.bn == 256 ? tc::launch<E, 256, 1>(ma, mw, MC, LP, M_max, m_ptr, N, K, num_sms, s)                \
-                        : tc::launch<E, 128, 1>(ma, mw, MC, LP, M_max, m_ptr, N, K, num_sms, s)
+  return sh.ctas == 2 ? tc::launch<E, 256, 2>(ma, mw, MC, LP, M_max, m_ptr, N, K, na, num_sms, s)          \
+         : sh.bn == 256 ? tc::launch<E, 256, 1>(ma, mw, MC, LP, M_max, m_ptr, N, K, na, num_sms, s)        \
+                        : tc::launch<E, 128, 1>(ma, mw, MC, LP, M_max, m_ptr, N, K, na, num_sms, s)
   if (epi == EPI_LSE) { GRAM_TC_LAUNCH(EPI_LSE, ma, (float2*)C); }
   if (!tc::get_map(C, M_max, N, ckind, tc::BLOCK_M, &mc)) return cudaErrorUnknown;
   switch (epi) {

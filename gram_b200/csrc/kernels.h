@@ -25,8 +25,22 @@ struct SmemAttr {
   }
 };
 
-enum { EPI_STORE = 0, EPI_RELU = 1, EPI_RESID = 2, EPI_F32 = 3, EPI_LSE = 4 };
+enum { EPI_STORE = 0, EPI_RELU = 1, EPI_RESID = 2, EPI_F32 = 3, EPI_LSE = 4, EPI_RESID_NORM = 5 };
 // EPI_LSE (tcgen05 GEMM only): C is float2 [M, ceil(N/128)] of per-tile (max, sum exp(x - max)); no logits are stored
+// EPI_RESID_NORM (tcgen05 GEMM only): C (fp32 residual stream) += A W^T like EPI_RESID, and the input of the RMSNorm that
+// follows is produced on the way (GemmNormAux): no separate normalisation pass over the residual stream
+
+// RMSNorm folded into the tcgen05 GEMMs on either side of it (reference T5LayerNorm, src/model/gram_t5_modeling.py:
+// 253-276: y = w * x * rsqrt(mean(x^2) + eps)).  The producer (EPI_RESID_NORM) writes xb = bf16(x * w) and the row's sums
+// of squares per 128-column block; the consumer (EPI_STORE / EPI_RELU over A = xb) scales output row i by
+// rsqrt(sum_b ss[i][b] / K + eps): (x w r) W^T = ((x w) W^T) r.
+struct GemmNormAux {
+  const float* row_ss = nullptr;   // consumer: [M][K/128]; nullptr = plain GEMM
+  void* xb = nullptr;              // producer: [M][N] bf16
+  float* ss_out = nullptr;         // producer: [M][N/128]
+  const float* ln_w = nullptr;     // producer: [N] weight of the next RMSNorm
+  float eps = 0.f;                 // consumer
+};
 
 // ---- gemm_simt.cu ------------------------------------------------------------------------------
 // C[M,N] = A[M,K] * W[N,K]^T.  M = *m_ptr when m_ptr != nullptr (grid sized for M_max), else M_max.
@@ -37,7 +51,7 @@ cudaError_t gemm_simt(int dtype, int epi, const void* A, const void* W, void* C,
 bool gemm_tc_supported(int N, int K);
 // max_ctas: 2 = large problems run on CTA pairs (tcgen05 cta_group::2, 256x256 tiles), 1 = single-CTA tiles only
 cudaError_t gemm_tc(int epi, const void* A, const void* W, void* C, int M_max, const int* m_ptr, int N, int K,
-                    int num_sms, int max_ctas, cudaStream_t s);
+                    int num_sms, int max_ctas, cudaStream_t s, const GemmNormAux* aux = nullptr);
 const char* gemm_tc_last_error();
 // number of column tiles (= per-row partials) the EPI_LSE epilogue writes for this problem
 int gemm_tc_lse_ntiles(int M_max, int N, int num_sms);
@@ -68,6 +82,9 @@ cudaError_t cached_pack_assemble(int dtype, const PackMeta& pm, const PackMeta& 
                                  void* mem, cudaStream_t s);
 cudaError_t embed_rows(int dtype, const void* table, const int* tok_id, float* x, int M_max, const int* m_ptr,
                        int D, cudaStream_t s);
+// bf16 only: embedding with the first RMSNorm folded (x fp32, xb = bf16(x * w), ss [M][D/128]); see GemmNormAux
+cudaError_t embed_rows_norm(const void* table, const int* tok_id, float* x, void* xb, float* ss, const float* w, int M_max,
+                            const int* m_ptr, int D, cudaStream_t s);
 // y = w * (x * rsqrt(mean(x^2)+eps)) * scale  [+ pos_table[tok_pos[row]]]   (x fp32 -> y dtype)
 cudaError_t rmsnorm_rows(int dtype, const float* x, const float* w, void* y, int M_max, const int* m_ptr, int D,
                          float eps, float scale, const float* pos_table, const int* tok_pos, cudaStream_t s);

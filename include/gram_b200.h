@@ -63,6 +63,11 @@ enum {
                                       persistent tcgen05/TMEM kernel (attention_tc.cu), which is the default for bf16,
                                       d_kv = 64 and passages of at most 128 tokens (A-B timing, cross-check)          */
   GRAM_FLAG_GEMM_1CTA = 16,        /* keep every tcgen05 GEMM on single-CTA tiles (no cta_group::2 pairs; A-B timing) */
+  GRAM_FLAG_FUSED_NORM = 64,       /* bf16 encoder: the per-layer RMSNorms are folded into the tcgen05 GEMMs around them (the
+                                      residual GEMM emits bf16(x * ln_w) and the row's sum of squares, the consumer GEMM
+                                      scales its output rows by rsqrt(mean x^2 + eps)): no normalisation pass over the
+                                      residual stream.  Same math, one rounding placed differently (x*w is rounded to
+                                      bf16 before the row scale instead of after)                                     */
   GRAM_FLAG_ALL_ROWS = 32          /* decode every beam row at every step, as the reference does (A-B timing).  Default:
                                       beams that are dead (-inf score: the user had fewer than K finite continuations,
                                       typically item ids that ended a token earlier) and the beams of users whose
@@ -179,6 +184,13 @@ int gram_encode_cached(gram_handle* h, const int64_t* prompt_ids, const uint8_t*
  * 1 = tcgen05 (bf16 only; CTA pairs on large problems), 2 = tcgen05 single-CTA tiles only.  epilogue: 0 store (dtype), 1 relu+store (dtype), 2 C_f32 += acc, 3 store fp32. */
 int gram_op_gemm(int32_t device, int32_t dtype, int32_t impl, int32_t epilogue, const void* A, const void* W,
                  void* C, int32_t M, int32_t N, int32_t K, void* stream);
+/* The tcgen05 GEMM with an RMSNorm (reference T5LayerNorm, src/model/gram_t5_modeling.py:253-276) folded into it, bf16.
+ * epilogue 5 (producer): C fp32 [M,N] += A W^T; xb bf16 [M,N] = (C) * ln_w; ss fp32 [M, N/128] = sums of squares of the new C
+ * rows per 128-column block.  epilogue 0 / 1 (consumer, row_ss != NULL): C = A W^T with output row i scaled by
+ * rsqrt(sum_b row_ss[i][b] / K + eps) (then ReLU for 1).  impl 1 = CTA pairs allowed, 2 = single-CTA tiles. */
+int gram_op_gemm_norm(int32_t device, int32_t impl, int32_t epilogue, const void* A, const void* W, void* C, void* xb,
+                      float* ss, const float* ln_w, const float* row_ss, float eps, int32_t M, int32_t N, int32_t K,
+                      void* stream);
 /* decoder cross-attention over an in-place K/V memory: q [users*K, H*dk], kv [kv_rows, 2*H*dk] (K|V),
  * user_start int32 [users+1], tok_valid uint8 [kv_rows] or NULL, out [users*K, H*dk] (all dtype).
  * impl 0 = CUDA-core kernel (fp32 or bf16), 1 = TMA + tensor-core kernel (bf16). */

@@ -295,6 +295,87 @@ def test_generate_bf16_overlap(built, name):
     assert np.abs(sc[:, 0] - gs[:, 0]).max() < 0.05 * np.abs(gs[:, 0]).max()
 
 
+@pytest.mark.parametrize("shape", [(300, 512, 512), (1000, 512, 2048), (77, 768, 768), (40000, 512, 512), (152000, 512, 512)])
+def test_gemm_tcgen05_folded_rmsnorm(shape):
+    """EPI_RESID_NORM (x += A W^T; xb = bf16(x * w); per-128-column sums of squares) and the row-scaled consumer
+    epilogue, against fp64 references; single-CTA tiles and CTA pairs (the last shape) give identical bits."""
+    from gram_b200 import _cabi
+    lib = _cabi.load_library()
+    M, N, K = shape
+    g = torch.Generator(device="cpu").manual_seed(M + N + K)
+    A = (torch.randn(M, K, generator=g)).cuda().bfloat16()
+    W = (torch.randn(N, K, generator=g) * K ** -0.5).cuda().bfloat16()
+    x0 = torch.randn(M, N, generator=g).cuda() * 3.0
+    lw = (1.0 + 0.25 * torch.randn(N, generator=g)).cuda()
+    want_x = x0.double() + A.double() @ W.double().t()
+    outs = []
+    for impl in (2, 1):
+        x = x0.clone()
+        xb = torch.zeros(M, N, device="cuda", dtype=torch.bfloat16)
+        ss = torch.zeros(M, N // 128, device="cuda")
+        rc = lib.gram_op_gemm_norm(0, impl, 5, C.c_void_p(A.data_ptr()), C.c_void_p(W.data_ptr()), C.c_void_p(x.data_ptr()),
+                                   C.c_void_p(xb.data_ptr()), C.c_void_p(ss.data_ptr()), C.c_void_p(lw.data_ptr()), None,
+                                   C.c_float(0.0), M, N, K, None)
+        assert rc == 0, lib.gram_last_error(None)
+        torch.cuda.synchronize()
+        assert rel_err(x, want_x) < 5e-6
+        assert rel_err(xb, want_x * lw.double()) < 8e-3                       # bf16 rounding
+        want_ss = (x.double() ** 2).view(M, N // 128, 128).sum(-1)
+        assert rel_err(ss, want_ss) < 1e-5
+        outs.append((x, xb, ss))
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1]) and torch.equal(outs[0][2], outs[1][2])
+    # consumer: rows of (xb W2^T) scaled by rsqrt(mean x^2 + eps) == RMSNorm(x) W2^T
+    x, xb, ss = outs[0]
+    N2, eps = 1536, 1e-6
+    W2 = (torch.randn(N2, N, generator=g) * N ** -0.5).cuda().bfloat16()
+    for epi in (0, 1):
+        y = torch.zeros(M, N2, device="cuda", dtype=torch.bfloat16)
+        rc = lib.gram_op_gemm_norm(0, 1, epi, C.c_void_p(xb.data_ptr()), C.c_void_p(W2.data_ptr()), C.c_void_p(y.data_ptr()), None,
+                                   None, None, C.c_void_p(ss.data_ptr()), C.c_float(eps), M, N2, N, None)
+        assert rc == 0, lib.gram_last_error(None)
+        torch.cuda.synchronize()
+        r = torch.rsqrt((x.double() ** 2).mean(-1, keepdim=True) + eps)
+        want = (xb.double() @ W2.double().t()) * r
+        if epi == 1:
+            want = want.clamp_min(0)
+        assert rel_err(y, want) < 8e-3
+
+
+def test_fused_norm_encoder_matches_unfused(built):
+    """GRAM_FLAG_FUSED_NORM (RMSNorms folded into the tcgen05 GEMMs) against the separate normalisation kernels: fused
+    memory within bf16 rounding on the T5-small case and on a many-passage batch, logits within 2e-2 of the golden."""
+    from gram_b200 import _cabi, synth, GRAM
+    from gram_b200.config import GramConfig
+    b = built["small"]
+    gold = _golden("small")
+    m_f = _model(b["case"], b["sd"], "bf16", flags=_cabi.GRAM_FLAG_FUSED_NORM)
+    m_u = _model(b["case"], b["sd"], "bf16")
+    ids, mask = b["ids"].cuda(), b["mask"].cuda()
+    err = rel_err(m_f.encode(ids, mask).cpu(), m_u.encode(ids, mask).cpu())
+    print(f"[fused norm] memory rel_err vs unfused = {err:.3e}")
+    assert err < 2e-2
+    dec = torch.from_numpy(gold["dec_ids"]).cuda()
+    logits = m_f.forward(ids, mask, decoder_input_ids=dec).logits.cpu()
+    vs = torch.from_numpy(gold["vocab_idx"]).long()
+    lerr = (logits[:, :, vs] - torch.from_numpy(gold["logits"])).abs().max().item() / float(gold["logits_absmax"])
+    print(f"[fused norm] logits rel_err vs golden = {lerr:.3e}")
+    assert lerr < BF16_TOL
+    cfg = GramConfig.t5_small(max_seq_len=128, max_item_num=8)
+    sd = synth.make_state_dict(cfg, seed=2)
+    ids, mask = synth.make_user_batch(cfg, 96, (1, 8), 128, seed=31, min_len=2)
+    ids, mask = torch.from_numpy(ids).cuda(), torch.from_numpy(mask).cuda()
+    outs = []
+    for flags in (_cabi.GRAM_FLAG_FUSED_NORM, 0):
+        m = GRAM(cfg, dtype="bf16", device="cuda:0", flags=flags)
+        m.load_state_dict(sd)
+        outs.append(m.encode(ids, mask).cpu())
+        del m
+    assert torch.isfinite(outs[0]).all()
+    err = rel_err(outs[0], outs[1])
+    print(f"[fused norm, {ids.shape[0] * ids.shape[1]} passages] memory rel_err vs unfused = {err:.3e}")
+    assert err < 2e-2
+
+
 def test_tcgen05_encoder_attention_matches_mma_path(built):
     """attention_tc.cu (the default: tcgen05.mma with an MN-major V operand, softmax out of TMEM) against the mma.sync
     encoder attention: same fused memory within bf16 rounding, and within 2e-2 of the reference golden logits."""
