@@ -55,7 +55,7 @@ def parse():
     ap.add_argument("--no-item-cache", action="store_true", help="skip the extra (non-headline) cached-item measurement")
     ap.add_argument("--gemm-1cta", action="store_true", help="keep every tcgen05 GEMM on single-CTA tiles (A/B timing)")
     ap.add_argument("--mma-enc-attn", action="store_true", help="encoder attention through the mma.sync kernel instead of the tcgen05 one (A/B timing)")
-    ap.add_argument("--fused-norm", action="store_true", help="fold the encoder RMSNorms into the tcgen05 GEMMs (A/B timing)")
+    ap.add_argument("--unfused-norm", action="store_true", help="encoder RMSNorms as separate kernels instead of folded into the tcgen05 GEMMs (A/B timing)")
     ap.add_argument("--all-rows", action="store_true",
                     help="decode dead beams / finished users too, as the reference does (A/B timing of live-row compaction)")
     return ap.parse_args()
@@ -292,7 +292,7 @@ def main():
     data, cfg, sd, cands, max_length, trie, fn = build_workload(args, rank, world)
     flags = (_cabi.GRAM_FLAG_SIMT_GEMM if args.simt else 0) | (_cabi.GRAM_FLAG_MMA_ENC_ATTN if args.mma_enc_attn else 0) | \
         (_cabi.GRAM_FLAG_GEMM_1CTA if args.gemm_1cta else 0) | (_cabi.GRAM_FLAG_ALL_ROWS if args.all_rows else 0) | \
-        (_cabi.GRAM_FLAG_FUSED_NORM if args.fused_norm else 0)
+        (_cabi.GRAM_FLAG_UNFUSED_NORM if args.unfused_norm else 0)
     model = GRAM(cfg, dtype=args.dtype, device=dev, flags=flags)
     model.load_state_dict(sd)
     B, K, W, S = args.batch, BEAMS, args.warmup, args.steps

@@ -16,7 +16,7 @@ _LIB_PATH = os.environ.get("GRAM_B200_LIB") or os.path.join(os.path.dirname(os.p
 GRAM_DTYPE_F32, GRAM_DTYPE_BF16 = 0, 1
 GRAM_FLAG_SIMT_GEMM, GRAM_FLAG_KEEP_LOGITS, GRAM_FLAG_SIMT_ATTN, GRAM_FLAG_MMA_ENC_ATTN, GRAM_FLAG_GEMM_1CTA = 1, 2, 4, 8, 16
 GRAM_FLAG_ALL_ROWS = 32
-GRAM_FLAG_FUSED_NORM = 64
+GRAM_FLAG_UNFUSED_NORM = 64
 K_CLASSES = ["gemm_enc", "enc_attn", "gemm_kv", "gemm_dec", "cross_attn", "lm_head", "beam", "other", "self_attn",
              "norm_enc", "norm_dec"]
 GRAM_K_COUNT = len(K_CLASSES)

@@ -313,7 +313,7 @@ int encoder_stack(gram_handle* h, const PackMeta& pm, int P, int L, int Mmax, cu
   const int D = h->D, HD = h->HD, F = h->F;
   // RMSNorm folded into the GEMMs (kernels.h: GemmNormAux): the producer of the residual stream (embedding, o and wo
   // projections) emits xn = bf16(x * ln_w) and the row sums of squares, the consumer (q|k|v, wi) scales its output rows
-  const bool fused = c.dtype == GRAM_DTYPE_BF16 && (c.flags & GRAM_FLAG_FUSED_NORM) && !(c.flags & GRAM_FLAG_SIMT_GEMM) &&
+  const bool fused = c.dtype == GRAM_DTYPE_BF16 && !(c.flags & (GRAM_FLAG_UNFUSED_NORM | GRAM_FLAG_SIMT_GEMM)) &&
                      (D % 128) == 0 && gemm_tc_supported(3 * HD, D) && gemm_tc_supported(D, HD) &&
                      gemm_tc_supported(F, D) && gemm_tc_supported(D, F);
   GemmNormAux scaled;                  // consumer side

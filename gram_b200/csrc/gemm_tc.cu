@@ -50,16 +50,18 @@ constexpr int THREADS = 192;
 constexpr uint32_t A_BYTES = BLOCK_M * BLOCK_K * 2;        // 16 KiB
 constexpr uint32_t CSTAGE_BYTES = 32 * 1024;               // epilogue staging: two 128-row x 128-byte boxes
 // EPI_RESID_NORM stages the residual stream through the SM: two 32 KiB buffers (x of the next round is prefetched
-// while the current round is updated in place).  The bf16 copy leaves straight from registers: a staging box for it
-// would cost the operand ring a stage, and with four stages the K = 2048 GEMM starves (ncu: tensor pipe 65 % busy
-// against 90 % with six)
-constexpr uint32_t NORM_EPI_BYTES = 2 * CSTAGE_BYTES;
+// while the current round is updated in place) and one 16 KiB box for the bf16 copy; the operand ring keeps 4 stages.
+// Measured alternative: the bf16 copy stored straight from registers (no box, 5 stages) is slower on both shapes
+// (o projection 1.49 ms vs 1.39 ms, wo 2.35 ms vs 2.27 ms for 1.13 M rows): row-per-thread 16-byte stores are
+// half-sector writes, and the K = 2048 GEMM is held by the power cap, not by the ring depth (77 % tensor-pipe
+// activity at 1.16 GHz vs 65 % at 1.40 GHz)
+constexpr uint32_t NORM_EPI_BYTES = 2 * CSTAGE_BYTES + 16 * 1024;
 template <int BN, int CTAS, bool NORM = false> struct Cfg {
   static constexpr int LOAD_N = BN / CTAS;                 // W rows each CTA loads per stage
   static constexpr uint32_t B_BYTES = LOAD_N * BLOCK_K * 2;   // 16 or 32 KiB
   static constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr uint32_t EPI_BYTES = NORM ? NORM_EPI_BYTES : CSTAGE_BYTES;
-  static constexpr int STAGES = NORM ? (STAGE_BYTES == 32768 ? 5 : 3) : (STAGE_BYTES == 32768 ? 6 : 4);
+  static constexpr int STAGES = NORM ? (STAGE_BYTES == 32768 ? 4 : 2) : (STAGE_BYTES == 32768 ? 6 : 4);
   static constexpr int TMEM_COLS = ACC_STAGES * BN;        // 256 or 512 (power of two)
   static constexpr size_t SMEM_BYTES = (size_t)STAGES * STAGE_BYTES + EPI_BYTES + 1024 /*align*/ + 256 /*barriers*/;
   // instruction descriptor: D=f32, A=B=bf16, both K-major, M=128 per CTA (256 for a pair), N=BN
@@ -204,7 +206,6 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
 struct NormArgs {
   const float* row_ss;    // consumer: [M][ss_blocks] sums of squares of the A rows; nullptr = no row scale
   float* ss_out;          // producer (EPI_RESID_NORM): [M][N/128]
-  bf16* xb;               // producer: [M][N] bf16
   const float* ln_w;      // producer: [N] weight of the next RMSNorm
   int ss_blocks;          // consumer: K / 128
   float inv_d, eps;       // consumer: 1 / K, epsilon
@@ -213,7 +214,8 @@ struct NormArgs {
 template <int EPI, int BLOCK_N, int CTAS>
 __global__ void __launch_bounds__(THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
-               const __grid_constant__ CUtensorMap map_c, float2* __restrict__ lse_partial, int M_imm, const int* __restrict__ m_ptr, int N, int K, NormArgs na) {
+               const __grid_constant__ CUtensorMap map_c, const __grid_constant__ CUtensorMap map_xb,
+               float2* __restrict__ lse_partial, int M_imm, const int* __restrict__ m_ptr, int N, int K, NormArgs na) {
   using C_ = Cfg<BLOCK_N, CTAS, EPI == EPI_RESID_NORM>;
   constexpr int STAGES = C_::STAGES;
   constexpr uint32_t STAGE_BYTES = C_::STAGE_BYTES;
@@ -352,13 +354,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       const int row0 = m_blk * TILE_M + rank * BLOCK_M;    // first row of this CTA's half of the tile
       // RMSNorm folded in from the producer side: this row of the output is scaled by rsqrt(mean(x^2) + eps) of its
       // input row (fetched while the accumulator is still being computed)
+      // Rows past M inside the last tile are written as zeros: with a gain of rsqrt(eps) they would feed garbage back
+      // through the residual stream of the next layers (and calls) until it overflows, and the attention kernel reads
+      // -- masked, but 0 * inf = nan -- key/value rows past the last passage.
       float rs = 1.f;
       if (kOutBf16 && na.row_ss != nullptr) {
         const int row = row0 + r;
-        float t = 0.f;
-        if (row < M)
+        rs = 0.f;
+        if (row < M) {
+          float t = 0.f;
           for (int b = 0; b < na.ss_blocks; ++b) t += na.row_ss[(size_t)row * na.ss_blocks + b];
-        rs = 1.0f / sqrtf(t * na.inv_d + na.eps);
+          rs = 1.0f / sqrtf(t * na.inv_d + na.eps);
+        }
       }
       mbar_wait(tfull_bar(acc), acc_phase);
       tcgen05_fence_after();
@@ -404,6 +411,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         // multiplies its output rows by rsqrt(mean x^2 + eps): y = ((x*w) W^T) * r = (w * x * r) W^T.
         float ssq = 0.f;
         const int row = row0 + r;
+        const bool live_row = row < M;                     // rows past M in the last tile are kept at zero
 #pragma unroll 1
         for (int rd = 0; rd < ROUNDS; ++rd, ++xround) {
           const uint32_t xb_cur = cstage + (xround & 1u) * CSTAGE_BYTES, xb_nxt = cstage + ((xround & 1u) ^ 1u) * CSTAGE_BYTES;
@@ -418,6 +426,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
               tma_load_2d(xb_nxt + 16384u, &map_c, xfull_bar((xround & 1u) ^ 1u), ncol + 32, nrow);
             }
           }
+          epi_bar();                                       // the bf16 box is free again
           mbar_wait(xfull_bar(xround & 1u), (xround >> 1) & 1u);
 #pragma unroll 1
           for (int cc = 0; cc < 2; ++cc) {
@@ -427,8 +436,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             tmem_ld32(taddr, v);
             tmem_ld_wait();
             const uint32_t xrow = xb_cur + (uint32_t)cc * 16384u + (uint32_t)r * 128u;
+            const uint32_t brow = cstage + 2 * CSTAGE_BYTES + (uint32_t)r * 128u;
             const float* gw = na.ln_w + n_blk * BLOCK_N + c * 32;
-            bf16* xbrow = na.xb + (size_t)row * N + n_blk * BLOCK_N + c * 32;
 #pragma unroll
             for (int g2 = 0; g2 < 4; ++g2) {
               uint32_t pk[4];
@@ -438,8 +447,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 const uint32_t addr = xrow + (uint32_t)((g ^ (r & 7)) << 4);
                 float4 xo;
                 asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(xo.x), "=f"(xo.y), "=f"(xo.z), "=f"(xo.w) : "r"(addr) : "memory");
-                xo.x += __uint_as_float(v[g * 4]); xo.y += __uint_as_float(v[g * 4 + 1]);
-                xo.z += __uint_as_float(v[g * 4 + 2]); xo.w += __uint_as_float(v[g * 4 + 3]);
+                xo.x = live_row ? xo.x + __uint_as_float(v[g * 4]) : 0.f;
+                xo.y = live_row ? xo.y + __uint_as_float(v[g * 4 + 1]) : 0.f;
+                xo.z = live_row ? xo.z + __uint_as_float(v[g * 4 + 2]) : 0.f;
+                xo.w = live_row ? xo.w + __uint_as_float(v[g * 4 + 3]) : 0.f;
                 asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(xo.x), "f"(xo.y), "f"(xo.z), "f"(xo.w) : "memory");
                 ssq = fmaf(xo.x, xo.x, ssq); ssq = fmaf(xo.y, xo.y, ssq); ssq = fmaf(xo.z, xo.z, ssq); ssq = fmaf(xo.w, xo.w, ssq);
                 const float4 w4 = __ldg(reinterpret_cast<const float4*>(gw + g * 4));
@@ -447,7 +458,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 pk[hh * 2] = *reinterpret_cast<uint32_t*>(&h0);
                 pk[hh * 2 + 1] = *reinterpret_cast<uint32_t*>(&h1);
               }
-              if (row < M) *reinterpret_cast<uint4*>(xbrow + g2 * 8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+              const uint32_t piece = (uint32_t)((cc * 4 + g2) ^ (r & 7));
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(brow + (piece << 4)), "r"(pk[0]), "r"(pk[1]),
+                           "r"(pk[2]), "r"(pk[3]) : "memory");
             }
           }
           if ((rd & 1) == 1) {
@@ -465,7 +478,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           epi_bar();
           if (issuer) {
             const int col0 = n_blk * BLOCK_N + rd * 64;
-            if (col0 < N) tma_store_2d(&map_c, xb_cur, col0, row0);
+            if (col0 < N) {
+              tma_store_2d(&map_c, xb_cur, col0, row0);
+              tma_store_2d(&map_xb, cstage + 2 * CSTAGE_BYTES, col0, row0);
+            }
             if (col0 + 32 < N) tma_store_2d(&map_c, xb_cur + 16384u, col0 + 32, row0);
             tma_store_commit();
           }
@@ -622,7 +638,8 @@ int max_pairs(Kern kern, size_t smem, int num_sms, int* cache) {
 int g_pairs[18][64];
 
 template <int EPI, int BN, int CTAS>
-cudaError_t launch(const CUtensorMap& ma, const CUtensorMap& mw, const CUtensorMap& mc, float2* lse_partial, int M_max, const int* m_ptr, int N, int K, const NormArgs& na, int num_sms,
+cudaError_t launch(const CUtensorMap& ma, const CUtensorMap& mw, const CUtensorMap& mc, const CUtensorMap& mxb,
+                   float2* lse_partial, int M_max, const int* m_ptr, int N, int K, const NormArgs& na, int num_sms,
                    cudaStream_t s) {
   auto kern = gemm_tc_kernel<EPI, BN, CTAS>;
   constexpr size_t smem = Cfg<BN, CTAS, EPI == EPI_RESID_NORM>::SMEM_BYTES;
@@ -634,7 +651,7 @@ cudaError_t launch(const CUtensorMap& ma, const CUtensorMap& mw, const CUtensorM
   const int tiles = ((M_max + BLOCK_M * CTAS - 1) / (BLOCK_M * CTAS)) * ((N + BN - 1) / BN);
   if (CTAS == 1) {
     const int grid = tiles < num_sms ? tiles : num_sms;
-    kern<<<grid, THREADS, smem, s>>>(ma, mw, mc, lse_partial, M_max, m_ptr, N, K, na);
+    kern<<<grid, THREADS, smem, s>>>(ma, mw, mc, mxb, lse_partial, M_max, m_ptr, N, K, na);
     return cudaGetLastError();
   }
   const int pairs = max_pairs(kern, smem, num_sms, g_pairs[slot]);
@@ -648,7 +665,7 @@ cudaError_t launch(const CUtensorMap& ma, const CUtensorMap& mw, const CUtensorM
   at[0].id = cudaLaunchAttributeClusterDimension;
   at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
   cfg.attrs = at; cfg.numAttrs = 1;
-  return cudaLaunchKernelEx(&cfg, kern, ma, mw, mc, lse_partial, M_max, m_ptr, N, K, na);
+  return cudaLaunchKernelEx(&cfg, kern, ma, mw, mc, mxb, lse_partial, M_max, m_ptr, N, K, na);
 }
 
 // Tile shape: 128 x 128 for small problems; 128 x 256 when that still gives every SM at least two tiles; a CTA pair
@@ -688,13 +705,14 @@ cudaError_t gemm_tc(int epi, const void* A, const void* W, void* C, int M_max, c
   if (epi == EPI_RESID_NORM) {
     // x += A W^T, plus bf16((x) * ln_w) and per-128-column sums of squares: 128-column single-CTA tiles, or CTA pairs
     if (!aux || !aux->xb || !aux->ss_out || !aux->ln_w || (N & 127)) return cudaErrorInvalidValue;
-    na.ss_out = aux->ss_out; na.ln_w = aux->ln_w; na.xb = (bf16*)aux->xb;
+    na.ss_out = aux->ss_out; na.ln_w = aux->ln_w;
     const bool pairs = tc::pick_shape(M_max, N, num_sms, max_ctas).ctas == 2;
+    CUtensorMap mxb;
     if (!tc::get_map(A, M_max, K, 0, tc::BLOCK_M, &ma) || !tc::get_map(W, N, K, 0, 128, &mw) ||
-        !tc::get_map(C, M_max, N, 1, tc::BLOCK_M, &mc))
+        !tc::get_map(C, M_max, N, 1, tc::BLOCK_M, &mc) || !tc::get_map(aux->xb, M_max, N, 0, tc::BLOCK_M, &mxb))
       return cudaErrorUnknown;
-    return pairs ? tc::launch<EPI_RESID_NORM, 256, 2>(ma, mw, mc, nullptr, M_max, m_ptr, N, K, na, num_sms, s)
-                 : tc::launch<EPI_RESID_NORM, 128, 1>(ma, mw, mc, nullptr, M_max, m_ptr, N, K, na, num_sms, s);
+    return pairs ? tc::launch<EPI_RESID_NORM, 256, 2>(ma, mw, mc, mxb, nullptr, M_max, m_ptr, N, K, na, num_sms, s)
+                 : tc::launch<EPI_RESID_NORM, 128, 1>(ma, mw, mc, mxb, nullptr, M_max, m_ptr, N, K, na, num_sms, s);
   }
   // the fused log-softmax epilogue stays on single-CTA tiles: it is exp2-bound, and making the leader wait for the
   // slower of two epilogues cost 11 % on the vocabulary head (measured)
@@ -702,9 +720,9 @@ cudaError_t gemm_tc(int epi, const void* A, const void* W, void* C, int M_max, c
   // the W box is the rows ONE CTA loads per stage
   if (!tc::get_map(A, M_max, K, 0, tc::BLOCK_M, &ma) || !tc::get_map(W, N, K, 0, sh.bn / sh.ctas, &mw)) return cudaErrorUnknown;
 #define GRAM_TC_LAUNCH(E, MC, LP)                                                                              \
-  return sh.ctas == 2 ? tc::launch<E, 256, 2>(ma, mw, MC, LP, M_max, m_ptr, N, K, na, num_sms, s)          \
-         : sh.bn == 256 ? tc::launch<E, 256, 1>(ma, mw, MC, LP, M_max, m_ptr, N, K, na, num_sms, s)        \
-                        : tc::launch<E, 128, 1>(ma, mw, MC, LP, M_max, m_ptr, N, K, na, num_sms, s)
+  return sh.ctas == 2 ? tc::launch<E, 256, 2>(ma, mw, MC, MC, LP, M_max, m_ptr, N, K, na, num_sms, s)          \
+         : sh.bn == 256 ? tc::launch<E, 256, 1>(ma, mw, MC, MC, LP, M_max, m_ptr, N, K, na, num_sms, s)        \
+                        : tc::launch<E, 128, 1>(ma, mw, MC, MC, LP, M_max, m_ptr, N, K, na, num_sms, s)
   if (epi == EPI_LSE) { GRAM_TC_LAUNCH(EPI_LSE, ma, (float2*)C); }
   if (!tc::get_map(C, M_max, N, ckind, tc::BLOCK_M, &mc)) return cudaErrorUnknown;
   switch (epi) {

@@ -63,11 +63,12 @@ enum {
                                       persistent tcgen05/TMEM kernel (attention_tc.cu), which is the default for bf16,
                                       d_kv = 64 and passages of at most 128 tokens (A-B timing, cross-check)          */
   GRAM_FLAG_GEMM_1CTA = 16,        /* keep every tcgen05 GEMM on single-CTA tiles (no cta_group::2 pairs; A-B timing) */
-  GRAM_FLAG_FUSED_NORM = 64,       /* bf16 encoder: the per-layer RMSNorms are folded into the tcgen05 GEMMs around them (the
-                                      residual GEMM emits bf16(x * ln_w) and the row's sum of squares, the consumer GEMM
-                                      scales its output rows by rsqrt(mean x^2 + eps)): no normalisation pass over the
-                                      residual stream.  Same math, one rounding placed differently (x*w is rounded to
-                                      bf16 before the row scale instead of after)                                     */
+  GRAM_FLAG_UNFUSED_NORM = 64,     /* bf16 encoder: run the per-layer RMSNorms as separate kernels (A-B timing).  Default: they
+                                      are folded into the tcgen05 GEMMs around them (the residual GEMM emits
+                                      bf16(x * ln_w) and the row's sums of squares, the consumer GEMM scales its output
+                                      rows by rsqrt(mean x^2 + eps)): no normalisation pass over the residual stream.
+                                      Same math, one rounding placed differently (x*w is rounded to bf16 before the
+                                      row scale instead of after)                                                     */
   GRAM_FLAG_ALL_ROWS = 32          /* decode every beam row at every step, as the reference does (A-B timing).  Default:
                                       beams that are dead (-inf score: the user had fewer than K finite continuations,
                                       typically item ids that ended a token earlier) and the beams of users whose

@@ -9,5 +9,5 @@ echo "pytest rc=$?" >> $O/${tag}_pytest.log
 ( timeout 300 python -c "import __graft_entry__ as g; g.smoke()" ) > $O/${tag}_smoke.log 2>&1
 echo "smoke rc=$?" >> $O/${tag}_smoke.log
 ( time timeout 600 python bench.py ) > $O/${tag}_bench.json 2> $O/${tag}_bench.err
-timeout 300 python bench.py --steps 10 --warmup 3 --no-item-cache --cpu-users 0 --no-e2e --mma-enc-attn > $O/${tag}_bench_mma.json 2> $O/${tag}_bench_mma.err
+timeout 300 python bench.py --steps 10 --warmup 3 --no-item-cache --cpu-users 0 --no-e2e --unfused-norm > $O/${tag}_bench_unfused.json 2> $O/${tag}_bench_unfused.err
 echo done > $O/${tag}_done

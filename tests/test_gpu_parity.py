@@ -342,14 +342,14 @@ def test_gemm_tcgen05_folded_rmsnorm(shape):
 
 
 def test_fused_norm_encoder_matches_unfused(built):
-    """GRAM_FLAG_FUSED_NORM (RMSNorms folded into the tcgen05 GEMMs) against the separate normalisation kernels: fused
+    """The default bf16 encoder (RMSNorms folded into the tcgen05 GEMMs) against GRAM_FLAG_UNFUSED_NORM (separate kernels): fused
     memory within bf16 rounding on the T5-small case and on a many-passage batch, logits within 2e-2 of the golden."""
     from gram_b200 import _cabi, synth, GRAM
     from gram_b200.config import GramConfig
     b = built["small"]
     gold = _golden("small")
-    m_f = _model(b["case"], b["sd"], "bf16", flags=_cabi.GRAM_FLAG_FUSED_NORM)
-    m_u = _model(b["case"], b["sd"], "bf16")
+    m_f = _model(b["case"], b["sd"], "bf16")
+    m_u = _model(b["case"], b["sd"], "bf16", flags=_cabi.GRAM_FLAG_UNFUSED_NORM)
     ids, mask = b["ids"].cuda(), b["mask"].cuda()
     err = rel_err(m_f.encode(ids, mask).cpu(), m_u.encode(ids, mask).cpu())
     print(f"[fused norm] memory rel_err vs unfused = {err:.3e}")
@@ -365,7 +365,7 @@ def test_fused_norm_encoder_matches_unfused(built):
     ids, mask = synth.make_user_batch(cfg, 96, (1, 8), 128, seed=31, min_len=2)
     ids, mask = torch.from_numpy(ids).cuda(), torch.from_numpy(mask).cuda()
     outs = []
-    for flags in (_cabi.GRAM_FLAG_FUSED_NORM, 0):
+    for flags in (0, _cabi.GRAM_FLAG_UNFUSED_NORM):
         m = GRAM(cfg, dtype="bf16", device="cuda:0", flags=flags)
         m.load_state_dict(sd)
         outs.append(m.encode(ids, mask).cpu())
