@@ -350,8 +350,11 @@ def main():
 
     # ---- per-class device time of the same steps (second pass, all classes bracketed) ----------------
     model.profile_begin(None)
+    executed = []                       # work the decode loop actually ran (live-row compaction, compact step 0)
     for i in range(W, W + S):
         kernel_step(i)
+        st = model.stats()              # synchronises: second pass only
+        executed.append((st["decoded_rows"], st["kv_tokens_read"]))
     prof_all = model.profile_end()
 
     # ---- e2e: public API with pinned host tensors ----------------------------------------------------
@@ -472,9 +475,25 @@ def main():
             by_class[cname] = dict(tflops=fl / (t_ms / 1000.0) / 1e12, frac=fl / (t_ms / 1000.0) / 1e12 / peaks["tensor"],
                                    ms_per_step=t_ms / S)
     roofline["by_class"] = by_class
+    # the figures above use the ALGORITHMIC work of SURVEY.md 8(d) (what the reference computes: B*K decoder rows and every
+    # user's K/V at each of the T steps); the decode loop runs less -- one row per user at step 0, live beams only later
+    dec_rows = sum(e[0] for e in executed)
+    kv_tok = sum(e[1] for e in executed)
+    d_, HD_, F_, V_, Ld_ = cfg.d_model, cfg.inner_dim, cfg.d_ff, cfg.vocab_size, cfg.num_decoder_layers
+    exec_dec_fl = dec_rows * Ld_ * (12 * d_ * HD_ + 4 * d_ * F_)
+    exec_head_fl = dec_rows * 2 * d_ * V_
+    exec_xa_bytes = kv_tok * Ld_ * 2 * HD_ * esz
+    executed_work = dict(
+        decoder_rows_per_step=dec_rows / S, algorithmic_decoder_rows_per_step=float(T * B * K),
+        kv_tokens_read_per_step=kv_tok / S, algorithmic_kv_tokens_per_step=float(T * np.mean(tok_timed)),
+        gemm_dec_tflops=exec_dec_fl / (prof["gemm_dec"]["ms"] / 1000.0) / 1e12 if prof["gemm_dec"]["ms"] > 0 else 0.0,
+        lm_head_tflops=exec_head_fl / (prof["lm_head"]["ms"] / 1000.0) / 1e12 if prof["lm_head"]["ms"] > 0 else 0.0,
+        note="TFLOP/s and GB/s of the decode-phase classes on the rows / K/V tokens actually processed")
     xa_ms = prof_all["cross_attn"]["ms"]
     xa_bytes = sum(w["xattn_bytes"] for w in work)
     xa_gbs = xa_bytes / (xa_ms / 1000.0) / 1e9 if xa_ms > 0 else 0.0
+    executed_work["cross_attention_gbs"] = exec_xa_bytes / (xa_ms / 1000.0) / 1e9 if xa_ms > 0 else 0.0
+    executed_work["cross_attention_frac"] = executed_work["cross_attention_gbs"] / peaks["hbm"]
     total_all = sum(v["ms"] for v in prof_all.values())
     kernels = {c: dict(ms_per_step=v["ms"] / S, launches_per_step=v["launches"] // S,
                        share=v["ms"] / total_all if total_all else 0.0) for c, v in prof_all.items()}
@@ -496,7 +515,7 @@ def main():
                 steps=S, warmup=W, ms_per_step=ms / S, higher_is_better=True, scaling="weak", vs_baseline=None,
                 dtype=args.dtype, data="synthetic", config=workload_config(args, data, max_length),
                 clocks=clocks.summary(), e2e=e2e, gpu_launches=int(model.stats()["launches"]) * S,
-                roofline=roofline, roofline_cross_attention=roofline_cross, kernel_classes=kernels,
+                roofline=roofline, roofline_cross_attention=roofline_cross, executed_work=executed_work, kernel_classes=kernels,
                 cpu_baseline=cpu, item_cache=item_cache, tokens_per_step=float(np.mean(tok_timed)),
                 gemm_impl="simt" if (args.simt or args.dtype == "fp32") else "tcgen05",
                 notes="roofline = all tcgen05 GEMM launches of the timed steps (CUDA events recorded by the library on the "

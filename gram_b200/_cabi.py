@@ -51,7 +51,7 @@ class GramConfigC(C.Structure):
 
 class GramStatsC(C.Structure):
     _fields_ = [("launches", C.c_int64), ("packed_tokens", C.c_int64), ("kv_bytes", C.c_int64),
-                ("workspace_bytes", C.c_int64)]
+                ("workspace_bytes", C.c_int64), ("decoded_rows", C.c_int64), ("kv_tokens_read", C.c_int64)]
 
 
 class GramLibraryError(RuntimeError):

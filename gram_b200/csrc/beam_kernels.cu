@@ -106,6 +106,7 @@ __global__ void beam_init_kernel(BeamState bs, int root, int users, int start_to
     bs.seq[0][(size_t)r * bs.max_length] = start_tok;
     bs.tok[r] = start_tok;
   }
+  if (r == 0) { bs.work[0] = 0ull; bs.work[1] = 0ull; }
   if (r < users) {
     bs.n_hyp[r] = 0;
     bs.worst[r] = 1e9;
@@ -508,15 +509,19 @@ cudaError_t beam_finalize(BeamState bs, int users, int t_final, int R_ret, int64
 // live-row compaction: slot ranges per user (one CTA, chunked block scan), then the row <-> slot maps
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(1024) live_scan_kernel(const int* __restrict__ live_cnt, int users, int* __restrict__ start,
-                                                         int* __restrict__ n_live) {
+                                                         int* __restrict__ n_live, const int* __restrict__ ustart,
+                                                         unsigned long long* __restrict__ work) {
   __shared__ int warp_tot[32];
   __shared__ int carry_s;
+  __shared__ unsigned long long tok_s;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  if (tid == 0) carry_s = 0;
+  if (tid == 0) { carry_s = 0; tok_s = 0ull; }
   __syncthreads();
+  unsigned long long toks = 0ull;                          // memory tokens of the users this thread found alive
   for (int u0 = 0; u0 < users; u0 += 1024) {
     const int u = u0 + tid;
     const int c = u < users ? live_cnt[u] : 0;
+    if (c > 0) toks += (unsigned long long)(ustart[u + 1] - ustart[u]);
     int x = c;                                              // inclusive scan within the warp
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -541,7 +546,24 @@ __global__ void __launch_bounds__(1024) live_scan_kernel(const int* __restrict__
     if (tid == 0) carry_s = carry + warp_tot[31];
     __syncthreads();
   }
-  if (tid == 0) { start[users] = carry_s; *n_live = carry_s; }
+  if (toks) atomicAdd(&tok_s, toks);
+  __syncthreads();
+  if (tid == 0) {
+    start[users] = carry_s;
+    *n_live = carry_s;
+    work[0] += (unsigned long long)carry_s;
+    work[1] += tok_s;
+  }
+}
+
+__global__ void work_add_kernel(unsigned long long* __restrict__ work, long long rows, const int* __restrict__ tokens_ptr) {
+  work[0] += (unsigned long long)rows;
+  work[1] += (unsigned long long)*tokens_ptr;
+}
+
+cudaError_t work_add(BeamState bs, long long rows, const int* tokens_ptr, cudaStream_t s) {
+  work_add_kernel<<<1, 1, 0, s>>>(bs.work, rows, tokens_ptr);
+  return cudaGetLastError();
 }
 
 __global__ void live_fill_kernel(BeamState bs, int users, int cur, LiveMap lm) {
@@ -562,9 +584,9 @@ __global__ void live_fill_kernel(BeamState bs, int users, int cur, LiveMap lm) {
   lm.row_slot[r] = slot;
 }
 
-cudaError_t live_compact(BeamState bs, int users, int cur, LiveMap lm, cudaStream_t s) {
+cudaError_t live_compact(BeamState bs, int users, int cur, LiveMap lm, const int* ustart, cudaStream_t s) {
   if (users <= 0) return cudaSuccess;
-  live_scan_kernel<<<1, 1024, 0, s>>>(bs.live_cnt, users, lm.start, lm.n_live);
+  live_scan_kernel<<<1, 1024, 0, s>>>(bs.live_cnt, users, lm.start, lm.n_live, ustart, bs.work);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
   const int R = users * bs.K;

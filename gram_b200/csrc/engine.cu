@@ -568,6 +568,7 @@ int gram_create(const gram_config* cfg, gram_handle** out) {
   DAC(h->live.start, (U + 1) * 4); DAC(h->live.slot_row, R * 4); DAC(h->live.row_slot, R * 4); DAC(h->live.tok, R * 4);
   DAC(h->live.n_live, 16);
   DAC(bs.err, 16);
+  DAC(bs.work, 16);
   h->pm.err = bs.err;
   h->pm.vocab = V;
   h->pm.cap = h->Mcap;
@@ -585,7 +586,7 @@ int gram_create(const gram_config* cfg, gram_handle** out) {
   if (cudaMemset(h->ckv, 0, Mc * (size_t)h->Ld * 2 * HD * esz) != cudaSuccess ||
       cudaMemset(h->qkv, 0, Mc * 3 * (size_t)HD * esz) != cudaSuccess ||   // rows past a passage are read (masked) by TMA
 
-      cudaMemset(h->d_zero_anc, 0, R * ML * 4) != cudaSuccess || cudaMemset(bs.err, 0, 16) != cudaSuccess ||
+      cudaMemset(h->d_zero_anc, 0, R * ML * 4) != cudaSuccess || cudaMemset(bs.err, 0, 16) != cudaSuccess || cudaMemset(bs.work, 0, 16) != cudaSuccess ||
       cudaMemset(bs.anc[0], 0, R * ML * 4) != cudaSuccess || cudaMemset(bs.anc[1], 0, R * ML * 4) != cudaSuccess) {
     h->err = "gram_create: cudaMemset failed"; return bail(GRAM_ERR_CUDA);
   }
@@ -867,8 +868,10 @@ int gram_generate(gram_handle* h, const int64_t* ids, const uint8_t* mask, int32
     // away on the device; the reference decodes them and discards the result)
     const bool live = t > 0 && !(c.flags & GRAM_FLAG_ALL_ROWS);
     if (live) {
-      CKL(GRAM_K_BEAM, live_compact(bs, users, t & 1, h->live, s));
+      CKL(GRAM_K_BEAM, live_compact(bs, users, t & 1, h->live, h->pm.ustart, s));
       h->launches += 1;   // live_compact issues two kernels
+    } else {
+      CKL(GRAM_K_OTHER, work_add(bs, Rt, h->pm.total, s));   // executed-work accounting (gram_get_stats)
     }
     const int* row_slot = live ? h->live.row_slot : nullptr;
     RC(decoder_step(h, Rt, Kt, users, t, bs.anc[t & 1], fused, live, s));
@@ -995,6 +998,10 @@ int gram_get_stats(gram_handle* h, gram_stats* out) {
   out->packed_tokens = h->encoded ? total : 0;
   out->kv_bytes = (int64_t)total * h->Ld * 2 * h->HD * (int64_t)h->esz;
   out->workspace_bytes = (int64_t)h->alloc_bytes;
+  unsigned long long work[2] = {0ull, 0ull};
+  CK(cudaMemcpy(work, h->bs.work, 16, cudaMemcpyDeviceToHost));
+  out->decoded_rows = (int64_t)work[0];
+  out->kv_tokens_read = (int64_t)work[1];
   return GRAM_OK;
 }
 

@@ -150,6 +150,7 @@ struct BeamState {           // all device pointers; rows R = users*K
   int* live_cnt;             // [U]   beams of the user that are still alive after the step (0 once the user is done);
                              //       they are the user's FIRST live_cnt beams (candidates are ranked best-first)
   int* err;                  // [1] sticky device-side error flag
+  unsigned long long* work;  // [2] executed work of the current generate: decoder rows, K/V tokens read per layer
   const double* len_pow;     // [max_length+1]
   // optional taps
   float* tap_lse; float* tap_score; int* tap_seq;                   // [steps][R](...)
@@ -178,7 +179,10 @@ struct LiveMap {
   int* tok;                  // [R]   input token of slot s
   int* n_live;               // [1]   number of slots = M of the step's GEMMs
 };
-cudaError_t live_compact(BeamState bs, int users, int cur, LiveMap lm, cudaStream_t s);
+// ustart [U+1] = packed memory rows per user (for the work counters in bs.work)
+cudaError_t live_compact(BeamState bs, int users, int cur, LiveMap lm, const int* ustart, cudaStream_t s);
+// bs.work += (rows, tokens): accounting of a step that runs without live_compact
+cudaError_t work_add(BeamState bs, long long rows, const int* tokens_ptr, cudaStream_t s);
 // compact != 0 (only at t == 0): all K beams of a user are identical, so the decoder ran ONE row per user; row u of
 // logits/hidden/lse serves every beam of user u and the step-0 self-attention cache row is recorded in the ancestry
 cudaError_t beam_finalize(BeamState bs, int users, int t_final, int R_ret, int64_t* out_seq, float* out_scores,

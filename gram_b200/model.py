@@ -475,7 +475,7 @@ class GRAM:
         st = _cabi.GramStatsC()
         _cabi.check(self._lib.gram_get_stats(self._handle, C.byref(st)), self._handle, "gram_get_stats")
         return dict(launches=st.launches, packed_tokens=st.packed_tokens, kv_bytes=st.kv_bytes,
-                    workspace_bytes=st.workspace_bytes)
+                    workspace_bytes=st.workspace_bytes, decoded_rows=st.decoded_rows, kv_tokens_read=st.kv_tokens_read)
 
     def profile_begin(self, classes=None):
         mask = 0

@@ -153,6 +153,11 @@ typedef struct gram_stats {
   int64_t packed_tokens;     /* valid encoder tokens of the last encode (needs a sync to read) */
   int64_t kv_bytes;          /* bytes of cross-attention K/V resident for the last batch      */
   int64_t workspace_bytes;   /* device memory owned by the handle                             */
+  int64_t decoded_rows;      /* decoder rows actually run by the last generate, summed over its steps (the reference
+                                runs B*K rows at every step; step 0 runs one row per user here, later steps only the
+                                live beams)                                                                          */
+  int64_t kv_tokens_read;    /* memory tokens whose K/V one decoder layer streamed, summed over the steps (a user
+                                without live beams is not read)                                                      */
 } gram_stats;
 int gram_get_stats(gram_handle* h, gram_stats* out);
 

@@ -20,7 +20,7 @@ def _run(case, sd, ids, mask, seqs, max_length, dtype, flags, K=None, lp=None):
                      num_beams=K, num_return_sequences=K, output_scores=True, return_dict_in_generate=True,
                      length_penalty=case.length_penalty if lp is None else lp)
     torch.cuda.synchronize()
-    return out["sequences"].cpu().numpy(), out["sequences_scores"].cpu().numpy(), m.stats()["launches"]
+    return out["sequences"].cpu().numpy(), out["sequences_scores"].cpu().numpy(), m.stats()
 
 
 @pytest.mark.parametrize("dtype", ["fp32", "bf16"])
@@ -29,10 +29,18 @@ def test_live_rows_bit_identical_to_all_rows(name, dtype):
     from gram_b200 import _cabi
     case = CASES[name]
     built = case.build()
-    seq_a, sc_a, _ = _run(case, *built, dtype, _cabi.GRAM_FLAG_ALL_ROWS)
-    seq_l, sc_l, _ = _run(case, *built, dtype, 0)
+    seq_a, sc_a, st_a = _run(case, *built, dtype, _cabi.GRAM_FLAG_ALL_ROWS)
+    seq_l, sc_l, st_l = _run(case, *built, dtype, 0)
     assert seq_a.shape == seq_l.shape and np.array_equal(seq_a, seq_l)
     assert np.array_equal(sc_a.view(np.uint32), sc_l.view(np.uint32)), "sequence scores differ bitwise"
+    # executed-work counters: the reference-like mode runs one row per user at step 0 and every beam row afterwards, and
+    # reads every user's K/V at every step; the default runs at most that
+    B, K, T = case.n_users, case.num_beams, built[4] - 1
+    assert st_a["decoded_rows"] == B + (T - 1) * B * K
+    assert st_a["kv_tokens_read"] == T * st_a["packed_tokens"]
+    assert B + (T - 1) <= st_l["decoded_rows"] <= st_a["decoded_rows"]
+    assert st_l["kv_tokens_read"] <= st_a["kv_tokens_read"]
+    assert st_l["decoded_rows"] < st_a["decoded_rows"], "these tries have two id lengths: the last step must shrink"
 
 
 @pytest.mark.parametrize("dtype", ["fp32", "bf16"])
