@@ -475,6 +475,9 @@ def main():
             by_class[cname] = dict(tflops=fl / (t_ms / 1000.0) / 1e12, frac=fl / (t_ms / 1000.0) / 1e12 / peaks["tensor"],
                                    ms_per_step=t_ms / S)
     roofline["by_class"] = by_class
+    if not (args.unfused_norm or args.simt or args.dtype == "fp32"):
+        roofline["note"] = ("the encoder GEMM time includes the 12 per-layer RMSNorms folded into the GEMM epilogues (12 ms per "
+                            "step as separate kernels at the default batch; --unfused-norm shows the GEMMs alone: frac 0.73-0.74)")
     # the figures above use the ALGORITHMIC work of SURVEY.md 8(d) (what the reference computes: B*K decoder rows and every
     # user's K/V at each of the T steps); the decode loop runs less -- one row per user at step 0, live beams only later
     dec_rows = sum(e[0] for e in executed)
