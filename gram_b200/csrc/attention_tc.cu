@@ -4,16 +4,17 @@
 // position bias (layer-0 table shared by all layers) + key padding mask, fp32 softmax, P V
 // (reference src/model/gram_t5_modeling.py:572-621, bias :452-477 and :1249, mask :1130).
 //
-// One CTA = one (passage, head), 128 threads:
-//   TMA      three 128-row x 64-col boxes (Q, K, V of this head) straight out of the packed qkv activation, 128B swizzle
-//   MMA 1    S[128 q x 128 keys] = Q K^T : 4 x tcgen05.mma (M=128, N=128, K=16), both operands K-major, fp32 in TMEM
-//   softmax  thread r owns query row r (TMEM lane r): tcgen05.ld of its 128 scores, + bias LUT, mask, max, exp2, sum --
+// Work item = one (passage, head); a persistent CTA (two per SM) walks its items, see the comment at the kernel:
+//   TMA      three 128-row x 64-col boxes (Q, K, V of this head) straight out of the packed qkv activation, 128B swizzle,
+//            into a 2-stage ring
+//   MMA 1    S[128 q x 128 keys] = Q K^T : 4 x tcgen05.mma (M=128, N=128, K=16), both operands K-major, fp32 in one of
+//            two TMEM accumulators
+//   softmax  thread r owns query row r (TMEM lane r): tcgen05.ld of its 128 scores, bias LUT, mask, max, exp2, sum --
 //            a row-wise softmax with no cross-thread traffic -- and writes P (bf16) into shared memory in the K-major
-//            128B-swizzled operand layout, over the dead Q and K tiles
+//            128B-swizzled operand layout, over the dead Q and K tiles of the stage
 //   MMA 2    O[128 q x 64 d] = P V : 8 x tcgen05.mma (M=128, N=64, K=16), A = P (K-major), B = V read in place in its
 //            MN-major (d-contiguous) layout; O re-uses the TMEM columns of S
-//   epilogue tcgen05.ld of the 64 outputs, 1/sum, bf16, one 128-byte row store per thread
-// 49 KiB of shared memory and 128 TMEM columns per CTA: four CTAs per SM overlap each other's TMA / MMA / softmax.
+//   epilogue tcgen05.ld of the 64 outputs, 1/sum, bf16, staged through the dead P rows to coalesced 128-byte stores
 // Rows past the passage length in the boxes belong to the next passage (finite values): masked as keys, and not
 // stored as queries.
 #include <cuda.h>

@@ -49,6 +49,23 @@ def test_config_struct_layout_matches_header():
     assert [ctype[f[1]] for f in fields] == [f[1] for f in _cabi.GramConfigC._fields_]
 
 
+def test_stats_struct_layout_matches_header():
+    header = open(os.path.join(ROOT, "include", "gram_b200.h")).read()
+    body = header[header.index("typedef struct gram_stats {"):header.index("} gram_stats;")]
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    names = [line.strip().rstrip(";").split()[-1] for line in body.splitlines()[1:] if line.strip()]
+    assert names == [f[0] for f in _cabi.GramStatsC._fields_]
+    assert all(f[1] is C.c_int64 for f in _cabi.GramStatsC._fields_)
+
+
+def test_flag_values_match_header():
+    header = open(os.path.join(ROOT, "include", "gram_b200.h")).read()
+    flags = dict(re.findall(r"\b(GRAM_FLAG_[A-Z0-9_]+)\s*=\s*(\d+)", header))
+    assert flags, "no flags parsed"
+    for name, value in flags.items():
+        assert getattr(_cabi, name) == int(value), name
+
+
 @pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
 def test_no_cpu_fallback():
     """Without a CUDA device the product path must fail loudly (never route through the oracle)."""
