@@ -160,3 +160,37 @@ def test_beam_search_properties():
         toks = row[:row.index(1) + 1]
         total = sum(lsm[toks[i], toks[i + 1]].item() for i in range(len(toks) - 1))
         assert math.isclose(s, total / (len(toks) - 1), rel_tol=1e-5, abs_tol=1e-5)
+
+
+@pytest.mark.parametrize("lp", [1.0, 0.6])
+def test_wide_beam_equals_exhaustive_teacher_forced_scoring(lp):
+    """An anchor for the beam loop that does not go through the beam loop: when the beam is at least as wide as the set
+    of live prefixes at every depth, nothing is ever pruned, so `generate` must return ALL items ranked by
+    sum_t log p(s_t | s_<t) / len ** length_penalty with len = tokens before EOS, start token included
+    (BeamHypotheses.add of transformers 4.26) -- computed here by teacher-forcing every item through the model
+    (`forward`, bit-identical to the reference modules) with the full-vocabulary log-softmax."""
+    from gram_b200 import synth
+    case = CASES["tiny"]
+    sd, ids, mask, _, _ = case.build()
+    seqs = synth.make_item_sequences(11, [3, 2, 2], case.cfg.vocab_size, seed=5, variable_tail=True)
+    assert len({len(s) for s in seqs}) == 2                      # two id lengths, as in the shipped ID files
+    ml = max(len(s) for s in seqs)
+    K = 16                                                       # >= number of prefixes at any depth (<= 11)
+    ora = oracle_for(case, sd)
+    out = ora.generate(ids, mask, ml, OracleTrie(seqs), K, K, lp)
+    B = ids.shape[0]
+    for u in range(B):
+        want = []
+        for s in seqs:
+            dec = torch.tensor([s[:-1]], dtype=torch.long)
+            logp = torch.log_softmax(ora.forward(ids[u:u + 1], mask[u:u + 1], dec)[0].float(), -1)
+            total = sum(logp[i, s[i + 1]].item() for i in range(len(s) - 1))
+            want.append((total / (len(s) - 1) ** lp, s))
+        want.sort(key=lambda t: -t[0])
+        got_seq = out["sequences"][u * K:(u + 1) * K].tolist()
+        got_sc = out["sequences_scores"][u * K:(u + 1) * K].tolist()
+        for rank, (sc, s) in enumerate(want):
+            row = got_seq[rank]
+            assert row[:len(s)] == s and all(t == 0 for t in row[len(s):]), (u, rank, row, s)
+            assert math.isclose(got_sc[rank], sc, rel_tol=2e-5, abs_tol=2e-5)
+        assert all(x == float("-inf") or x < want[-1][0] for x in got_sc[len(want):])
