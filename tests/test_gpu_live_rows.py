@@ -58,3 +58,34 @@ def test_live_rows_with_many_dead_beams(dtype):
         b = _run(case, sd, ids, mask, seqs, max_length, dtype, 0, K=K)
         assert np.array_equal(a[0], b[0])
         assert np.array_equal(a[1].view(np.uint32), b[1].view(np.uint32))
+
+
+@pytest.mark.parametrize("lp", [1.0, 0.6])
+def test_wide_beam_equals_exhaustive_scoring_on_the_gpu(lp):
+    """The CUDA path (fp32) against a ranking that never went through a beam loop: with a beam wider than the live
+    prefix set, `generate` must return every item ordered by sum log p / len**lp, recomputed by teacher-forcing each
+    item through the CPU oracle's model (tests/test_oracle.py pins the same property for the oracle's own loop).  Most
+    beams are dead from the first steps on, so this also drives the live-row compaction hard."""
+    import math
+    from helpers import oracle_for
+    from gram_b200 import synth
+    case = CASES["tiny"]
+    sd, ids, mask, _, _ = case.build()
+    seqs = synth.make_item_sequences(11, [3, 2, 2], case.cfg.vocab_size, seed=5, variable_tail=True)
+    ml = max(len(s) for s in seqs)
+    K = 16
+    got_seq, got_sc, _ = _run(case, sd, ids, mask, seqs, ml, "fp32", 0, K=K, lp=lp)
+    ora = oracle_for(case, sd)
+    for u in range(ids.shape[0]):
+        want = []
+        for s in seqs:
+            dec = torch.tensor([s[:-1]], dtype=torch.long)
+            logp = torch.log_softmax(ora.forward(ids[u:u + 1], mask[u:u + 1], dec)[0].float(), -1)
+            total = sum(logp[i, s[i + 1]].item() for i in range(len(s) - 1))
+            want.append((total / (len(s) - 1) ** lp, s))
+        want.sort(key=lambda t: -t[0])
+        for rank, (sc, s) in enumerate(want):
+            row = got_seq[u * K + rank].tolist()
+            row = row + [0] * (len(s) - len(row))
+            assert row[:len(s)] == s and all(t == 0 for t in row[len(s):]), (u, rank, row, s)
+            assert math.isclose(float(got_sc[u * K + rank]), sc, rel_tol=1e-4, abs_tol=1e-4)
