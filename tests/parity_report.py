@@ -1,7 +1,7 @@
 """Parity report at the headline configuration (Beauty, T5-small, beam 20, 12,101-item trie): the CUDA path against
 the CPU oracle on N real test users.  Test infrastructure (imports the oracle); writes a JSON summary.
 
-    python scripts/parity_report.py [--users 32] [--out profiles/r1_parity_beauty.json]
+    python tests/parity_report.py [--users 32] [--out profiles/r1_parity_beauty.json]
 
 fp32: ranked item ids must be identical (north star); the smallest gap between adjacent oracle scores is reported so
 near-ties can be told apart from real mismatches.  bf16: top-10 overlap and score error.
