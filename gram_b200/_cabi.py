@@ -1,8 +1,8 @@
 """ctypes binding of `libgram_b200.so` (declared in `include/gram_b200.h`).
 
 There is no CPU fallback: if the shared library is missing, fails to load, or no sm_100 device is
-visible, the product path raises.  The library is built in-tree by `__graft_entry__.build()` /
-`make -C gram_b200/csrc`.
+visible, the product path raises.  The library is built in-tree by `__graft_entry__.build()`
+(`python __graft_entry__.py`).
 """
 from __future__ import annotations
 
@@ -17,6 +17,7 @@ GRAM_DTYPE_F32, GRAM_DTYPE_BF16 = 0, 1
 GRAM_FLAG_SIMT_GEMM, GRAM_FLAG_KEEP_LOGITS, GRAM_FLAG_SIMT_ATTN, GRAM_FLAG_MMA_ENC_ATTN, GRAM_FLAG_GEMM_1CTA = 1, 2, 4, 8, 16
 GRAM_FLAG_ALL_ROWS = 32
 GRAM_FLAG_UNFUSED_NORM = 64
+GRAM_FLAG_UNFUSED_HEAD = 128
 K_CLASSES = ["gemm_enc", "enc_attn", "gemm_kv", "gemm_dec", "cross_attn", "lm_head", "beam", "other", "self_attn",
              "norm_enc", "norm_dec"]
 GRAM_K_COUNT = len(K_CLASSES)
@@ -27,7 +28,7 @@ EXPORTED_SYMBOLS = [
     "gram_set_rel_buckets", "gram_finalize_weights", "gram_set_trie", "gram_encode", "gram_generate",
     "gram_get_memory", "gram_decoder_logits", "gram_get_step_taps", "gram_get_stats",
     "gram_profile_begin", "gram_profile_end", "gram_op_gemm", "gram_op_gemm_norm", "gram_op_cross_attention",
-    "gram_cache_items", "gram_encode_cached", "gram_check_errors",
+    "gram_cache_items", "gram_encode_cached", "gram_check_errors", "gram_op_lse_head",
 ]
 
 
@@ -120,6 +121,8 @@ def load_library():
     lib.gram_op_gemm_norm.restype = C.c_int
     lib.gram_op_cross_attention.argtypes = [i32, i32, i32, vp, vp, i32, i32p, u8p, vp, i32, i32, i32, i32, vp]
     lib.gram_op_cross_attention.restype = C.c_int
+    lib.gram_op_lse_head.argtypes = [i32, vp, vp, vp, vp, i32, i32, i32, vp]
+    lib.gram_op_lse_head.restype = C.c_int
     _lib = lib
     return lib
 

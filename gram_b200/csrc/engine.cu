@@ -65,6 +65,7 @@ struct gram_handle {
 
   // trie
   TrieCSR trie{};
+  int* trie_bufs[3] = {nullptr, nullptr, nullptr};   // child_offsets / child_tokens / child_nodes (freed on re-upload)
   bool trie_set = false;
   int cand_cap = 0;
 
@@ -133,6 +134,14 @@ namespace {
 int fail(gram_handle* h, int code, const std::string& msg) {
   h->err = msg;
   return code;
+}
+
+void free_trie(gram_handle* h) {
+  for (int i = 0; i < 3; ++i) {
+    if (h->trie_bufs[i]) cudaFree(h->trie_bufs[i]);
+    h->trie_bufs[i] = nullptr;
+  }
+  h->trie_set = false;
 }
 
 void free_item_cache(gram_handle* h) {
@@ -450,6 +459,7 @@ void gram_destroy(gram_handle* h) {
   if (!h) return;
   cudaSetDevice(h->cfg.device);
   free_item_cache(h);
+  free_trie(h);
   for (void* p : h->allocs) cudaFree(p);
   for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
   if (h->len_pow_ev) cudaEventDestroy(h->len_pow_ev);
@@ -542,7 +552,8 @@ int gram_create(const gram_config* cfg, gram_handle** out) {
   DAC(h->d_ids, (size_t)full * 8); DAC(h->d_mask, (size_t)full);
   DAC(h->x, Mc * D * 4);
   DAC(h->xn, Mc * D * esz); DAC(h->qkv, Mc * 3 * HD * esz); DAC(h->ao, Mc * HD * esz);
-  DAC(h->ff, Mc * F * esz); DAC(h->mem, Mc * D * esz);
+  DAC(h->ff, Mc * std::max<size_t>((size_t)F * esz, (size_t)D * 4));   // also an fp32 [rows, D] scratch (item cache)
+  DAC(h->mem, Mc * D * esz);
   DAC(h->ckv, Mc * (size_t)h->Ld * 2 * HD * esz);
   DAC(h->ss, Mc * (size_t)((D + 127) / 128) * 4);
   // ---- decoder workspace ----
@@ -677,7 +688,10 @@ int gram_set_trie(gram_handle* h, const int32_t* child_offsets, const int32_t* c
   if (!h || !child_offsets || n_nodes <= 0 || n_edges < 0) return GRAM_ERR_INVALID;
   if (n_edges > 0 && (!child_tokens || !child_nodes)) return GRAM_ERR_INVALID;
   CK(cudaSetDevice(h->cfg.device));
-  if (root_node >= n_nodes) return fail(h, GRAM_ERR_INVALID, "gram_set_trie: root_node out of range");
+  // root_node < 0: no item starts with the decoder start token (Trie.to_csr) -- every beam would be dead and the
+  // result all padding; the reference's HF loop raises in that situation, so refuse the trie here
+  if (root_node < 0 || root_node >= n_nodes)
+    return fail(h, GRAM_ERR_INVALID, "gram_set_trie: root_node out of range (no item sequence starts with the decoder start token?)");
   if (child_offsets[0] != 0 || child_offsets[n_nodes] != n_edges) return fail(h, GRAM_ERR_INVALID, "gram_set_trie: malformed CSR offsets");
   int max_fan = 0;
   for (int i = 0; i < n_nodes; ++i) {
@@ -692,8 +706,18 @@ int gram_set_trie(gram_handle* h, const int32_t* child_offsets, const int32_t* c
   const int cap = next_pow2((max_fan > 0 ? max_fan : 1) * h->cfg.max_beams);
   if (beam_step_smem(cap) > 200 * 1024)
     return fail(h, GRAM_ERR_UNSUPPORTED, "gram_set_trie: max_beams * max trie fan-out exceeds the shared-memory candidate buffer");
+  // the CSR arrays live outside h->allocs: a re-upload (Trie.add bumps the version) frees the previous ones
+  // (cudaFree waits for the kernels that may still read them)
+  free_trie(h);
   int *d_off = nullptr, *d_tok = nullptr, *d_node = nullptr;
-  DA(d_off, ((size_t)n_nodes + 1) * 4); DA(d_tok, ((size_t)n_edges + 1) * 4); DA(d_node, ((size_t)n_edges + 1) * 4);
+  if (cudaMalloc(&d_off, ((size_t)n_nodes + 1) * 4) != cudaSuccess || cudaMalloc(&d_tok, ((size_t)n_edges + 1) * 4) != cudaSuccess ||
+      cudaMalloc(&d_node, ((size_t)n_edges + 1) * 4) != cudaSuccess) {
+    cudaGetLastError();
+    if (d_off) cudaFree(d_off);
+    if (d_tok) cudaFree(d_tok);
+    return fail(h, GRAM_ERR_CUDA, "gram_set_trie: cudaMalloc of the CSR arrays failed");
+  }
+  h->trie_bufs[0] = d_off; h->trie_bufs[1] = d_tok; h->trie_bufs[2] = d_node;
   CK(cudaMemcpy(d_off, child_offsets, ((size_t)n_nodes + 1) * 4, cudaMemcpyHostToDevice));
   if (n_edges) {
     CK(cudaMemcpy(d_tok, child_tokens, (size_t)n_edges * 4, cudaMemcpyHostToDevice));
@@ -748,7 +772,9 @@ int gram_cache_items(gram_handle* h, const int64_t* ids, const uint8_t* mask, in
 #undef DAC2
     h->pm_prompt.err = h->pm.err;
     h->pm_prompt.vocab = h->V;
-    h->pm_prompt.cap = (long long)U * c.max_seq_len;
+    // the prompt pass writes the same Mcap-row workspace as an ordinary batch: the packing scan empties a batch whose
+    // prompts alone exceed it (err 4) before any kernel writes a row
+    h->pm_prompt.cap = std::min<long long>((long long)U * c.max_seq_len, (long long)h->Mcap);
   }
   // encode the items in chunks shaped like an ordinary batch [Bc, N, L] (item = first + b*N + n)
   const int N = c.max_passages;
@@ -764,7 +790,7 @@ int gram_cache_items(gram_handle* h, const int64_t* ids, const uint8_t* mask, in
     CK(cudaMemsetAsync(h->d_ids, 0, full * 8, s));
     CK(cudaMemcpyAsync(h->d_ids, ids + first * L, have * 8, dev_in ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, s));
     CK(cudaMemcpyAsync(h->d_mask, mask + first * L, have, dev_mask ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, s));
-    const int Mmax = (int)full;
+    const int Mmax = (int)std::min<int64_t>((int64_t)full, h->Mcap);
     CKL(GRAM_K_OTHER, enc_pack(h->d_ids, h->d_mask, Bc, N, L, h->pm, s));
     RC(encoder_stack(h, h->pm, Bc * N, L, Mmax, s));
     // final norm in fp32, WITHOUT the position row (h->ff is free after the last block and holds >= Mcap*D floats)
@@ -811,8 +837,9 @@ int gram_encode_cached(gram_handle* h, const int64_t* prompt_ids, const uint8_t*
   // 1. the encoder stack on the prompts alone
   CKL(GRAM_K_OTHER, enc_pack(dids, dmask, B, 1, L, h->pm_prompt, s));
   h->launches += 3;
-  RC(encoder_stack(h, h->pm_prompt, B, L, (int)n, s));
-  CKL(GRAM_K_NORM_ENC, rmsnorm_rows(GRAM_DTYPE_F32, h->x, h->enc_final_ln, h->ff, (int)n, h->pm_prompt.total, h->D, c.ln_eps,
+  const int Mprompt = (int)std::min<int64_t>((int64_t)n, h->Mcap);
+  RC(encoder_stack(h, h->pm_prompt, B, L, Mprompt, s));
+  CKL(GRAM_K_NORM_ENC, rmsnorm_rows(GRAM_DTYPE_F32, h->x, h->enc_final_ln, h->ff, Mprompt, h->pm_prompt.total, h->D, c.ln_eps,
                                  1.f, nullptr, nullptr, s));
   // 2. user layout + memory = prompt rows / cached item rows + position rows
   const int Mmax = (int)std::min<int64_t>((int64_t)B * N * L, h->Mcap);
@@ -857,7 +884,8 @@ int gram_generate(gram_handle* h, const int64_t* ids, const uint8_t* mask, int32
   CKL(GRAM_K_BEAM, beam_init(bs, h->trie, users, c.start_id, s));
   // fused head (bf16 + tcgen05 GEMM): log-softmax statistics come out of the GEMM epilogue and candidate logits are
   // recomputed from the trie children only; otherwise (fp32 parity mode) full logits are materialised
-  const bool fused = c.dtype == GRAM_DTYPE_BF16 && !(c.flags & (GRAM_FLAG_SIMT_GEMM | GRAM_FLAG_KEEP_LOGITS)) &&
+  // (GRAM_FLAG_KEEP_LOGITS only records the per-step taps: the benchmarked fused head is the one they observe)
+  const bool fused = c.dtype == GRAM_DTYPE_BF16 && !(c.flags & (GRAM_FLAG_SIMT_GEMM | GRAM_FLAG_UNFUSED_HEAD)) &&
                      gemm_tc_supported(h->V, h->D) && (h->D % 8) == 0;
   for (int t = 0; t < T; ++t) {
     // step 0: the K beams of a user all hold the start token and attend to the same memory, i.e. K identical rows
@@ -1065,6 +1093,19 @@ int gram_op_gemm_norm(int32_t device, int32_t impl, int32_t epilogue, const void
   aux.row_ss = row_ss; aux.xb = xb; aux.ss_out = ss; aux.ln_w = ln_w; aux.eps = eps;
   cudaError_t e = gemm_tc(epilogue, A, W, C, M, nullptr, N, K, sms, impl == 2 ? 1 : 2, (cudaStream_t)stream, &aux);
   if (e != cudaSuccess) { g_create_error = std::string("gemm_tc: ") + cudaGetErrorString(e) + " / " + gemm_tc_last_error(); return GRAM_ERR_CUDA; }
+  return GRAM_OK;
+}
+
+int gram_op_lse_head(int32_t device, const void* hidden, const void* head, float* lse, void* partial, int32_t M, int32_t V,
+                     int32_t D, void* stream) {
+  if (cudaSetDevice(device) != cudaSuccess) return GRAM_ERR_CUDA;
+  if (!hidden || !head || !lse || !partial || M <= 0) return GRAM_ERR_INVALID;
+  if (!gemm_tc_supported(V, D)) { g_create_error = "gram_op_lse_head: unsupported (V, D)"; return GRAM_ERR_UNSUPPORTED; }
+  int sms = 148;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+  cudaError_t e = gemm_tc(EPI_LSE, hidden, head, partial, M, nullptr, V, D, sms, 1, (cudaStream_t)stream);
+  if (e == cudaSuccess) e = lse_combine(partial, lse, M, gemm_tc_lse_ntiles(M, V, sms), nullptr, (cudaStream_t)stream);
+  if (e != cudaSuccess) { g_create_error = std::string("lse_head: ") + cudaGetErrorString(e) + " / " + gemm_tc_last_error(); return GRAM_ERR_CUDA; }
   return GRAM_OK;
 }
 

@@ -50,11 +50,17 @@ def _ptr(t: Optional[torch.Tensor]):
     return None if t is None else C.c_void_p(t.data_ptr())
 
 
-class GRAM:
+class GRAM(torch.nn.Module):
+    """An `nn.Module` like the reference's `GRAM` (src/model/gram.py:22), so the runners' wrapping code works:
+    `DistributedDataParallel(model, device_ids=[rank])` (src/runner/distributed_runner_gram.py:47-52) needs a module with
+    at least one trainable parameter -- `_ddp_anchor` is that parameter and nothing else; the weights live in the engine."""
+
     main_input_name = "input_ids"
 
     def __init__(self, config, dtype: str = None, device=None, max_users: int = 1, max_beams: int = None,
                  max_length: int = 16, max_passages: int = None, max_seq_len: int = None, flags: int = 0):
+        super().__init__()
+        self._ddp_anchor = torch.nn.Parameter(torch.zeros(1))
         self.config = config
         self.gcfg = config if isinstance(config, GramConfig) else GramConfig.from_hf(config)
         g = self.gcfg
@@ -76,27 +82,24 @@ class GRAM:
         self._lib = None
         self.encoder = _Holder(n_passages=None, position_embedding=None, main_input_name="input_ids")
         self.position_embedding = None
-        self.training = False
+        self.training = False           # inference only: the module is born in eval mode
         self.user_limit = 256           # auto-grow max_users up to this; larger batches are chunked
 
     # ---- nn.Module-ish conveniences the runner touches -------------------------------------------
     @property
     def module(self):
-        return self
-
-    def eval(self):
+        """`model_rec.module.generate(...)` (distributed_runner_gram.py:775) also works on the unwrapped model."""
         return self
 
     def train(self, mode=True):
         if mode:
             raise NotImplementedError("gram_b200 implements the inference/scoring path only")
-        return self
+        return super().train(False)
 
-    def zero_grad(self):
-        return None
-
-    def to(self, device):
-        self._device = torch.device(device)
+    def to(self, device=None, *args, **kwargs):
+        if device is not None and not isinstance(device, torch.dtype):
+            self._device = torch.device(device)
+            super().to(self._device)
         return self
 
     def cuda(self, device=None):
@@ -133,7 +136,7 @@ class GRAM:
             pe = pseudo_normal((self.gcfg.max_item_num + 1, self.gcfg.d_model), 0.02, 20250101)
             self.load_state_dict({"position_embedding.weight": pe})
 
-    def state_dict(self):
+    def state_dict(self, *args, **kwargs):
         return dict(self._weights or {})
 
     # ---- engine lifetime ----------------------------------------------------------------------------
@@ -460,8 +463,6 @@ class GRAM:
                                                      labels.reshape(-1).to(logits.device), ignore_index=-100)
         return GenerateOutput(loss=loss, logits=logits)
 
-    __call__ = forward
-
     def _shift_right(self, labels):
         start, pad = self.gcfg.decoder_start_token_id, self.gcfg.pad_token_id
         out = labels.new_zeros(labels.shape)
@@ -469,6 +470,13 @@ class GRAM:
         out[..., 0] = start
         out.masked_fill_(out == -100, pad)
         return out
+
+    def check_errors(self):
+        """Raise the sticky device-side error of earlier calls, if any (token id outside the vocabulary, more valid
+        tokens than `max_tokens`, candidate overflow ...).  `generate` / `generate_cached` call it themselves; loops over
+        `generate_into` / `generate_cached_into` (which never synchronise) call it once at the end."""
+        if self._handle is not None:
+            _cabi.check(self._lib.gram_check_errors(self._handle, self._stream()), self._handle, "gram_check_errors")
 
     # ---- measurement helpers (bench.py / tests) -----------------------------------------------------------
     def stats(self):

@@ -145,16 +145,25 @@ class GramRunner:
             if getattr(model, "_item_table_owner", None) is not data:
                 model.cache_items(*data.item_table())
                 model._item_table_owner = data
-        rows = []                                # (user index, gold string, predictions, scores, hit rank)
+        # per-batch results as arrays (what the multi-GPU gather moves): user index, gold ids, ranked ids, scores and the
+        # 0/1 relevance row of evaluate.rel_results (string comparison, as the reference)
+        parts = []                               # (users [n], gold [n, ML], seqs [n, G, ML], scores [n, G], rel [n, G])
 
         def post(batch, seqs, scores):
             gold = self.tokenizer.batch_decode(batch["target_ids"], skip_special_tokens=True)
             sents = self.tokenizer.batch_decode(seqs, skip_special_tokens=True)
             rel = evaluate.rel_results(sents, gold, scores, G)
-            for i, u in enumerate(batch["user_index"]):
-                r = rel[i]
-                rows.append((u, gold[i], sents[i * G:(i + 1) * G], scores[i * G:(i + 1) * G].tolist(),
-                             r.index(1) if 1 in r else -1))
+            n = len(batch["user_index"])
+            g_ids = np.zeros((n, max_length), dtype=np.int32)
+            for i, t in enumerate(batch["target_ids"]):
+                t = [int(x) for x in t if int(x) >= 0][:max_length]
+                g_ids[i, :len(t)] = t
+            s_ids = np.zeros((n, G, max_length), dtype=np.int32)
+            sq = seqs.numpy() if hasattr(seqs, "numpy") else np.asarray(seqs)
+            s_ids[:, :, :sq.shape[1]] = sq.reshape(n, G, -1)
+            sc = (scores.numpy() if hasattr(scores, "numpy") else np.asarray(scores)).astype(np.float32).reshape(n, G)
+            parts.append((np.asarray(batch["user_index"], dtype=np.int64), g_ids, s_ids, sc,
+                          np.asarray(rel, dtype=np.uint8).reshape(n, G)))
 
         def batches():
             if not pipeline:
@@ -198,39 +207,118 @@ class GramRunner:
                     post(batch, seqs, scores)
         if pending is not None:
             pending.join()
-        # ---- one gather after the loop (reference: all_reduce(metrics), all_reduce(total), TSV merge) ----
-        rows = self._gather(rows)
-        rows.sort(key=lambda r: r[0])
-        ranks = np.array([r[4] for r in rows], dtype=np.int64)
-        test_total = len(rows)
-        sums = evaluate.metric_sums_from_ranks(ranks, self.metrics)
+        # ---- after the loop: ONE all-gather of the ranked lists + an integer all-reduce of the hit counts
+        #      (reference: all_reduce(metrics_res), all_reduce(test_total), TSV merge through the file system;
+        #      distributed_runner_gram.py:832-838,854-874) ----
+        t0 = time.time()
+        local_rel = np.concatenate([p[4] for p in parts]) if parts else np.zeros((0, G), np.uint8)
+        hist = self._reduce_hit_histogram(self._first_hit(local_rel), G)          # from each rank's OWN users
+        users, gold_ids, seq_ids, scores, rel = self._gather(parts, G, max_length)
+        gather_seconds = time.time() - t0
+        order = np.argsort(users, kind="stable")
+        users, gold_ids, seq_ids, scores, rel = users[order], gold_ids[order], seq_ids[order], scores[order], rel[order]
+        test_total = len(users)
+        # metrics from the relevance ROWS (a row may hold more than one 1 when two token paths decode to the same
+        # string; the reference's ndcg_at_k sums every match), in user order on every rank: identical at any world size
+        sums = evaluate.get_metrics_results(rel.tolist(), self.metrics) if test_total else np.zeros(len(self.metrics))
         metrics_res = sums / max(test_total, 1)
+        first = self._first_hit(rel)
+        if int(hist[-1]) != test_total or not np.array_equal(hist[:G + 1], np.bincount(first + 1, minlength=G + 1)):
+            raise RuntimeError("multi-GPU eval: the all-reduced hit-rank histogram disagrees with the gathered rankings")
         result = dict(metrics={m: float(v) for m, v in zip(self.metrics, metrics_res)}, test_total=test_total,
-                      generate_seconds=total_time, hit_ranks=ranks, rows=rows if self.rank == 0 else None)
+                      generate_seconds=total_time, gather_seconds=gather_seconds, hit_ranks=first, rel_rows=rel,
+                      hit_rank_histogram=hist[:G + 1], users=users, sequences=seq_ids, sequences_scores=scores, rows=None)
         if self.rank == 0:
+            gold = self.tokenizer.batch_decode(gold_ids, skip_special_tokens=True)
+            sents = self.tokenizer.batch_decode(seq_ids.reshape(-1, max_length), skip_special_tokens=True)
+            result["rows"] = [(int(u), gold[i], sents[i * G:(i + 1) * G], scores[i].tolist(), int(first[i]))
+                              for i, u in enumerate(users)]
             for m, v in result["metrics"].items():
                 logging.info(f"{mode} {m}: {v}")
             logging.info(f"Total inference time: {total_time:.2f}s for {len(testloader)} batches")
             if self.save_predictions:
-                result["pred_file"] = self._write_tsv(rows, data, mode, result["metrics"])
+                result["pred_file"] = self._write_tsv(result["rows"], data, mode, result["metrics"], rel)
         return result
 
-    def _gather(self, rows):
-        if self.world_size <= 1:
-            return rows
+    # ---- the path's only collectives -----------------------------------------------------------------------------
+    def _comm_device(self):
         import torch.distributed as dist
-        gathered = [None] * self.world_size
-        dist.all_gather_object(gathered, rows)
-        out = []
-        for part in gathered:
-            out.extend(part)
-        return out
+        if dist.get_backend() == "nccl":
+            return torch.device(self.device) if self.device is not None else torch.device("cuda", torch.cuda.current_device())
+        return torch.device("cpu")
 
-    def _write_tsv(self, rows, data, mode, metrics):
+    def _gather(self, parts, G, max_length):
+        """(users int64 [n], gold int32 [n, ML], seqs int32 [n, G, ML], scores fp32 [n, G], rel uint8 [n, G]) of ALL ranks.
+        world > 1: every rank packs its users into one int32 matrix (ids | scores bit-cast | relevance | user index),
+        pads it to the largest shard and ONE `all_gather_into_tensor` (ncclAllGather under NCCL) moves
+        it; no pickling, no file system."""
+        ML = max_length
+        if parts:
+            users = np.concatenate([p[0] for p in parts])
+            gold = np.concatenate([p[1] for p in parts])
+            seqs = np.concatenate([p[2] for p in parts])
+            scores = np.concatenate([p[3] for p in parts])
+            rel = np.concatenate([p[4] for p in parts])
+        else:
+            users, gold = np.zeros(0, np.int64), np.zeros((0, ML), np.int32)
+            seqs, scores, rel = np.zeros((0, G, ML), np.int32), np.zeros((0, G), np.float32), np.zeros((0, G), np.uint8)
+        if self.world_size <= 1:
+            return users, gold, seqs, scores, rel
+        import torch.distributed as dist
+        dev = self._comm_device()
+        n = len(users)
+        width = ML + G * ML + G + G + 2
+        mine = np.zeros((n, width), dtype=np.int32)
+        o = 0
+        mine[:, o:o + ML] = gold; o += ML
+        mine[:, o:o + G * ML] = seqs.reshape(n, G * ML); o += G * ML
+        mine[:, o:o + G] = scores.view(np.int32); o += G
+        mine[:, o:o + G] = rel; o += G
+        mine[:, o] = (users & 0x7fffffff).astype(np.int32)
+        mine[:, o + 1] = (users >> 31).astype(np.int32)
+        counts = torch.zeros(self.world_size, dtype=torch.int64, device=dev)
+        counts[self.rank] = n
+        dist.all_reduce(counts)                                   # shard sizes (a loader may carry a custom user list)
+        counts = counts.cpu().tolist()
+        n_pad = max(max(counts), 1)
+        send = torch.zeros((n_pad, width), dtype=torch.int32, device=dev)
+        send[:n] = torch.from_numpy(mine).to(dev)
+        recv = torch.empty((self.world_size * n_pad, width), dtype=torch.int32, device=dev)
+        dist.all_gather_into_tensor(recv, send)
+        recv = recv.cpu().numpy().reshape(self.world_size, n_pad, width)
+        allr = np.concatenate([recv[r, :counts[r]] for r in range(self.world_size)])
+        o = 0
+        gold = allr[:, o:o + ML].copy(); o += ML
+        seqs = allr[:, o:o + G * ML].reshape(-1, G, ML).copy(); o += G * ML
+        scores = np.ascontiguousarray(allr[:, o:o + G]).view(np.float32); o += G
+        rel = allr[:, o:o + G].astype(np.uint8); o += G
+        users = allr[:, o].astype(np.int64) | (allr[:, o + 1].astype(np.int64) << 31)
+        return users, gold, seqs, scores, rel
+
+    @staticmethod
+    def _first_hit(rel):
+        """rank of the first 1 of every relevance row, -1 when the gold item is absent"""
+        if len(rel) == 0:
+            return np.zeros(0, np.int64)
+        return np.where(rel.any(axis=1), rel.argmax(axis=1), -1).astype(np.int64)
+
+    def _reduce_hit_histogram(self, first_hit, G):
+        """int64 [G + 2]: users per first-hit rank (bin 0 = no hit, bin r + 1 = gold at rank r) and the user count, summed
+        over the ranks from each rank's OWN users -- the integer counterpart of the reference's all_reduce(metrics_res) /
+        all_reduce(test_total); it cross-checks the gathered rankings."""
+        h = np.concatenate([np.bincount(first_hit + 1, minlength=G + 1), [len(first_hit)]]).astype(np.int64)
+        if self.world_size <= 1:
+            return h
+        import torch.distributed as dist
+        t = torch.from_numpy(h).to(self._comm_device())
+        dist.all_reduce(t)
+        return t.cpu().numpy()
+
+    def _write_tsv(self, rows, data, mode, metrics, rel):
         os.makedirs(self.pred_dir, exist_ok=True)
         stamp = time.strftime("%Y%m%d_%H%M%S")
         path = os.path.join(self.pred_dir, f"{stamp}_{data.dataset}_{data.task}_pred_{mode}.tsv")
-        per_user = [evaluate.metric_sums_from_ranks(np.array([r[4]]), self.metrics) for r in rows]
+        per_user = [evaluate.get_metrics_results([r.tolist()], self.metrics) for r in rel]
         formats.write_predictions_tsv(path, rows, metrics, per_user, self.metrics)
         return path
 

@@ -57,7 +57,8 @@ typedef struct gram_config {
 
 enum {
   GRAM_FLAG_SIMT_GEMM = 1,         /* force the CUDA-core GEMM even for bf16 (debug / A-B timing) */
-  GRAM_FLAG_KEEP_LOGITS = 2,       /* record per-step taps (lse, beam scores, prefixes) for parity tests */
+  GRAM_FLAG_KEEP_LOGITS = 2,       /* record per-step taps (lse, beam scores, prefixes) for parity tests; the decode path
+                                      itself is unchanged (bf16: the fused log-softmax head stays on)               */
   GRAM_FLAG_SIMT_ATTN = 4,         /* force the CUDA-core attention kernels even for bf16 (A-B timing)   */
   GRAM_FLAG_MMA_ENC_ATTN = 8,      /* encoder attention through the mma.sync kernel (attention_mma.cu) instead of the
                                       persistent tcgen05/TMEM kernel (attention_tc.cu), which is the default for bf16,
@@ -69,6 +70,8 @@ enum {
                                       rows by rsqrt(mean x^2 + eps)): no normalisation pass over the residual stream.
                                       Same math, one rounding placed differently (x*w is rounded to bf16 before the
                                       row scale instead of after)                                                     */
+  GRAM_FLAG_UNFUSED_HEAD = 128,    /* bf16: materialise the [rows, V] fp32 logits and reduce them with lse_rows instead of the
+                                      fused log-softmax epilogue of the vocabulary GEMM (A-B timing / cross-check)     */
   GRAM_FLAG_ALL_ROWS = 32          /* decode every beam row at every step, as the reference does (A-B timing).  Default:
                                       beams that are dead (-inf score: the user had fewer than K finite continuations,
                                       typically item ids that ended a token earlier) and the beams of users whose
@@ -103,7 +106,8 @@ int gram_finalize_weights(gram_handle* h);
 /* replaces: Trie(sequences) + prefix_allowed_tokens_fn(trie) (src/utils/generation_trie.py:5-95) as
  * consumed by PrefixConstrainedLogitsProcessor.  CSR: children of node n are
  * child_tokens/child_nodes[child_offsets[n] .. child_offsets[n+1]).  `root_node` is the node reached
- * by the decoder start token (Trie.get([0]) lists its children); -1 if absent. */
+ * by the decoder start token (Trie.get([0]) lists its children); a trie without it (root_node < 0) is rejected
+ * with GRAM_ERR_INVALID.  Calling it again replaces (and frees) the previous trie. */
 int gram_set_trie(gram_handle* h, const int32_t* child_offsets, const int32_t* child_tokens,
                   const int32_t* child_nodes, int32_t n_nodes, int32_t n_edges, int32_t root_node);
 
@@ -197,6 +201,12 @@ int gram_op_gemm(int32_t device, int32_t dtype, int32_t impl, int32_t epilogue, 
 int gram_op_gemm_norm(int32_t device, int32_t impl, int32_t epilogue, const void* A, const void* W, void* C, void* xb,
                       float* ss, const float* ln_w, const float* row_ss, float eps, int32_t M, int32_t N, int32_t K,
                       void* stream);
+/* Kernel (c) head: lse[i] = log sum_v exp(hidden[i] . head[v]) with the log-softmax statistics fused into the epilogue of the
+ * tcgen05 vocabulary GEMM (the [M, V] logits are never written) + the per-row combine -- the path gram_generate runs in
+ * bf16 (reference: lm_head then log_softmax, src/model/gram_t5.py:249-254 and HF beam_search).  hidden bf16 [M, D],
+ * head bf16 [V, D], lse fp32 [M], partial = scratch of M * ceil(V / 128) * 8 bytes; device pointers. */
+int gram_op_lse_head(int32_t device, const void* hidden, const void* head, float* lse, void* partial, int32_t M, int32_t V,
+                     int32_t D, void* stream);
 /* decoder cross-attention over an in-place K/V memory: q [users*K, H*dk], kv [kv_rows, 2*H*dk] (K|V),
  * user_start int32 [users+1], tok_valid uint8 [kv_rows] or NULL, out [users*K, H*dk] (all dtype).
  * impl 0 = CUDA-core kernel (fp32 or bf16), 1 = TMA + tensor-core kernel (bf16). */

@@ -204,3 +204,23 @@ def test_collator_contract():
     assert d.tokenizer.batch_decode([b["target_ids"][4]])[0] == d.tokenizer.decode(cands[tgt])
     v = GramTestData("Beauty", mode="validation")
     assert v.split(17)[1] == items[-2]
+
+
+def test_gram_is_a_module_that_ddp_can_wrap(tmp_path):
+    """The reference wraps the model in DistributedDataParallel and calls `self.model_rec.module.generate`
+    (src/runner/distributed_runner_gram.py:47-52,775): GRAM must be an nn.Module DDP accepts, wrapped or not."""
+    import torch
+    import torch.distributed as dist
+    from gram_b200 import GRAM, GramConfig
+    m = GRAM(GramConfig.tiny())
+    assert isinstance(m, torch.nn.Module) and not m.training
+    assert m.module is m and m.eval() is m
+    with pytest.raises(NotImplementedError):
+        m.train()
+    dist.init_process_group("gloo", init_method=f"file://{tmp_path}/pg", rank=0, world_size=1)
+    try:
+        ddp = torch.nn.parallel.DistributedDataParallel(m)
+        assert ddp.module is m and ddp.module.generate.__func__ is GRAM.generate
+        assert ddp.module.module is m                      # `.module` also on the unwrapped model
+    finally:
+        dist.destroy_process_group()

@@ -65,6 +65,11 @@ def _run(rank, world, port, out_dir):
                 row = b * num_beams + (u % num_beams)
                 out["sequences"][row] = 0
                 out["sequences"][row, :len(gold)] = torch.tensor(gold)
+                if u % 6 == 0:
+                    # the same item twice in one ranking (two token paths that decode to one string do this in the
+                    # reference): ndcg must count both matches, as evaluate.ndcg_at_k does
+                    row2 = b * num_beams + ((u + 3) % num_beams)
+                    out["sequences"][row2] = out["sequences"][row]
         return out
 
     model.generate = generate
@@ -87,6 +92,11 @@ def _run(rank, world, port, out_dir):
     runner._generate = _generate
     res = runner.test_dataset_task(loader, "test")
     np.save(os.path.join(out_dir, f"ranks_w{world}_r{rank}.npy"), res["hit_ranks"])
+    np.save(os.path.join(out_dir, f"rel_w{world}_r{rank}.npy"), res["rel_rows"])
+    np.save(os.path.join(out_dir, f"seq_w{world}_r{rank}.npy"), res["sequences"])
+    np.save(os.path.join(out_dir, f"sc_w{world}_r{rank}.npy"), res["sequences_scores"])
+    assert res["gather_seconds"] >= 0 and int(res["hit_rank_histogram"].sum()) == N_USERS
+    assert (res["rows"] is not None) == (rank == 0)
     np.save(os.path.join(out_dir, f"metrics_w{world}_r{rank}.npy"), np.array([res["metrics"][m] for m in runner.metrics]))
     assert res["test_total"] == N_USERS
     if world > 1:
@@ -121,5 +131,14 @@ def test_sharded_eval_equals_single_process(tmp_path):
     for r in range(2):
         assert np.array_equal(np.load(os.path.join(out, f"ranks_w2_r{r}.npy")), ranks1)
         assert np.array_equal(np.load(os.path.join(out, f"metrics_w2_r{r}.npy")), single)     # bit-for-bit
+        # the gathered ranked lists themselves (one all_gather_into_tensor of int32 ids + bit-cast fp32 scores)
+        for name in ("rel", "seq", "sc"):
+            assert np.array_equal(np.load(os.path.join(out, f"{name}_w2_r{r}.npy")), np.load(os.path.join(out, f"{name}_w1_r0.npy")))
     assert (ranks1 >= 0).sum() == len([u for u in range(N_USERS) if u % 3 == 0])
     assert single[1] > 0
+    # metrics are the reference's functions applied to the 0/1 relevance rows, multi-hit rows included
+    from gram_b200 import evaluate
+    rel = np.load(os.path.join(out, "rel_w1_r0.npy"))
+    assert (rel.sum(1) > 1).any()
+    want = evaluate.get_metrics_results(rel.tolist(), ["hit@5", "hit@10", "ndcg@5", "ndcg@10"]) / N_USERS
+    assert np.array_equal(want, single)
