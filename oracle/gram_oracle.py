@@ -24,7 +24,7 @@ What it restates, and where the original lives (all paths relative to the refere
                       from the published 4.26.0 algorithm and anchored on the reference call sites
                       `src/model/gram.py:93-99`, `src/runner/single_runner_gram.py:641-651`.
 
-Pinning status.  The model math is pinned: `tests/test_oracle_pin.py` checks this file bit-for-bit
+Pinning status.  The model math is pinned: `tests/test_oracle.py` checks this file bit-for-bit
 (torch.equal) against the real reference modules when `/root/reference` is present, and
 `tests/golden/*.npz` (made by `oracle/make_golden.py`, which drives the real reference modules) are
 checked everywhere.  The trie and metrics are pinned against the reference's own functions and its
@@ -346,12 +346,7 @@ def hf426_beam_search(decode_fn, reorder_fn, trie, memory, memory_mask, max_leng
         logits, past = decode_fn(dec_in, memory, mem_mask, past)
         next_token_logits = logits[:, -1, :]
         lsm = F.log_softmax(next_token_logits, dim=-1)
-        # PrefixConstrainedLogitsProcessor: mask = -inf everywhere, 0 at allowed tokens
-        mask = torch.full_like(lsm, -math.inf)
-        for row in range(B * K):
-            allowed = trie.get(seqs[row].tolist())
-            mask[row, allowed] = 0
-        processed = lsm + mask
+        processed = prefix_constrained_scores(trie, seqs, lsm)
         scores = processed + beam_scores[:, None].expand_as(processed)
         scores = scores.view(B, K * V)
         next_scores, nt = torch.topk(scores, 2 * K, dim=1, largest=True, sorted=True)
@@ -421,6 +416,19 @@ def hf426_beam_search(decode_fn, reorder_fn, trie, memory, memory_mask, max_leng
             out[i, lengths[i]] = eos
     return dict(sequences=out, sequences_scores=torch.tensor(best_scores, dtype=torch.float32),
                 n_steps=cur_len - 1)
+
+
+def prefix_constrained_scores(trie, input_ids, scores):
+    """transformers 4.26.0 `PrefixConstrainedLogitsProcessor.__call__` with the reference's
+    `prefix_allowed_tokens_fn` (src/utils/generation_trie.py:89-95: `trie.get(sentence.tolist())`): a mask that is -inf
+    everywhere and 0 at the allowed tokens of every row, ADDED to the (already log-softmaxed) scores -- no
+    renormalisation.  4.26 does not raise on an empty allowed list (5.x does): such a row becomes all -inf.
+    Pinned against the installed transformers' processor in tests/test_oracle.py."""
+    mask = torch.full_like(scores, -math.inf)
+    for row in range(input_ids.shape[0]):
+        allowed = trie.get(input_ids[row].tolist())
+        mask[row, allowed] = 0
+    return scores + mask
 
 
 class _BeamHypotheses:

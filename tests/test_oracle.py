@@ -194,3 +194,72 @@ def test_wide_beam_equals_exhaustive_teacher_forced_scoring(lp):
             assert row[:len(s)] == s and all(t == 0 for t in row[len(s):]), (u, rank, row, s)
             assert math.isclose(got_sc[rank], sc, rel_tol=2e-5, abs_tol=2e-5)
         assert all(x == float("-inf") or x < want[-1][0] for x in got_sc[len(want):])
+
+
+# ---------------------------------------------------------------------------------------------
+# pins of the third-party (transformers 4.26.0) pieces that CAN still be pinned offline
+# ---------------------------------------------------------------------------------------------
+def test_prefix_mask_equals_installed_transformers_processor():
+    """`PrefixConstrainedLogitsProcessor` still exists in the installed transformers (5.x) with the 4.26 mask-then-add
+    body (plus a new empty-list ValueError): the oracle's mask step must equal it bit for bit, driven by the reference's
+    own `Trie` / `prefix_allowed_tokens_fn` when the reference is mounted (ours otherwise -- tests/test_host.py shows
+    they agree on every prefix of every shipped id file)."""
+    from transformers.generation.logits_process import PrefixConstrainedLogitsProcessor
+    from oracle.gram_oracle import prefix_constrained_scores
+    from gram_b200.data import GramTestData
+    if ref_shim.reference_available():
+        gt = ref_shim.load_reference().generation_trie
+    else:
+        from gram_b200 import generation_trie as gt
+    cands = GramTestData("Beauty").encoded_candidates()
+    trie = gt.Trie(cands)
+    fn = gt.prefix_allowed_tokens_fn(trie)
+    K, V, users = 5, 32128, 4
+    g = torch.Generator().manual_seed(3)
+    for depth in (1, 2, 4, 6):
+        pick = torch.randint(0, len(cands), (users * K,), generator=g).tolist()
+        ids = torch.tensor([cands[i][:depth] for i in pick], dtype=torch.long)
+        scores = torch.log_softmax(torch.randn(users * K, V, generator=g), -1)
+        want = PrefixConstrainedLogitsProcessor(fn, K)(ids, scores)
+        got = prefix_constrained_scores(trie, ids, scores)
+        assert torch.equal(got, want)
+        assert int(torch.isfinite(got).sum()) == sum(len(trie.get(r.tolist())) for r in ids)
+    # a prefix outside the trie: 4.26 (and the oracle, and the device: a dead beam) give an all -inf row; 5.x raises
+    bad = torch.tensor([[0, 31999]], dtype=torch.long)
+    assert trie.get(bad[0].tolist()) == []
+    assert not torch.isfinite(prefix_constrained_scores(trie, bad, torch.zeros(1, V))).any()
+    with pytest.raises(ValueError):
+        PrefixConstrainedLogitsProcessor(fn, 1)(bad, torch.zeros(1, V))
+
+
+def test_beam_hypotheses_hand_computed_cases():
+    """`BeamHypotheses.add / is_done` (transformers 4.26.0 generation/beam_search.py, early_stopping=False) on cases worked
+    out by hand from the published source: length normalisation counts the start token and not EOS, the worst hypothesis
+    is replaced (earliest among equal scores), `worst_score` follows, `is_done` compares with best_sum / cur_len**lp and is
+    not monotone in the step."""
+    from oracle.gram_oracle import _BeamHypotheses
+    h = _BeamHypotheses(2, 1.0)
+    assert not h.is_done(0.0, 1)                                 # fewer than num_beams hypotheses: never done
+    h.add(torch.tensor([0, 7, 9]), -6.0)                         # [start, a, b]: len 3 -> -2.0
+    assert h.beams[0][0] == -2.0 and h.worst_score == -2.0
+    h.add(torch.tensor([0, 7]), -6.0)                            # len 2 -> -3.0
+    assert h.worst_score == -3.0 and len(h) == 2
+    h.add(torch.tensor([0, 5, 5, 5]), -10.0)                     # -2.5 > worst: joins, -3.0 leaves, worst becomes -2.5
+    assert sorted(s for s, _ in h.beams) == [-2.5, -2.0] and h.worst_score == -2.5
+    h.add(torch.tensor([0, 1]), -8.0)                            # -4.0 <= worst and full: ignored
+    assert len(h) == 2 and h.worst_score == -2.5
+    # is_done: worst_score >= best_sum_logprobs / cur_len ** lp
+    assert not h.is_done(-2.0, 1)                                # -2.0 / 1 = -2.0 > -2.5
+    assert h.is_done(-2.5, 1) and h.is_done(-6.0, 2)             # equality counts; -3.0 < -2.5
+    assert not h.is_done(-6.0, 3)                                # the SAME candidate score later: -2.0 again -> not done
+    # equal scores: sorted((score, idx)) removes the EARLIEST of the equal worst ones
+    e = _BeamHypotheses(2, 1.0)
+    e.add(torch.tensor([0, 2]), -4.0)                            # idx 0: -2.0
+    e.add(torch.tensor([0, 3]), -4.0)                            # idx 1: -2.0
+    e.add(torch.tensor([0, 4]), -2.0)                            # -1.0: idx 0 leaves
+    assert [hyp.tolist() for _, hyp in e.beams] == [[0, 3], [0, 4]] and e.worst_score == -2.0
+    # length penalty: score = sum / len ** lp
+    p = _BeamHypotheses(1, 0.6)
+    p.add(torch.tensor([0, 1, 2, 3]), -3.0)
+    assert p.beams[0][0] == -3.0 / (4 ** 0.6)
+    assert p.is_done(-3.0, 4) and not p.is_done(-3.0 * 0.999, 4)
