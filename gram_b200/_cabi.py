@@ -18,6 +18,8 @@ GRAM_FLAG_SIMT_GEMM, GRAM_FLAG_KEEP_LOGITS, GRAM_FLAG_SIMT_ATTN, GRAM_FLAG_MMA_E
 GRAM_FLAG_ALL_ROWS = 32
 GRAM_FLAG_UNFUSED_NORM = 64
 GRAM_FLAG_UNFUSED_HEAD = 128
+GRAM_FLAG_NO_CHAIN = 256
+GRAM_FLAG_NO_L2_HINTS = 512
 K_CLASSES = ["gemm_enc", "enc_attn", "gemm_kv", "gemm_dec", "cross_attn", "lm_head", "beam", "other", "self_attn",
              "norm_enc", "norm_dec"]
 GRAM_K_COUNT = len(K_CLASSES)
@@ -28,7 +30,7 @@ EXPORTED_SYMBOLS = [
     "gram_set_rel_buckets", "gram_finalize_weights", "gram_set_trie", "gram_encode", "gram_generate",
     "gram_get_memory", "gram_decoder_logits", "gram_get_step_taps", "gram_get_stats",
     "gram_profile_begin", "gram_profile_end", "gram_op_gemm", "gram_op_gemm_norm", "gram_op_cross_attention",
-    "gram_cache_items", "gram_encode_cached", "gram_check_errors", "gram_op_lse_head",
+    "gram_cache_items", "gram_encode_cached", "gram_check_errors", "gram_op_lse_head", "gram_op_enc_chain",
 ]
 
 
@@ -121,6 +123,8 @@ def load_library():
     lib.gram_op_gemm_norm.restype = C.c_int
     lib.gram_op_cross_attention.argtypes = [i32, i32, i32, vp, vp, i32, i32p, u8p, vp, i32, i32, i32, i32, vp]
     lib.gram_op_cross_attention.restype = C.c_int
+    lib.gram_op_enc_chain.argtypes = [i32, vp, vp, vp, vp, vp, vp, vp, vp, C.c_int64, vp, vp, C.c_float, i32, i32, i32, i32, i32, vp, vp]
+    lib.gram_op_enc_chain.restype = C.c_int
     lib.gram_op_lse_head.argtypes = [i32, vp, vp, vp, vp, i32, i32, i32, vp]
     lib.gram_op_lse_head.restype = C.c_int
     _lib = lib

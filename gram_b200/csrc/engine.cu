@@ -76,6 +76,7 @@ struct gram_handle {
   uint8_t* d_mask = nullptr;
   float* x = nullptr;
   void *xn = nullptr, *qkv = nullptr, *ao = nullptr, *ff = nullptr, *mem = nullptr, *ckv = nullptr;
+  void* ffs = nullptr;        // per-CTA ff scratch of the row-block chain kernel (gemm_chain.cu), L2 resident
   float* ss = nullptr;        // [Mcap][D/128] row sums of squares of the residual stream (RMSNorm folded into the GEMMs)
   int enc_B = 0, enc_N = 0, enc_L = 0;
   bool encoded = false;
@@ -325,6 +326,7 @@ int encoder_stack(gram_handle* h, const PackMeta& pm, int P, int L, int Mmax, cu
   const bool fused = c.dtype == GRAM_DTYPE_BF16 && !(c.flags & (GRAM_FLAG_UNFUSED_NORM | GRAM_FLAG_SIMT_GEMM)) &&
                      (D % 128) == 0 && gemm_tc_supported(3 * HD, D) && gemm_tc_supported(D, HD) &&
                      gemm_tc_supported(F, D) && gemm_tc_supported(D, F);
+  const bool chained = fused && !(c.flags & GRAM_FLAG_NO_CHAIN) && h->ffs != nullptr;
   GemmNormAux scaled;                  // consumer side
   scaled.row_ss = h->ss; scaled.eps = c.ln_eps;
   auto produce = [&](const float* ln_w) { GemmNormAux a; a.xb = h->xn; a.ss_out = h->ss; a.ln_w = ln_w; return a; };
@@ -345,7 +347,13 @@ int encoder_stack(gram_handle* h, const PackMeta& pm, int P, int L, int Mmax, cu
       CKL(GRAM_K_ENC_ATTN, enc_attention(c.dtype, h->qkv, h->ao, pm.plen, pm.poff, pm.tok_valid,
                                          h->enc_bias_lut, h->Lb, P, h->H, h->dk, L, s));
     }
-    if (fused) {
+    if (fused && chained) {
+      // o-projection -> RMSNorm -> wi -> ReLU -> wo (+ the next layer's RMSNorm) as ONE persistent launch: each CTA walks
+      // 128-row blocks and hands ff / xn from GEMM to GEMM through its L2-resident scratch (gemm_chain.cu)
+      CKL(GRAM_K_GEMM_ENC, enc_chain(h->ao, W.o, h->x, h->xn, h->ss, W.wi, W.wo, h->ffs, W.ln1,
+                                     l + 1 < h->Le ? h->enc[l + 1].ln0 : nullptr, c.ln_eps, Mmax, mp, D, HD, F, h->num_sms,
+                                     (c.flags & GRAM_FLAG_NO_L2_HINTS) ? 0 : 1, h->pm.err, s));
+    } else if (fused) {
       const GemmNormAux a1 = produce(W.ln1);
       RC(gemm(h, GRAM_K_GEMM_ENC, EPI_RESID_NORM, h->ao, W.o, h->x, Mmax, mp, D, HD, s, &a1));
       RC(gemm(h, GRAM_K_GEMM_ENC, EPI_RELU, h->xn, W.wi, h->ff, Mmax, mp, F, D, s, &scaled));
@@ -556,6 +564,7 @@ int gram_create(const gram_config* cfg, gram_handle** out) {
   DAC(h->mem, Mc * D * esz);
   DAC(h->ckv, Mc * (size_t)h->Ld * 2 * HD * esz);
   DAC(h->ss, Mc * (size_t)((D + 127) / 128) * 4);
+  if (c.dtype == GRAM_DTYPE_BF16 && enc_chain_supported(D, HD, F)) DAC(h->ffs, enc_chain_scratch_bytes(F, h->num_sms));
   // ---- decoder workspace ----
   h->Rcap = c.max_users * c.max_beams;
   const size_t R = (size_t)h->Rcap + 128;
@@ -934,6 +943,7 @@ int gram_generate(gram_handle* h, const int64_t* ids, const uint8_t* mask, int32
                                        : code == 3 ? "gram_generate: item index outside the cached item table"
                                        : code == 4 ? "gram_generate: the batch holds more valid tokens than max_tokens"
                                        : code == 5 ? "gram_generate: internal error, live beams are not a prefix of the user's beams"
+                                       : code == 7 ? "gram_generate: internal error, a barrier of the chain kernel never completed (watchdog)"
                                                    : "gram_generate: candidate buffer overflow (trie fan-out larger than declared)");
     }
   }
@@ -1014,6 +1024,7 @@ int gram_check_errors(gram_handle* h, void* stream) {
                                    : code == 3 ? "item index outside the cached item table"
                                    : code == 4 ? "the batch holds more valid tokens than max_tokens"
                                    : code == 5 ? "internal error, live beams are not a prefix of the user's beams"
+                                   : code == 7 ? "internal error, a barrier of the chain kernel never completed (watchdog)"
                                                : "candidate buffer overflow (trie fan-out larger than declared)");
 }
 
@@ -1093,6 +1104,21 @@ int gram_op_gemm_norm(int32_t device, int32_t impl, int32_t epilogue, const void
   aux.row_ss = row_ss; aux.xb = xb; aux.ss_out = ss; aux.ln_w = ln_w; aux.eps = eps;
   cudaError_t e = gemm_tc(epilogue, A, W, C, M, nullptr, N, K, sms, impl == 2 ? 1 : 2, (cudaStream_t)stream, &aux);
   if (e != cudaSuccess) { g_create_error = std::string("gemm_tc: ") + cudaGetErrorString(e) + " / " + gemm_tc_last_error(); return GRAM_ERR_CUDA; }
+  return GRAM_OK;
+}
+
+int gram_op_enc_chain(int32_t device, const void* ao, const void* w_o, float* x, void* xn, float* ss, const void* w_i,
+                      const void* w_o2, void* scratch, int64_t scratch_bytes, const float* ln_mid, const float* ln_next, float eps,
+                      int32_t M, int32_t D, int32_t HD, int32_t F, int32_t hints, int32_t* err, void* stream) {
+  if (cudaSetDevice(device) != cudaSuccess) return GRAM_ERR_CUDA;
+  if (!ao || !w_o || !x || !xn || !ss || !w_i || !w_o2 || !scratch || !ln_mid || !err || M <= 0) return GRAM_ERR_INVALID;
+  if (!enc_chain_supported(D, HD, F)) { g_create_error = "gram_op_enc_chain: needs d_model % 256 == d_ff % 256 == inner_dim % 64 == 0"; return GRAM_ERR_UNSUPPORTED; }
+  int sms = 148;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+  if (scratch_bytes < (int64_t)enc_chain_scratch_bytes(F, sms)) { g_create_error = "gram_op_enc_chain: scratch smaller than num_sms * 128 * d_ff * 2 bytes"; return GRAM_ERR_INVALID; }
+  cudaError_t e = enc_chain(ao, w_o, x, xn, ss, w_i, w_o2, scratch, ln_mid, ln_next, eps, M, nullptr, D, HD, F, sms, hints, err,
+                            (cudaStream_t)stream);
+  if (e != cudaSuccess) { g_create_error = std::string("enc_chain: ") + cudaGetErrorString(e) + " / " + gemm_tc_last_error(); return GRAM_ERR_CUDA; }
   return GRAM_OK;
 }
 

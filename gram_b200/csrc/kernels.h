@@ -56,6 +56,16 @@ const char* gemm_tc_last_error();
 // number of column tiles (= per-row partials) the EPI_LSE epilogue writes for this problem
 int gemm_tc_lse_ntiles(int M_max, int N, int num_sms);
 
+// ---- gemm_chain.cu (tcgen05 / TMEM / TMA, bf16): one encoder layer's residual sublayers chained per 128-row block --------
+// x += ao w_o^T; xn = bf16(x * ln_mid), ss;   ff = relu(RMSNorm-scaled xn w_i^T) (kept in an L2-resident per-CTA scratch);
+// x += ff w_o2^T; xn = bf16(x * ln_next), ss (ln_next == nullptr: last layer, x only).  D % 256 == F % 256 == HD % 64 == 0.
+bool enc_chain_supported(int D, int HD, int F);
+size_t enc_chain_scratch_bytes(int F, int num_sms);
+// hints: 1 = L2 cache-policy hints on the TMA traffic; err: sticky device flag (7 = watchdog)
+cudaError_t enc_chain(const void* ao, const void* w_o, float* x, void* xn, float* ss, const void* w_i, const void* w_o2,
+                      void* scratch, const float* ln_mid, const float* ln_next, float eps, int M_max, const int* m_ptr,
+                      int D, int HD, int F, int num_sms, int hints, int* err, cudaStream_t s);
+
 // ---- encoder_kernels.cu --------------------------------------------------------------------------
 struct PackMeta {            // device-resident description of the packed (valid-token) layout
   int* plen;                 // [P]    valid length of passage p (last valid index + 1)

@@ -72,6 +72,11 @@ enum {
                                       row scale instead of after)                                                     */
   GRAM_FLAG_UNFUSED_HEAD = 128,    /* bf16: materialise the [rows, V] fp32 logits and reduce them with lse_rows instead of the
                                       fused log-softmax epilogue of the vocabulary GEMM (A-B timing / cross-check)     */
+  GRAM_FLAG_NO_CHAIN = 256,        /* bf16 encoder: run the o-projection, wi and wo GEMMs of a layer as three launches (A-B timing).
+                                      Default: one persistent launch per layer chains them per 128-token row block and
+                                      keeps ff / the normalised rows in an L2-resident per-CTA scratch (gemm_chain.cu);
+                                      same arithmetic per element, bit-identical results                              */
+  GRAM_FLAG_NO_L2_HINTS = 512,     /* chain kernel without L2 cache-policy hints on its TMA traffic (A-B timing)      */
   GRAM_FLAG_ALL_ROWS = 32          /* decode every beam row at every step, as the reference does (A-B timing).  Default:
                                       beams that are dead (-inf score: the user had fewer than K finite continuations,
                                       typically item ids that ended a token earlier) and the beams of users whose
@@ -201,6 +206,15 @@ int gram_op_gemm(int32_t device, int32_t dtype, int32_t impl, int32_t epilogue, 
 int gram_op_gemm_norm(int32_t device, int32_t impl, int32_t epilogue, const void* A, const void* W, void* C, void* xb,
                       float* ss, const float* ln_w, const float* row_ss, float eps, int32_t M, int32_t N, int32_t K,
                       void* stream);
+/* One encoder layer's residual sublayers chained per 128-row block in ONE launch (gemm_chain.cu; reference
+ * T5LayerSelfAttention output projection + T5LayerFF, src/model/gram_t5_modeling.py:297-310,337-352,622,634-667), bf16:
+ *   x fp32 [M,D] += ao [M,HD] w_o[D,HD]^T;  xn bf16 [M,D] = x * ln_mid;  ss fp32 [M, D/128] = row sums of squares per 128 columns;
+ *   ff = relu((xn w_i[F,D]^T) * rsqrt(sum ss / D + eps))  (never leaves the L2-resident scratch);
+ *   x += ff w_o2[D,F]^T;  xn = x * ln_next, ss   (ln_next NULL: x only).
+ * scratch: num_SMs * 128 * F * 2 bytes; err: device int32 (7 = internal watchdog).  D % 256 == F % 256 == HD % 64 == 0. */
+int gram_op_enc_chain(int32_t device, const void* ao, const void* w_o, float* x, void* xn, float* ss, const void* w_i,
+                      const void* w_o2, void* scratch, int64_t scratch_bytes, const float* ln_mid, const float* ln_next, float eps,
+                      int32_t M, int32_t D, int32_t HD, int32_t F, int32_t hints, int32_t* err, void* stream);
 /* Kernel (c) head: lse[i] = log sum_v exp(hidden[i] . head[v]) with the log-softmax statistics fused into the epilogue of the
  * tcgen05 vocabulary GEMM (the [M, V] logits are never written) + the per-row combine -- the path gram_generate runs in
  * bf16 (reference: lm_head then log_softmax, src/model/gram_t5.py:249-254 and HF beam_search).  hidden bf16 [M, D],

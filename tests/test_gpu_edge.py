@@ -106,10 +106,18 @@ def test_capacity_and_argument_errors():
         bad_ids = ids.clone()
         bad_ids[0, 0, 3] = cfg.vocab_size + 9
         m.generate(bad_ids.cpu(), mask.cpu(), 3, prefix_allowed_tokens_fn=fn, num_beams=2)
-    # a start token that is not in the trie: every beam is dead, scores are -inf, nothing crashes
-    dead = prefix_allowed_tokens_fn(Trie([[7, 5, 1]]))
-    out = m.generate(ids, mask, 3, prefix_allowed_tokens_fn=dead, num_beams=2, num_return_sequences=2, return_dict_in_generate=True)
-    assert np.isinf(out["sequences_scores"].cpu().numpy()).all()
+    # a start token that is not in the trie: every beam would be dead and the result all padding (HF raises in that
+    # situation) -- the trie is refused
+    with pytest.raises(ValueError):
+        dead = prefix_allowed_tokens_fn(Trie([[7, 5, 1]]))
+        m.generate(ids, mask, 3, prefix_allowed_tokens_fn=dead, num_beams=2, num_return_sequences=2, return_dict_in_generate=True)
+    # re-uploading a grown trie replaces (and frees) the old arrays: same handle, new candidates reachable
+    t2 = Trie([[0, 5, 1], [0, 6, 1]])
+    fn2 = prefix_allowed_tokens_fn(t2)
+    o1 = m.generate(ids, mask, 3, prefix_allowed_tokens_fn=fn2, num_beams=2, num_return_sequences=2, return_dict_in_generate=True)
+    t2.add([0, 7, 1])
+    o2 = m.generate(ids, mask, 3, prefix_allowed_tokens_fn=fn2, num_beams=3, num_return_sequences=3, return_dict_in_generate=True)
+    assert set(o1["sequences"][:2, 1].tolist()) == {5, 6} and set(o2["sequences"][:3, 1].tolist()) == {5, 6, 7}
 
 
 def test_large_synthetic_trie_beam50():
