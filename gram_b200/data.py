@@ -86,6 +86,47 @@ class SurrogateTokenizer:
         out.append(self.eos_token_id)
         return out
 
+    def encode_text(self, text: str) -> List[int]:
+        """A whole passage as the collator sees it: known words, lexical ids ('|piece|piece', separator ids emitted as by
+        `encode`), and raw ids written as '<123>' (the synthetic metadata); no EOS."""
+        if self._piece2id is None:
+            self._piece2id = {p: int(i) for p, i in zip(self.pieces, self.piece_id)}
+        out: List[int] = []
+        for word in text.replace("similar items:", "similar\x00items:").split():
+            word = word.replace("\x00", " ")
+            if word in self.word_id:
+                out.append(self.word_id[word])
+            elif word[0] == "|":
+                for p in word.split("|"):
+                    if p:
+                        out.append(SEPARATOR_IDS[0])
+                        out.append(self._piece2id[p])
+            elif word[0] == "<" and word[-1] == ">":
+                out.append(int(word[1:-1]))
+            else:
+                raise KeyError(f"surrogate tokenizer: unknown word {word!r}")
+        return out
+
+    def batch_encode_plus(self, texts, max_length=None, truncation=False, padding=None, pad_to_max_length=False,
+                          return_tensors=None, **kw):
+        """The slice of the HF tokenizer API the collators use (reference src/processor/Collator.py:354-360,287-293): EOS
+        appended, truncation keeps it, optional padding with 0."""
+        rows = []
+        for t in texts:
+            r = self.encode_text(t)
+            if truncation and max_length is not None:
+                r = r[:max_length - 1]
+            rows.append(r + [self.eos_token_id])
+        width = max_length if pad_to_max_length else (max(len(r) for r in rows) if padding == "longest" else None)
+        if width is None:
+            return {"input_ids": rows, "attention_mask": [[1] * len(r) for r in rows]}
+        ids = [r + [0] * (width - len(r)) for r in rows]
+        am = [[1] * len(r) + [0] * (width - len(r)) for r in rows]
+        if return_tensors == "pt":
+            import torch
+            return {"input_ids": torch.tensor(ids), "attention_mask": torch.tensor(am)}
+        return {"input_ids": ids, "attention_mask": am}
+
     def decode(self, ids, skip_special_tokens: bool = True) -> str:
         toks = []
         for i in ids:
@@ -113,6 +154,28 @@ class SurrogateTokenizer:
                     cache[key] = text
             out.append(text)
         return out
+
+
+def find_t5_tokenizer(path: str = None):
+    """The reference's tokenizer (`T5Tokenizer.from_pretrained(backbone)`, src/main_generative_gram.py) if a SentencePiece
+    model exists on this machine: `path` / $GRAM_T5_TOKENIZER (a directory or a spiece.model file), the Hugging Face cache of
+    t5-small / t5-base, or a copy under the reference tree.  Returns None when there is none (the offline image ships none):
+    callers then use the surrogate tokenizer and say so.  With a real tokenizer the text path is
+    `CollatorGRAM(tokenizer, args)(samples)` (gram_b200/collator.py), exactly as in the reference."""
+    import glob
+    cands = [path, os.environ.get("GRAM_T5_TOKENIZER")]
+    home = os.path.expanduser("~/.cache/huggingface/hub")
+    for name in ("t5-small", "t5-base", "google-t5--t5-small", "google-t5--t5-base"):
+        cands += sorted(glob.glob(os.path.join(home, f"models--{name}", "snapshots", "*", "spiece.model")))
+    cands += sorted(glob.glob("/root/reference/**/spiece.model", recursive=True))
+    for c in cands:
+        if not c:
+            continue
+        f = os.path.join(c, "spiece.model") if os.path.isdir(c) else c
+        if os.path.isfile(f):
+            from transformers import T5Tokenizer
+            return T5Tokenizer(vocab_file=f)
+    return None
 
 
 class GramTestData:
@@ -248,6 +311,37 @@ class GramTestData:
         tgt = [[0] + self.item_tok[t].tolist() + [1] for t in targets]
         return dict(item_text_ids=ids, item_text_masks=mask, target_ids=tgt, target_items=list(targets),
                     user_ids=[f"u{u}" for u in users])
+
+    # ---- the same users as TEXT, for the collator (reference TestDatasetGRAM.construct_sentence / get_item) -----------
+    def item_text(self, i: int) -> str:
+        """'item: <lexid> ; similar items: <lexids joined by ' , '> ; <metadata>' (src/utils/indexing.py:209-211,315-320);
+        the synthetic metadata tokens are written as '<id>' words."""
+        tab, _ = self.item_passages()
+        parts = ["item:", self.all_items[i], ";", "similar items:"]
+        n_row = 1 + len(self.item_tok[i]) + 2
+        if self.similar is not None and self.top_k > 0:
+            sims = [s for s in self.similar[i, :self.top_k] if s >= 0]
+            for j, sidx in enumerate(sims):
+                if j:
+                    parts.append(",")
+                    n_row += 1
+                parts.append(self.all_items[sidx])
+                n_row += len(self.item_tok[sidx])
+        parts.append(";")
+        n_row += 1
+        parts += [f"<{int(t)}>" for t in tab[i, n_row:self.L - 1]]
+        return " ".join(parts)
+
+    def text_samples(self, users: Sequence[int]):
+        """[{'input': [user sentence, item passage, ...], 'output': target lexid, 'user_id': ...}] -- what the reference's
+        `TestDatasetGRAM.__getitem__` yields (src/data/test_dataset_gram.py:179-231) and `CollatorGRAM` consumes."""
+        out = []
+        for u in users:
+            hist, target = self.split(u)
+            sent = "What would user purchase after " + " ; ".join(self.all_items[h] for h in hist) + " ?"
+            out.append({"input": [sent] + [self.item_text(h) for h in hist], "output": self.all_items[target],
+                        "user_id": f"u{u}"})
+        return out
 
     # ---- cached-item path (SURVEY.md 8(f)-1): the item passages once, users as (prompt, item indices) ----------
     def item_table(self):
