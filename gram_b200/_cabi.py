@@ -18,7 +18,8 @@ GRAM_FLAG_SIMT_GEMM, GRAM_FLAG_KEEP_LOGITS, GRAM_FLAG_SIMT_ATTN, GRAM_FLAG_MMA_E
 GRAM_FLAG_ALL_ROWS = 32
 GRAM_FLAG_UNFUSED_NORM = 64
 GRAM_FLAG_UNFUSED_HEAD = 128
-GRAM_FLAG_NO_CHAIN = 256
+GRAM_FLAG_ENC_CHAIN = 256
+GRAM_FLAG_NO_DEC_CHAIN = 1024
 GRAM_FLAG_NO_L2_HINTS = 512
 K_CLASSES = ["gemm_enc", "enc_attn", "gemm_kv", "gemm_dec", "cross_attn", "lm_head", "beam", "other", "self_attn",
              "norm_enc", "norm_dec"]

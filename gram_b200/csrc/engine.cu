@@ -93,6 +93,7 @@ struct gram_handle {
   int Rcap = 0;
   float* dx = nullptr;
   void *dxn = nullptr, *dqkv = nullptr, *dao = nullptr, *dq = nullptr, *dff = nullptr;
+  float* dss = nullptr;                  // [Rcap][D/128] row sums of squares of dx (RMSNorm folded into the decoder GEMMs)
   void *sk = nullptr, *sv = nullptr;     // [Ld][Tmax][Rcap][HD]
   float *logits = nullptr, *lse = nullptr;
   void* lse_partial = nullptr;           // float2 [Rcap][ceil(V/128)]
@@ -326,7 +327,7 @@ int encoder_stack(gram_handle* h, const PackMeta& pm, int P, int L, int Mmax, cu
   const bool fused = c.dtype == GRAM_DTYPE_BF16 && !(c.flags & (GRAM_FLAG_UNFUSED_NORM | GRAM_FLAG_SIMT_GEMM)) &&
                      (D % 128) == 0 && gemm_tc_supported(3 * HD, D) && gemm_tc_supported(D, HD) &&
                      gemm_tc_supported(F, D) && gemm_tc_supported(D, F);
-  const bool chained = fused && !(c.flags & GRAM_FLAG_NO_CHAIN) && h->ffs != nullptr;
+  const bool chained = fused && (c.flags & GRAM_FLAG_ENC_CHAIN) && h->ffs != nullptr;
   GemmNormAux scaled;                  // consumer side
   scaled.row_ss = h->ss; scaled.eps = c.ln_eps;
   auto produce = [&](const float* ln_w) { GemmNormAux a; a.xb = h->xn; a.ss_out = h->ss; a.ln_w = ln_w; return a; };
@@ -415,9 +416,55 @@ int decoder_step(gram_handle* h, int R, int K, int users, int t, const int* anc,
   const int* mp = live ? lm.n_live : nullptr;
   const int* slot_row = live ? lm.slot_row : nullptr;
   const int *lstart = live ? lm.start : nullptr, *lcount = live ? h->bs.live_cnt : nullptr;
-  CKL(GRAM_K_OTHER, embed_rows(c.dtype, h->shared, live ? lm.tok : h->bs.tok, h->dx, R, mp, D, s));
+  // bf16: the three RMSNorms of every decoder layer are folded into the GEMMs around them exactly as in the encoder (the
+  // producer of the residual stream emits bf16(x * w) and the row sums of squares, the consumer scales its output rows),
+  // and cross-attention output projection -> wi -> wo run as one chain launch (gemm_chain.cu): 6 launches per layer
+  // instead of 12.  fp32 parity mode and GRAM_FLAG_UNFUSED_NORM keep the separate kernels.
+  const bool fused = c.dtype == GRAM_DTYPE_BF16 && !(c.flags & (GRAM_FLAG_UNFUSED_NORM | GRAM_FLAG_SIMT_GEMM)) &&
+                     (D % 128) == 0 && gemm_tc_supported(3 * HD, D) && gemm_tc_supported(D, HD) &&
+                     gemm_tc_supported(F, D) && gemm_tc_supported(D, F) && gemm_tc_supported(HD, D);
+  const bool chained = fused && !(c.flags & GRAM_FLAG_NO_DEC_CHAIN) && h->ffs != nullptr;
+  GemmNormAux scaled;
+  scaled.row_ss = h->dss; scaled.eps = c.ln_eps;
+  auto produce = [&](const float* ln_w) { GemmNormAux a; a.xb = h->dxn; a.ss_out = h->dss; a.ln_w = ln_w; return a; };
+  const int* toks = live ? lm.tok : h->bs.tok;
+  if (fused) CKL(GRAM_K_OTHER, embed_rows_norm(h->shared, toks, h->dx, h->dxn, h->dss, h->dec[0].ln0, R, mp, D, s));
+  else CKL(GRAM_K_OTHER, embed_rows(c.dtype, h->shared, toks, h->dx, R, mp, D, s));
   for (int l = 0; l < h->Ld; ++l) {
     const LayerW& W = h->dec[l];
+    if (fused) {
+      const float* ln_next = l + 1 < h->Ld ? h->dec[l + 1].ln0 : nullptr;
+      RC(gemm(h, GRAM_K_GEMM_DEC, EPI_STORE, h->dxn, W.qkv, h->dqkv, R, mp, 3 * HD, D, s, &scaled));
+      CKL(GRAM_K_SELF_ATTN, dec_self_attention(c.dtype, h->dqkv, (char*)h->sk + l * layer_cache, (char*)h->sv + l * layer_cache,
+                                           anc, c.max_length, h->dec_bias_lut, h->n_dec_lut, h->dao, R, K, h->H, h->dk, t,
+                                           slot_row, mp, s));
+      const GemmNormAux a1 = produce(W.ln1);
+      RC(gemm(h, GRAM_K_GEMM_DEC, EPI_RESID_NORM, h->dao, W.o, h->dx, R, mp, D, HD, s, &a1));
+      RC(gemm(h, GRAM_K_GEMM_DEC, EPI_STORE, h->dxn, W.cq, h->dq, R, mp, HD, D, s, &scaled));
+      if (!(c.flags & GRAM_FLAG_SIMT_ATTN) && cross_attention_mma_supported(K, h->H, h->dk)) {
+        CKL(GRAM_K_CROSS_ATTN, cross_attention_mma(h->dq, h->ckv, (size_t)h->Mcap + 256, (size_t)h->Ld * 2 * HD, l * 2 * HD,
+                                                   l * 2 * HD + HD, h->pm.ustart, h->pm.uorder, h->pm.tok_valid, h->dao, users, K, h->H,
+                                                   lstart, lcount, s));
+      } else {
+        CKL(GRAM_K_CROSS_ATTN, cross_attention(c.dtype, h->dq, h->ckv, (size_t)h->Ld * 2 * HD, l * 2 * HD, l * 2 * HD + HD,
+                                               h->pm.ustart, h->pm.tok_valid, h->dao, users, K, h->H, h->dk, lstart, lcount, s));
+      }
+      if (chained) {
+        CKL(GRAM_K_GEMM_DEC, enc_chain(h->dao, W.co, h->dx, h->dxn, h->dss, W.wi, W.wo, h->ffs, W.ln2, ln_next, c.ln_eps, R, mp,
+                                       D, HD, F, h->num_sms, (c.flags & GRAM_FLAG_NO_L2_HINTS) ? 0 : 1, h->pm.err, s));
+      } else {
+        const GemmNormAux a2 = produce(W.ln2);
+        RC(gemm(h, GRAM_K_GEMM_DEC, EPI_RESID_NORM, h->dao, W.co, h->dx, R, mp, D, HD, s, &a2));
+        RC(gemm(h, GRAM_K_GEMM_DEC, EPI_RELU, h->dxn, W.wi, h->dff, R, mp, F, D, s, &scaled));
+        if (ln_next) {
+          const GemmNormAux a0 = produce(ln_next);
+          RC(gemm(h, GRAM_K_GEMM_DEC, EPI_RESID_NORM, h->dff, W.wo, h->dx, R, mp, D, F, s, &a0));
+        } else {
+          RC(gemm(h, GRAM_K_GEMM_DEC, EPI_RESID, h->dff, W.wo, h->dx, R, mp, D, F, s));
+        }
+      }
+      continue;
+    }
     CKL(GRAM_K_NORM_DEC, rmsnorm_rows(c.dtype, h->dx, W.ln0, h->dxn, R, mp, D, c.ln_eps, 1.f, nullptr, nullptr, s));
     RC(gemm(h, GRAM_K_GEMM_DEC, EPI_STORE, h->dxn, W.qkv, h->dqkv, R, mp, 3 * HD, D, s));
     // cache slices are indexed [t][R][HD] with the *current* R as the row pitch
@@ -572,6 +619,7 @@ int gram_create(const gram_config* cfg, gram_handle** out) {
   DAC(h->dx, R * D * 4);
   DAC(h->dxn, R * D * esz); DAC(h->dqkv, R * 3 * HD * esz); DAC(h->dao, R * HD * esz); DAC(h->dq, R * HD * esz);
   DAC(h->dff, R * F * esz);
+  DAC(h->dss, R * (size_t)((D + 127) / 128) * 4);
   DAC(h->sk, (size_t)h->Ld * ML * R * HD * esz); DAC(h->sv, (size_t)h->Ld * ML * R * HD * esz);
   DAC(h->logits, R * V * 4); DAC(h->lse, R * 4);
   DAC(h->lse_partial, R * (size_t)((V + 127) / 128) * 8);

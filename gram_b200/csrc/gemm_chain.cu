@@ -233,6 +233,7 @@ enc_chain_kernel(const __grid_constant__ CUtensorMap map_ao, const __grid_consta
     const int r = quad * 32 + lane;
     const bool issuer = (warp == 2 && lane == 0);
     int acc = 0; uint32_t acc_phase = 0;
+    int published = 0;                                        // issuer: tiles announced complete to the producer warp
     uint32_t xround = 0;                                      // residual rounds consumed so far; round q lives in staging buffer q & 1
     const int ssb = a.D >> 7;
     const float inv_d = 1.0f / (float)a.D;
@@ -251,10 +252,17 @@ enc_chain_kernel(const __grid_constant__ CUtensorMap map_ao, const __grid_consta
       const int m_blk = cta + t.it * G;
       const int row0 = m_blk * BM, row = row0 + r;
       if (issuer) {
-        // every store of the earlier tiles has completed (not merely been read): publish it to the producer warp
-        tma_store_wait_all();
-        fence_proxy_async_all();
-        *done_ctr = (uint32_t)seq;
+        // staging buffers: every earlier store has READ its source.  Publication to the producer warp: all stores of the
+        // tiles before the previous one have COMPLETED -- only the previous tile's own bulk groups (2 for a first-half
+        // tile, one per round for a residual tile) may still be in flight, so this wait is on stores that are at least a
+        // whole tile old and never stalls the epilogue (waiting for everything here cost a store round trip per tile)
+        tma_store_wait_read();
+        if (seq >= 1) {
+          if (decode(seq - 1, n_iter, nd, nf).type == T_WI) asm volatile("cp.async.bulk.wait_group 2;" ::: "memory");
+          else asm volatile("cp.async.bulk.wait_group 4;" ::: "memory");
+          fence_proxy_async_all();
+          if (seq - 1 > published) { published = seq - 1; *done_ctr = (uint32_t)published; }   // never moves backwards
+        }
       }
       if (t.type == T_WI) {
         // ---- first half of the FF: relu(acc * rsqrt(mean x^2 + eps)) -> bf16 -> this CTA's ff scratch ----
@@ -390,15 +398,19 @@ enc_chain_kernel(const __grid_constant__ CUtensorMap map_ao, const __grid_consta
           }
         }
       }
-      if (issuer && seq + 1 < total) {
-        // the NEXT tile reads what this one wrote (first block of the CTA: o-projection -> first half; last block:
-        // first half -> second half): its producer cannot wait for the lazy publication above
-        const Tile nx = decode(seq + 1, n_iter, nd, nf);
-        const int nkb = nx.type == T_WI ? kb_wi : kb_wo;
-        if (nx.type != T_O && need_of(nx, nkb - 1, nd, nf) == seq + 1) {
+      if (issuer) {
+        // one of the next two tiles reads what this one wrote (first block of the CTA: o-projection -> first half; last
+        // block: first half -> second half): the lazy publication above would come too late for its producer
+        bool eager = false;
+        for (int j = 1; j <= 2 && seq + j < total; ++j) {
+          const Tile nx = decode(seq + j, n_iter, nd, nf);
+          if (nx.type != T_O && need_of(nx, (nx.type == T_WI ? kb_wi : kb_wo) - 1, nd, nf) >= seq + 1) eager = true;
+        }
+        if (eager) {
           tma_store_wait_all();
           fence_proxy_async_all();
-          *done_ctr = (uint32_t)(seq + 1);
+          published = seq + 1;
+          *done_ctr = (uint32_t)published;
         }
       }
       if (++acc == 2) { acc = 0; acc_phase ^= 1u; }

@@ -72,11 +72,14 @@ enum {
                                       row scale instead of after)                                                     */
   GRAM_FLAG_UNFUSED_HEAD = 128,    /* bf16: materialise the [rows, V] fp32 logits and reduce them with lse_rows instead of the
                                       fused log-softmax epilogue of the vocabulary GEMM (A-B timing / cross-check)     */
-  GRAM_FLAG_NO_CHAIN = 256,        /* bf16 encoder: run the o-projection, wi and wo GEMMs of a layer as three launches (A-B timing).
-                                      Default: one persistent launch per layer chains them per 128-token row block and
-                                      keeps ff / the normalised rows in an L2-resident per-CTA scratch (gemm_chain.cu);
-                                      same arithmetic per element, bit-identical results                              */
+  GRAM_FLAG_ENC_CHAIN = 256,       /* bf16 encoder: ONE persistent launch per layer chains the o-projection, wi and wo GEMMs per
+                                      128-token row block and hands ff / the normalised rows from GEMM to GEMM through a per-CTA
+                                      scratch (gemm_chain.cu) instead of three launches.  Same arithmetic per element,
+                                      bit-identical results.  Opt-in: measured slower than the three launches at the
+                                      headline batch (the scratch does not stay L2-resident there)  */
   GRAM_FLAG_NO_L2_HINTS = 512,     /* chain kernel without L2 cache-policy hints on its TMA traffic (A-B timing)      */
+  GRAM_FLAG_NO_DEC_CHAIN = 1024,   /* bf16 decoder: cross-attention output projection, wi and wo as three launches instead of
+                                      one chain launch per layer (A-B timing)                                         */
   GRAM_FLAG_ALL_ROWS = 32          /* decode every beam row at every step, as the reference does (A-B timing).  Default:
                                       beams that are dead (-inf score: the user had fewer than K finite continuations,
                                       typically item ids that ended a token earlier) and the beams of users whose

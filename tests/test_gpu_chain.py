@@ -107,8 +107,9 @@ def test_chain_op_last_layer_variant():
 
 
 def test_chained_encoder_is_bit_identical_to_three_launches():
-    """The engine with the chain (default) against GRAM_FLAG_NO_CHAIN on a many-passage batch: the fused memory, and the
-    rankings that follow from it, are identical bits."""
+    """The engine with the encoder chain (GRAM_FLAG_ENC_CHAIN) against the three launches per layer on a many-passage batch:
+    the fused memory, and the rankings that follow from it, are identical bits; the decoder-side chain likewise
+    (GRAM_FLAG_NO_DEC_CHAIN is the three-launch decoder)."""
     from gram_b200 import GRAM, GramConfig, Trie, _cabi, prefix_allowed_tokens_fn, synth
     cfg = GramConfig.t5_small(max_seq_len=128, max_item_num=8)
     sd = synth.make_state_dict(cfg, seed=2)
@@ -118,7 +119,7 @@ def test_chained_encoder_is_bit_identical_to_three_launches():
     fn = prefix_allowed_tokens_fn(Trie(seqs))
     ml = max(len(s) for s in seqs)
     outs = []
-    for flags in (0, _cabi.GRAM_FLAG_NO_CHAIN):
+    for flags in (_cabi.GRAM_FLAG_ENC_CHAIN, 0, _cabi.GRAM_FLAG_NO_DEC_CHAIN):
         m = GRAM(cfg, dtype="bf16", device="cuda:0", flags=flags, max_users=96)
         m.load_state_dict(sd)
         mem = m.encode(ids, mask)
@@ -127,5 +128,6 @@ def test_chained_encoder_is_bit_identical_to_three_launches():
         outs.append((mem.cpu(), o["sequences"].cpu(), o["sequences_scores"].cpu()))
         del m
     assert torch.isfinite(outs[0][0]).all()
-    assert torch.equal(outs[0][0], outs[1][0])
-    assert torch.equal(outs[0][1], outs[1][1]) and torch.equal(outs[0][2], outs[1][2])
+    for o in outs[1:]:
+        assert torch.equal(outs[0][0], o[0])
+        assert torch.equal(outs[0][1], o[1]) and torch.equal(outs[0][2], o[2])
