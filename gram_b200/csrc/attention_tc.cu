@@ -1,4 +1,6 @@
-// tcgen05 / TMEM encoder self-attention for passages of up to 128 tokens (bf16, d_kv = 64).
+// tcgen05 / TMEM encoder self-attention for passages of up to 256 tokens (bf16, d_kv = 64).
+// (NKB = 1: passages of <= 128 tokens, the shipped datasets; NKB = 2: up to 256 tokens = two 128-key blocks and up to two
+//  128-row query blocks per passage, BASELINE.json configs[4])
 //
 // Reference semantics: per-passage bidirectional T5 self-attention, scores = Q K^T (no 1/sqrt(d) scale) + relative
 // position bias (layer-0 table shared by all layers) + key padding mask, fp32 softmax, P V
@@ -99,13 +101,21 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
 }
 // D = f32, A = B = bf16, M = 128
 constexpr uint32_t IDESC_QK = (1u << 4) | (1u << 7) | (1u << 10) | ((128u >> 3) << 17) | ((128u >> 4) << 24);              // N=128, B K-major
+constexpr uint32_t IDESC_QK2 = (1u << 4) | (1u << 7) | (1u << 10) | ((256u >> 3) << 17) | ((128u >> 4) << 24);             // N=256 (two key blocks)
 constexpr uint32_t IDESC_PV = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 16) | ((64u >> 3) << 17) | ((128u >> 4) << 24);  // N=64, B MN-major
 
 constexpr int CONSUMERS = 128;            // warps 0-3: softmax + epilogue, thread r = query row r = TMEM lane r
 constexpr int THREADS = CONSUMERS + 32;   // warp 4: one elected thread issues every TMA load and every tcgen05.mma
-constexpr int TMEM_COLS = 256;            // two S/O accumulators of 128 columns
-constexpr uint32_t STAGE = 3 * BOX;       // Q | K | V of one (passage, head); P later overwrites Q | K
 constexpr int NSTAGE = 2;
+// Stage of one work item with NKB key blocks: Q | K_0 .. K_{NKB-1} | (pad) | V_0 .. V_{NKB-1}.  P (128 rows x 128*NKB keys,
+// bf16, K-major boxes of 64 keys) later overwrites everything in front of V: Q | K (NKB = 1), Q | K_0 | K_1 | pad (NKB = 2).
+template <int NKB> struct Geo {
+  static constexpr uint32_t P_BYTES = 2u * NKB * BOX;              // 32 / 64 KiB
+  static constexpr uint32_t V_OFF = P_BYTES;
+  static constexpr uint32_t STAGE = P_BYTES + NKB * BOX;           // 48 / 96 KiB
+  static constexpr int TMEM_COLS = 2 * 128 * NKB;                  // two S/O accumulators of 128*NKB columns
+  static constexpr int ACC = 128 * NKB;
+};
 enum { B_FULL = 0, B_EMPTY = 2, B_SFULL = 4, B_SFREE = 6, B_PREADY = 8, B_OFULL = 10, B_COUNT = 12 };
 
 __device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
@@ -137,10 +147,18 @@ __device__ __forceinline__ void consumer_bar() { asm volatile("bar.sync 1, 128;"
 // The non-persistent version (one CTA per item, four CTAs per SM) spent 5.9 us per item on a serial chain of CTA start,
 // TMEM allocation, LUT load, TMA latency, MMA, softmax, MMA, store for 0.4 us of issue work (ncu: 28 % issue
 // utilisation, long-scoreboard stalls).
-__global__ void __launch_bounds__(THREADS, 2)
+// NKB = 2 (passages of 129-256 tokens): a work item is (passage, 128-row query block, head); it loads the query block's Q
+// rows and the passage's key blocks that hold tokens (one or two), S is 128 x 128*nkb, P covers 128*nkb keys; the
+// 96 KiB stages and 512 TMEM columns leave room for one CTA per SM.
+template <int NKB>
+__global__ void __launch_bounds__(THREADS, NKB == 1 ? 2 : 1)
 enc_attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, bf16* __restrict__ out,
                         const int* __restrict__ plen, const int* __restrict__ poff,
                         const uint8_t* __restrict__ tok_valid, const float* __restrict__ bias_lut, int Lb, int H, int P) {
+  using G = Geo<NKB>;
+  constexpr uint32_t STAGE = G::STAGE;
+  constexpr uint32_t ACC = (uint32_t)G::ACC;
+  constexpr int NCH = 4 * NKB;                                                  // 32-key chunks of a score row
   const int HD = H * DK;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
@@ -152,9 +170,9 @@ enc_attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, bf16* __res
   float* lut = reinterpret_cast<float*>(aux);                                  // [H][lut_n], log2 units
   float* bhi = reinterpret_cast<float*>(aux + lut_bytes);                      // [H] largest LUT entry of the head
   float* blo = bhi + 32;                                                       // [H] smallest
-  uint32_t* masks = reinterpret_cast<uint32_t*>(aux + lut_bytes + 256);        // [4] key visibility of the current passage
-  const uint32_t bars = base + NSTAGE * STAGE + lut_bytes + 256 + 16;          // B_COUNT mbarriers
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aux + lut_bytes + 256 + 16 + 8 * B_COUNT);
+  uint32_t* masks = reinterpret_cast<uint32_t*>(aux + lut_bytes + 256);        // [8] key visibility of the current passage
+  const uint32_t bars = base + NSTAGE * STAGE + lut_bytes + 256 + 32;          // B_COUNT mbarriers
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aux + lut_bytes + 256 + 32 + 8 * B_COUNT);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   auto bar = [&](int i) { return bars + 8u * (uint32_t)i; };
 
@@ -165,7 +183,7 @@ enc_attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, bf16* __res
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 4) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(G::TMEM_COLS) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   // bias LUTs of every head in log2 units (the softmax runs on exp2), and each head's range
@@ -190,28 +208,37 @@ enc_attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, bf16* __res
   if (warp == 4) {
     // ===================== producer: TMA + MMA issue =====================
     if (lane == 0) {
-      int p_it = (int)blockIdx.x - (int)gridDim.x, h_it = H - 1, row0_it = 0;
+      // items of this CTA in the order (passage, query block, head); nkb = key blocks of the passage that hold tokens
+      int p_it = (int)blockIdx.x - (int)gridDim.x, h_it = H - 1, qb_it = 0, nqb_it = 1, row0_it = 0;
       bool tma_done = false;
-      auto advance = [&]() {                               // next (passage, head) of this CTA, skipping empty passages
+      auto advance = [&]() {
         if (++h_it < H) return;
         h_it = 0;
+        if (++qb_it < nqb_it) return;
+        qb_it = 0;
         for (;;) {
           p_it += (int)gridDim.x;
           if (p_it >= P) { tma_done = true; return; }
-          if (plen[p_it] > 0) { row0_it = poff[p_it]; return; }
+          const int l = plen[p_it];
+          if (l > 0) { row0_it = poff[p_it]; nqb_it = (l + LQ - 1) / LQ; return; }
         }
       };
       advance();
       uint32_t k_tma = 0, k_m1 = 0, k_m2 = 0;              // items loaded / S issued / O issued
+      uint32_t nkb_of[NSTAGE] = {1u, 1u};                  // key blocks of the item in each stage
       while (!(tma_done && k_m2 == k_tma)) {
         if (!tma_done && k_tma < k_m2 + NSTAGE) {
           const uint32_t st = k_tma & 1u, ph = (k_tma >> 1) & 1u;
           if (mbar_test(bar(B_EMPTY + st), ph ^ 1u)) {
             const uint32_t sb = base + st * STAGE;
-            mbar_arrive_expect_tx(bar(B_FULL + st), STAGE);
-            tma_load_2d(sb, &map_qkv, bar(B_FULL + st), h_it * DK, row0_it);
-            tma_load_2d(sb + BOX, &map_qkv, bar(B_FULL + st), HD + h_it * DK, row0_it);
-            tma_load_2d(sb + 2 * BOX, &map_qkv, bar(B_FULL + st), 2 * HD + h_it * DK, row0_it);
+            const uint32_t nkb = (uint32_t)nqb_it;         // = ceil(len / 128)
+            nkb_of[st] = nkb;
+            mbar_arrive_expect_tx(bar(B_FULL + st), BOX * (1u + 2u * nkb));
+            tma_load_2d(sb, &map_qkv, bar(B_FULL + st), h_it * DK, row0_it + qb_it * LQ);
+            for (uint32_t kb = 0; kb < nkb; ++kb) {
+              tma_load_2d(sb + BOX * (1u + kb), &map_qkv, bar(B_FULL + st), HD + h_it * DK, row0_it + (int)kb * LQ);
+              tma_load_2d(sb + G::V_OFF + BOX * kb, &map_qkv, bar(B_FULL + st), 2 * HD + h_it * DK, row0_it + (int)kb * LQ);
+            }
             ++k_tma;
             advance();
           }
@@ -221,10 +248,11 @@ enc_attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, bf16* __res
           if (mbar_test(bar(B_FULL + st), ph) && mbar_test(bar(B_SFREE + st), ph ^ 1u)) {
             tcgen05_fence_after();
             const uint32_t sb = base + st * STAGE;
-            const uint64_t dq = make_desc(sb), dk = make_desc(sb + BOX);
+            const uint64_t dq = make_desc(sb), dk = make_desc(sb + BOX);     // key blocks are contiguous 8-row groups
+            const uint32_t idesc = (NKB == 2 && nkb_of[st] == 2u) ? IDESC_QK2 : IDESC_QK;
 #pragma unroll
             for (int kk = 0; kk < DK / 16; ++kk)
-              umma_bf16(tmem + st * 128u, dq + (uint64_t)(kk * 2), dk + (uint64_t)(kk * 2), IDESC_QK, kk ? 1u : 0u);
+              umma_bf16(tmem + st * ACC, dq + (uint64_t)(kk * 2), dk + (uint64_t)(kk * 2), idesc, kk ? 1u : 0u);
             umma_commit(bar(B_SFULL + st));
             ++k_m1;
           }
@@ -234,11 +262,11 @@ enc_attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, bf16* __res
           if (mbar_test(bar(B_PREADY + st), ph)) {
             tcgen05_fence_after();
             const uint32_t sb = base + st * STAGE;
-#pragma unroll
-            for (int ks = 0; ks < LQ / 16; ++ks) {
-              const uint64_t dp = make_desc(sb + ((ks >> 2) ? BOX : 0u) + (uint32_t)(ks & 3) * 32u);
-              const uint64_t dv = make_desc(sb + 2 * BOX + (uint32_t)ks * 2048u);
-              umma_bf16(tmem + st * 128u, dp, dv, IDESC_PV, ks ? 1u : 0u);     // O re-uses the (fully read) S columns
+            const int nks = (LQ / 16) * (int)nkb_of[st];   // 16-key steps over the key blocks that were loaded
+            for (int ks = 0; ks < nks; ++ks) {
+              const uint64_t dp = make_desc(sb + (uint32_t)(ks >> 2) * BOX + (uint32_t)(ks & 3) * 32u);
+              const uint64_t dv = make_desc(sb + G::V_OFF + (uint32_t)ks * 2048u);
+              umma_bf16(tmem + st * ACC, dp, dv, IDESC_PV, ks ? 1u : 0u);      // O re-uses the (fully read) S columns
             }
             umma_commit(bar(B_OFULL + st));
             ++k_m2;
@@ -248,15 +276,19 @@ enc_attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, bf16* __res
     }
     __syncwarp();
   } else {
-    // ===================== softmax + epilogue: thread r owns query row r =====================
+    // ===================== softmax + epilogue: thread r owns query row r of the block =====================
     const int r = tid;
     const uint32_t tlane = (uint32_t)(warp * 32) << 16;
     // ---- iteration over this CTA's items; the key-visibility masks are rebuilt when the passage changes ----
-    int p = (int)blockIdx.x - (int)gridDim.x, h = H - 1, len = 0, row0 = 0;
-    uint32_t mkc[4] = {0u, 0u, 0u, 0u};
+    int p = (int)blockIdx.x - (int)gridDim.x, h = H - 1, qb = 0, nqb = 1, len = 0, row0 = 0;
+    uint32_t mkc[NCH];
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) mkc[c] = 0u;
     auto next_item = [&]() -> bool {
       if (++h < H) return true;
       h = 0;
+      if (++qb < nqb) return true;
+      qb = 0;
       for (;;) {
         p += (int)gridDim.x;
         if (p >= P) return false;
@@ -264,13 +296,22 @@ enc_attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, bf16* __res
         if (len > 0) break;
       }
       row0 = poff[p];
-      const bool vis = r < len && tok_valid[row0 + r] != 0;
-      const unsigned m = __ballot_sync(0xffffffffu, vis);
+      nqb = (len + LQ - 1) / LQ;
+      unsigned m[NKB];
+#pragma unroll
+      for (int kb = 0; kb < NKB; ++kb) {
+        const int key = kb * LQ + r;
+        const bool vis = key < len && tok_valid[row0 + key] != 0;
+        m[kb] = __ballot_sync(0xffffffffu, vis);
+      }
       consumer_bar();                                    // every warp is done with the previous passage's masks
-      if (lane == 0) masks[warp] = m;
+      if (lane == 0) {
+#pragma unroll
+        for (int kb = 0; kb < NKB; ++kb) masks[kb * 4 + warp] = m[kb];
+      }
       consumer_bar();
 #pragma unroll
-      for (int c = 0; c < 4; ++c) mkc[c] = masks[c];
+      for (int c = 0; c < NCH; ++c) mkc[c] = masks[c];
       return true;
     };
     // Pass 1 of item k (head hh): an upper bound of the row maximum in log2 units.  Softmax is invariant to the shift
@@ -278,17 +319,17 @@ enc_attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, bf16* __res
     // takes max(raw s) -- one FMNMX per score -- and bounds the bias by the head's largest LUT entry; the exact
     // bias + mask walk is kept for the passage's tail chunk, and for every chunk when the bias table spans more than
     // 2^64 (then the bound could push small terms into underflow).
-    auto pass1 = [&](uint32_t k, int hh) -> float {
+    auto pass1 = [&](uint32_t k, int hh, int qrow) -> float {
       const uint32_t st = k & 1u, ph = (k >> 1) & 1u;
-      const uint32_t trow = tmem + st * 128u + tlane;
-      const float* lrow = lut + hh * lut_n + (Lb - 1 - r);
+      const uint32_t trow = tmem + st * ACC + tlane;
+      const float* lrow = lut + hh * lut_n + (Lb - 1 - min(qrow, Lb - 1));     // rows past the table are rows past the passage
       const float bias_hi = bhi[hh];
       const bool exact = !(bias_hi - blo[hh] <= 64.f);
       mbar_wait(bar(B_SFULL + st), ph);
       tcgen05_fence_after();
       float mraw = -INFINITY, mex = -INFINITY;
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
+      for (int c = 0; c < NCH; ++c) {
         const uint32_t mk = mkc[c];
         if (mk == 0u) continue;                          // chunk past the passage (uniform across the CTA)
         uint32_t v[32];
@@ -308,18 +349,20 @@ enc_attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, bf16* __res
 
     uint32_t k = 0;
     bool have = next_item();
-    float mb = have ? pass1(0u, h) : 0.f;
+    float mb = have ? pass1(0u, h, qb * LQ + r) : 0.f;
     while (have) {
       const uint32_t st = k & 1u, ph = (k >> 1) & 1u;
-      const uint32_t trow = tmem + st * 128u + tlane;
-      const uint32_t sQ = base + st * STAGE, sK = sQ + BOX;
-      // bias2 of (query r, key j) = lut[h][j - r + Lb - 1]; only read for j < len <= Lb
-      const float* lrow = lut + h * lut_n + (Lb - 1 - r);
+      const uint32_t trow = tmem + st * ACC + tlane;
+      const uint32_t sQ = base + st * STAGE;
+      const int nch = 4 * ((len + LQ - 1) / LQ);         // chunks of the key blocks that were loaded
+      // bias2 of (query q, key j) = lut[h][j - q + Lb - 1]; only read for j < len <= Lb
+      const float* lrow = lut + h * lut_n + (Lb - 1 - min(qb * LQ + r, Lb - 1));
       // ---- pass 2: p = 2^(s*log2e + bias2 - mb), row sum, P (bf16) into the K-major 128B-swizzled operand layout:
       //      box b = keys [64b, 64b+64), row r, 16-byte chunk j ^ (r & 7) ----
       float sum = 0.f;
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
+      for (int c = 0; c < NCH; ++c) {
+        if (c >= nch) break;                             // key block without tokens: not loaded, not multiplied
         const uint32_t mk = mkc[c];
         float pr[32];
         if (mk == 0u) {
@@ -353,8 +396,8 @@ enc_attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, bf16* __res
             __nv_bfloat162 h2 = __floats2bfloat162_rn(pr[q4 * 8 + 2 * e], pr[q4 * 8 + 2 * e + 1]);
             pk[e] = *reinterpret_cast<uint32_t*>(&h2);
           }
-          const int ch = c * 4 + q4;                     // 16-byte chunk of the 128-key row
-          const uint32_t box = (ch >> 3) ? sK : sQ;
+          const int ch = c * 4 + q4;                     // 16-byte chunk of the key row
+          const uint32_t box = sQ + (uint32_t)(ch >> 3) * BOX;
           const uint32_t addr = box + (uint32_t)r * 128u + (uint32_t)((((ch & 7) ^ (r & 7)) & 7) << 4);
           asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pk[0]), "r"(pk[1]), "r"(pk[2]), "r"(pk[3]) : "memory");
         }
@@ -363,10 +406,10 @@ enc_attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, bf16* __res
       fence_async_smem();                                // P is visible to the tensor core's (async) proxy
       mbar_arrive(bar(B_PREADY + st));
       // ---- while the tensor core computes O = P V: move on to the next item and run its pass 1 ----
-      const int cur_h = h, cur_len = len, cur_row0 = row0;
+      const int cur_h = h, cur_len = len, cur_row0 = row0, cur_q0 = qb * LQ;
       have = next_item();
       float mb_next = 0.f;
-      if (have) mb_next = pass1(k + 1u, h);
+      if (have) mb_next = pass1(k + 1u, h, qb * LQ + r);
       // ---- epilogue of the current item ----
       mbar_wait(bar(B_OFULL + st), ph);
       tcgen05_fence_after();
@@ -403,7 +446,8 @@ enc_attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, bf16* __res
           uint4 val;
           asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(val.x), "=r"(val.y), "=r"(val.z), "=r"(val.w)
                        : "r"(sQ + (uint32_t)rr * 128u + (uint32_t)(((chunk ^ (rr & 7)) & 7) << 4)) : "memory");
-          if (rr < cur_len) *reinterpret_cast<uint4*>(out + (size_t)(cur_row0 + rr) * HD + cur_h * DK + chunk * 8) = val;
+          if (cur_q0 + rr < cur_len)
+            *reinterpret_cast<uint4*>(out + (size_t)(cur_row0 + cur_q0 + rr) * HD + cur_h * DK + chunk * 8) = val;
         }
       }
       mbar_arrive(bar(B_EMPTY + st));                    // the stage (P/O staging rows and V) may be reloaded
@@ -415,7 +459,7 @@ enc_attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, bf16* __res
   __syncthreads();
   if (warp == 4) {
     tcgen05_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(G::TMEM_COLS) : "memory");
   }
 }
 
@@ -453,20 +497,29 @@ bool get_map(const void* ptr, size_t rows, size_t cols, CUtensorMap* out) {
 
 }  // namespace ta
 
-bool enc_attention_tc_supported(int dk, int Lmax, int Lb) { return dk == ta::DK && Lmax <= ta::LQ && Lb <= 256; }
+static size_t tc_smem_bytes(int nkb, int H, int Lb) {
+  const size_t stage = nkb == 1 ? ta::Geo<1>::STAGE : ta::Geo<2>::STAGE;
+  return (size_t)ta::NSTAGE * stage + (((size_t)H * (2 * Lb - 1) * 4 + 15) / 16) * 16 + 256 + 32 + 8 * ta::B_COUNT + 16 + 1024;
+}
+
+// Lmax <= 128: two CTAs per SM with 48 KiB stages; Lmax <= 256: one CTA per SM, 96 KiB stages + the bias LUT must fit 227 KiB
+bool enc_attention_tc_supported(int dk, int Lmax, int Lb, int H) {
+  if (dk != ta::DK || Lb > 256 || H > 32 || Lmax > 2 * ta::LQ) return false;
+  return tc_smem_bytes(Lmax <= ta::LQ ? 1 : 2, H, Lb) <= 227 * 1024;
+}
 
 cudaError_t enc_attention_tc(const void* qkv, size_t qkv_rows, void* out, const int* plen, const int* poff,
-                             const uint8_t* tok_valid, const float* bias_lut, int Lb, int P, int H, cudaStream_t s) {
+                             const uint8_t* tok_valid, const float* bias_lut, int Lb, int P, int H, int Lmax, cudaStream_t s) {
   if (P <= 0) return cudaSuccess;
-  if (H > 32) return cudaErrorInvalidValue;
+  if (!enc_attention_tc_supported(ta::DK, Lmax, Lb, H)) return cudaErrorInvalidValue;
   std::lock_guard<std::mutex> lk(ta::g_mu);
   CUtensorMap map;
   if (!ta::get_map(qkv, qkv_rows, (size_t)3 * H * ta::DK, &map)) return cudaErrorUnknown;
-  const size_t smem = (size_t)ta::NSTAGE * ta::STAGE + (((size_t)H * (2 * Lb - 1) * 4 + 15) / 16) * 16 + 256 + 16 +
-                      8 * ta::B_COUNT + 16 + 1024;
-  static SmemAttr attr;
+  const int nkb = Lmax <= ta::LQ ? 1 : 2;
+  const size_t smem = tc_smem_bytes(nkb, H, Lb);
+  static SmemAttr attr[2];
   {
-    cudaError_t e = attr.ensure(ta::enc_attention_tc_kernel, smem);
+    cudaError_t e = nkb == 1 ? attr[0].ensure(ta::enc_attention_tc_kernel<1>, smem) : attr[1].ensure(ta::enc_attention_tc_kernel<2>, smem);
     if (e != cudaSuccess) return e;
   }
   static int sms[64];
@@ -474,8 +527,13 @@ cudaError_t enc_attention_tc(const void* qkv, size_t qkv_rows, void* out, const 
   cudaGetDevice(&dev);
   dev &= 63;
   if (sms[dev] == 0 && cudaDeviceGetAttribute(&sms[dev], cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return cudaGetLastError();
-  const int grid = P < 2 * sms[dev] ? P : 2 * sms[dev];            // two persistent CTAs per SM
-  ta::enc_attention_tc_kernel<<<grid, ta::THREADS, smem, s>>>(map, (bf16*)out, plen, poff, tok_valid, bias_lut, Lb, H, P);
+  if (nkb == 1) {
+    const int grid = P < 2 * sms[dev] ? P : 2 * sms[dev];          // two persistent CTAs per SM
+    ta::enc_attention_tc_kernel<1><<<grid, ta::THREADS, smem, s>>>(map, (bf16*)out, plen, poff, tok_valid, bias_lut, Lb, H, P);
+  } else {
+    const int grid = P < sms[dev] ? P : sms[dev];
+    ta::enc_attention_tc_kernel<2><<<grid, ta::THREADS, smem, s>>>(map, (bf16*)out, plen, poff, tok_valid, bias_lut, Lb, H, P);
+  }
   return cudaGetLastError();
 }
 

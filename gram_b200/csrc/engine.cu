@@ -338,9 +338,9 @@ int encoder_stack(gram_handle* h, const PackMeta& pm, int P, int L, int Mmax, cu
     if (!fused) CKL(GRAM_K_NORM_ENC, rmsnorm_rows(c.dtype, h->x, W.ln0, h->xn, Mmax, mp, D, c.ln_eps, 1.f, nullptr, nullptr, s));
     RC(gemm(h, GRAM_K_GEMM_ENC, EPI_STORE, h->xn, W.qkv, h->qkv, Mmax, mp, 3 * HD, D, s, fused ? &scaled : nullptr));
     if (c.dtype == GRAM_DTYPE_BF16 && !(c.flags & (GRAM_FLAG_MMA_ENC_ATTN | GRAM_FLAG_SIMT_ATTN)) &&
-        enc_attention_tc_supported(h->dk, L, h->Lb)) {
+        enc_attention_tc_supported(h->dk, L, h->Lb, h->H) && (L <= 128 || !(c.flags & GRAM_FLAG_MMA_LONG_ATTN))) {
       CKL(GRAM_K_ENC_ATTN, enc_attention_tc(h->qkv, (size_t)h->Mcap + 256, h->ao, pm.plen, pm.poff, pm.tok_valid,
-                                            h->enc_bias_lut, h->Lb, P, h->H, s));
+                                            h->enc_bias_lut, h->Lb, P, h->H, L, s));
     } else if (c.dtype == GRAM_DTYPE_BF16 && !(c.flags & GRAM_FLAG_SIMT_ATTN) && enc_attention_mma_supported(h->dk, L)) {
       CKL(GRAM_K_ENC_ATTN, enc_attention_mma(h->qkv, h->ao, pm.plen, pm.poff, pm.tok_valid, h->enc_bias_lut,
                                              h->Lb, P, h->H, L, s));

@@ -135,11 +135,12 @@ bool enc_attention_mma_supported(int dk, int Lmax);
 cudaError_t enc_attention_mma(const void* qkv, void* out, const int* plen, const int* poff, const uint8_t* tok_valid,
                               const float* bias_lut, int Lb, int P, int H, int Lmax, cudaStream_t s);
 
-// ---- attention_tc.cu (bf16, tcgen05/TMEM, passages of <= 128 tokens) ---------------------------------------
-bool enc_attention_tc_supported(int dk, int Lmax, int Lb);
-// qkv_rows = rows of the allocation behind `qkv` (TMA bound); rows past a passage are masked / not stored
+// ---- attention_tc.cu (bf16, tcgen05/TMEM, passages of <= 256 tokens) ---------------------------------------
+bool enc_attention_tc_supported(int dk, int Lmax, int Lb, int H);
+// qkv_rows = rows of the allocation behind `qkv` (TMA bound); rows past a passage are masked / not stored.
+// Lmax <= 128 selects the one-key-block kernel (two CTAs per SM), Lmax <= 256 the two-key-block kernel
 cudaError_t enc_attention_tc(const void* qkv, size_t qkv_rows, void* out, const int* plen, const int* poff,
-                             const uint8_t* tok_valid, const float* bias_lut, int Lb, int P, int H, cudaStream_t s);
+                             const uint8_t* tok_valid, const float* bias_lut, int Lb, int P, int H, int Lmax, cudaStream_t s);
 
 // ---- beam_kernels.cu -------------------------------------------------------------------------------
 struct TrieCSR {

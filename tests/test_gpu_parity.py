@@ -431,3 +431,37 @@ def test_generate_errors(built):
         m.generate(b["ids"].cuda(), b["mask"].cuda(), 5, prefix_allowed_tokens_fn=fn, num_beams=2, num_return_sequences=3)
     with pytest.raises(NotImplementedError):
         m.generate(b["ids"].cuda(), b["mask"].cuda(), 5, prefix_allowed_tokens_fn=lambda b_, s: [1], num_beams=2)
+
+
+def test_tcgen05_encoder_attention_long_passages():
+    """attention_tc.cu with two key blocks (passages of 129-256 tokens, BASELINE configs[4]): ragged lengths from 2 to 256 --
+    so one- and two-key-block items and one- and two-query-block passages alternate inside a CTA --, masked holes, more
+    passages than SMs: fused memory against the mma.sync path (GRAM_FLAG_MMA_LONG_ATTN) and against the fp32 oracle."""
+    from gram_b200 import GRAM, _cabi, synth
+    from gram_b200.config import GramConfig
+    from oracle.gram_oracle import OracleGRAM
+    cfg = GramConfig.t5_small(max_seq_len=256, max_item_num=8)
+    sd = synth.make_state_dict(cfg, seed=4)
+    ids, mask = synth.make_user_batch(cfg, 40, (1, 8), 256, seed=77, min_len=2)
+    mask = mask.copy()
+    mask[3, 0, 5:9] = False
+    mask[7, 1, 130:140] = False
+    ids_t, mask_t = torch.from_numpy(ids).cuda(), torch.from_numpy(mask).cuda()
+    assert ids.shape[0] * ids.shape[1] > 148 and (mask.sum(-1) > 128).any() and ((mask.sum(-1) > 0) & (mask.sum(-1) <= 128)).any()
+    outs = []
+    for flags in (0, _cabi.GRAM_FLAG_MMA_LONG_ATTN):
+        m = GRAM(cfg, dtype="bf16", device="cuda:0", flags=flags, max_users=40)
+        m.load_state_dict(sd)
+        outs.append(m.encode(ids_t, mask_t).cpu())
+        del m
+    assert torch.isfinite(outs[0]).all()
+    err = rel_err(outs[0], outs[1])
+    print(f"[tcgen05 enc-attn L<=256, {ids.shape[0] * ids.shape[1]} passages] memory rel_err vs mma.sync path = {err:.3e}")
+    assert err < 2e-2
+    torch.set_num_threads(os.cpu_count() or 1)
+    sub = slice(0, 6)
+    want = OracleGRAM(cfg, sd).encode(torch.from_numpy(ids[sub]), torch.from_numpy(mask[sub]))
+    fm = torch.from_numpy(mask[sub]).view(6, -1)
+    err = rel_err(outs[0][sub][fm], want[fm])
+    print(f"[tcgen05 enc-attn L<=256] memory rel_err vs oracle = {err:.3e}")
+    assert err < BF16_TOL
