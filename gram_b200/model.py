@@ -255,27 +255,56 @@ class GRAM(torch.nn.Module):
         self._set_trie(trie)
         len_pow = (C.c_double * (max_length + 1))(*[float(c) ** float(length_penalty) if c > 0 else 1.0
                                                     for c in range(max_length + 1)])
-        dev = ids.device
         cap_u = self._cap["max_users"]
         seq_parts, score_parts, widths = [], [], []
         for b0 in range(0, B, cap_u):
             b1 = min(B, b0 + cap_u)
             nb = b1 - b0
-            out_seq = torch.zeros((nb * R, max_length), dtype=torch.int64, device=dev)
-            out_scores = torch.zeros((nb * R,), dtype=torch.float32, device=dev)
-            out_width = torch.zeros((1,), dtype=torch.int32, device=dev)
+            out_seq, out_scores, out_width = self._out_buffers(nb * R, max_length, ids.device, len(seq_parts))
             _cabi.check(self._lib.gram_generate(
                 self._handle, _ptr(ids[b0:b1]), _ptr(mask[b0:b1]), nb, N, L, K, R, max_length, len_pow,
                 _ptr(out_seq), _ptr(out_width), _ptr(out_scores), self._stream()), self._handle, "gram_generate")
             seq_parts.append(out_seq)
             score_parts.append(out_scores)
             widths.append(out_width)
-        width = max(int(w.item()) for w in widths)
-        _cabi.check(self._lib.gram_check_errors(self._handle, self._stream()), self._handle, "gram_generate")
-        sequences = torch.cat(seq_parts, 0)[:, :width].contiguous()
-        scores = torch.cat(score_parts, 0)
-        if not return_dict_in_generate:
+        return self._finish_generate(seq_parts, score_parts, widths, ids.device, return_dict_in_generate, "gram_generate")
+
+    def _out_buffers(self, rows, max_length, device, slot=0):
+        """Result buffers of one C-ABI call.  Host callers get PINNED buffers (kept per shape and reused: the library's
+        device-to-host copies then run at full PCIe rate and nothing is allocated per call); the finished result is copied
+        out of them in `_finish_generate`."""
+        if device.type == "cuda":
+            return (torch.empty((rows, max_length), dtype=torch.int64, device=device),
+                    torch.empty((rows,), dtype=torch.float32, device=device), torch.empty((1,), dtype=torch.int32, device=device))
+        cache = self.__dict__.setdefault("_pinned_out", {})
+        key = (rows, max_length, slot)                  # one buffer per chunk of a call: chunks are concatenated afterwards
+        buf = cache.get(key)
+        if buf is None:
+            pin = torch.cuda.is_available()
+            buf = (torch.empty((rows, max_length), dtype=torch.int64, pin_memory=pin),
+                   torch.empty((rows,), dtype=torch.float32, pin_memory=pin), torch.empty((1,), dtype=torch.int32, pin_memory=pin))
+            if len(cache) > 16:
+                cache.clear()
+            cache[key] = buf
+        return buf
+
+    def _finish_generate(self, seq_parts, score_parts, widths, device, return_dict, what):
+        if device.type == "cuda":
+            # device outputs: the calls above did not synchronise; one check (it synchronises the stream) surfaces the
+            # sticky device-side input errors, after which the widths are plain reads
+            _cabi.check(self._lib.gram_check_errors(self._handle, self._stream()), self._handle, what)
+        # host outputs: gram_generate synchronised and checked the error flag itself before returning
+        width = max(int(w[0]) for w in widths)
+        if len(seq_parts) == 1:
+            sequences = seq_parts[0][:, :width].clone() if device.type != "cuda" else seq_parts[0][:, :width].contiguous()
+            scores = score_parts[0].clone() if device.type != "cuda" else score_parts[0]
+        else:
+            sequences = torch.cat([p[:, :width] for p in seq_parts], 0)
+            scores = torch.cat(score_parts, 0)
+        if not return_dict:
             return sequences
+        # `scores` / `beam_indices`: the reference asks for them (output_scores=True) but never reads them; producing the
+        # per-step [B*K, V] score matrices is exactly what the fused head avoids, so they stay None
         return GenerateOutput(sequences=sequences, sequences_scores=scores, scores=None, beam_indices=None)
 
     @torch.no_grad()
@@ -354,15 +383,12 @@ class GRAM(torch.nn.Module):
         self._ensure_items()
         len_pow = (C.c_double * (max_length + 1))(*[float(c) ** float(length_penalty) if c > 0 else 1.0
                                                     for c in range(max_length + 1)])
-        dev = ids.device if ids.is_cuda else self.device
         cap_u = self._cap["max_users"]
         seq_parts, score_parts, widths = [], [], []
         for b0 in range(0, B, cap_u):
             b1 = min(B, b0 + cap_u)
             nb = b1 - b0
-            out_seq = torch.zeros((nb * R, max_length), dtype=torch.int64, device=dev)
-            out_scores = torch.zeros((nb * R,), dtype=torch.float32, device=dev)
-            out_width = torch.zeros((1,), dtype=torch.int32, device=dev)
+            out_seq, out_scores, out_width = self._out_buffers(nb * R, max_length, ids.device, len(seq_parts))
             _cabi.check(self._lib.gram_encode_cached(self._handle, _ptr(ids[b0:b1]), _ptr(mask[b0:b1]), _ptr(items[b0:b1]),
                                                      nb, NI, L, self._stream()), self._handle, "gram_encode_cached")
             _cabi.check(self._lib.gram_generate(
@@ -371,13 +397,7 @@ class GRAM(torch.nn.Module):
             seq_parts.append(out_seq)
             score_parts.append(out_scores)
             widths.append(out_width)
-        width = max(int(w.item()) for w in widths)
-        _cabi.check(self._lib.gram_check_errors(self._handle, self._stream()), self._handle, "gram_generate_cached")
-        sequences = torch.cat(seq_parts, 0)[:, :width].contiguous().to(ids.device)
-        scores = torch.cat(score_parts, 0).to(ids.device)
-        if not return_dict_in_generate:
-            return sequences
-        return GenerateOutput(sequences=sequences, sequences_scores=scores, scores=None, beam_indices=None)
+        return self._finish_generate(seq_parts, score_parts, widths, ids.device, return_dict_in_generate, "gram_generate_cached")
 
     @torch.no_grad()
     def generate_cached_into(self, prompt_ids, prompt_mask, item_index, max_length, trie, num_beams, num_return_sequences,

@@ -81,6 +81,61 @@ class GramEvalLoader:
             yield b
 
 
+class _ItemStrings:
+    """String comparison of predictions and gold items (reference single_runner_gram.py:657-666: both sides are DECODED and
+    compared as strings) without decoding 20 rows per user in Python: every candidate id row is decoded once, rows are
+    looked up by their bytes, and two rows are "equal" iff their decoded strings are (items whose strings coincide share a
+    class).  Rows that are not candidates (cannot happen under the trie constraint, except -inf fillers) fall back to the
+    tokenizer."""
+
+    def __init__(self, tokenizer, encoded, width):
+        self.tokenizer, self.width = tokenizer, width
+        tab = np.zeros((len(encoded), width), dtype=np.int32)
+        for i, c in enumerate(encoded):
+            tab[i, :len(c)] = c
+        strings = tokenizer.batch_decode(tab, skip_special_tokens=True)
+        cls, self.class_string = {}, []
+        item_class = np.empty(len(encoded), dtype=np.int64)
+        for i, st in enumerate(strings):
+            k = cls.get(st)
+            if k is None:
+                k = cls[st] = len(self.class_string)
+                self.class_string.append(st)
+            item_class[i] = k
+        self._by_string = cls
+        keys = np.ascontiguousarray(tab).view(np.dtype((np.void, width * 4))).ravel()
+        order = np.argsort(keys)
+        self._keys, self._class = keys[order], item_class[order]
+
+    def classes(self, rows):
+        """class id of every id row [n, <= width] (int), or a fresh negative id per distinct unknown string"""
+        rows = np.asarray(rows)
+        pad = np.zeros((rows.shape[0], self.width), dtype=np.int32)
+        pad[:, :rows.shape[1]] = rows[:, :self.width]
+        keys = np.ascontiguousarray(pad).view(np.dtype((np.void, self.width * 4))).ravel()
+        pos = np.searchsorted(self._keys, keys).clip(0, len(self._keys) - 1)
+        hit = self._keys[pos] == keys
+        out = np.where(hit, self._class[pos], -1)
+        if not hit.all():
+            miss = np.nonzero(~hit)[0]
+            for i, st in zip(miss, self.tokenizer.batch_decode(pad[miss], skip_special_tokens=True)):
+                k = self._by_string.get(st)
+                if k is None:
+                    k = self._by_string[st] = -2 - len(self._by_string)      # a string no item has
+                out[i] = k
+        return out
+
+
+def rel_rows_fast(pred_class, gold_class, scores, k):
+    """`evaluate.rel_results` on class ids: per user the k predictions re-ordered by score (descending, stable, NaN last) and
+    compared with the gold item -> uint8 [n, k]"""
+    n = len(gold_class)
+    sc = np.asarray(scores, dtype=np.float64).reshape(n, k)
+    order = np.argsort(-sc, axis=1, kind="stable")
+    pc = np.take_along_axis(np.asarray(pred_class).reshape(n, k), order, axis=1)
+    return (pc == np.asarray(gold_class)[:, None]).astype(np.uint8)
+
+
 class GramRunner:
     """`test_dataset_task` / `test` / `validate` of the reference runners for the inference path."""
 
@@ -136,10 +191,19 @@ class GramRunner:
         data = testloader.dataset
         logging.info(f"[{mode}] testing {data.dataset} dataset on {data.task} task")
         G = self.generate_num
-        encoded = self.encode_candidates(data.all_items)
-        candidate_trie = gt.Trie(encoded)
-        prefix_fn = gt.prefix_allowed_tokens_fn(candidate_trie)
-        max_length = max(len(c) for c in encoded)
+        # candidate encoding, trie and the item-string table depend on the item list only: built once per item list and
+        # kept (the reference rebuilds them at every call, single:594-619; repeated validation / test calls reuse them, and
+        # the engine keeps the uploaded CSR arrays as long as the trie object is the same)
+        key = (id(data.all_items), len(data.all_items), self.item_id_type)
+        cached = getattr(self, "_candidates", None)
+        if cached is None or cached[0] != key:
+            encoded = self.encode_candidates(data.all_items)
+            candidate_trie = gt.Trie(encoded)
+            max_length = max(len(c) for c in encoded)
+            cached = (key, encoded, candidate_trie, gt.prefix_allowed_tokens_fn(candidate_trie), max_length,
+                      _ItemStrings(self.tokenizer, encoded, max_length), data.all_items)
+            self._candidates = cached
+        _, encoded, candidate_trie, prefix_fn, max_length, strings, _ = cached
         if getattr(testloader, "item_cache", False):
             model = getattr(self.model_rec, "module", self.model_rec)
             if getattr(model, "_item_table_owner", None) is not data:
@@ -150,20 +214,21 @@ class GramRunner:
         parts = []                               # (users [n], gold [n, ML], seqs [n, G, ML], scores [n, G], rel [n, G])
 
         def post(batch, seqs, scores):
-            gold = self.tokenizer.batch_decode(batch["target_ids"], skip_special_tokens=True)
-            sents = self.tokenizer.batch_decode(seqs, skip_special_tokens=True)
-            rel = evaluate.rel_results(sents, gold, scores, G)
             n = len(batch["user_index"])
             g_ids = np.zeros((n, max_length), dtype=np.int32)
             for i, t in enumerate(batch["target_ids"]):
-                t = [int(x) for x in t if int(x) >= 0][:max_length]
+                t = [int(x) for x in t if int(x) >= 0]
+                if t and t[0] != 0 and len(t) < max_length:
+                    t = [0] + t                           # collator targets carry no decoder start token; candidates do
+                t = t[:max_length]
                 g_ids[i, :len(t)] = t
             s_ids = np.zeros((n, G, max_length), dtype=np.int32)
             sq = seqs.numpy() if hasattr(seqs, "numpy") else np.asarray(seqs)
-            s_ids[:, :, :sq.shape[1]] = sq.reshape(n, G, -1)
+            s_ids[:, :, :sq.shape[1]] = sq.reshape(n, G, -1)[:, :, :max_length]
             sc = (scores.numpy() if hasattr(scores, "numpy") else np.asarray(scores)).astype(np.float32).reshape(n, G)
-            parts.append((np.asarray(batch["user_index"], dtype=np.int64), g_ids, s_ids, sc,
-                          np.asarray(rel, dtype=np.uint8).reshape(n, G)))
+            # decoded-string equality through the item table (one decode per item, not per prediction)
+            rel = rel_rows_fast(strings.classes(s_ids.reshape(n * G, max_length)), strings.classes(g_ids), sc, G)
+            parts.append((np.asarray(batch["user_index"], dtype=np.int64), g_ids, s_ids, sc, rel))
 
         def batches():
             if not pipeline:

@@ -224,3 +224,38 @@ def test_gram_is_a_module_that_ddp_can_wrap(tmp_path):
         assert ddp.module.module is m                      # `.module` also on the unwrapped model
     finally:
         dist.destroy_process_group()
+
+
+def test_fast_relevance_rows_equal_the_string_path():
+    """runner.rel_rows_fast + _ItemStrings (row bytes -> item -> decoded-string class) == evaluate.rel_results on decoded
+    strings, including two token paths that decode to ONE string, unknown rows, -inf fillers, ties and NaN scores."""
+    from gram_b200 import evaluate
+    from gram_b200.runner import _ItemStrings, rel_rows_fast
+
+    class Tok:
+        def batch_decode(self, rows, skip_special_tokens=True):
+            names = {2: "a", 3: "b", 4: "ab", 5: "c", 6: "bc"}
+            return ["".join(names.get(int(t), f"<{int(t)}>") for t in r if int(t) > 1) for r in rows]
+
+    tok = Tok()
+    cands = [[0, 2, 6, 1], [0, 4, 5, 1], [0, 2, 3, 1], [0, 5, 1], [0, 3, 5, 5, 1]]       # "abc", "abc", "ab", "c", "bcc"
+    W, G = 5, 4
+    st = _ItemStrings(tok, cands, W)
+    rng = np.random.default_rng(0)
+    n = 64
+    rows = np.zeros((n * G, W), dtype=np.int64)
+    for i in range(n * G):
+        c = cands[rng.integers(0, len(cands))] if rng.random() < 0.85 else [0, 7, 1]       # sometimes a non-item row
+        rows[i, :len(c)] = c
+    rows[5] = 0                                                                            # an all-pad filler row
+    gold = [cands[rng.integers(0, len(cands))] for _ in range(n)]
+    scores = rng.integers(-5, 0, size=n * G).astype(np.float32)                            # many ties
+    scores[7] = np.nan
+    scores[5] = -np.inf
+    want = evaluate.rel_results(tok.batch_decode(rows), tok.batch_decode(gold), torch.from_numpy(scores), G)
+    g = np.zeros((n, W), dtype=np.int32)
+    for i, c in enumerate(gold):
+        g[i, :len(c)] = c
+    got = rel_rows_fast(st.classes(rows), st.classes(g), scores, G)
+    assert np.array_equal(got, np.asarray(want, dtype=np.uint8))
+    assert (got.sum(1) > 1).any()            # rows with the same string twice exist in this sample
