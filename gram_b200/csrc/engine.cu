@@ -110,6 +110,12 @@ struct gram_handle {
   int64_t* d_dec_ids = nullptr;
   int last_steps = 0, last_R = 0;
 
+  // CUDA-graph replay of a whole generate call (GRAM_FLAG_CUDA_GRAPH): one instantiated graph per call shape
+  struct GraphRec { int calls = 0; cudaGraphExec_t exec = nullptr; int64_t launches = 0; };
+  std::map<std::vector<int>, GraphRec> graphs;
+  cudaStream_t gstream = nullptr;         // capture / replay stream (the caller's may be the legacy default stream)
+  cudaEvent_t g_in = nullptr, g_out = nullptr;
+
   // measurement
   int64_t launches = 0;
   uint32_t prof_mask = 0;
@@ -138,7 +144,14 @@ int fail(gram_handle* h, int code, const std::string& msg) {
   return code;
 }
 
+void free_graphs(gram_handle* h) {
+  for (auto& kv : h->graphs)
+    if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+  h->graphs.clear();
+}
+
 void free_trie(gram_handle* h) {
+  free_graphs(h);                          // captured launches hold the CSR pointers
   for (int i = 0; i < 3; ++i) {
     if (h->trie_bufs[i]) cudaFree(h->trie_bufs[i]);
     h->trie_bufs[i] = nullptr;
@@ -374,7 +387,7 @@ int encoder_stack(gram_handle* h, const PackMeta& pm, int P, int L, int Mmax, cu
   return GRAM_OK;
 }
 
-int run_encode(gram_handle* h, const int64_t* ids, const uint8_t* mask, int B, int N, int L, cudaStream_t s) {
+int check_encode_args(gram_handle* h, int B, int N, int L) {
   const gram_config& c = h->cfg;
   if (!h->weights_ready) return fail(h, GRAM_ERR_STATE, "gram_encode: weights not finalised");
   if (B <= 0 || N <= 0 || L <= 0) return fail(h, GRAM_ERR_INVALID, "gram_encode: empty batch");
@@ -383,11 +396,24 @@ int run_encode(gram_handle* h, const int64_t* ids, const uint8_t* mask, int B, i
   if ((int64_t)B * N * L > 0x7fffffff) return fail(h, GRAM_ERR_INVALID, "gram_encode: B*N*L exceeds 2^31");
   if (c.n_positions > 0 && N > c.n_positions)
     return fail(h, GRAM_ERR_INVALID, "gram_encode: more passages than rows in the position table");
+  return GRAM_OK;
+}
+
+// device copies of the caller's ids / mask: host pointers always go through the handle's staging buffers; with `always`
+// device pointers do too (a captured graph must read fixed addresses)
+int stage_inputs(gram_handle* h, const int64_t* ids, const uint8_t* mask, size_t n, bool always, const int64_t** dids,
+                 const uint8_t** dmask, cudaStream_t s) {
+  *dids = ids; *dmask = mask;
+  const bool dev_i = is_device_ptr(ids), dev_m = is_device_ptr(mask);
+  if (!dev_i || always) { CK(cudaMemcpyAsync(h->d_ids, ids, n * sizeof(int64_t), dev_i ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, s)); *dids = h->d_ids; }
+  if (!dev_m || always) { CK(cudaMemcpyAsync(h->d_mask, mask, n, dev_m ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, s)); *dmask = h->d_mask; }
+  return GRAM_OK;
+}
+
+// pack + encoder + fused memory + cross-attention K/V of a batch whose ids / mask are on the device
+int enqueue_encode(gram_handle* h, const int64_t* dids, const uint8_t* dmask, int B, int N, int L, cudaStream_t s) {
+  const gram_config& c = h->cfg;
   const size_t n = (size_t)B * N * L;
-  const int64_t* dids = ids;
-  const uint8_t* dmask = mask;
-  if (!is_device_ptr(ids)) { CK(cudaMemcpyAsync(h->d_ids, ids, n * sizeof(int64_t), cudaMemcpyHostToDevice, s)); dids = h->d_ids; }
-  if (!is_device_ptr(mask)) { CK(cudaMemcpyAsync(h->d_mask, mask, n, cudaMemcpyHostToDevice, s)); dmask = h->d_mask; }
   h->encoded = false;
   h->enc_B = B; h->enc_N = N; h->enc_L = L;
   // rows the batch can occupy: its padded size, or the workspace when max_tokens caps it below that (the VALID
@@ -402,6 +428,13 @@ int run_encode(gram_handle* h, const int64_t* ids, const uint8_t* mask, int B, i
   RC(gemm(h, GRAM_K_GEMM_KV, EPI_STORE, h->mem, h->ckv_w, h->ckv, Mmax, h->pm.total, h->Ld * 2 * h->HD, h->D, s));
   h->encoded = true;
   return GRAM_OK;
+}
+
+int run_encode(gram_handle* h, const int64_t* ids, const uint8_t* mask, int B, int N, int L, cudaStream_t s) {
+  RC(check_encode_args(h, B, N, L));
+  const int64_t* dids; const uint8_t* dmask;
+  RC(stage_inputs(h, ids, mask, (size_t)B * N * L, false, &dids, &dmask, s));
+  return enqueue_encode(h, dids, dmask, B, N, L, s);
 }
 
 // ---- one decoder step (all layers + lm_head) for R rows ---------------------------------------------
@@ -499,6 +532,46 @@ int decoder_step(gram_handle* h, int R, int K, int users, int t, const int* anc,
   return GRAM_OK;
 }
 
+// beam search over the batch that is encoded in the handle: init, T decode steps, finalize into h->d_out_*
+int enqueue_decode(gram_handle* h, int users, int K, int R_ret, int max_length, cudaStream_t s) {
+  const gram_config& c = h->cfg;
+  const int R = users * K, T = max_length - 1;
+  // the candidate buffer was sized for cfg.max_beams; K <= max_beams so it is sufficient
+  BeamState bs = h->bs;
+  bs.K = K; bs.max_length = c.max_length; bs.gen_len = max_length;
+  CKL(GRAM_K_BEAM, beam_init(bs, h->trie, users, c.start_id, s));
+  // fused head (bf16 + tcgen05 GEMM): log-softmax statistics come out of the GEMM epilogue and candidate logits are
+  // recomputed from the trie children only; otherwise (fp32 parity mode) full logits are materialised
+  // (GRAM_FLAG_KEEP_LOGITS only records the per-step taps: the benchmarked fused head is the one they observe)
+  const bool fused = c.dtype == GRAM_DTYPE_BF16 && !(c.flags & (GRAM_FLAG_SIMT_GEMM | GRAM_FLAG_UNFUSED_HEAD)) &&
+                     gemm_tc_supported(h->V, h->D) && (h->D % 8) == 0;
+  for (int t = 0; t < T; ++t) {
+    // step 0: the K beams of a user all hold the start token and attend to the same memory, i.e. K identical rows
+    // (HF computes them K times); one row per user is decoded and shared by the user's beams
+    const int compact = (t == 0 && K > 1) ? 1 : 0;
+    const int Rt = compact ? users : R, Kt = compact ? 1 : K;
+    // later steps: only beams that can still reach an output are decoded (dead beams and finished users are compacted
+    // away on the device; the reference decodes them and discards the result)
+    const bool live = t > 0 && !(c.flags & GRAM_FLAG_ALL_ROWS);
+    if (live) {
+      CKL(GRAM_K_BEAM, live_compact(bs, users, t & 1, h->live, h->pm.ustart, s));
+      h->launches += 1;   // live_compact issues two kernels
+    } else {
+      CKL(GRAM_K_OTHER, work_add(bs, Rt, h->pm.total, s));   // executed-work accounting (gram_get_stats)
+    }
+    const int* row_slot = live ? h->live.row_slot : nullptr;
+    RC(decoder_step(h, Rt, Kt, users, t, bs.anc[t & 1], fused, live, s));
+    if (fused) {
+      CKL(GRAM_K_BEAM, beam_step(bs, h->trie, nullptr, h->dxn, h->lm_head, h->D, h->lse, users, t, h->cand_cap, compact, row_slot, s));
+    } else {
+      CKL(GRAM_K_LM_HEAD, lse_rows(h->logits, h->lse, Rt, h->V, live ? h->live.n_live : nullptr, s));
+      CKL(GRAM_K_BEAM, beam_step(bs, h->trie, h->logits, nullptr, nullptr, h->D, h->lse, users, t, h->cand_cap, compact, row_slot, s));
+    }
+  }
+  CKL(GRAM_K_BEAM, beam_finalize(bs, users, T, R_ret, h->d_out_seq, h->d_out_scores, h->d_out_width, s));
+  return GRAM_OK;
+}
+
 }  // namespace
 
 // =====================================================================================================
@@ -515,6 +588,9 @@ void gram_destroy(gram_handle* h) {
   cudaSetDevice(h->cfg.device);
   free_item_cache(h);
   free_trie(h);
+  if (h->gstream) cudaStreamDestroy(h->gstream);
+  if (h->g_in) cudaEventDestroy(h->g_in);
+  if (h->g_out) cudaEventDestroy(h->g_out);
   for (void* p : h->allocs) cudaFree(p);
   for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
   if (h->len_pow_ev) cudaEventDestroy(h->len_pow_ev);
@@ -920,54 +996,67 @@ int gram_generate(gram_handle* h, const int64_t* ids, const uint8_t* mask, int32
   if (K <= 0 || K > c.max_beams) return fail(h, GRAM_ERR_INVALID, "gram_generate: num_beams exceeds max_beams");
   if (R_ret <= 0 || R_ret > K) return fail(h, GRAM_ERR_INVALID, "`num_return_sequences` has to be smaller or equal to `num_beams`.");
   if (max_length < 2 || max_length > c.max_length) return fail(h, GRAM_ERR_INVALID, "gram_generate: max_length outside [2, cfg.max_length]");
-  if (ids) {
+  const bool have_ids = ids != nullptr;
+  if (have_ids) {
     if (!mask) return GRAM_ERR_INVALID;
-    h->launches = 0;
-    RC(run_encode(h, ids, mask, B, N, L, s));
+    RC(check_encode_args(h, B, N, L));
   } else {
     if (!h->encoded) return fail(h, GRAM_ERR_STATE, "gram_generate: ids == NULL but nothing has been encoded");
-    B = h->enc_B;
+    B = h->enc_B; N = h->enc_N; L = h->enc_L;
   }
   const int users = B, R = B * K, T = max_length - 1;
-  // the candidate buffer was sized for cfg.max_beams; K <= max_beams so it is sufficient
-  BeamState bs = h->bs;
-  bs.K = K; bs.max_length = c.max_length; bs.gen_len = max_length;
+  // GRAM_FLAG_CUDA_GRAPH: everything between the input staging and the result copy-out -- ~70 launches of the encoder and
+  // ~40 per decode step, none of which depends on a host-side value -- is captured once per call shape and replayed
+  cudaStream_t caller = s;
+  const bool graphed = (c.flags & GRAM_FLAG_CUDA_GRAPH) && h->prof_mask == 0;
+  if (graphed) {
+    if (!h->gstream) {
+      CK(cudaStreamCreateWithFlags(&h->gstream, cudaStreamNonBlocking));
+      CK(cudaEventCreateWithFlags(&h->g_in, cudaEventDisableTiming));
+      CK(cudaEventCreateWithFlags(&h->g_out, cudaEventDisableTiming));
+    }
+    CK(cudaEventRecord(h->g_in, caller));
+    s = h->gstream;
+    CK(cudaStreamWaitEvent(s, h->g_in, 0));
+  }
+  const int64_t* dids = nullptr; const uint8_t* dmask = nullptr;
+  if (have_ids) RC(stage_inputs(h, ids, mask, (size_t)B * N * L, graphed, &dids, &dmask, s));
   if (h->len_pow_ev) CK(cudaEventSynchronize(h->len_pow_ev));
   else CK(cudaEventCreateWithFlags(&h->len_pow_ev, cudaEventDisableTiming));
   memcpy(h->h_len_pow, len_pow, ((size_t)max_length + 1) * sizeof(double));
   for (int i = max_length + 1; i <= c.max_length; ++i) h->h_len_pow[i] = 1.0;
   CK(cudaMemcpyAsync(h->d_len_pow, h->h_len_pow, ((size_t)c.max_length + 1) * 8, cudaMemcpyHostToDevice, s));
   CK(cudaEventRecord(h->len_pow_ev, s));
-  CKL(GRAM_K_BEAM, beam_init(bs, h->trie, users, c.start_id, s));
-  // fused head (bf16 + tcgen05 GEMM): log-softmax statistics come out of the GEMM epilogue and candidate logits are
-  // recomputed from the trie children only; otherwise (fp32 parity mode) full logits are materialised
-  // (GRAM_FLAG_KEEP_LOGITS only records the per-step taps: the benchmarked fused head is the one they observe)
-  const bool fused = c.dtype == GRAM_DTYPE_BF16 && !(c.flags & (GRAM_FLAG_SIMT_GEMM | GRAM_FLAG_UNFUSED_HEAD)) &&
-                     gemm_tc_supported(h->V, h->D) && (h->D % 8) == 0;
-  for (int t = 0; t < T; ++t) {
-    // step 0: the K beams of a user all hold the start token and attend to the same memory, i.e. K identical rows
-    // (HF computes them K times); one row per user is decoded and shared by the user's beams
-    const int compact = (t == 0 && K > 1) ? 1 : 0;
-    const int Rt = compact ? users : R, Kt = compact ? 1 : K;
-    // later steps: only beams that can still reach an output are decoded (dead beams and finished users are compacted
-    // away on the device; the reference decodes them and discards the result)
-    const bool live = t > 0 && !(c.flags & GRAM_FLAG_ALL_ROWS);
-    if (live) {
-      CKL(GRAM_K_BEAM, live_compact(bs, users, t & 1, h->live, h->pm.ustart, s));
-      h->launches += 1;   // live_compact issues two kernels
+  auto enqueue = [&](cudaStream_t st) -> int {
+    if (have_ids) { h->launches = 0; RC(enqueue_encode(h, dids, dmask, B, N, L, st)); }
+    return enqueue_decode(h, users, K, R_ret, max_length, st);
+  };
+  if (!graphed) {
+    RC(enqueue(s));
+  } else {
+    gram_handle::GraphRec& g = h->graphs[{B, N, L, K, R_ret, max_length, have_ids ? 1 : 0}];
+    ++g.calls;
+    if (g.calls == 1) {
+      RC(enqueue(s));                                   // first call of a shape runs eagerly (lazy one-time set-up inside)
+    } else if (!g.exec) {
+      CK(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+      const int64_t before = have_ids ? 0 : h->launches;
+      const int rc = enqueue(s);
+      cudaGraph_t graph = nullptr;
+      const cudaError_t e = cudaStreamEndCapture(s, &graph);
+      if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+      CK(e);
+      CK(cudaGraphInstantiate(&g.exec, graph, 0));
+      cudaGraphDestroy(graph);
+      g.launches = h->launches - before;
+      CK(cudaGraphLaunch(g.exec, s));
     } else {
-      CKL(GRAM_K_OTHER, work_add(bs, Rt, h->pm.total, s));   // executed-work accounting (gram_get_stats)
-    }
-    const int* row_slot = live ? h->live.row_slot : nullptr;
-    RC(decoder_step(h, Rt, Kt, users, t, bs.anc[t & 1], fused, live, s));
-    if (fused) {
-      CKL(GRAM_K_BEAM, beam_step(bs, h->trie, nullptr, h->dxn, h->lm_head, h->D, h->lse, users, t, h->cand_cap, compact, row_slot, s));
-    } else {
-      CKL(GRAM_K_LM_HEAD, lse_rows(h->logits, h->lse, Rt, h->V, live ? h->live.n_live : nullptr, s));
-      CKL(GRAM_K_BEAM, beam_step(bs, h->trie, h->logits, nullptr, nullptr, h->D, h->lse, users, t, h->cand_cap, compact, row_slot, s));
+      if (have_ids) { h->launches = 0; h->enc_B = B; h->enc_N = N; h->enc_L = L; h->encoded = true; }
+      h->launches += g.launches;
+      CK(cudaGraphLaunch(g.exec, s));
     }
   }
-  CKL(GRAM_K_BEAM, beam_finalize(bs, users, T, R_ret, h->d_out_seq, h->d_out_scores, h->d_out_width, s));
+  BeamState bs = h->bs;
   h->last_steps = T; h->last_R = R;
   // ---- copy-out: the library's result layout is [B*R_ret, cfg.max_length]; the ABI promises max_length ----
   const size_t rows = (size_t)users * R_ret;
@@ -982,6 +1071,10 @@ int gram_generate(gram_handle* h, const int64_t* ids, const uint8_t* mask, int32
   CK(cudaMemcpyAsync(out_width, h->d_out_width, 4, is_device_ptr(out_width) ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, s));
   CK(cudaMemcpyAsync(&h->h_flags[0], bs.err, 4, cudaMemcpyDeviceToHost, s));
   CK(cudaMemcpyAsync(&h->h_flags[2], h->pm.total, 4, cudaMemcpyDeviceToHost, s));
+  if (graphed) {                                        // the caller's stream continues after the replay stream
+    CK(cudaEventRecord(h->g_out, s));
+    CK(cudaStreamWaitEvent(caller, h->g_out, 0));
+  }
   if (host_out || !is_device_ptr(out_scores) || !is_device_ptr(out_width)) {
     CK(cudaStreamSynchronize(s));
     if (h->h_flags[0] != 0) {

@@ -80,6 +80,11 @@ enum {
   GRAM_FLAG_NO_L2_HINTS = 512,     /* chain kernel without L2 cache-policy hints on its TMA traffic (A-B timing)      */
   GRAM_FLAG_MMA_LONG_ATTN = 2048,  /* passages of 129-256 tokens through the mma.sync encoder attention instead of the two-key-block
                                       tcgen05 kernel (A-B timing; GRAM_FLAG_MMA_ENC_ATTN covers every length)       */
+  GRAM_FLAG_CUDA_GRAPH = 4096,     /* gram_generate: capture everything between the input staging and the result copy-out (the
+                                      encoder's ~70 launches and ~40 per decode step; nothing in it depends on a host value) as a
+                                      CUDA graph per call shape and replay it (first call of a shape eager, second captures).
+                                      Same kernels, same results; it removes the host's per-launch cost, which only shows at
+                                      small batches                                             */
   GRAM_FLAG_NO_DEC_CHAIN = 1024,   /* bf16 decoder: cross-attention output projection, wi and wo as three launches instead of
                                       one chain launch per layer (A-B timing)                                         */
   GRAM_FLAG_ALL_ROWS = 32          /* decode every beam row at every step, as the reference does (A-B timing).  Default:
