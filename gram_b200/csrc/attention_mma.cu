@@ -459,6 +459,145 @@ cross_attention_mma_kernel(const __grid_constant__ CUtensorMap map_kv, const bf1
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Persistent variant (default): one CTA per SM walks work items (user, head group) -- users longest first, items dealt
+// round-robin so every CTA gets the same mix of long and short memories.  The TMA producer warp never stops: it streams the
+// K/V tiles of item i+1 into the ring while the consumer warps finish item i (normalise, store) and fetch the next
+// item's query fragments, so the per-CTA costs of the one-CTA-per-item kernel above -- CTA launch, barrier set-up, the
+// first tiles' load latency with an empty ring, an idle memory system during the epilogue (~2-3 us of a ~25 us item) --
+// are paid once per launch instead of once per item.
+// ------------------------------------------------------------------------------------------------
+template <int HEADS, int BH, int MT = 2>
+__global__ void __launch_bounds__(xa_threads(HEADS * BH), 1)
+cross_attention_persist_kernel(const __grid_constant__ CUtensorMap map_kv, const bf16* __restrict__ qg,
+                               bf16* __restrict__ out, const int* __restrict__ ustart, const int* __restrict__ uorder,
+                               const uint8_t* __restrict__ tok_valid, int K_all, int H, int k_col0, int v_col0,
+                               const int* __restrict__ live_start, const int* __restrict__ live_count, int users) {
+  constexpr int XA_HEADS = HEADS;
+  constexpr uint32_t XA_STAGE_BYTES = 2 * HEADS * BOX_BYTES;   // K boxes then V boxes
+  constexpr int XA_STAGES = 3 * XA_STAGE_TARGET / (int)XA_STAGE_BYTES;
+  constexpr int XA_WARPS = HEADS * BH;                         // consumer warps
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (base - raw);
+  const uint32_t bars = base + XA_STAGES * XA_STAGE_BYTES;     // full[ST], empty[ST]
+  unsigned long long* masks = reinterpret_cast<unsigned long long*>(smem + XA_STAGES * XA_STAGE_BYTES + 128);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_hg = H / XA_HEADS, n_items = users * n_hg;
+  const int HD = H * DK;
+
+  if (threadIdx.x == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_kv) : "memory");
+    for (int s = 0; s < XA_STAGES; ++s) { mbar_init(bars + 8u * s, 1); mbar_init(bars + 8u * (XA_STAGES + s), XA_WARPS); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  if (warp == XA_WARPS) {
+    // ===================== TMA producer: one uninterrupted tile stream over all items of this CTA =====================
+    int stage = 0; uint32_t phase = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+      const int ui = item / n_hg, hg = item - ui * n_hg;
+      const int u = uorder ? uorder[ui] : ui;
+      if ((live_start ? live_count[u] : K_all) == 0) continue;       // no live beam: the consumers skip it too
+      const int s_beg = ustart[u], s_end = ustart[u + 1];
+      const int n_tiles = (s_end - s_beg + TS - 1) / TS;
+      for (int t = 0; t < n_tiles; ++t) {
+        mbar_wait(bars + 8u * (XA_STAGES + stage), phase ^ 1u);
+        const int s0 = s_beg + t * TS;
+        const int r0 = s0 + lane, r1 = s0 + 32 + lane;
+        const bool v0 = (r0 < s_end) && (tok_valid == nullptr || tok_valid[r0] != 0);
+        const bool v1 = (r1 < s_end) && (tok_valid == nullptr || tok_valid[r1] != 0);
+        const unsigned lo = __ballot_sync(0xffffffffu, v0), hi = __ballot_sync(0xffffffffu, v1);
+        if (lane == 0) {
+          masks[stage] = ((unsigned long long)hi << 32) | lo;
+          const uint32_t full = bars + 8u * stage;
+          const uint32_t sb = base + stage * XA_STAGE_BYTES;
+          mbar_arrive_expect_tx(full, XA_STAGE_BYTES);
+#pragma unroll
+          for (int hh = 0; hh < XA_HEADS; ++hh) {
+            const int col = (hg * XA_HEADS + hh) * DK;
+            tma_load_2d(sb + hh * BOX_BYTES, &map_kv, full, k_col0 + col, s0);
+            tma_load_2d(sb + (XA_HEADS + hh) * BOX_BYTES, &map_kv, full, v_col0 + col, s0);
+          }
+        }
+        __syncwarp();
+        if (++stage == XA_STAGES) { stage = 0; phase ^= 1u; }
+      }
+    }
+    return;
+  }
+
+  // ===================== consumers: warp = (head, beam half) =====================
+  const int hl = warp / BH, b_off = (warp % BH) * (MT * 16);
+  const int g = lane >> 2, q = lane & 3;
+  int stage = 0; uint32_t phase = 0;
+  for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+    const int ui = item / n_hg, hg = item - ui * n_hg;
+    const int u = uorder ? uorder[ui] : ui;
+    const int K = live_start ? live_count[u] : K_all;
+    if (K == 0) continue;
+    const int qrow0 = live_start ? live_start[u] : u * K_all;
+    const int n_tiles = (ustart[u + 1] - ustart[u] + TS - 1) / TS;
+    const int h = hg * XA_HEADS + hl;
+    uint32_t qf[MT][4][4];
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt) {
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int b = b_off + mt * 16 + g + ((e & 1) << 3);
+          const int d = ks * 16 + 2 * q + ((e >> 1) << 3);
+          uint32_t v = 0u;
+          if (b < K) v = *reinterpret_cast<const uint32_t*>(qg + (size_t)(qrow0 + b) * HD + h * DK + d);
+          qf[mt][ks][e] = v;
+        }
+      }
+    }
+    float o[MT][8][4];
+    float m_run[MT][2], l_run[MT][2];
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt) {
+      m_run[mt][0] = m_run[mt][1] = -INFINITY;
+      l_run[mt][0] = l_run[mt][1] = 0.f;
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) o[mt][nt][e] = 0.f;
+    }
+    for (int t = 0; t < n_tiles; ++t) {
+      mbar_wait(bars + 8u * stage, phase);
+      const unsigned long long kmask = masks[stage];
+      const uint32_t sb = base + stage * XA_STAGE_BYTES;
+      flash_tile<MT, 8, false>(qf, sb + hl * BOX_BYTES, sb + (XA_HEADS + hl) * BOX_BYTES, 0, kmask, NoBias(), o, m_run, l_run, lane);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bars + 8u * (XA_STAGES + stage));
+      if (++stage == XA_STAGES) { stage = 0; phase ^= 1u; }
+    }
+    // ---- normalise and store (the row range is re-read here instead of staying live across the key loop) ----
+    const int out_row0 = live_start ? live_start[u] : u * K_all, out_rows = live_start ? live_count[u] : K_all;
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt) {
+#pragma unroll
+      for (int hf = 0; hf < 2; ++hf) {
+        float l = l_run[mt][hf];
+        l += __shfl_xor_sync(0xffffffffu, l, 1);
+        l += __shfl_xor_sync(0xffffffffu, l, 2);
+        const float inv = l > 0.f ? 1.0f / l : 0.f;
+        const int b = b_off + mt * 16 + g + hf * 8;
+        if (b < out_rows) {
+          bf16* orow = out + (size_t)(out_row0 + b) * HD + h * DK;
+#pragma unroll
+          for (int nt = 0; nt < 8; ++nt)
+            *reinterpret_cast<uint32_t*>(orow + nt * 8 + 2 * q) = pack_bf16(o[mt][nt][hf * 2] * inv, o[mt][nt][hf * 2 + 1] * inv);
+        }
+      }
+    }
+  }
+}
+
 // ================================================================================================
 // encoder self-attention: shared definitions
 // ================================================================================================
@@ -611,14 +750,24 @@ bool cross_attention_mma_supported(int K, int H, int dk) { return dk == fa::DK &
 
 cudaError_t cross_attention_mma(const void* q, const void* kv, size_t kv_rows, size_t kv_stride, int k_off, int v_off,
                                 const int* ustart, const int* uorder, const uint8_t* tok_valid, void* out, int users,
-                                int K, int H, const int* live_start, const int* live_count, cudaStream_t s) {
+                                int K, int H, const int* live_start, const int* live_count, int num_sms, cudaStream_t s) {
   if (users <= 0) return cudaSuccess;
   std::lock_guard<std::mutex> lk(fa::g_mu);
   CUtensorMap map;
   if (!fa::get_kv_map(kv, kv_rows, kv_stride, &map)) return cudaErrorUnknown;
   constexpr size_t smem = (size_t)3 * fa::XA_STAGE_TARGET + 1024 + 256;
-  static SmemAttr attr[2];
+  static SmemAttr attr[4];
+  const bool persist = num_sms > 0;          // num_sms <= 0: one CTA per (user, head group), the round-1 kernel (A/B timing)
   if (K <= 32 && (H % 4) == 0) {
+    if (persist) {
+      auto kern = fa::cross_attention_persist_kernel<4, 1>;
+      cudaError_t e = attr[2].ensure(kern, smem);
+      if (e != cudaSuccess) return e;
+      const int items = users * (H / 4);
+      kern<<<items < num_sms ? items : num_sms, fa::xa_threads(4), smem, s>>>(map, (const bf16*)q, (bf16*)out, ustart, uorder, tok_valid,
+                                                                          K, H, k_off, v_off, live_start, live_count, users);
+      return cudaGetLastError();
+    }
     auto kern = fa::cross_attention_mma_kernel<4, 1, 1, 1>;
     {
       cudaError_t e = attr[0].ensure(kern, smem);
@@ -627,6 +776,15 @@ cudaError_t cross_attention_mma(const void* q, const void* kv, size_t kv_rows, s
     kern<<<dim3(users, H / 4), fa::xa_threads(4), smem, s>>>(map, (const bf16*)q, (bf16*)out, ustart, uorder, tok_valid, K, H,
                                                           k_off, v_off, live_start, live_count);
   } else {
+    if (persist) {
+      auto kern = fa::cross_attention_persist_kernel<2, 2>;
+      cudaError_t e = attr[3].ensure(kern, smem);
+      if (e != cudaSuccess) return e;
+      const int items = users * (H / 2);
+      kern<<<items < num_sms ? items : num_sms, fa::xa_threads(4), smem, s>>>(map, (const bf16*)q, (bf16*)out, ustart, uorder, tok_valid,
+                                                                          K, H, k_off, v_off, live_start, live_count, users);
+      return cudaGetLastError();
+    }
     auto kern = fa::cross_attention_mma_kernel<2, 2, 1, 1>;
     {
       cudaError_t e = attr[1].ensure(kern, smem);

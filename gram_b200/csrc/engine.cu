@@ -477,7 +477,7 @@ int decoder_step(gram_handle* h, int R, int K, int users, int t, const int* anc,
       if (!(c.flags & GRAM_FLAG_SIMT_ATTN) && cross_attention_mma_supported(K, h->H, h->dk)) {
         CKL(GRAM_K_CROSS_ATTN, cross_attention_mma(h->dq, h->ckv, (size_t)h->Mcap + 256, (size_t)h->Ld * 2 * HD, l * 2 * HD,
                                                    l * 2 * HD + HD, h->pm.ustart, h->pm.uorder, h->pm.tok_valid, h->dao, users, K, h->H,
-                                                   lstart, lcount, s));
+                                                   lstart, lcount, (c.flags & GRAM_FLAG_XATTN_PER_ITEM) ? 0 : h->num_sms, s));
       } else {
         CKL(GRAM_K_CROSS_ATTN, cross_attention(c.dtype, h->dq, h->ckv, (size_t)h->Ld * 2 * HD, l * 2 * HD, l * 2 * HD + HD,
                                                h->pm.ustart, h->pm.tok_valid, h->dao, users, K, h->H, h->dk, lstart, lcount, s));
@@ -510,7 +510,7 @@ int decoder_step(gram_handle* h, int R, int K, int users, int t, const int* anc,
     if (c.dtype == GRAM_DTYPE_BF16 && !(c.flags & GRAM_FLAG_SIMT_ATTN) && cross_attention_mma_supported(K, h->H, h->dk)) {
       CKL(GRAM_K_CROSS_ATTN, cross_attention_mma(h->dq, h->ckv, (size_t)h->Mcap + 256, (size_t)h->Ld * 2 * HD, l * 2 * HD,
                                                  l * 2 * HD + HD, h->pm.ustart, h->pm.uorder, h->pm.tok_valid, h->dao, users, K, h->H,
-                                                 lstart, lcount, s));
+                                                 lstart, lcount, (c.flags & GRAM_FLAG_XATTN_PER_ITEM) ? 0 : h->num_sms, s));
     } else {
       CKL(GRAM_K_CROSS_ATTN, cross_attention(c.dtype, h->dq, h->ckv, (size_t)h->Ld * 2 * HD, l * 2 * HD, l * 2 * HD + HD,
                                              h->pm.ustart, h->pm.tok_valid, h->dao, users, K, h->H, h->dk, lstart, lcount, s));
@@ -1281,13 +1281,16 @@ int gram_op_cross_attention(int32_t device, int32_t dtype, int32_t impl, const v
                             int32_t H, int32_t dk, void* stream) {
   if (cudaSetDevice(device) != cudaSuccess) return GRAM_ERR_CUDA;
   cudaError_t e;
-  if (impl == 1) {
+  if (impl == 1 || impl == 2) {
     if (dtype != GRAM_DTYPE_BF16 || !cross_attention_mma_supported(K, H, dk)) {
       g_create_error = "gram_op_cross_attention: tensor-core path needs bf16, d_kv 64, K <= 64 and H % 4 == 0 (K <= 32) or H % 2 == 0";
       return GRAM_ERR_UNSUPPORTED;
     }
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    // impl 1 = persistent kernel (default in the engine), impl 2 = one CTA per (user, head group)
     e = cross_attention_mma(q, kv, (size_t)kv_rows, (size_t)2 * H * dk, 0, H * dk, user_start, nullptr, tok_valid, out, users, K, H,
-                            nullptr, nullptr, (cudaStream_t)stream);
+                            nullptr, nullptr, impl == 2 ? 0 : sms, (cudaStream_t)stream);
   } else {
     e = cross_attention(dtype, q, kv, (size_t)2 * H * dk, 0, H * dk, user_start, tok_valid, out, users, K, H, dk,
                         nullptr, nullptr, (cudaStream_t)stream);

@@ -130,6 +130,7 @@ cudaError_t cross_attention_mma(const void* q, const void* kv, size_t kv_rows, s
                                 const int* ustart, const int* uorder /* nullable: users longest-first */,
                                 const uint8_t* tok_valid, void* out, int users, int K, int H,
                                 const int* live_start, const int* live_count /* nullable, see cross_attention */,
+                                int num_sms /* > 0: persistent kernel, one CTA per SM; <= 0: one CTA per (user, head group) */,
                                 cudaStream_t s);
 bool enc_attention_mma_supported(int dk, int Lmax);
 cudaError_t enc_attention_mma(const void* qkv, void* out, const int* plen, const int* poff, const uint8_t* tok_valid,

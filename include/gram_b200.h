@@ -85,6 +85,8 @@ enum {
                                       CUDA graph per call shape and replay it (first call of a shape eager, second captures).
                                       Same kernels, same results; it removes the host's per-launch cost, which only shows at
                                       small batches                                             */
+  GRAM_FLAG_XATTN_PER_ITEM = 8192, /* cross-attention with one CTA per (user, head group) instead of the persistent kernel that
+                                      streams the K/V tiles of consecutive items without a gap (A-B timing)            */
   GRAM_FLAG_NO_DEC_CHAIN = 1024,   /* bf16 decoder: cross-attention output projection, wi and wo as three launches instead of
                                       one chain launch per layer (A-B timing)                                         */
   GRAM_FLAG_ALL_ROWS = 32          /* decode every beam row at every step, as the reference does (A-B timing).  Default:
@@ -233,7 +235,8 @@ int gram_op_lse_head(int32_t device, const void* hidden, const void* head, float
                      int32_t D, void* stream);
 /* decoder cross-attention over an in-place K/V memory: q [users*K, H*dk], kv [kv_rows, 2*H*dk] (K|V),
  * user_start int32 [users+1], tok_valid uint8 [kv_rows] or NULL, out [users*K, H*dk] (all dtype).
- * impl 0 = CUDA-core kernel (fp32 or bf16), 1 = TMA + tensor-core kernel (bf16). */
+ * impl 0 = CUDA-core kernel (fp32 or bf16), 1 = TMA + tensor-core kernel, persistent (bf16), 2 = the same, one CTA per
+ * (user, head group). */
 int gram_op_cross_attention(int32_t device, int32_t dtype, int32_t impl, const void* q, const void* kv, int32_t kv_rows,
                             const int32_t* user_start, const uint8_t* tok_valid, void* out,
                             int32_t users, int32_t K, int32_t H, int32_t dk, void* stream);

@@ -134,15 +134,15 @@ def test_gemm_tcgen05_cta_pairs(shape, epi):
     assert torch.equal(outs[0], outs[1])
 
 
-@pytest.mark.parametrize("dtype,impl", [("fp32", 0), ("bf16", 0), ("bf16", 1)])
+@pytest.mark.parametrize("dtype,impl", [("fp32", 0), ("bf16", 0), ("bf16", 1), ("bf16", 2)])   # 1 = persistent, 2 = CTA per item
 @pytest.mark.parametrize("dk,H,K", [(16, 4, 4), (64, 8, 20), (64, 12, 50), (64, 8, 1), (64, 4, 33)])
 def test_cross_attention_op(dtype, impl, dk, H, K):
-    if impl == 1 and dk != 64:
+    if impl >= 1 and dk != 64:
         pytest.skip("tensor-core kernel is specialised for d_kv = 64")
     from gram_b200 import _cabi
     lib = _cabi.load_library()
-    users = 3
-    lens = [70, 33, 257]
+    users = 3 if impl != 1 else 200                           # persistent: more items than SMs, every CTA walks several
+    lens = [70, 33, 257] if impl != 1 else [1 + (i * 37) % 300 for i in range(users)]
     ustart = np.concatenate([[0], np.cumsum(lens)]).astype(np.int32)
     T = int(ustart[-1])
     HD = H * dk
