@@ -24,6 +24,7 @@ GRAM_FLAG_MMA_LONG_ATTN = 2048
 GRAM_FLAG_CUDA_GRAPH = 4096
 GRAM_FLAG_XATTN_PER_ITEM = 8192
 GRAM_FLAG_NO_L2_HINTS = 512
+GRAM_FLAG_FP32_RESID = 16384
 K_CLASSES = ["gemm_enc", "enc_attn", "gemm_kv", "gemm_dec", "cross_attn", "lm_head", "beam", "other", "self_attn",
              "norm_enc", "norm_dec"]
 GRAM_K_COUNT = len(K_CLASSES)

@@ -272,6 +272,34 @@ cudaError_t embed_rows_norm(const void* table, const int* tok_id, float* x, void
   return cudaGetLastError();
 }
 
+// bf16 residual stream (bf16 mode unless GRAM_FLAG_FP32_RESID): the stream starts as the embedding row itself (exact: the table is bf16)
+// with its sums of squares per 128-column block; the first RMSNorm's gain lives in the consumer GEMM's weights
+__global__ void embed_rows_stream_kernel(const bf16* __restrict__ table, const int* __restrict__ tok_id, bf16* __restrict__ xr,
+                                         float* __restrict__ ss, int M_imm, const int* __restrict__ m_ptr, int D) {
+  const int M = m_ptr ? *m_ptr : M_imm;
+  const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (row >= M) return;
+  const bf16* src = table + (size_t)tok_id[row] * D;
+  for (int c0 = 0; c0 < D; c0 += 128) {
+    const int c = c0 + lane * 4;
+    const uint2 raw = *reinterpret_cast<const uint2*>(src + c);
+    *reinterpret_cast<uint2*>(xr + (size_t)row * D + c) = raw;
+    const float4 v = load4(src + c);
+    float t = v.x * v.x;
+    t = fmaf(v.y, v.y, t); t = fmaf(v.z, v.z, t); t = fmaf(v.w, v.w, t);
+    t = warp_sum(t);
+    if (lane == 0) ss[(size_t)row * (D >> 7) + (c0 >> 7)] = t;
+  }
+}
+
+cudaError_t embed_rows_stream(const void* table, const int* tok_id, void* xr, float* ss, int M_max, const int* m_ptr, int D,
+                              cudaStream_t s) {
+  if (M_max <= 0) return cudaSuccess;
+  if (D & 127) return cudaErrorInvalidValue;
+  embed_rows_stream_kernel<<<(M_max + 7) / 8, 256, 0, s>>>((const bf16*)table, tok_id, (bf16*)xr, ss, M_max, m_ptr, D);
+  return cudaGetLastError();
+}
+
 cudaError_t embed_rows(int dtype, const void* table, const int* tok_id, float* x, int M_max, const int* m_ptr, int D,
                        cudaStream_t s) {
   if (M_max <= 0) return cudaSuccess;
@@ -284,14 +312,14 @@ cudaError_t embed_rows(int dtype, const void* table, const int* tok_id, float* x
 // ------------------------------------------------------------------------------------------------
 // RMS norm: one warp per row
 // ------------------------------------------------------------------------------------------------
-template <typename T>
-__global__ void rmsnorm_rows_kernel(const float* __restrict__ x, const float* __restrict__ w, T* __restrict__ y,
+template <typename T, typename TX = float>
+__global__ void rmsnorm_rows_kernel(const TX* __restrict__ x, const float* __restrict__ w, T* __restrict__ y,
                                     int M_imm, const int* __restrict__ m_ptr, int D, float eps, float scale,
                                     const float* __restrict__ pos_table, const int* __restrict__ tok_pos) {
   const int M = m_ptr ? *m_ptr : M_imm;
   const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (row >= M) return;
-  const float* xr = x + (size_t)row * D;
+  const TX* xr = x + (size_t)row * D;
   float ss = 0.f;
   for (int c = lane * 4; c < D; c += 128) {
     const float4 v = load4(xr + c);
@@ -316,6 +344,18 @@ __global__ void rmsnorm_rows_kernel(const float* __restrict__ x, const float* __
     }
     store4(yr + c, o);
   }
+}
+
+// the same norm over a bf16 residual stream (bf16 mode unless GRAM_FLAG_FP32_RESID)
+cudaError_t rmsnorm_rows_stream(int dtype, const void* x, const float* w, void* y, int M_max, const int* m_ptr, int D,
+                                float eps, float scale, const float* pos_table, const int* tok_pos, cudaStream_t s) {
+  if (M_max <= 0) return cudaSuccess;
+  const int grid = (M_max + 7) / 8;
+  if (dtype == 0)
+    rmsnorm_rows_kernel<float, bf16><<<grid, 256, 0, s>>>((const bf16*)x, w, (float*)y, M_max, m_ptr, D, eps, scale, pos_table, tok_pos);
+  else
+    rmsnorm_rows_kernel<bf16, bf16><<<grid, 256, 0, s>>>((const bf16*)x, w, (bf16*)y, M_max, m_ptr, D, eps, scale, pos_table, tok_pos);
+  return cudaGetLastError();
 }
 
 cudaError_t rmsnorm_rows(int dtype, const float* x, const float* w, void* y, int M_max, const int* m_ptr, int D,

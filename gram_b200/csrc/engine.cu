@@ -35,6 +35,10 @@ struct LayerW {
   void *qkv = nullptr, *o = nullptr, *wi = nullptr, *wo = nullptr;      // self-attn + FF
   void *cq = nullptr, *co = nullptr;                                     // decoder cross-attn q / o
   float *ln0 = nullptr, *ln1 = nullptr, *ln2 = nullptr;
+  // the bf16 residual stream (encoder): fp32 copies of q|k|v and wi kept until finalize, and their bf16 versions with the
+  // RMSNorm gain folded into the columns, W'[n][k] = bf16(W[n][k] * ln[k])
+  float *qkv_f = nullptr, *wi_f = nullptr;
+  void *qkv_g = nullptr, *wi_g = nullptr;
 };
 
 }  // namespace
@@ -127,6 +131,15 @@ struct gram_handle {
 };
 
 namespace {
+
+// bf16 residual stream in the encoder (default for bf16; GRAM_FLAG_FP32_RESID turns it off): needs the folded-norm tcgen05 path
+bool stream_mode(const gram_handle* h) {
+  const gram_config& c = h->cfg;
+  return c.dtype == GRAM_DTYPE_BF16 && !(c.flags & GRAM_FLAG_FP32_RESID) &&
+         !(c.flags & (GRAM_FLAG_UNFUSED_NORM | GRAM_FLAG_SIMT_GEMM | GRAM_FLAG_ENC_CHAIN)) && (h->D % 128) == 0 &&
+         gemm_tc_supported(3 * h->HD, h->D) && gemm_tc_supported(h->D, h->HD) && gemm_tc_supported(h->F, h->D) &&
+         gemm_tc_supported(h->D, h->F);
+}
 
 #define CK(call)                                                                                       \
   do {                                                                                                 \
@@ -224,6 +237,10 @@ __global__ void convert_kernel_f32(const float* __restrict__ src, float* __restr
 __global__ void convert_kernel_bf16(const float* __restrict__ src, bf16* __restrict__ dst, size_t n) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) dst[i] = __float2bfloat16_rn(src[i]);
+}
+__global__ void fold_gain_kernel(const float* __restrict__ w, const float* __restrict__ ln, bf16* __restrict__ out, size_t n, int cols) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = __float2bfloat16_rn(w[i] * ln[i % cols]);
 }
 __global__ void build_lut_kernel(const float* __restrict__ rel, const int* __restrict__ buckets, int n, int H,
                                  float* __restrict__ lut) {
@@ -343,6 +360,30 @@ int encoder_stack(gram_handle* h, const PackMeta& pm, int P, int L, int Mmax, cu
   const bool chained = fused && (c.flags & GRAM_FLAG_ENC_CHAIN) && h->ffs != nullptr;
   GemmNormAux scaled;                  // consumer side
   scaled.row_ss = h->ss; scaled.eps = c.ln_eps;
+  if (stream_mode(h)) {
+    // bf16 residual stream: h->xn IS the stream (h->x is not touched); see the bf16 residual stream
+    GemmNormAux upd; upd.ss_out = h->ss;
+    CKL(GRAM_K_OTHER, embed_rows_stream(h->shared, pm.tok_id, h->xn, h->ss, Mmax, mp, D, s));
+    for (int l = 0; l < h->Le; ++l) {
+      const LayerW& W = h->enc[l];
+      RC(gemm(h, GRAM_K_GEMM_ENC, EPI_STORE, h->xn, W.qkv_g, h->qkv, Mmax, mp, 3 * HD, D, s, &scaled));
+      if (!(c.flags & GRAM_FLAG_MMA_ENC_ATTN) && enc_attention_tc_supported(h->dk, L, h->Lb, h->H) &&
+          (L <= 128 || !(c.flags & GRAM_FLAG_MMA_LONG_ATTN))) {
+        CKL(GRAM_K_ENC_ATTN, enc_attention_tc(h->qkv, (size_t)h->Mcap + 256, h->ao, pm.plen, pm.poff, pm.tok_valid,
+                                              h->enc_bias_lut, h->Lb, P, h->H, L, s));
+      } else if (enc_attention_mma_supported(h->dk, L)) {
+        CKL(GRAM_K_ENC_ATTN, enc_attention_mma(h->qkv, h->ao, pm.plen, pm.poff, pm.tok_valid, h->enc_bias_lut,
+                                               h->Lb, P, h->H, L, s));
+      } else {
+        CKL(GRAM_K_ENC_ATTN, enc_attention(c.dtype, h->qkv, h->ao, pm.plen, pm.poff, pm.tok_valid,
+                                           h->enc_bias_lut, h->Lb, P, h->H, h->dk, L, s));
+      }
+      RC(gemm(h, GRAM_K_GEMM_ENC, EPI_RESID_BF16, h->ao, W.o, h->xn, Mmax, mp, D, HD, s, &upd));
+      RC(gemm(h, GRAM_K_GEMM_ENC, EPI_RELU, h->xn, W.wi_g, h->ff, Mmax, mp, F, D, s, &scaled));
+      RC(gemm(h, GRAM_K_GEMM_ENC, EPI_RESID_BF16, h->ff, W.wo, h->xn, Mmax, mp, D, F, s, &upd));
+    }
+    return GRAM_OK;
+  }
   auto produce = [&](const float* ln_w) { GemmNormAux a; a.xb = h->xn; a.ss_out = h->ss; a.ln_w = ln_w; return a; };
   if (fused) CKL(GRAM_K_OTHER, embed_rows_norm(h->shared, pm.tok_id, h->x, h->xn, h->ss, h->enc[0].ln0, Mmax, mp, D, s));
   else CKL(GRAM_K_OTHER, embed_rows(c.dtype, h->shared, pm.tok_id, h->x, Mmax, mp, D, s));
@@ -387,6 +428,14 @@ int encoder_stack(gram_handle* h, const PackMeta& pm, int P, int L, int Mmax, cu
   return GRAM_OK;
 }
 
+// final encoder norm over whichever residual stream encoder_stack left behind
+cudaError_t enc_final_norm(gram_handle* h, int out_dtype, void* out, int M_max, const int* m_ptr, const float* pos,
+                           const int* tok_pos, cudaStream_t s) {
+  if (stream_mode(h))
+    return rmsnorm_rows_stream(out_dtype, h->xn, h->enc_final_ln, out, M_max, m_ptr, h->D, h->cfg.ln_eps, 1.f, pos, tok_pos, s);
+  return rmsnorm_rows(out_dtype, h->x, h->enc_final_ln, out, M_max, m_ptr, h->D, h->cfg.ln_eps, 1.f, pos, tok_pos, s);
+}
+
 int check_encode_args(gram_handle* h, int B, int N, int L) {
   const gram_config& c = h->cfg;
   if (!h->weights_ready) return fail(h, GRAM_ERR_STATE, "gram_encode: weights not finalised");
@@ -422,8 +471,7 @@ int enqueue_encode(gram_handle* h, const int64_t* dids, const uint8_t* dmask, in
   CKL(GRAM_K_OTHER, enc_pack(dids, dmask, B, N, L, h->pm, s));
   h->launches += 3;   // enc_pack issues four kernels
   RC(encoder_stack(h, h->pm, B * N, L, Mmax, s));
-  CKL(GRAM_K_NORM_ENC, rmsnorm_rows(c.dtype, h->x, h->enc_final_ln, h->mem, Mmax, h->pm.total, h->D, c.ln_eps, 1.f,
-                                 h->pos_emb, h->pos_emb ? h->pm.tok_pos : nullptr, s));
+  CKL(GRAM_K_NORM_ENC, enc_final_norm(h, c.dtype, h->mem, Mmax, h->pm.total, h->pos_emb, h->pos_emb ? h->pm.tok_pos : nullptr, s));
   // cross-attention K/V of every decoder layer, written in place in the layout kernel (b) reads
   RC(gemm(h, GRAM_K_GEMM_KV, EPI_STORE, h->mem, h->ckv_w, h->ckv, Mmax, h->pm.total, h->Ld * 2 * h->HD, h->D, s));
   h->encoded = true;
@@ -656,6 +704,10 @@ int gram_create(const gram_config* cfg, gram_handle** out) {
     DAC(L.qkv, (size_t)3 * HD * D * esz); DAC(L.o, (size_t)D * HD * esz);
     DAC(L.wi, (size_t)F * D * esz); DAC(L.wo, (size_t)D * F * esz);
     DAC(L.ln0, (size_t)D * 4); DAC(L.ln1, (size_t)D * 4);
+    if (stream_mode(h)) {
+      DAC(L.qkv_f, (size_t)3 * HD * D * 4); DAC(L.wi_f, (size_t)F * D * 4);
+      DAC(L.qkv_g, (size_t)3 * HD * D * esz); DAC(L.wi_g, (size_t)F * D * esz);
+    }
   }
   for (int i = 0; i < h->Ld; ++i) {
     LayerW& L = h->dec[i];
@@ -681,7 +733,7 @@ int gram_create(const gram_config* cfg, gram_handle** out) {
   DAC(h->pm.total, 16);
   DAC(h->pm.tok_id, Mc * 4); DAC(h->pm.tok_pos, Mc * 4); DAC(h->pm.tok_valid, Mc); DAC(h->pm.row_src, Mc * 4);
   DAC(h->d_ids, (size_t)full * 8); DAC(h->d_mask, (size_t)full);
-  DAC(h->x, Mc * D * 4);
+  if (!stream_mode(h)) DAC(h->x, Mc * D * 4);   // the bf16 stream lives in xn
   DAC(h->xn, Mc * D * esz); DAC(h->qkv, Mc * 3 * HD * esz); DAC(h->ao, Mc * HD * esz);
   DAC(h->ff, Mc * std::max<size_t>((size_t)F * esz, (size_t)D * 4));   // also an fp32 [rows, D] scratch (item cache)
   DAC(h->mem, Mc * D * esz);
@@ -768,6 +820,18 @@ int gram_load_weight(gram_handle* h, const char* name, const float* data, const 
   if (ws.f32 || h->cfg.dtype == GRAM_DTYPE_F32) convert_kernel_f32<<<grid, 256>>>(h->stage, (float*)ws.dst, n);
   else convert_kernel_bf16<<<grid, 256>>>(h->stage, (bf16*)ws.dst, n);
   CK(cudaGetLastError());
+  {
+    // the bf16 residual stream: the encoder's q|k|v and wi are folded with their RMSNorm gain from the fp32 values at finalize
+    int idx; char what[32];
+    if (stream_mode(h) && sscanf(name, "enc.%d.%31s", &idx, what) == 2 && idx >= 0 && idx < h->Le) {
+      LayerW& L = h->enc[idx];
+      const std::string w = what;
+      float* keep = w == "q" ? L.qkv_f : w == "k" ? L.qkv_f + (size_t)h->HD * h->D : w == "v" ? L.qkv_f + 2 * (size_t)h->HD * h->D
+                    : w == "wi" ? L.wi_f : nullptr;
+      if (keep) convert_kernel_f32<<<grid, 256>>>(h->stage, keep, n);
+      CK(cudaGetLastError());
+    }
+  }
   CK(cudaDeviceSynchronize());
   h->loaded.insert(name);
   h->weights_ready = false;
@@ -810,6 +874,16 @@ int gram_finalize_weights(gram_handle* h) {
   build_lut_kernel<<<(h->n_dec_lut * h->H + 255) / 256, 256>>>(h->dec_rel, tmp, h->n_dec_lut, h->H, h->dec_bias_lut);
   CK(cudaDeviceSynchronize());
   cudaFree(tmp);
+  if (stream_mode(h)) {
+    for (int l = 0; l < h->Le; ++l) {
+      LayerW& L = h->enc[l];
+      const size_t nq = (size_t)3 * h->HD * h->D, nw = (size_t)h->F * h->D;
+      fold_gain_kernel<<<(int)((nq + 255) / 256), 256>>>(L.qkv_f, L.ln0, (bf16*)L.qkv_g, nq, h->D);
+      fold_gain_kernel<<<(int)((nw + 255) / 256), 256>>>(L.wi_f, L.ln1, (bf16*)L.wi_g, nw, h->D);
+    }
+    CK(cudaGetLastError());
+    CK(cudaDeviceSynchronize());
+  }
   if (h->stage) { cudaFree(h->stage); h->stage = nullptr; h->stage_elems = 0; }
   h->buckets_set = false;    // LUT buffers now hold values; buckets must be re-sent before another finalize
   h->weights_ready = true;
@@ -927,8 +1001,7 @@ int gram_cache_items(gram_handle* h, const int64_t* ids, const uint8_t* mask, in
     CKL(GRAM_K_OTHER, enc_pack(h->d_ids, h->d_mask, Bc, N, L, h->pm, s));
     RC(encoder_stack(h, h->pm, Bc * N, L, Mmax, s));
     // final norm in fp32, WITHOUT the position row (h->ff is free after the last block and holds >= Mcap*D floats)
-    CKL(GRAM_K_NORM_ENC, rmsnorm_rows(GRAM_DTYPE_F32, h->x, h->enc_final_ln, h->ff, Mmax, h->pm.total, h->D, c.ln_eps, 1.f,
-                                   nullptr, nullptr, s));
+    CKL(GRAM_K_NORM_ENC, enc_final_norm(h, GRAM_DTYPE_F32, h->ff, Mmax, h->pm.total, nullptr, nullptr, s));
     CKL(GRAM_K_OTHER, cache_scatter((const float*)h->ff, h->pm, Mmax, h->D, first * L, h->item_mem, h->item_valid, s));
     CK(cudaMemcpyAsync(h->item_len + first, h->pm.plen, (size_t)cnt * 4, cudaMemcpyDeviceToDevice, s));
     if (!dev_in || !dev_mask) CK(cudaStreamSynchronize(s));     // the caller's host buffers are consumed per chunk
@@ -972,8 +1045,7 @@ int gram_encode_cached(gram_handle* h, const int64_t* prompt_ids, const uint8_t*
   h->launches += 3;
   const int Mprompt = (int)std::min<int64_t>((int64_t)n, h->Mcap);
   RC(encoder_stack(h, h->pm_prompt, B, L, Mprompt, s));
-  CKL(GRAM_K_NORM_ENC, rmsnorm_rows(GRAM_DTYPE_F32, h->x, h->enc_final_ln, h->ff, Mprompt, h->pm_prompt.total, h->D, c.ln_eps,
-                                 1.f, nullptr, nullptr, s));
+  CKL(GRAM_K_NORM_ENC, enc_final_norm(h, GRAM_DTYPE_F32, h->ff, Mprompt, h->pm_prompt.total, nullptr, nullptr, s));
   // 2. user layout + memory = prompt rows / cached item rows + position rows
   const int Mmax = (int)std::min<int64_t>((int64_t)B * N * L, h->Mcap);
   CKL(GRAM_K_OTHER, cached_pack_assemble(c.dtype, h->pm, h->pm_prompt, (const float*)h->ff, ditems, h->item_mem, h->item_valid,

@@ -33,6 +33,7 @@
 #include <map>
 #include <tuple>
 #include <string>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "kernels.h"
@@ -47,7 +48,6 @@ namespace tc {
 // tile is used whenever the problem still yields at least two waves of tiles.
 constexpr int BLOCK_M = 128, BLOCK_K = 64, UMMA_K = 16;
 constexpr int ACC_STAGES = 2;
-constexpr int THREADS = 192;
 constexpr uint32_t A_BYTES = BLOCK_M * BLOCK_K * 2;        // 16 KiB
 constexpr uint32_t CSTAGE_BYTES = 32 * 1024;               // epilogue staging: two 128-row x 128-byte boxes
 // EPI_RESID_NORM stages the residual stream through the SM: two 32 KiB buffers (x of the next round is prefetched
@@ -57,14 +57,28 @@ constexpr uint32_t CSTAGE_BYTES = 32 * 1024;               // epilogue staging: 
 // half-sector writes, and the K = 2048 GEMM is held by the power cap, not by the ring depth (77 % tensor-pipe
 // activity at 1.16 GHz vs 65 % at 1.40 GHz)
 constexpr uint32_t NORM_EPI_BYTES = 2 * CSTAGE_BYTES + 16 * 1024;
-template <int BN, int CTAS, bool NORM = false> struct Cfg {
+// EG = epilogue warp groups (4 warps each, one per TMEM lane quadrant).  With K = 512 a 256-column accumulator is
+// produced in 8 k-blocks = 4096 tensor-pipe clocks, which one group barely drains (ncu source view of the q|k|v GEMM,
+// round 2: the MMA warp waited for a free accumulator, not for operands; tensor pipe 60 % busy; 25 % of the samples on
+// un-pipelined tcgen05.ld waits, 16 % on the MEMBAR.GPU of a release-arrive).  Fixed in the epilogue itself (pipelined
+// TMEM reads, relaxed hand-back); a second group (EG = 2, alternate 32 KiB rounds through its own staging buffer) is
+// what the bf16-stream epilogue uses and an opt-in for the plain ones (see pair_epilogue_groups()).
+// MODE 0: plain epilogues, 1: EPI_RESID_NORM (fp32 stream through the SM), 2: EPI_RESID_BF16 (bf16 stream through the SM:
+// three 16 KiB boxes per epilogue group -- the box of round r+1 is prefetched and the store of round r-1 may still be
+// reading its box while round r is updated in place)
+constexpr uint32_t XBOX_BYTES = 16 * 1024;
+template <int BN, int CTAS, int MODE = 0, int EG = 1> struct Cfg {
   static constexpr int LOAD_N = BN / CTAS;                 // W rows each CTA loads per stage
   static constexpr uint32_t B_BYTES = LOAD_N * BLOCK_K * 2;   // 16 or 32 KiB
   static constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr uint32_t EPI_BYTES = NORM ? NORM_EPI_BYTES : CSTAGE_BYTES;
-  static constexpr int STAGES = NORM ? (STAGE_BYTES == 32768 ? 4 : 2) : (STAGE_BYTES == 32768 ? 6 : 4);
+  static constexpr uint32_t EPI_BYTES = MODE == 1 ? NORM_EPI_BYTES : MODE == 2 ? 3 * XBOX_BYTES * EG : CSTAGE_BYTES * EG;
+  static constexpr int STAGES = MODE == 1 ? (STAGE_BYTES == 32768 ? 4 : 2)
+                                : MODE == 2 ? (STAGE_BYTES == 32768 ? (EG == 2 ? 4 : 5) : 3)
+                                            : (STAGE_BYTES == 32768 ? (EG == 2 ? 5 : 6) : (EG == 2 ? 3 : 4));
+  static constexpr int THREADS = 64 + 128 * EG;
   static constexpr int TMEM_COLS = ACC_STAGES * BN;        // 256 or 512 (power of two)
   static constexpr size_t SMEM_BYTES = (size_t)STAGES * STAGE_BYTES + EPI_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+  static_assert(SMEM_BYTES <= 232448, "227 KiB of shared memory per CTA");
   // instruction descriptor: D=f32, A=B=bf16, both K-major, M=128 per CTA (256 for a pair), N=BN
   static constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) |
                                     ((uint32_t)((BLOCK_M * CTAS) >> 4) << 24);
@@ -79,12 +93,13 @@ struct NormArgs {
   float inv_d, eps;       // consumer: 1 / K, epsilon
 };
 
-template <int EPI, int BLOCK_N, int CTAS>
-__global__ void __launch_bounds__(THREADS, 1)
+template <int EPI, int BLOCK_N, int CTAS, int EG = 1>
+__global__ void __launch_bounds__(64 + 128 * EG, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
                const __grid_constant__ CUtensorMap map_c, const __grid_constant__ CUtensorMap map_xb,
                float2* __restrict__ lse_partial, int M_imm, const int* __restrict__ m_ptr, int N, int K, NormArgs na) {
-  using C_ = Cfg<BLOCK_N, CTAS, EPI == EPI_RESID_NORM>;
+  using C_ = Cfg<BLOCK_N, CTAS, EPI == EPI_RESID_NORM ? 1 : EPI == EPI_RESID_BF16 ? 2 : 0, EG>;
+  static_assert(EG == 1 || (EPI != EPI_RESID_NORM && EPI != EPI_LSE), "two epilogue groups: plain store / reduce epilogues only");
   constexpr int STAGES = C_::STAGES;
   constexpr uint32_t STAGE_BYTES = C_::STAGE_BYTES;
   constexpr int TMEM_COLS = C_::TMEM_COLS;
@@ -95,13 +110,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   const uint32_t base = (raw + 1023u) & ~1023u;           // 1024-byte alignment for the 128B swizzle atoms
   uint8_t* smem = smem_raw + (base - raw);
   const uint32_t cstage = base + STAGES * STAGE_BYTES;    // epilogue staging (1024-aligned)
-  const uint32_t bars = cstage + C_::EPI_BYTES;           // full[STAGES], empty[STAGES], tfull[2], tempty[2], xfull[2], tmem ptr
+  const uint32_t bars = cstage + C_::EPI_BYTES;           // full[STAGES], empty[STAGES], tfull[2], tempty[2], xfull[6], tmem ptr
   auto full_bar = [&](int s) { return bars + 8u * s; };
   auto empty_bar = [&](int s) { return bars + 8u * (STAGES + s); };
   auto tfull_bar = [&](int s) { return bars + 8u * (2 * STAGES + s); };
   auto tempty_bar = [&](int s) { return bars + 8u * (2 * STAGES + ACC_STAGES + s); };
   auto xfull_bar = [&](int s) { return bars + 8u * (2 * STAGES + 2 * ACC_STAGES + s); };
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + STAGES * STAGE_BYTES + C_::EPI_BYTES + 8 * (2 * STAGES + 2 * ACC_STAGES + 2));
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + STAGES * STAGE_BYTES + C_::EPI_BYTES + 8 * (2 * STAGES + 2 * ACC_STAGES + 6));
+  static_assert(8 * (2 * STAGES + 2 * ACC_STAGES + 6) + 4 <= 256, "barrier block");
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int M = m_ptr ? *m_ptr : M_imm;
@@ -117,8 +133,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_c) : "memory");
     for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-    for (int s = 0; s < ACC_STAGES; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 4 * CTAS); }
-    for (int s = 0; s < 2; ++s) mbar_init(xfull_bar(s), 1);
+    for (int s = 0; s < ACC_STAGES; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 4 * CTAS * EG); }
+    for (int s = 0; s < 6; ++s) mbar_init(xfull_bar(s), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -197,17 +213,27 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1u; }
     }
   } else {
-    // ===================== epilogue (warps 2..5) =====================
+    // ===================== epilogue (warps 2..5; with EG = 2 also warps 6..9) =====================
     const int quad = warp & 3;                             // TMEM lane quadrant this warp may access
     const int r = quad * 32 + lane;                        // row of the tile this thread owns
-    const bool issuer = (warp == 2 && lane == 0);
+    const int grp = EG == 2 ? ((warp - 2) >> 2) : 0;       // epilogue group: takes rounds grp, grp + EG, ...
+    const bool issuer = (warp == 2 + 4 * grp && lane == 0);
+    const uint32_t gstage = cstage + (uint32_t)grp * CSTAGE_BYTES;   // this group's staging buffer
     constexpr bool kOutBf16 = (EPI == EPI_STORE || EPI == EPI_RELU);
     constexpr int CHUNKS_PER_ROUND = kOutBf16 ? 4 : 2;     // 32 KiB of staging = 128 bf16 or 64 fp32 columns
     constexpr int ROUNDS = (BLOCK_N / 32) / CHUNKS_PER_ROUND;
+    static_assert(ROUNDS % EG == 0 || EPI == EPI_RESID_BF16, "every epilogue group takes part in every tile");
     int acc = 0; uint32_t acc_phase = 0;
+    // Handing the accumulator back orders nothing but tcgen05 operations (the tcgen05.ld's have completed and
+    // tcgen05.fence::before_thread_sync precedes the arrive), so the remote arrive is relaxed: the release form
+    // costs MEMBAR.ALL.GPU + ERRBAR per warp per tile (11 % of the q|k|v GEMM's stall samples)
     auto release_acc = [&](int a) {
-      if (CTAS == 2) mbar_arrive_cluster(leader_addr(tempty_bar(a)));
+      if (CTAS == 2) mbar_arrive_cluster_relaxed(leader_addr(tempty_bar(a)));
       else mbar_arrive(tempty_bar(a));
+    };
+    auto group_bar = [&]() {
+      if (EG == 2 && grp == 1) asm volatile("bar.sync 2, 128;" ::: "memory");
+      else epi_bar();
     };
     uint32_t xround = 0;                                   // EPI_RESID_NORM: rounds processed so far (buffer = parity)
     if constexpr (EPI == EPI_RESID_NORM) {
@@ -215,6 +241,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         mbar_arrive_expect_tx(xfull_bar(0), CSTAGE_BYTES);
         tma_load_2d(cstage, &map_c, xfull_bar(0), (tile0 % num_n) * BLOCK_N, (tile0 / num_n) * TILE_M + rank * BLOCK_M);
         tma_load_2d(cstage + 16384u, &map_c, xfull_bar(0), (tile0 % num_n) * BLOCK_N + 32, (tile0 / num_n) * TILE_M + rank * BLOCK_M);
+      }
+    }
+    if constexpr (EPI == EPI_RESID_BF16) {
+      if (issuer && tile0 < num_tiles) {                   // this group's box of the very first round
+        mbar_arrive_expect_tx(xfull_bar(grp * 3), XBOX_BYTES);
+        tma_load_2d(cstage + (uint32_t)grp * 3u * XBOX_BYTES, &map_c, xfull_bar(grp * 3),
+                    (tile0 % num_n) * BLOCK_N + grp * 128, (tile0 / num_n) * TILE_M + rank * BLOCK_M);
       }
     }
     for (int tile = tile0; tile < num_tiles; tile += tile_step) {
@@ -357,26 +390,99 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1u; }
         continue;
       }
+      if constexpr (EPI == EPI_RESID_BF16) {
+        // bf16 residual stream updated in place: per round one 128-row x 64-column box of the stream arrives by TMA
+        // (prefetched a round ahead), thread = row adds its accumulator slice, rounds to bf16, sums the squares of the
+        // ROUNDED values (what the consumer GEMM will read) and the box goes back by TMA.  Group g owns the tile's
+        // 128-column block g, i.e. one sum-of-squares partial per (row, block) -- same owner rule as EPI_RESID_NORM.
+        constexpr int RPG = (BLOCK_N / 64) / EG;           // rounds per group per tile (2)
+        static_assert(RPG == 2, "a group owns one 128-column block of the tile");
+        const uint32_t gx = cstage + (uint32_t)grp * 3u * XBOX_BYTES;
+        const int row = row0 + r;
+        const bool live_row = row < M;
+        float ssq = 0.f;
 #pragma unroll 1
-      for (int rd = 0; rd < ROUNDS; ++rd) {
+        for (int rl = 0; rl < RPG; ++rl, ++xround) {
+          const uint32_t bsel = xround % 3u, nsel = (xround + 1u) % 3u;
+          const uint32_t xb_cur = gx + bsel * XBOX_BYTES;
+          const int colt = (grp * RPG + rl) * 64;          // first column of this round inside the tile
+          if (issuer) {
+            tma_store_wait_read1();                        // the store of round r-2 has read the box round r+1 lands in
+            int nt = tile, nrl = rl + 1;
+            if (nrl == RPG) { nt = tile + tile_step; nrl = 0; }
+            if (nt < num_tiles) {
+              const int ncol = (nt % num_n) * BLOCK_N + (grp * RPG + nrl) * 64, nrow = (nt / num_n) * TILE_M + rank * BLOCK_M;
+              mbar_arrive_expect_tx(xfull_bar(grp * 3 + nsel), XBOX_BYTES);
+              tma_load_2d(gx + nsel * XBOX_BYTES, &map_c, xfull_bar(grp * 3 + nsel), ncol, nrow);
+            }
+          }
+          uint32_t v[2][32];
+          const uint32_t taddr0 = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BLOCK_N + colt);
+          tmem_ld32(taddr0, v[0]);
+          mbar_wait(xfull_bar(grp * 3 + bsel), (xround / 3u) & 1u);
+#pragma unroll
+          for (int cc = 0; cc < 2; ++cc) {
+            tmem_ld_wait();
+            if (cc == 0) tmem_ld32(taddr0 + 32u, v[1]);
+            uint32_t (&w)[32] = v[cc];
+            const uint32_t xrow = xb_cur + (uint32_t)r * 128u;
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              const uint32_t addr = xrow + (uint32_t)(((cc * 4 + g) ^ (r & 7)) << 4);
+              uint32_t o[4];
+              asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(o[0]), "=r"(o[1]), "=r"(o[2]), "=r"(o[3]) : "r"(addr) : "memory");
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const float2 xo = __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&o[e]));
+                __nv_bfloat162 h2 = __floats2bfloat162_rn(xo.x + __uint_as_float(w[g * 8 + 2 * e]), xo.y + __uint_as_float(w[g * 8 + 2 * e + 1]));
+                if (!live_row) h2 = __floats2bfloat162_rn(0.f, 0.f);
+                const float2 xn2 = __bfloat1622float2(h2);
+                ssq = fmaf(xn2.x, xn2.x, ssq); ssq = fmaf(xn2.y, xn2.y, ssq);
+                o[e] = *reinterpret_cast<uint32_t*>(&h2);
+              }
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(o[0]), "r"(o[1]), "r"(o[2]), "r"(o[3]) : "memory");
+            }
+          }
+          if (rl == RPG - 1) {
+            if (live_row) na.ss_out[(size_t)row * (N >> 7) + n_blk * (BLOCK_N >> 7) + grp] = ssq;
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) release_acc(acc);
+          }
+          fence_async_smem();
+          group_bar();
+          if (issuer) {
+            const int col0 = n_blk * BLOCK_N + colt;
+            if (col0 < N) tma_store_2d(&map_c, xb_cur, col0, row0);
+            tma_store_commit();
+          }
+        }
+        if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1u; }
+        continue;
+      }
+#pragma unroll 1
+      for (int rd = grp; rd < ROUNDS; rd += EG) {
         if (issuer) tma_store_wait_read();                 // previous bulk store has finished reading the staging tile
-        epi_bar();
-#pragma unroll 1
+        group_bar();
+        // software-pipelined TMEM reads: chunk cc + 1 is in flight while chunk cc is converted and staged
+        uint32_t v[2][32];
+        const uint32_t taddr0 = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BLOCK_N + rd * CHUNKS_PER_ROUND * 32);
+        tmem_ld32(taddr0, v[0]);
+#pragma unroll
         for (int cc = 0; cc < CHUNKS_PER_ROUND; ++cc) {
           const int c = rd * CHUNKS_PER_ROUND + cc;        // 32-column chunk of the accumulator
-          uint32_t v[32];
-          const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BLOCK_N + c * 32);
-          tmem_ld32(taddr, v);
           tmem_ld_wait();
+          if (cc + 1 < CHUNKS_PER_ROUND) tmem_ld32(taddr0 + (uint32_t)((cc + 1) * 32), v[(cc + 1) & 1]);
+          uint32_t (&w)[32] = v[cc & 1];
           if (kOutBf16) {
             // box (cc/2): 128 rows x 64 bf16 (128 B per row); this chunk is the 16-byte pieces (c%2)*4 .. +3
-            const uint32_t box = cstage + (uint32_t)(cc >> 1) * 16384u + (uint32_t)r * 128u;
+            const uint32_t box = gstage + (uint32_t)(cc >> 1) * 16384u + (uint32_t)r * 128u;
 #pragma unroll
             for (int g = 0; g < 4; ++g) {
               uint32_t pk[4];
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
-                float a = __uint_as_float(v[g * 8 + 2 * e]) * rs, b = __uint_as_float(v[g * 8 + 2 * e + 1]) * rs;
+                float a = __uint_as_float(w[g * 8 + 2 * e]) * rs, b = __uint_as_float(w[g * 8 + 2 * e + 1]) * rs;
                 if (EPI == EPI_RELU) { a = fmaxf(a, 0.f); b = fmaxf(b, 0.f); }
                 __nv_bfloat162 h2 = __floats2bfloat162_rn(a, b);
                 pk[e] = *reinterpret_cast<uint32_t*>(&h2);
@@ -387,30 +493,30 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             }
           } else {
             // box cc: 128 rows x 32 fp32 (128 B per row)
-            const uint32_t box = cstage + (uint32_t)cc * 16384u + (uint32_t)r * 128u;
+            const uint32_t box = gstage + (uint32_t)cc * 16384u + (uint32_t)r * 128u;
 #pragma unroll
             for (int g = 0; g < 8; ++g) {
               const uint32_t piece = (uint32_t)(g ^ (r & 7));
-              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(box + (piece << 4)), "r"(v[g * 4]),
-                           "r"(v[g * 4 + 1]), "r"(v[g * 4 + 2]), "r"(v[g * 4 + 3]) : "memory");
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(box + (piece << 4)), "r"(w[g * 4]),
+                           "r"(w[g * 4 + 1]), "r"(w[g * 4 + 2]), "r"(w[g * 4 + 3]) : "memory");
             }
           }
         }
-        if (rd == ROUNDS - 1) {
-          // every tcgen05.ld of this accumulator has completed: hand it back to the MMA warp
+        if (rd + EG >= ROUNDS) {
+          // every tcgen05.ld of this group's share of the accumulator has completed: hand it back to the MMA warp
           tcgen05_fence_before();
           __syncwarp();
           if (lane == 0) release_acc(acc);
         }
         fence_async_smem();                                // generic-proxy writes -> visible to the async proxy
-        epi_bar();
+        group_bar();
         if (issuer) {
 #pragma unroll
           for (int bx = 0; bx < 2; ++bx) {
             const int col0 = n_blk * BLOCK_N + (kOutBf16 ? (rd * 2 + bx) * 64 : (rd * 2 + bx) * 32);
             if (col0 < N) {
-              if (EPI == EPI_RESID) tma_reduce_add_2d(&map_c, cstage + bx * 16384u, col0, row0);
-              else tma_store_2d(&map_c, cstage + bx * 16384u, col0, row0);
+              if (EPI == EPI_RESID) tma_reduce_add_2d(&map_c, gstage + bx * 16384u, col0, row0);
+              else tma_store_2d(&map_c, gstage + bx * 16384u, col0, row0);
             }
           }
           tma_store_commit();
@@ -439,7 +545,7 @@ std::mutex g_mu;
 EncodeTiledFn g_encode = nullptr;
 std::string g_err;
 std::map<std::tuple<const void*, int, long long>, CUtensorMap> g_maps;
-SmemAttr g_attr[18];
+SmemAttr g_attr[42];
 
 bool get_encode() {
   if (g_encode) return true;
@@ -483,14 +589,14 @@ bool get_map(const void* ptr, int rows, int cols, int kind, int box_rows, CUtens
 
 // resident CTA pairs the device can hold for one instantiation (cached per device)
 template <typename Kern>
-int max_pairs(Kern kern, size_t smem, int num_sms, int* cache) {
+int max_pairs(Kern kern, size_t smem, int threads, int num_sms, int* cache) {
   int dev = 0;
   cudaGetDevice(&dev);
   dev &= 63;
   if (cache[dev] == 0) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(num_sms & ~1);
-    cfg.blockDim = dim3(THREADS);
+    cfg.blockDim = dim3(threads);
     cfg.dynamicSmemBytes = smem;
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeClusterDimension;
@@ -503,15 +609,17 @@ int max_pairs(Kern kern, size_t smem, int num_sms, int* cache) {
   return cache[dev];
 }
 
-int g_pairs[18][64];
+int g_pairs[42][64];
 
-template <int EPI, int BN, int CTAS>
+template <int EPI, int BN, int CTAS, int EG = 1>
 cudaError_t launch(const CUtensorMap& ma, const CUtensorMap& mw, const CUtensorMap& mc, const CUtensorMap& mxb,
                    float2* lse_partial, int M_max, const int* m_ptr, int N, int K, const NormArgs& na, int num_sms,
                    cudaStream_t s) {
-  auto kern = gemm_tc_kernel<EPI, BN, CTAS>;
-  constexpr size_t smem = Cfg<BN, CTAS, EPI == EPI_RESID_NORM>::SMEM_BYTES;
-  constexpr int slot = EPI * 3 + (BN == 256) + (CTAS == 2);
+  auto kern = gemm_tc_kernel<EPI, BN, CTAS, EG>;
+  using C_ = Cfg<BN, CTAS, EPI == EPI_RESID_NORM ? 1 : EPI == EPI_RESID_BF16 ? 2 : 0, EG>;
+  constexpr size_t smem = C_::SMEM_BYTES;
+  constexpr int threads = C_::THREADS;
+  constexpr int slot = EPI * 3 + (BN == 256) + (CTAS == 2) + 21 * (EG - 1);
   {
     cudaError_t e = g_attr[slot].ensure(kern, smem);
     if (e != cudaSuccess) return e;
@@ -519,14 +627,14 @@ cudaError_t launch(const CUtensorMap& ma, const CUtensorMap& mw, const CUtensorM
   const int tiles = ((M_max + BLOCK_M * CTAS - 1) / (BLOCK_M * CTAS)) * ((N + BN - 1) / BN);
   if (CTAS == 1) {
     const int grid = tiles < num_sms ? tiles : num_sms;
-    kern<<<grid, THREADS, smem, s>>>(ma, mw, mc, mxb, lse_partial, M_max, m_ptr, N, K, na);
+    kern<<<grid, threads, smem, s>>>(ma, mw, mc, mxb, lse_partial, M_max, m_ptr, N, K, na);
     return cudaGetLastError();
   }
-  const int pairs = max_pairs(kern, smem, num_sms, g_pairs[slot]);
+  const int pairs = max_pairs(kern, smem, threads, num_sms, g_pairs[slot]);
   if (pairs <= 0) return cudaErrorLaunchOutOfResources;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(2 * (tiles < pairs ? tiles : pairs));
-  cfg.blockDim = dim3(THREADS);
+  cfg.blockDim = dim3(threads);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = s;
   cudaLaunchAttribute at[1];
@@ -534,6 +642,16 @@ cudaError_t launch(const CUtensorMap& ma, const CUtensorMap& mw, const CUtensorM
   at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
   cfg.attrs = at; cfg.numAttrs = 1;
   return cudaLaunchKernelEx(&cfg, kern, ma, mw, mc, mxb, lse_partial, M_max, m_ptr, N, K, na);
+}
+
+// GRAM_GEMM_EG=2 runs TWO epilogue groups on the CTA-pair tiles of the plain epilogues (A/B).  Measured (round 2, one call,
+// M = 1 M rows): q|k|v 1153 vs 1229 TFLOP/s, wi 1170 vs 1241 with ONE group -- the fifth ring stage the second staging
+// buffer costs and the 128 extra threads lose more than the second group gains once the TMEM reads are pipelined and the
+// accumulator hand-back is a relaxed arrive; one group is the default
+inline int pair_epilogue_groups() {
+  static int v = 0;
+  if (v == 0) { const char* e = getenv("GRAM_GEMM_EG"); v = (e && e[0] == '2') ? 2 : 1; }
+  return v;
 }
 
 // Tile shape: 128 x 128 for small problems; 128 x 256 when that still gives every SM at least two tiles; a CTA pair
@@ -565,7 +683,7 @@ cudaError_t gemm_tc(int epi, const void* A, const void* W, void* C, int M_max, c
   if (!gemm_tc_supported(N, K)) return cudaErrorInvalidValue;
   std::lock_guard<std::mutex> lk(tc::g_mu);
   CUtensorMap ma, mw, mc;
-  const int ckind = (epi == EPI_STORE || epi == EPI_RELU) ? 0 : 1;
+  const int ckind = (epi == EPI_STORE || epi == EPI_RELU || epi == EPI_RESID_BF16) ? 0 : 1;
   tc::NormArgs na = {};
   if (aux && aux->row_ss) {
     if ((epi != EPI_STORE && epi != EPI_RELU) || (K & 127)) return cudaErrorInvalidValue;
@@ -583,6 +701,17 @@ cudaError_t gemm_tc(int epi, const void* A, const void* W, void* C, int M_max, c
     return pairs ? tc::launch<EPI_RESID_NORM, 256, 2>(ma, mw, mc, mxb, nullptr, M_max, m_ptr, N, K, na, num_sms, s)
                  : tc::launch<EPI_RESID_NORM, 128, 1>(ma, mw, mc, mxb, nullptr, M_max, m_ptr, N, K, na, num_sms, s);
   }
+  if (epi == EPI_RESID_BF16) {
+    // bf16 residual stream updated in place (kernels.h): 128-column single-CTA tiles, or CTA pairs with two epilogue groups
+    if (!aux || !aux->ss_out || (N & 127)) return cudaErrorInvalidValue;
+    na.ss_out = aux->ss_out;
+    const bool pairs = tc::pick_shape(M_max, N, num_sms, max_ctas).ctas == 2;
+    if (!tc::get_map(A, M_max, K, 0, tc::BLOCK_M, &ma) || !tc::get_map(W, N, K, 0, 128, &mw) ||
+        !tc::get_map(C, M_max, N, 0, tc::BLOCK_M, &mc))
+      return cudaErrorUnknown;
+    return pairs ? tc::launch<EPI_RESID_BF16, 256, 2, 2>(ma, mw, mc, mc, nullptr, M_max, m_ptr, N, K, na, num_sms, s)
+                 : tc::launch<EPI_RESID_BF16, 128, 1, 1>(ma, mw, mc, mc, nullptr, M_max, m_ptr, N, K, na, num_sms, s);
+  }
   // the fused log-softmax epilogue stays on single-CTA tiles: it is exp2-bound, and making the leader wait for the
   // slower of two epilogues cost 11 % on the vocabulary head (measured)
   const tc::Shape sh = tc::pick_shape(M_max, N, num_sms, epi == EPI_LSE ? 1 : max_ctas);
@@ -592,15 +721,20 @@ cudaError_t gemm_tc(int epi, const void* A, const void* W, void* C, int M_max, c
   return sh.ctas == 2 ? tc::launch<E, 256, 2>(ma, mw, MC, MC, LP, M_max, m_ptr, N, K, na, num_sms, s)          \
          : sh.bn == 256 ? tc::launch<E, 256, 1>(ma, mw, MC, MC, LP, M_max, m_ptr, N, K, na, num_sms, s)        \
                         : tc::launch<E, 128, 1>(ma, mw, MC, MC, LP, M_max, m_ptr, N, K, na, num_sms, s)
+#define GRAM_TC_LAUNCH_EG(E, MC)                                                                               \
+  if (sh.ctas == 2 && tc::pair_epilogue_groups() == 2)                                                         \
+    return tc::launch<E, 256, 2, 2>(ma, mw, MC, MC, nullptr, M_max, m_ptr, N, K, na, num_sms, s);              \
+  GRAM_TC_LAUNCH(E, MC, nullptr)
   if (epi == EPI_LSE) { GRAM_TC_LAUNCH(EPI_LSE, ma, (float2*)C); }
   if (!tc::get_map(C, M_max, N, ckind, tc::BLOCK_M, &mc)) return cudaErrorUnknown;
   switch (epi) {
-    case EPI_STORE: GRAM_TC_LAUNCH(EPI_STORE, mc, nullptr);
-    case EPI_RELU: GRAM_TC_LAUNCH(EPI_RELU, mc, nullptr);
-    case EPI_RESID: GRAM_TC_LAUNCH(EPI_RESID, mc, nullptr);
-    case EPI_F32: GRAM_TC_LAUNCH(EPI_F32, mc, nullptr);
+    case EPI_STORE: { GRAM_TC_LAUNCH_EG(EPI_STORE, mc); }
+    case EPI_RELU: { GRAM_TC_LAUNCH_EG(EPI_RELU, mc); }
+    case EPI_RESID: { GRAM_TC_LAUNCH_EG(EPI_RESID, mc); }
+    case EPI_F32: { GRAM_TC_LAUNCH_EG(EPI_F32, mc); }
     default: return cudaErrorInvalidValue;
   }
+#undef GRAM_TC_LAUNCH_EG
 #undef GRAM_TC_LAUNCH
 }
 

@@ -25,10 +25,15 @@ struct SmemAttr {
   }
 };
 
-enum { EPI_STORE = 0, EPI_RELU = 1, EPI_RESID = 2, EPI_F32 = 3, EPI_LSE = 4, EPI_RESID_NORM = 5 };
+enum { EPI_STORE = 0, EPI_RELU = 1, EPI_RESID = 2, EPI_F32 = 3, EPI_LSE = 4, EPI_RESID_NORM = 5, EPI_RESID_BF16 = 6 };
 // EPI_LSE (tcgen05 GEMM only): C is float2 [M, ceil(N/128)] of per-tile (max, sum exp(x - max)); no logits are stored
 // EPI_RESID_NORM (tcgen05 GEMM only): C (fp32 residual stream) += A W^T like EPI_RESID, and the input of the RMSNorm that
 // follows is produced on the way (GemmNormAux): no separate normalisation pass over the residual stream
+
+// EPI_RESID_BF16 (tcgen05 GEMM only; bf16 mode unless GRAM_FLAG_FP32_RESID): C is a bf16 residual stream updated in place,
+// C = bf16(C + A W^T), with the row sums of squares of the ROUNDED rows per 128-column block (aux->ss_out).  The stream
+// itself is the next GEMM's A operand (the RMSNorm gain is folded into that GEMM's weight columns at load time), so a
+// residual GEMM moves 2 + 2 B per element of the stream instead of 4 + 4 + 2
 
 // RMSNorm folded into the tcgen05 GEMMs on either side of it (reference T5LayerNorm, src/model/gram_t5_modeling.py:
 // 253-276: y = w * x * rsqrt(mean(x^2) + eps)).  The producer (EPI_RESID_NORM) writes xb = bf16(x * w) and the row's sums
@@ -98,6 +103,11 @@ cudaError_t embed_rows_norm(const void* table, const int* tok_id, float* x, void
 // y = w * (x * rsqrt(mean(x^2)+eps)) * scale  [+ pos_table[tok_pos[row]]]   (x fp32 -> y dtype)
 cudaError_t rmsnorm_rows(int dtype, const float* x, const float* w, void* y, int M_max, const int* m_ptr, int D,
                          float eps, float scale, const float* pos_table, const int* tok_pos, cudaStream_t s);
+// bf16 residual stream (bf16 mode unless GRAM_FLAG_FP32_RESID): the stream's first value (= the embedding row) + ss [M][D/128]; the norm over it
+cudaError_t embed_rows_stream(const void* table, const int* tok_id, void* xr, float* ss, int M_max, const int* m_ptr, int D,
+                              cudaStream_t s);
+cudaError_t rmsnorm_rows_stream(int dtype, const void* x, const float* w, void* y, int M_max, const int* m_ptr, int D,
+                                float eps, float scale, const float* pos_table, const int* tok_pos, cudaStream_t s);
 // bidirectional self-attention of every (passage, head): qkv [M, 3*H*dk] -> out [M, H*dk]
 cudaError_t enc_attention(int dtype, const void* qkv, void* out, const int* plen, const int* poff,
                           const uint8_t* tok_valid, const float* bias_lut /*[H, 2*Lb-1]*/, int Lb, int P, int H,

@@ -87,6 +87,15 @@ enum {
                                       small batches                                             */
   GRAM_FLAG_XATTN_PER_ITEM = 8192, /* cross-attention with one CTA per (user, head group) instead of the persistent kernel that
                                       streams the K/V tiles of consecutive items without a gap (A-B timing)            */
+  GRAM_FLAG_FP32_RESID = 16384,    /* bf16 encoder: keep the residual stream in fp32 (the round-1 arithmetic; A-B timing and a more
+                                      conservative precision mode).  Default for dtype bf16: the encoder's residual stream is bf16,
+                                      as in the reference run under model.bfloat16(): the residual GEMMs (o, wo) update it in
+                                      place (x = bf16(x + A W^T), sums of squares of the rounded rows on the way) and the stream
+                                      itself is the A operand of q|k|v and wi, whose weight columns carry the RMSNorm gain
+                                      (folded from the fp32 weights when they are finalised): 4 B per stream element per
+                                      residual GEMM instead of 10 (fp32 read + fp32 write + bf16 copy).  One more bf16
+                                      rounding per sublayer; measured parity and speed in DESIGN.md section 5h.  The decoder's
+                                      stream (a few thousand rows) stays fp32                                              */
   GRAM_FLAG_NO_DEC_CHAIN = 1024,   /* bf16 decoder: cross-attention output projection, wi and wo as three launches instead of
                                       one chain launch per layer (A-B timing)                                         */
   GRAM_FLAG_ALL_ROWS = 32          /* decode every beam row at every step, as the reference does (A-B timing).  Default:

@@ -119,7 +119,8 @@ def test_chained_encoder_is_bit_identical_to_three_launches():
     fn = prefix_allowed_tokens_fn(Trie(seqs))
     ml = max(len(s) for s in seqs)
     outs = []
-    for flags in (_cabi.GRAM_FLAG_ENC_CHAIN, 0, _cabi.GRAM_FLAG_NO_DEC_CHAIN):
+    F32 = _cabi.GRAM_FLAG_FP32_RESID     # the encoder chain works on the fp32 residual stream: compare like with like
+    for flags in (_cabi.GRAM_FLAG_ENC_CHAIN, F32, F32 | _cabi.GRAM_FLAG_NO_DEC_CHAIN, 0, _cabi.GRAM_FLAG_NO_DEC_CHAIN):
         m = GRAM(cfg, dtype="bf16", device="cuda:0", flags=flags, max_users=96)
         m.load_state_dict(sd)
         mem = m.encode(ids, mask)
@@ -127,7 +128,9 @@ def test_chained_encoder_is_bit_identical_to_three_launches():
                        num_return_sequences=20, return_dict_in_generate=True)
         outs.append((mem.cpu(), o["sequences"].cpu(), o["sequences_scores"].cpu()))
         del m
-    assert torch.isfinite(outs[0][0]).all()
-    for o in outs[1:]:
+    assert torch.isfinite(outs[0][0]).all() and torch.isfinite(outs[3][0]).all()
+    for o in outs[1:3]:
         assert torch.equal(outs[0][0], o[0])
         assert torch.equal(outs[0][1], o[1]) and torch.equal(outs[0][2], o[2])
+    # the default encoder (bf16 residual stream) with and without the decoder chain
+    assert torch.equal(outs[3][0], outs[4][0]) and torch.equal(outs[3][1], outs[4][1]) and torch.equal(outs[3][2], outs[4][2])

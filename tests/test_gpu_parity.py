@@ -341,6 +341,37 @@ def test_gemm_tcgen05_folded_rmsnorm(shape):
         assert rel_err(y, want) < 8e-3
 
 
+@pytest.mark.parametrize("shape", [(300, 512, 512), (1000, 512, 2048), (77, 768, 768), (40000, 512, 512), (152000, 512, 512),
+                                   (151937, 512, 2048)])
+def test_gemm_tcgen05_bf16_stream_update(shape):
+    """EPI_RESID_BF16 (the bf16 encoder's residual GEMMs): x = bf16(x + A W^T) in place + sums of squares of the ROUNDED rows per 128-column
+    block, against an fp64 reference; single-CTA tiles and CTA pairs with two epilogue groups (the last shapes) agree bit for bit."""
+    from gram_b200 import _cabi
+    lib = _cabi.load_library()
+    M, N, K = shape
+    g = torch.Generator(device="cpu").manual_seed(M + N + K + 1)
+    A = (torch.randn(M, K, generator=g)).cuda().bfloat16()
+    W = (torch.randn(N, K, generator=g) * K ** -0.5).cuda().bfloat16()
+    x0 = (torch.randn(M, N, generator=g) * 3.0).cuda().bfloat16()
+    acc = A.float() @ W.float().t()                             # fp32 accumulation of exact bf16 products
+    want = (x0.float() + acc)
+    outs = []
+    for impl in (2, 1):
+        x = x0.clone()
+        ss = torch.zeros(M, N // 128, device="cuda")
+        rc = lib.gram_op_gemm_norm(0, impl, 6, C.c_void_p(A.data_ptr()), C.c_void_p(W.data_ptr()), C.c_void_p(x.data_ptr()),
+                                   None, C.c_void_p(ss.data_ptr()), None, None, C.c_float(0.0), M, N, K, None)
+        assert rc == 0, lib.gram_last_error(None)
+        torch.cuda.synchronize()
+        # bf16 rounding of the sum: half an ulp of the result, plus the accumulation-order difference of the fp32 sum
+        d = (x.float() - want).abs()
+        assert float((d / want.abs().clamp_min(1.0)).max()) < 2.0 ** -8
+        want_ss = (x.double() ** 2).view(M, N // 128, 128).sum(-1)
+        assert rel_err(ss, want_ss) < 1e-5
+        outs.append((x, ss))
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+
+
 def test_fused_norm_encoder_matches_unfused(built):
     """The default bf16 encoder (RMSNorms folded into the tcgen05 GEMMs) against GRAM_FLAG_UNFUSED_NORM (separate kernels): fused
     memory within bf16 rounding on the T5-small case and on a many-passage batch, logits within 2e-2 of the golden."""
