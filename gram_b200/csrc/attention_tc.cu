@@ -101,7 +101,6 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
 }
 // D = f32, A = B = bf16, M = 128
 constexpr uint32_t IDESC_QK = (1u << 4) | (1u << 7) | (1u << 10) | ((128u >> 3) << 17) | ((128u >> 4) << 24);              // N=128, B K-major
-constexpr uint32_t IDESC_QK2 = (1u << 4) | (1u << 7) | (1u << 10) | ((256u >> 3) << 17) | ((128u >> 4) << 24);             // N=256 (two key blocks)
 constexpr uint32_t IDESC_PV = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 16) | ((64u >> 3) << 17) | ((128u >> 4) << 24);  // N=64, B MN-major
 
 constexpr int CONSUMERS = 128;            // warps 0-3: softmax + epilogue, thread r = query row r = TMEM lane r
@@ -209,7 +208,7 @@ enc_attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, bf16* __res
     // ===================== producer: TMA + MMA issue =====================
     if (lane == 0) {
       // items of this CTA in the order (passage, query block, head); nkb = key blocks of the passage that hold tokens
-      int p_it = (int)blockIdx.x - (int)gridDim.x, h_it = H - 1, qb_it = 0, nqb_it = 1, row0_it = 0;
+      int p_it = (int)blockIdx.x - (int)gridDim.x, h_it = H - 1, qb_it = 0, nqb_it = 1, row0_it = 0, len_it = 0;
       bool tma_done = false;
       auto advance = [&]() {
         if (++h_it < H) return;
@@ -220,12 +219,13 @@ enc_attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, bf16* __res
           p_it += (int)gridDim.x;
           if (p_it >= P) { tma_done = true; return; }
           const int l = plen[p_it];
-          if (l > 0) { row0_it = poff[p_it]; nqb_it = (l + LQ - 1) / LQ; return; }
+          if (l > 0) { row0_it = poff[p_it]; nqb_it = (l + LQ - 1) / LQ; len_it = l; return; }
         }
       };
       advance();
       uint32_t k_tma = 0, k_m1 = 0, k_m2 = 0;              // items loaded / S issued / O issued
       uint32_t nkb_of[NSTAGE] = {1u, 1u};                  // key blocks of the item in each stage
+      uint32_t keys_of[NSTAGE] = {128u, 128u};             // keys of the item's passage, rounded up to the MMA's 16
       while (!(tma_done && k_m2 == k_tma)) {
         if (!tma_done && k_tma < k_m2 + NSTAGE) {
           const uint32_t st = k_tma & 1u, ph = (k_tma >> 1) & 1u;
@@ -233,6 +233,7 @@ enc_attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, bf16* __res
             const uint32_t sb = base + st * STAGE;
             const uint32_t nkb = (uint32_t)nqb_it;         // = ceil(len / 128)
             nkb_of[st] = nkb;
+            keys_of[st] = (uint32_t)((len_it + 15) & ~15);
             mbar_arrive_expect_tx(bar(B_FULL + st), BOX * (1u + 2u * nkb));
             tma_load_2d(sb, &map_qkv, bar(B_FULL + st), h_it * DK, row0_it + qb_it * LQ);
             for (uint32_t kb = 0; kb < nkb; ++kb) {
@@ -249,7 +250,9 @@ enc_attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, bf16* __res
             tcgen05_fence_after();
             const uint32_t sb = base + st * STAGE;
             const uint64_t dq = make_desc(sb), dk = make_desc(sb + BOX);     // key blocks are contiguous 8-row groups
-            const uint32_t idesc = (NKB == 2 && nkb_of[st] == 2u) ? IDESC_QK2 : IDESC_QK;
+            // S only as wide as the passage (N = keys rounded up to 16): columns past it are never read unmasked, and
+            // every score is the same dot product whatever N is
+            const uint32_t idesc = (IDESC_QK & ~(0x3Fu << 17)) | ((keys_of[st] >> 3) << 17);
 #pragma unroll
             for (int kk = 0; kk < DK / 16; ++kk)
               umma_bf16(tmem + st * ACC, dq + (uint64_t)(kk * 2), dk + (uint64_t)(kk * 2), idesc, kk ? 1u : 0u);
@@ -262,7 +265,9 @@ enc_attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, bf16* __res
           if (mbar_test(bar(B_PREADY + st), ph)) {
             tcgen05_fence_after();
             const uint32_t sb = base + st * STAGE;
-            const int nks = (LQ / 16) * (int)nkb_of[st];   // 16-key steps over the key blocks that were loaded
+            // 16-key steps over the passage's keys only: the steps past them would add P = 0 times (finite) rows of the
+            // next passage, i.e. exact zeros -- leaving them out changes no bit
+            const int nks = (int)(keys_of[st] >> 4);
             for (int ks = 0; ks < nks; ++ks) {
               const uint64_t dp = make_desc(sb + (uint32_t)(ks >> 2) * BOX + (uint32_t)(ks & 3) * 32u);
               const uint64_t dv = make_desc(sb + G::V_OFF + (uint32_t)ks * 2048u);
@@ -319,6 +324,9 @@ enc_attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, bf16* __res
     // takes max(raw s) -- one FMNMX per score -- and bounds the bias by the head's largest LUT entry; the exact
     // bias + mask walk is kept for the passage's tail chunk, and for every chunk when the bias table spans more than
     // 2^64 (then the bound could push small terms into underflow).
+    // A warp whose 32 query rows all lie past the passage (a 46-token passage leaves warps 2 and 3 without rows) keeps the
+    // barrier protocol -- it waits and arrives exactly like the others, so it can never run a phase ahead -- but reads no
+    // scores, writes no P rows (the stale bf16 there is finite; its O rows are never stored) and stores nothing.
     auto pass1 = [&](uint32_t k, int hh, int qrow) -> float {
       const uint32_t st = k & 1u, ph = (k >> 1) & 1u;
       const uint32_t trow = tmem + st * ACC + tlane;
@@ -327,6 +335,7 @@ enc_attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, bf16* __res
       const bool exact = !(bias_hi - blo[hh] <= 64.f);
       mbar_wait(bar(B_SFULL + st), ph);
       tcgen05_fence_after();
+      if (qrow - r + warp * 32 >= len) return 0.f;       // no row of this warp belongs to the passage (warp-uniform)
       float mraw = -INFINITY, mex = -INFINITY;
 #pragma unroll
       for (int c = 0; c < NCH; ++c) {
@@ -354,15 +363,16 @@ enc_attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, bf16* __res
       const uint32_t st = k & 1u, ph = (k >> 1) & 1u;
       const uint32_t trow = tmem + st * ACC + tlane;
       const uint32_t sQ = base + st * STAGE;
-      const int nch = 4 * ((len + LQ - 1) / LQ);         // chunks of the key blocks that were loaded
+      const int nch = (len + 31) >> 5;                   // 32-key chunks that hold keys of the passage (P past them is not multiplied)
       // bias2 of (query q, key j) = lut[h][j - q + Lb - 1]; only read for j < len <= Lb
       const float* lrow = lut + h * lut_n + (Lb - 1 - min(qb * LQ + r, Lb - 1));
       // ---- pass 2: p = 2^(s*log2e + bias2 - mb), row sum, P (bf16) into the K-major 128B-swizzled operand layout:
       //      box b = keys [64b, 64b+64), row r, 16-byte chunk j ^ (r & 7) ----
       float sum = 0.f;
+      const bool warp_live = qb * LQ + warp * 32 < len;
 #pragma unroll
       for (int c = 0; c < NCH; ++c) {
-        if (c >= nch) break;                             // key block without tokens: not loaded, not multiplied
+        if (c >= nch || !warp_live) break;               // key block without tokens: not loaded, not multiplied
         const uint32_t mk = mkc[c];
         float pr[32];
         if (mk == 0u) {
@@ -414,15 +424,18 @@ enc_attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, bf16* __res
       mbar_wait(bar(B_OFULL + st), ph);
       tcgen05_fence_after();
       uint32_t ov[2][32];
-      tmem_ld32(trow, ov[0]);
-      tmem_ld32(trow + 32, ov[1]);
-      tmem_ld_wait();
+      const bool store_live = cur_q0 + warp * 32 < cur_len;
+      if (store_live) {
+        tmem_ld32(trow, ov[0]);
+        tmem_ld32(trow + 32, ov[1]);
+        tmem_ld_wait();
+      }
       tcgen05_fence_before();
       mbar_arrive(bar(B_SFREE + st));                    // the accumulator may be overwritten by item k + 2
       // O rows go through the (dead) P rows of this warp in the stage -- row r, 16-byte chunk g ^ (r & 7) -- and leave as
       // full 128-byte lines: a row-per-thread store writes 32 half sectors per instruction and its slow drain held the
       // registers of the next item (ncu: 12.7 % of the samples on that write-after-read)
-      {
+      if (store_live) {
         const float inv = 1.0f / sum;
         const uint32_t srow = sQ + (uint32_t)r * 128u;
 #pragma unroll
