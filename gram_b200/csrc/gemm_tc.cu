@@ -275,6 +275,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         // themselves are never written (reference computes log_softmax over the materialised [rows, V] logits)
         float mx = -INFINITY, sum = 0.f;
         const int row = row0 + r;
+        // (pipelining these TMEM reads as in the store epilogues was measured and is slower here: the vocabulary head went
+        //  from 8.3-8.8 to 10.5-11.0 ms per step -- this loop is paced by its 256 ex2 per row, not by the load latency)
 #pragma unroll 1
         for (int c = 0; c < BLOCK_N / 32; ++c) {
           uint32_t v[32];
@@ -714,7 +716,8 @@ cudaError_t gemm_tc(int epi, const void* A, const void* W, void* C, int M_max, c
   }
   // the fused log-softmax epilogue stays on single-CTA tiles: it is exp2-bound, and making the leader wait for the
   // slower of two epilogues cost 11 % on the vocabulary head (measured)
-  const tc::Shape sh = tc::pick_shape(M_max, N, num_sms, epi == EPI_LSE ? 1 : max_ctas);
+  static const bool lse_pairs = [] { const char* e = getenv("GRAM_LSE_PAIRS"); return e && e[0] == '1'; }();   // A/B
+  const tc::Shape sh = tc::pick_shape(M_max, N, num_sms, (epi == EPI_LSE && !lse_pairs) ? 1 : max_ctas);
   // the W box is the rows ONE CTA loads per stage
   if (!tc::get_map(A, M_max, K, 0, tc::BLOCK_M, &ma) || !tc::get_map(W, N, K, 0, sh.bn / sh.ctas, &mw)) return cudaErrorUnknown;
 #define GRAM_TC_LAUNCH(E, MC, LP)                                                                              \
