@@ -496,35 +496,54 @@ cross_attention_persist_kernel(const __grid_constant__ CUtensorMap map_kv, const
 
   if (warp == XA_WARPS) {
     // ===================== TMA producer: one uninterrupted tile stream over all items of this CTA =====================
+    // The key-validity bytes of tile t+1 are requested right after tile t's loads are issued, so their L2 round trip runs
+    // under the wait for the next free ring slot instead of in front of every tile's TMA issue: the per-launch in-step
+    // times (GRAM_PROF_DUMP) showed 905 us per launch between busy decoder kernels against 765 us at step 0 and 720 us
+    // alone under ncu -- a dependent global load per 64-token tile in the only thread that feeds a 3-stage ring is what
+    // turns a lower clock into lost bandwidth.
     int stage = 0; uint32_t phase = 0;
-    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-      const int ui = item / n_hg, hg = item - ui * n_hg;
-      const int u = uorder ? uorder[ui] : ui;
-      if ((live_start ? live_count[u] : K_all) == 0) continue;       // no live beam: the consumers skip it too
-      const int s_beg = ustart[u], s_end = ustart[u + 1];
-      const int n_tiles = (s_end - s_beg + TS - 1) / TS;
-      for (int t = 0; t < n_tiles; ++t) {
-        mbar_wait(bars + 8u * (XA_STAGES + stage), phase ^ 1u);
-        const int s0 = s_beg + t * TS;
-        const int r0 = s0 + lane, r1 = s0 + 32 + lane;
-        const bool v0 = (r0 < s_end) && (tok_valid == nullptr || tok_valid[r0] != 0);
-        const bool v1 = (r1 < s_end) && (tok_valid == nullptr || tok_valid[r1] != 0);
-        const unsigned lo = __ballot_sync(0xffffffffu, v0), hi = __ballot_sync(0xffffffffu, v1);
-        if (lane == 0) {
-          masks[stage] = ((unsigned long long)hi << 32) | lo;
-          const uint32_t full = bars + 8u * stage;
-          const uint32_t sb = base + stage * XA_STAGE_BYTES;
-          mbar_arrive_expect_tx(full, XA_STAGE_BYTES);
-#pragma unroll
-          for (int hh = 0; hh < XA_HEADS; ++hh) {
-            const int col = (hg * XA_HEADS + hh) * DK;
-            tma_load_2d(sb + hh * BOX_BYTES, &map_kv, full, k_col0 + col, s0);
-            tma_load_2d(sb + (XA_HEADS + hh) * BOX_BYTES, &map_kv, full, v_col0 + col, s0);
-          }
-        }
-        __syncwarp();
-        if (++stage == XA_STAGES) { stage = 0; phase ^= 1u; }
+    int item = blockIdx.x, hg = 0, s_beg = 0, s_end = 0, n_tiles = 0, t = 0;
+    auto open_item = [&]() -> bool {                      // first item at or after `item` whose user has live beams
+      for (; item < n_items; item += gridDim.x) {
+        const int ui = item / n_hg;
+        const int u = uorder ? uorder[ui] : ui;
+        if ((live_start ? live_count[u] : K_all) == 0) continue;       // no live beam: the consumers skip it too
+        hg = item - ui * n_hg;
+        s_beg = ustart[u]; s_end = ustart[u + 1];
+        n_tiles = (s_end - s_beg + TS - 1) / TS;
+        t = 0;
+        if (n_tiles > 0) return true;
       }
+      return false;
+    };
+    bool more = open_item();
+    bool v0 = false, v1 = false;
+    auto fetch_valid = [&]() {
+      const int r0 = s_beg + t * TS + lane, r1 = r0 + 32;
+      v0 = (r0 < s_end) && (tok_valid == nullptr || tok_valid[r0] != 0);
+      v1 = (r1 < s_end) && (tok_valid == nullptr || tok_valid[r1] != 0);
+    };
+    if (more) fetch_valid();
+    while (more) {
+      mbar_wait(bars + 8u * (XA_STAGES + stage), phase ^ 1u);
+      const int s0 = s_beg + t * TS;
+      const unsigned lo = __ballot_sync(0xffffffffu, v0), hi = __ballot_sync(0xffffffffu, v1);
+      if (lane == 0) {
+        masks[stage] = ((unsigned long long)hi << 32) | lo;
+        const uint32_t full = bars + 8u * stage;
+        const uint32_t sb = base + stage * XA_STAGE_BYTES;
+        mbar_arrive_expect_tx(full, XA_STAGE_BYTES);
+#pragma unroll
+        for (int hh = 0; hh < XA_HEADS; ++hh) {
+          const int col = (hg * XA_HEADS + hh) * DK;
+          tma_load_2d(sb + hh * BOX_BYTES, &map_kv, full, k_col0 + col, s0);
+          tma_load_2d(sb + (XA_HEADS + hh) * BOX_BYTES, &map_kv, full, v_col0 + col, s0);
+        }
+      }
+      __syncwarp();
+      if (++t == n_tiles) { item += gridDim.x; more = open_item(); }
+      if (more) fetch_valid();
+      if (++stage == XA_STAGES) { stage = 0; phase ^= 1u; }
     }
     return;
   }

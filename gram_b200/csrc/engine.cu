@@ -1274,11 +1274,17 @@ int gram_profile_end(gram_handle* h, float* ms_per_class, int64_t* launches_per_
   CK(cudaSetDevice(h->cfg.device));
   CK(cudaDeviceSynchronize());
   float acc[GRAM_K_COUNT] = {0};
+  // GRAM_PROF_DUMP=<file>: one line "class ms" per bracketed launch, in launch order (in-step per-launch times under the
+  // step's real clocks; ncu's launch list runs every kernel alone at boost clocks with a cold L2)
+  FILE* dump = nullptr;
+  if (const char* path = getenv("GRAM_PROF_DUMP")) dump = fopen(path, "a");
   for (const auto& r : h->ev_log) {
     float ms = 0.f;
     CK(cudaEventElapsedTime(&ms, r.a, r.b));
     acc[r.cls] += ms;
+    if (dump) fprintf(dump, "%d %.4f\n", r.cls, ms);
   }
+  if (dump) { fprintf(dump, "-1 0\n"); fclose(dump); }
   for (int i = 0; i < GRAM_K_COUNT; ++i) {
     if (ms_per_class) ms_per_class[i] = acc[i];
     if (launches_per_class) launches_per_class[i] = h->cls_launches[i];
