@@ -369,7 +369,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           if ((rd & 1) == 1) {
             // rounds 2b and 2b+1 cover 128-column block b of the tile: one partial per (row, block), owned by this
             // thread alone -- no atomics, and the same summation order whatever the tile shape
-            if (row < M) na.ss_out[(size_t)row * (N >> 7) + n_blk * (BLOCK_N >> 7) + (rd >> 1)] = ssq;
+            if (row < M && n_blk * (BLOCK_N >> 7) + (rd >> 1) < (N >> 7))
+              na.ss_out[(size_t)row * (N >> 7) + n_blk * (BLOCK_N >> 7) + (rd >> 1)] = ssq;
             ssq = 0.f;
           }
           if (rd == ROUNDS - 1) {
@@ -446,7 +447,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             }
           }
           if (rl == RPG - 1) {
-            if (live_row) na.ss_out[(size_t)row * (N >> 7) + n_blk * (BLOCK_N >> 7) + grp] = ssq;
+            if (live_row && n_blk * (BLOCK_N >> 7) + grp < (N >> 7))   // N = 128 (mod 256): the tile's second block does not exist
+              na.ss_out[(size_t)row * (N >> 7) + n_blk * (BLOCK_N >> 7) + grp] = ssq;
             tcgen05_fence_before();
             __syncwarp();
             if (lane == 0) release_acc(acc);
@@ -664,7 +666,8 @@ inline Shape pick_shape(int M_max, int N, int num_sms, int max_ctas) {
   if (N < 256) return {128, 1};
   const long long tiles256 = (long long)((M_max + BLOCK_M - 1) / BLOCK_M) * ((N + 255) / 256);
   if (tiles256 < 2LL * num_sms) return {128, 1};
-  return {256, (max_ctas >= 2 && tiles256 >= 16LL * num_sms) ? 2 : 1};
+  static const long long pair_tiles = [] { const char* e = getenv("GRAM_PAIR_TILES"); return e ? atoll(e) : 16LL; }();   // A/B
+  return {256, (max_ctas >= 2 && tiles256 >= pair_tiles * num_sms) ? 2 : 1};
 }
 
 }  // namespace tc

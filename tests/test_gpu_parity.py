@@ -295,7 +295,8 @@ def test_generate_bf16_overlap(built, name):
     assert np.abs(sc[:, 0] - gs[:, 0]).max() < 0.05 * np.abs(gs[:, 0]).max()
 
 
-@pytest.mark.parametrize("shape", [(300, 512, 512), (1000, 512, 2048), (77, 768, 768), (40000, 512, 512), (152000, 512, 512)])
+@pytest.mark.parametrize("shape", [(300, 512, 512), (1000, 512, 2048), (77, 768, 768), (40000, 512, 512), (152000, 512, 512),
+                                   (152000, 640, 512)])     # the last: CTA pairs whose final tile holds one 128-column block
 def test_gemm_tcgen05_folded_rmsnorm(shape):
     """EPI_RESID_NORM (x += A W^T; xb = bf16(x * w); per-128-column sums of squares) and the row-scaled consumer
     epilogue, against fp64 references; single-CTA tiles and CTA pairs (the last shape) give identical bits."""
@@ -342,7 +343,7 @@ def test_gemm_tcgen05_folded_rmsnorm(shape):
 
 
 @pytest.mark.parametrize("shape", [(300, 512, 512), (1000, 512, 2048), (77, 768, 768), (40000, 512, 512), (152000, 512, 512),
-                                   (151937, 512, 2048)])
+                                   (151937, 512, 2048), (101500, 768, 768), (152000, 640, 512)])
 def test_gemm_tcgen05_bf16_stream_update(shape):
     """EPI_RESID_BF16 (the bf16 encoder's residual GEMMs): x = bf16(x + A W^T) in place + sums of squares of the ROUNDED rows per 128-column
     block, against an fp64 reference; single-CTA tiles and CTA pairs with two epilogue groups (the last shapes) agree bit for bit."""
