@@ -327,6 +327,9 @@ def workload_config(args, wl, batch):
                 parallelism=f"user-sharded dp{args.gpus}", inputs=wl.inputs,
                 decode_rows="every beam row (reference behaviour)" if args.all_rows else
                 "live beams only: dead (-inf) beams and finished users are compacted away on the device before each decode step; rankings and scores bit-identical (tests/test_gpu_live_rows.py)",
+                residual_stream=("fp32 (parity mode)" if args.dtype == "fp32" else
+                                 "fp32 in the encoder (GRAM_FLAG_FP32_RESID)" if (int(args.flags) & 16384) else
+                                 "bf16 in the encoder (updated in place by the residual GEMMs, as under model.bfloat16()), fp32 in the decoder"),
                 cache="per-step working set (K/V memory + activations, > 8 GB) exceeds the 126 MB L2; every step uses different users")
 
 
@@ -674,7 +677,7 @@ def main():
     kernels = {c: dict(ms_per_step=v["ms"] / S, launches_per_step=v["launches"] // S,
                        share=v["ms"] / total_all if total_all else 0.0) for c, v in prof_all.items()}
     xcap = ncu_metrics("xattn")
-    roofline_cross = dict(bound="hbm", kernel="cross_attention_mma_kernel", achieved=xa_gbs, peak=peaks["hbm"], unit="GB/s",
+    roofline_cross = dict(bound="hbm", kernel="cross_attention_persist_kernel (cross_attention_mma_kernel with --flags 8192)", achieved=xa_gbs, peak=peaks["hbm"], unit="GB/s",
                           frac=xa_gbs / peaks["hbm"], work="executed bytes (K and V of users that still have live beams)",
                           algorithmic_gbs=xa_alg_bytes / (xa_ms / 1000.0) / 1e9 if xa_ms > 0 else 0.0,
                           traffic=xcap["traffic"] if xcap else None,

@@ -223,7 +223,9 @@ int gram_op_gemm(int32_t device, int32_t dtype, int32_t impl, int32_t epilogue, 
 /* The tcgen05 GEMM with an RMSNorm (reference T5LayerNorm, src/model/gram_t5_modeling.py:253-276) folded into it, bf16.
  * epilogue 5 (producer): C fp32 [M,N] += A W^T; xb bf16 [M,N] = (C) * ln_w; ss fp32 [M, N/128] = sums of squares of the new C
  * rows per 128-column block.  epilogue 0 / 1 (consumer, row_ss != NULL): C = A W^T with output row i scaled by
- * rsqrt(sum_b row_ss[i][b] / K + eps) (then ReLU for 1).  impl 1 = CTA pairs allowed, 2 = single-CTA tiles. */
+ * rsqrt(sum_b row_ss[i][b] / K + eps) (then ReLU for 1).  epilogue 6 (the bf16 encoder's residual GEMMs): C is a bf16 [M,N] residual
+ * stream updated in place, C = bf16(C + A W^T), ss = sums of squares of the rounded rows per 128-column block; xb / ln_w unused.
+ * impl 1 = CTA pairs allowed, 2 = single-CTA tiles. */
 int gram_op_gemm_norm(int32_t device, int32_t impl, int32_t epilogue, const void* A, const void* W, void* C, void* xb,
                       float* ss, const float* ln_w, const float* row_ss, float eps, int32_t M, int32_t N, int32_t K,
                       void* stream);
