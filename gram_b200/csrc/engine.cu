@@ -750,7 +750,7 @@ int gram_create(const gram_config* cfg, gram_handle** out) {
   DAC(h->dss, R * (size_t)((D + 127) / 128) * 4);
   DAC(h->sk, (size_t)h->Ld * ML * R * HD * esz); DAC(h->sv, (size_t)h->Ld * ML * R * HD * esz);
   DAC(h->logits, R * V * 4); DAC(h->lse, R * 4);
-  DAC(h->lse_partial, R * (size_t)((V + 127) / 128) * 8);
+  DAC(h->lse_partial, R * (size_t)((V + 127) / 128 + 2) * 8);   // + 2: 256-column tiles with two partials each
   BeamState& bs = h->bs;
   bs.max_length = ML; bs.gen_len = ML; bs.V = V; bs.eos = c.eos_id; bs.pad = c.pad_id; bs.K = c.max_beams;
   for (int i = 0; i < 2; ++i) {

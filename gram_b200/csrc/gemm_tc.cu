@@ -71,9 +71,11 @@ template <int BN, int CTAS, int MODE = 0, int EG = 1> struct Cfg {
   static constexpr int LOAD_N = BN / CTAS;                 // W rows each CTA loads per stage
   static constexpr uint32_t B_BYTES = LOAD_N * BLOCK_K * 2;   // 16 or 32 KiB
   static constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr uint32_t EPI_BYTES = MODE == 1 ? NORM_EPI_BYTES : MODE == 2 ? 3 * XBOX_BYTES * EG : CSTAGE_BYTES * EG;
+  // MODE 3: EPI_LSE with two epilogue groups -- nothing is staged (the statistics go straight to global memory)
+  static constexpr uint32_t EPI_BYTES = MODE == 1 ? NORM_EPI_BYTES : MODE == 2 ? 3 * XBOX_BYTES * EG : MODE == 3 ? 0u : CSTAGE_BYTES * EG;
   static constexpr int STAGES = MODE == 1 ? (STAGE_BYTES == 32768 ? 4 : 2)
                                 : MODE == 2 ? (STAGE_BYTES == 32768 ? (EG == 2 ? 4 : 5) : 3)
+                                : MODE == 3 ? (STAGE_BYTES == 32768 ? 6 : 4)
                                             : (STAGE_BYTES == 32768 ? (EG == 2 ? 5 : 6) : (EG == 2 ? 3 : 4));
   static constexpr int THREADS = 64 + 128 * EG;
   static constexpr int TMEM_COLS = ACC_STAGES * BN;        // 256 or 512 (power of two)
@@ -98,8 +100,8 @@ __global__ void __launch_bounds__(64 + 128 * EG, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
                const __grid_constant__ CUtensorMap map_c, const __grid_constant__ CUtensorMap map_xb,
                float2* __restrict__ lse_partial, int M_imm, const int* __restrict__ m_ptr, int N, int K, NormArgs na) {
-  using C_ = Cfg<BLOCK_N, CTAS, EPI == EPI_RESID_NORM ? 1 : EPI == EPI_RESID_BF16 ? 2 : 0, EG>;
-  static_assert(EG == 1 || (EPI != EPI_RESID_NORM && EPI != EPI_LSE), "two epilogue groups: plain store / reduce epilogues only");
+  using C_ = Cfg<BLOCK_N, CTAS, EPI == EPI_RESID_NORM ? 1 : EPI == EPI_RESID_BF16 ? 2 : (EPI == EPI_LSE && EG == 2) ? 3 : 0, EG>;
+  static_assert(EG == 1 || EPI != EPI_RESID_NORM, "EPI_RESID_NORM runs one epilogue group");
   constexpr int STAGES = C_::STAGES;
   constexpr uint32_t STAGE_BYTES = C_::STAGE_BYTES;
   constexpr int TMEM_COLS = C_::TMEM_COLS;
@@ -277,8 +279,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         const int row = row0 + r;
         // (pipelining these TMEM reads as in the store epilogues was measured and is slower here: the vocabulary head went
         //  from 8.3-8.8 to 10.5-11.0 ms per step -- this loop is paced by its 256 ex2 per row, not by the load latency)
+        // EG = 2: group g reduces the tile's column half g to its own (max, sum) partial
 #pragma unroll 1
-        for (int c = 0; c < BLOCK_N / 32; ++c) {
+        for (int c = grp * (BLOCK_N / 32 / EG); c < (grp + 1) * (BLOCK_N / 32 / EG); ++c) {
           uint32_t v[32];
           const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BLOCK_N + c * 32);
           tmem_ld32(taddr, v);
@@ -303,7 +306,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         tcgen05_fence_before();
         __syncwarp();
         if (lane == 0) release_acc(acc);
-        if (row < M) lse_partial[(size_t)row * num_n + n_blk] = make_float2(mx, sum);
+        if (row < M) lse_partial[((size_t)row * num_n + n_blk) * EG + grp] = make_float2(mx, sum);
         if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1u; }
         continue;
       }
@@ -620,7 +623,7 @@ cudaError_t launch(const CUtensorMap& ma, const CUtensorMap& mw, const CUtensorM
                    float2* lse_partial, int M_max, const int* m_ptr, int N, int K, const NormArgs& na, int num_sms,
                    cudaStream_t s) {
   auto kern = gemm_tc_kernel<EPI, BN, CTAS, EG>;
-  using C_ = Cfg<BN, CTAS, EPI == EPI_RESID_NORM ? 1 : EPI == EPI_RESID_BF16 ? 2 : 0, EG>;
+  using C_ = Cfg<BN, CTAS, EPI == EPI_RESID_NORM ? 1 : EPI == EPI_RESID_BF16 ? 2 : (EPI == EPI_LSE && EG == 2) ? 3 : 0, EG>;
   constexpr size_t smem = C_::SMEM_BYTES;
   constexpr int threads = C_::THREADS;
   constexpr int slot = EPI * 3 + (BN == 256) + (CTAS == 2) + 21 * (EG - 1);
@@ -677,9 +680,18 @@ bool gemm_tc_supported(int N, int K) { return (K % tc::BLOCK_K) == 0 && (N % 16)
 const char* gemm_tc_last_error() { return tc::g_err.c_str(); }
 namespace tc { const char* last_error() { return g_err.c_str(); } std::mutex& mutex() { return g_mu; } }
 
+namespace tc {
+// GRAM_LSE_EG=2: two epilogue groups on the 128 x 256 tiles of the vocabulary head (A/B)
+inline int lse_groups() {
+  static int v = 0;
+  if (v == 0) { const char* e = getenv("GRAM_LSE_EG"); v = (e && e[0] == '2') ? 2 : 1; }
+  return v;
+}
+}  // namespace tc
+
 int gemm_tc_lse_ntiles(int M_max, int N, int num_sms) {
   const int bn = tc::pick_shape(M_max, N, num_sms, 1).bn;
-  return (N + bn - 1) / bn;
+  return ((N + bn - 1) / bn) * (bn == 256 ? tc::lse_groups() : 1);
 }
 
 cudaError_t gemm_tc(int epi, const void* A, const void* W, void* C, int M_max, const int* m_ptr, int N, int K,
@@ -731,7 +743,11 @@ cudaError_t gemm_tc(int epi, const void* A, const void* W, void* C, int M_max, c
   if (sh.ctas == 2 && tc::pair_epilogue_groups() == 2)                                                         \
     return tc::launch<E, 256, 2, 2>(ma, mw, MC, MC, nullptr, M_max, m_ptr, N, K, na, num_sms, s);              \
   GRAM_TC_LAUNCH(E, MC, nullptr)
-  if (epi == EPI_LSE) { GRAM_TC_LAUNCH(EPI_LSE, ma, (float2*)C); }
+  if (epi == EPI_LSE) {
+    if (sh.bn == 256 && sh.ctas == 1 && tc::lse_groups() == 2)
+      return tc::launch<EPI_LSE, 256, 1, 2>(ma, mw, ma, ma, (float2*)C, M_max, m_ptr, N, K, na, num_sms, s);
+    GRAM_TC_LAUNCH(EPI_LSE, ma, (float2*)C);
+  }
   if (!tc::get_map(C, M_max, N, ckind, tc::BLOCK_M, &mc)) return cudaErrorUnknown;
   switch (epi) {
     case EPI_STORE: { GRAM_TC_LAUNCH_EG(EPI_STORE, mc); }
