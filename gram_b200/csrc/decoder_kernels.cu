@@ -13,6 +13,7 @@
 //    the user's K/V -- written in place by the projection GEMM in packed [token][layer][K|V][head][dk]
 //    order, no concat copy -- is read once.  This file holds the CUDA-core version used by the fp32
 //    parity mode; cross_attention_mma.cu holds the bf16 tensor-core version.
+#include <stdlib.h>
 #include "common.cuh"
 #include "kernels.h"
 
@@ -160,7 +161,10 @@ template <> struct Raw8<float> {
 
 // One warp = (row, 4 heads): lane = (head hq = lane/8, 16-byte chunk c = lane%8), positions are walked with an
 // online softmax, UN positions' K and V chunks requested per iteration.  Work is proportional to t+1.
-template <typename T, int UN, int MINB>
+// ROWMAJ: consecutive warps = consecutive rows of ONE head quad (warp = quad * rows + row) instead of the quads of one row:
+// the 4 warps of a CTA are then 4 beams of (almost always) one user, which share most of their ancestors, so the K/V
+// chunks of a shared ancestor are fetched into L1 once per CTA instead of once per warp.
+template <typename T, int UN, int MINB, bool ROWMAJ = false>
 __global__ void __launch_bounds__(128, MINB)
 dec_self_attention64_kernel(const T* __restrict__ qkv, T* __restrict__ cache_k, T* __restrict__ cache_v,
                             const int* __restrict__ anc, int Tmax, const float* __restrict__ dec_bias, int n_dec,
@@ -169,8 +173,10 @@ dec_self_attention64_kernel(const T* __restrict__ qkv, T* __restrict__ cache_k, 
   constexpr int DK = 64;
   const int HQ = H >> 2;                                 // head quads per row
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  if (warp >= (n_rows ? *n_rows : R) * HQ) return;
-  const int slot = warp / HQ, h = (warp % HQ) * 4 + (lane >> 3), c = lane & 7;
+  const int rows = n_rows ? *n_rows : R;
+  if (warp >= rows * HQ) return;
+  const int slot = ROWMAJ ? warp % rows : warp / HQ;
+  const int h = (ROWMAJ ? warp / rows : warp % HQ) * 4 + (lane >> 3), c = lane & 7;
   const int r = slot_row ? slot_row[slot] : slot;        // beam row: cache row, ancestry, user membership
   const int HD = H * DK;
   const int ubase = (r / K) * K;
@@ -255,7 +261,11 @@ static cudaError_t launch_dec_self(const void* qkv, void* ck, void* cv, const in
       // 4 positions, 80 registers, 24 warps: 6.1 ms; 4 positions, 64 registers (32 bytes spilled), 32 warps: 5.5 ms;
       // 8-byte lanes (2 heads per warp), 8 positions, 32 warps: 8.4 ms.  Occupancy beats batch depth.
       if constexpr (sizeof(T) == 2) {
-        dec_self_attention64_kernel<T, 4, 8><<<grid, 128, 0, s>>>((const T*)qkv, (T*)ck, (T*)cv, anc, Tmax, dec_bias, n_dec, (T*)out, R, K, H, t, slot_row, n_rows);
+        static const bool rowmaj = [] { const char* e = getenv("GRAM_SELF_ATTN_ROWMAJ"); return e && e[0] == '1'; }();   // A/B
+        if (rowmaj)
+          dec_self_attention64_kernel<T, 4, 8, true><<<grid, 128, 0, s>>>((const T*)qkv, (T*)ck, (T*)cv, anc, Tmax, dec_bias, n_dec, (T*)out, R, K, H, t, slot_row, n_rows);
+        else
+          dec_self_attention64_kernel<T, 4, 8><<<grid, 128, 0, s>>>((const T*)qkv, (T*)ck, (T*)cv, anc, Tmax, dec_bias, n_dec, (T*)out, R, K, H, t, slot_row, n_rows);
       } else {
         dec_self_attention64_kernel<T, 4, 4><<<grid, 128, 0, s>>>((const T*)qkv, (T*)ck, (T*)cv, anc, Tmax, dec_bias, n_dec, (T*)out, R, K, H, t, slot_row, n_rows);
       }
