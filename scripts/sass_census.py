@@ -39,7 +39,8 @@ def main():
     for fn in order:
         c = counts[fn]
         name = re.sub(r"\s+", " ", demangle(fn))
-        name = re.sub(r"\(.*", "", name)[:98]
+        name = re.sub(r"\((int|bool)\)", "", name)             # template-argument casts
+        name = re.sub(r"\(.*", "", name).replace("void ", "").replace("gram::", "")[:98]
         lines.append(name.ljust(100) + "".join((str(c[m]) if c[m] else "").rjust(9) for m in MNEMONICS) + str(c["_total"]).rjust(9))
         tot.update(c)
     lines.append("ALL KERNELS".ljust(100) + "".join(str(tot[m]).rjust(9) for m in MNEMONICS) + str(tot["_total"]).rjust(9))
