@@ -13,7 +13,6 @@
 //    the user's K/V -- written in place by the projection GEMM in packed [token][layer][K|V][head][dk]
 //    order, no concat copy -- is read once.  This file holds the CUDA-core version used by the fp32
 //    parity mode; cross_attention_mma.cu holds the bf16 tensor-core version.
-#include <stdlib.h>
 #include "common.cuh"
 #include "kernels.h"
 
@@ -161,10 +160,7 @@ template <> struct Raw8<float> {
 
 // One warp = (row, 4 heads): lane = (head hq = lane/8, 16-byte chunk c = lane%8), positions are walked with an
 // online softmax, UN positions' K and V chunks requested per iteration.  Work is proportional to t+1.
-// ROWMAJ: consecutive warps = consecutive rows of ONE head quad (warp = quad * rows + row) instead of the quads of one row:
-// the 4 warps of a CTA are then 4 beams of (almost always) one user, which share most of their ancestors, so the K/V
-// chunks of a shared ancestor are fetched into L1 once per CTA instead of once per warp.
-template <typename T, int UN, int MINB, bool ROWMAJ = false>
+template <typename T, int UN, int MINB>
 __global__ void __launch_bounds__(128, MINB)
 dec_self_attention64_kernel(const T* __restrict__ qkv, T* __restrict__ cache_k, T* __restrict__ cache_v,
                             const int* __restrict__ anc, int Tmax, const float* __restrict__ dec_bias, int n_dec,
@@ -173,10 +169,8 @@ dec_self_attention64_kernel(const T* __restrict__ qkv, T* __restrict__ cache_k, 
   constexpr int DK = 64;
   const int HQ = H >> 2;                                 // head quads per row
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  const int rows = n_rows ? *n_rows : R;
-  if (warp >= rows * HQ) return;
-  const int slot = ROWMAJ ? warp % rows : warp / HQ;
-  const int h = (ROWMAJ ? warp / rows : warp % HQ) * 4 + (lane >> 3), c = lane & 7;
+  if (warp >= (n_rows ? *n_rows : R) * HQ) return;
+  const int slot = warp / HQ, h = (warp % HQ) * 4 + (lane >> 3), c = lane & 7;
   const int r = slot_row ? slot_row[slot] : slot;        // beam row: cache row, ancestry, user membership
   const int HD = H * DK;
   const int ubase = (r / K) * K;
@@ -259,13 +253,10 @@ static cudaError_t launch_dec_self(const void* qkv, void* ck, void* cv, const in
       // bf16, per 1,888-user step on one B200 (A/B in one gpurun call): K/V widened to fp32 on load, 127 registers,
       // 16 warps per SM: 8.2 ms; storage-form chunks with 8 positions in flight, 117 registers, 16 warps: 8.0 ms;
       // 4 positions, 80 registers, 24 warps: 6.1 ms; 4 positions, 64 registers (32 bytes spilled), 32 warps: 5.5 ms;
-      // 8-byte lanes (2 heads per warp), 8 positions, 32 warps: 8.4 ms.  Occupancy beats batch depth.
+      // 8-byte lanes (2 heads per warp), 8 positions, 32 warps: 8.4 ms.  Occupancy beats batch depth.  Round 2: consecutive
+      // warps = consecutive beams of one head quad (shared ancestors as L1 hits): 6.1 vs 5.9-6.1 ms, no gain.
       if constexpr (sizeof(T) == 2) {
-        static const bool rowmaj = [] { const char* e = getenv("GRAM_SELF_ATTN_ROWMAJ"); return e && e[0] == '1'; }();   // A/B
-        if (rowmaj)
-          dec_self_attention64_kernel<T, 4, 8, true><<<grid, 128, 0, s>>>((const T*)qkv, (T*)ck, (T*)cv, anc, Tmax, dec_bias, n_dec, (T*)out, R, K, H, t, slot_row, n_rows);
-        else
-          dec_self_attention64_kernel<T, 4, 8><<<grid, 128, 0, s>>>((const T*)qkv, (T*)ck, (T*)cv, anc, Tmax, dec_bias, n_dec, (T*)out, R, K, H, t, slot_row, n_rows);
+        dec_self_attention64_kernel<T, 4, 8><<<grid, 128, 0, s>>>((const T*)qkv, (T*)ck, (T*)cv, anc, Tmax, dec_bias, n_dec, (T*)out, R, K, H, t, slot_row, n_rows);
       } else {
         dec_self_attention64_kernel<T, 4, 4><<<grid, 128, 0, s>>>((const T*)qkv, (T*)ck, (T*)cv, anc, Tmax, dec_bias, n_dec, (T*)out, R, K, H, t, slot_row, n_rows);
       }
