@@ -494,39 +494,70 @@ cross_attention_persist_kernel(const __grid_constant__ CUtensorMap map_kv, const
   }
   __syncthreads();
 
+  // ---- item schedule shared by the producer and the consumer warps -------------------------------------------------
+  // The items of this CTA are sequence entries k = 0, 1, ...: item blockIdx.x + k * gridDim.x; users without live beams are
+  // skipped.  Every warp keeps a WINDOW of 32 consecutive entries, one per lane (user's live rows, first query row, tile
+  // count, K/V row range), loaded with one round of lane-parallel loads, and steps through it with a ballot + shuffles:
+  // no dependent global load (uorder -> live_count / live_start / ustart) is left on any warp's per-item path: 751 -> 738 us
+  // per launch alone, 36-37 -> 34.5-35.4 ms per step.  (What is left of the gap to a 1-row launch, 675 us, is not a code
+  // path: with the query loads compiled out -- all-zero fragments -- the same 20-row launch takes 705 us, and staging the
+  // query rows through shared memory a whole item ahead changes nothing (739 us): zero operands draw less power, and this
+  // kernel sits on the power cap even when it runs alone, scripts/exp_xattn_hot.py.)
+  int kwin = 0, w_item = 0, w_K = 0, w_qrow0 = 0, w_beg = 0, w_end = 0;
+  auto load_window = [&]() {
+    w_item = (int)blockIdx.x + (kwin + lane) * (int)gridDim.x;
+    w_K = 0; w_qrow0 = 0; w_beg = 0; w_end = 0;
+    if (w_item < n_items) {
+      const int ui = w_item / n_hg;
+      const int u = uorder ? uorder[ui] : ui;
+      w_K = live_start ? live_count[u] : K_all;
+      w_qrow0 = live_start ? live_start[u] : u * K_all;
+      w_beg = ustart[u]; w_end = ustart[u + 1];
+    }
+  };
+  struct Item { int K, qrow0, s_beg, s_end, n_tiles, hg, k; };
+  // first entry with sequence index >= kmin whose user has live beams; the producer (need_tiles) also skips users without
+  // memory tokens -- the consumers still visit those and store zeros, without touching the ring
+  auto next_item = [&](int kmin, Item& it, bool need_tiles) -> bool {
+    for (;;) {
+      const bool ok = (kwin + lane >= kmin) && (w_item < n_items) && (w_K > 0) && (!need_tiles || w_end > w_beg);
+      const unsigned m = __ballot_sync(0xffffffffu, ok);
+      if (m) {
+        const int j = __ffs(m) - 1;
+        it.K = __shfl_sync(0xffffffffu, w_K, j);
+        it.qrow0 = __shfl_sync(0xffffffffu, w_qrow0, j);
+        it.s_beg = __shfl_sync(0xffffffffu, w_beg, j);
+        it.s_end = __shfl_sync(0xffffffffu, w_end, j);
+        it.n_tiles = (it.s_end - it.s_beg + TS - 1) / TS;
+        it.hg = __shfl_sync(0xffffffffu, w_item, j) % n_hg;
+        it.k = kwin + j;
+        return true;
+      }
+      if (__shfl_sync(0xffffffffu, w_item, 31) >= n_items) return false;   // the sequence ended inside this window
+      kwin += 32;
+      load_window();
+    }
+  };
+  load_window();
+
   if (warp == XA_WARPS) {
     // ===================== TMA producer: one uninterrupted tile stream over all items of this CTA =====================
     // The key-validity bytes of tile t+1 are requested right after tile t's loads are issued, so their L2 round trip runs
-    // under the wait for the next free ring slot instead of in front of every tile's TMA issue: the per-launch in-step
-    // times (GRAM_PROF_DUMP) showed 905 us per launch between busy decoder kernels against 765 us at step 0 and 720 us
-    // alone under ncu -- a dependent global load per 64-token tile in the only thread that feeds a 3-stage ring is what
-    // turns a lower clock into lost bandwidth.
+    // under the wait for the next free ring slot instead of in front of every tile's TMA issue.
     int stage = 0; uint32_t phase = 0;
-    int item = blockIdx.x, hg = 0, s_beg = 0, s_end = 0, n_tiles = 0, t = 0;
-    auto open_item = [&]() -> bool {                      // first item at or after `item` whose user has live beams
-      for (; item < n_items; item += gridDim.x) {
-        const int ui = item / n_hg;
-        const int u = uorder ? uorder[ui] : ui;
-        if ((live_start ? live_count[u] : K_all) == 0) continue;       // no live beam: the consumers skip it too
-        hg = item - ui * n_hg;
-        s_beg = ustart[u]; s_end = ustart[u + 1];
-        n_tiles = (s_end - s_beg + TS - 1) / TS;
-        t = 0;
-        if (n_tiles > 0) return true;
-      }
-      return false;
-    };
-    bool more = open_item();
+    Item it;
+    int t = 0;
+    bool more = next_item(0, it, true);
     bool v0 = false, v1 = false;
     auto fetch_valid = [&]() {
-      const int r0 = s_beg + t * TS + lane, r1 = r0 + 32;
-      v0 = (r0 < s_end) && (tok_valid == nullptr || tok_valid[r0] != 0);
-      v1 = (r1 < s_end) && (tok_valid == nullptr || tok_valid[r1] != 0);
+      const int r0 = it.s_beg + t * TS + lane, r1 = r0 + 32;
+      v0 = (r0 < it.s_end) && (tok_valid == nullptr || tok_valid[r0] != 0);
+      v1 = (r1 < it.s_end) && (tok_valid == nullptr || tok_valid[r1] != 0);
     };
     if (more) fetch_valid();
     while (more) {
       mbar_wait(bars + 8u * (XA_STAGES + stage), phase ^ 1u);
-      const int s0 = s_beg + t * TS;
+      const int s0 = it.s_beg + t * TS;
       const unsigned lo = __ballot_sync(0xffffffffu, v0), hi = __ballot_sync(0xffffffffu, v1);
       if (lane == 0) {
         masks[stage] = ((unsigned long long)hi << 32) | lo;
@@ -535,13 +566,13 @@ cross_attention_persist_kernel(const __grid_constant__ CUtensorMap map_kv, const
         mbar_arrive_expect_tx(full, XA_STAGE_BYTES);
 #pragma unroll
         for (int hh = 0; hh < XA_HEADS; ++hh) {
-          const int col = (hg * XA_HEADS + hh) * DK;
+          const int col = (it.hg * XA_HEADS + hh) * DK;
           tma_load_2d(sb + hh * BOX_BYTES, &map_kv, full, k_col0 + col, s0);
           tma_load_2d(sb + (XA_HEADS + hh) * BOX_BYTES, &map_kv, full, v_col0 + col, s0);
         }
       }
       __syncwarp();
-      if (++t == n_tiles) { item += gridDim.x; more = open_item(); }
+      if (++t == it.n_tiles) { more = next_item(it.k + 1, it, true); t = 0; }
       if (more) fetch_valid();
       if (++stage == XA_STAGES) { stage = 0; phase ^= 1u; }
     }
@@ -549,18 +580,14 @@ cross_attention_persist_kernel(const __grid_constant__ CUtensorMap map_kv, const
   }
 
   // ===================== consumers: warp = (head, beam half) =====================
+  // The next item's query fragments are requested right after the tile loop -- qf is dead by then -- so that their round
+  // trip runs under the normalise-and-store epilogue of the current item.
   const int hl = warp / BH, b_off = (warp % BH) * (MT * 16);
   const int g = lane >> 2, q = lane & 3;
   int stage = 0; uint32_t phase = 0;
-  for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-    const int ui = item / n_hg, hg = item - ui * n_hg;
-    const int u = uorder ? uorder[ui] : ui;
-    const int K = live_start ? live_count[u] : K_all;
-    if (K == 0) continue;
-    const int qrow0 = live_start ? live_start[u] : u * K_all;
-    const int n_tiles = (ustart[u + 1] - ustart[u] + TS - 1) / TS;
-    const int h = hg * XA_HEADS + hl;
-    uint32_t qf[MT][4][4];
+  uint32_t qf[MT][4][4];
+  auto load_q = [&](const Item& it) {
+    const int h = it.hg * XA_HEADS + hl;
 #pragma unroll
     for (int mt = 0; mt < MT; ++mt) {
 #pragma unroll
@@ -570,11 +597,16 @@ cross_attention_persist_kernel(const __grid_constant__ CUtensorMap map_kv, const
           const int b = b_off + mt * 16 + g + ((e & 1) << 3);
           const int d = ks * 16 + 2 * q + ((e >> 1) << 3);
           uint32_t v = 0u;
-          if (b < K) v = *reinterpret_cast<const uint32_t*>(qg + (size_t)(qrow0 + b) * HD + h * DK + d);
+          if (b < it.K) v = *reinterpret_cast<const uint32_t*>(qg + (size_t)(it.qrow0 + b) * HD + h * DK + d);
           qf[mt][ks][e] = v;
         }
       }
     }
+  };
+  Item cur, nxt;
+  bool have = next_item(0, cur, false);
+  if (have) load_q(cur);
+  while (have) {
     float o[MT][8][4];
     float m_run[MT][2], l_run[MT][2];
 #pragma unroll
@@ -586,7 +618,7 @@ cross_attention_persist_kernel(const __grid_constant__ CUtensorMap map_kv, const
 #pragma unroll
         for (int e = 0; e < 4; ++e) o[mt][nt][e] = 0.f;
     }
-    for (int t = 0; t < n_tiles; ++t) {
+    for (int t = 0; t < cur.n_tiles; ++t) {
       mbar_wait(bars + 8u * stage, phase);
       const unsigned long long kmask = masks[stage];
       const uint32_t sb = base + stage * XA_STAGE_BYTES;
@@ -595,8 +627,10 @@ cross_attention_persist_kernel(const __grid_constant__ CUtensorMap map_kv, const
       if (lane == 0) mbar_arrive(bars + 8u * (XA_STAGES + stage));
       if (++stage == XA_STAGES) { stage = 0; phase ^= 1u; }
     }
-    // ---- normalise and store (the row range is re-read here instead of staying live across the key loop) ----
-    const int out_row0 = live_start ? live_start[u] : u * K_all, out_rows = live_start ? live_count[u] : K_all;
+    const int out_row0 = cur.qrow0, out_rows = cur.K, h = cur.hg * XA_HEADS + hl;
+    const bool have_n = next_item(cur.k + 1, nxt, false);
+    if (have_n) load_q(nxt);
+    // ---- normalise and store ----
 #pragma unroll
     for (int mt = 0; mt < MT; ++mt) {
 #pragma unroll
@@ -614,6 +648,8 @@ cross_attention_persist_kernel(const __grid_constant__ CUtensorMap map_kv, const
         }
       }
     }
+    have = have_n;
+    cur = nxt;
   }
 }
 
@@ -779,10 +815,21 @@ cudaError_t cross_attention_mma(const void* q, const void* kv, size_t kv_rows, s
   const bool persist = num_sms > 0;          // num_sms <= 0: one CTA per (user, head group), the round-1 kernel (A/B timing)
   if (K <= 32 && (H % 4) == 0) {
     if (persist) {
+      const int items = users * (H / 4);
+      // GRAM_XATTN_WARPS=8: two consumer warps per head, 16 beam rows each (A/B; measured equal in the step)
+      static const bool eight = [] { const char* e = getenv("GRAM_XATTN_WARPS"); return e && e[0] == '8'; }();
+      if (eight) {
+        auto kern8 = fa::cross_attention_persist_kernel<4, 2, 1>;
+        static SmemAttr attr8;
+        cudaError_t e8 = attr8.ensure(kern8, smem);
+        if (e8 != cudaSuccess) return e8;
+        kern8<<<items < num_sms ? items : num_sms, fa::xa_threads(8), smem, s>>>(map, (const bf16*)q, (bf16*)out, ustart, uorder,
+                                                                             tok_valid, K, H, k_off, v_off, live_start, live_count, users);
+        return cudaGetLastError();
+      }
       auto kern = fa::cross_attention_persist_kernel<4, 1>;
       cudaError_t e = attr[2].ensure(kern, smem);
       if (e != cudaSuccess) return e;
-      const int items = users * (H / 4);
       kern<<<items < num_sms ? items : num_sms, fa::xa_threads(4), smem, s>>>(map, (const bf16*)q, (bf16*)out, ustart, uorder, tok_valid,
                                                                           K, H, k_off, v_off, live_start, live_count, users);
       return cudaGetLastError();
