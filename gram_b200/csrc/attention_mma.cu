@@ -266,6 +266,109 @@ __device__ __forceinline__ void flash_tile(const uint32_t (&qf)[MT][4][4], uint3
   }
 }
 
+// 8x8 transpose of a b16 matrix held in the ldmatrix / mma fragment distribution (lane = (row g, columns 2q, 2q+1))
+__device__ __forceinline__ uint32_t movm_t(uint32_t a) {
+  uint32_t d;
+  asm volatile("movmatrix.sync.aligned.m8n8.trans.b16 %0, %1;" : "=r"(d) : "r"(a));
+  return d;
+}
+
+// Transposed flash tile for the cross-attention (no bias): the 64 keys of the tile are the M dimension and the beams the N
+// dimension, S^T = K Q^T and O^T += V^T P^T, so that 20 beams cost NT = 3 eight-beam n-tiles instead of two 16-row m-tiles:
+// 96 mma.sync and 48 exponentials per lane per tile instead of 128 and 64.  The kernel sits on the power cap even alone
+// (scripts/exp_xattn_hot.py, exp_hot_memory.py): instructions it does not issue are bandwidth it gets back.
+//   qb      B fragments of Q^T: [beam n-tile][16-wide step over d][2]
+//   ot      O^T accumulators [d m-tile][beam n-tile][4]: rows d = 16 j + g (+ 8), columns beam = 8 nt + 2q (+ 1)
+//   m_run / l_run  per beam column held by this lane; l_run is this lane's partial over its keys (summed over g at the end)
+template <int NT>
+__device__ __forceinline__ void flash_tile_t(const uint32_t (&qb)[NT][4][2], uint32_t kbase, uint32_t vbase,
+                                             unsigned long long kmask, float (&ot)[4][NT][4], float (&m_run)[NT][2],
+                                             float (&l_run)[NT][2], int lane) {
+  const int g = lane >> 2;
+  float st[4][NT][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) st[i][nt][e] = 0.f;
+  // ---- S^T = K Q^T: A = 16 keys x 16 d straight out of the swizzled K tile ----
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+      uint32_t a[4];
+      ldsm_x4(swz(kbase, i * 16 + (lane & 7) + (((lane >> 3) & 1) << 3), ks * 2 + (lane >> 4)), a[0], a[1], a[2], a[3]);
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt) mma_bf16(st[i][nt], a, qb[nt][ks][0], qb[nt][ks][1]);
+    }
+  }
+  // ---- mask + online softmax over the keys (rows): this lane holds keys 16 i + g (+ 8) of columns 2q, 2q + 1 ----
+  bool vis[4][2];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    vis[i][0] = (kmask >> (i * 16 + g)) & 1ull;
+    vis[i][1] = (kmask >> (i * 16 + g + 8)) & 1ull;
+  }
+#pragma unroll
+  for (int nt = 0; nt < NT; ++nt) {
+#pragma unroll
+    for (int e2 = 0; e2 < 2; ++e2) {
+      float t = -INFINITY;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf) {
+          const float v = vis[i][hf] ? st[i][nt][hf * 2 + e2] : -INFINITY;
+          st[i][nt][hf * 2 + e2] = v;
+          t = fmaxf(t, v);
+        }
+      }
+      t = fmaxf(t, __shfl_xor_sync(0xffffffffu, t, 4));
+      t = fmaxf(t, __shfl_xor_sync(0xffffffffu, t, 8));
+      t = fmaxf(t, __shfl_xor_sync(0xffffffffu, t, 16));
+      const float m_old = m_run[nt][e2];
+      const float m_new = fmaxf(m_old, t);
+      const float corr = (m_old == -INFINITY) ? 0.f : ex2_ftz((m_old - m_new) * LOG2E);
+      m_run[nt][e2] = m_new;
+      const float mb = (m_new == -INFINITY) ? 0.f : m_new * LOG2E;
+      float psum = 0.f;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf) {
+          const float pv = ex2_ftz(st[i][nt][hf * 2 + e2] * LOG2E - mb);     // exp2(-inf) = 0 for masked keys
+          st[i][nt][hf * 2 + e2] = pv;
+          psum += pv;
+        }
+      }
+      l_run[nt][e2] = l_run[nt][e2] * corr + psum;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        ot[j][nt][e2] *= corr;
+        ot[j][nt][2 + e2] *= corr;
+      }
+    }
+  }
+  // ---- O^T += V^T P^T: B = P^T (the accumulator blocks transposed in registers), A = V^T via ldmatrix.trans ----
+#pragma unroll
+  for (int kk = 0; kk < 4; ++kk) {                 // 16-key steps
+    uint32_t pb[NT][2];
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) {
+      pb[nt][0] = movm_t(pack_bf16(st[kk][nt][0], st[kk][nt][1]));     // keys 16 kk + 0..7
+      pb[nt][1] = movm_t(pack_bf16(st[kk][nt][2], st[kk][nt][3]));     // keys 16 kk + 8..15
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {                  // 16-wide d m-tiles
+      uint32_t a[4];
+      ldsm_x4_t(swz(vbase, kk * 16 + (lane & 7) + (((lane >> 4) & 1) << 3), j * 2 + ((lane >> 3) & 1)), a[0], a[1], a[2], a[3]);
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt) mma_bf16(ot[j][nt], a, pb[nt][0], pb[nt][1]);
+    }
+  }
+}
+
 struct NoBias {
   static constexpr bool kZero = true;
   __device__ __forceinline__ float operator()(int, int) const { return 0.f; }
@@ -467,7 +570,7 @@ cross_attention_mma_kernel(const __grid_constant__ CUtensorMap map_kv, const bf1
 // first tiles' load latency with an empty ring, an idle memory system during the epilogue (~2-3 us of a ~25 us item) --
 // are paid once per launch instead of once per item.
 // ------------------------------------------------------------------------------------------------
-template <int HEADS, int BH, int MT = 2>
+template <int HEADS, int BH, int MT = 2, int NT = 0>      // NT > 0: transposed tiles (flash_tile_t), NT eight-beam n-tiles
 __global__ void __launch_bounds__(xa_threads(HEADS * BH), 1)
 cross_attention_persist_kernel(const __grid_constant__ CUtensorMap map_kv, const bf16* __restrict__ qg,
                                bf16* __restrict__ out, const int* __restrict__ ustart, const int* __restrict__ uorder,
@@ -585,6 +688,77 @@ cross_attention_persist_kernel(const __grid_constant__ CUtensorMap map_kv, const
   const int hl = warp / BH, b_off = (warp % BH) * (MT * 16);
   const int g = lane >> 2, q = lane & 3;
   int stage = 0; uint32_t phase = 0;
+  if constexpr (NT > 0) {
+    // ---- transposed tiles (beams on the N dimension): one warp per head holds all of the user's beams ----
+    static_assert(NT == 0 || BH == 1, "transposed tiles: one warp per head");
+    uint32_t qb[NT][4][2];
+    auto load_qb = [&](const Item& it) {
+      const int h = it.hg * XA_HEADS + hl;
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt) {
+        const int b = nt * 8 + g;
+        const bf16* qrow = qg + (size_t)(it.qrow0 + (b < it.K ? b : 0)) * HD + h * DK + 2 * q;
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+          qb[nt][ks][0] = b < it.K ? *reinterpret_cast<const uint32_t*>(qrow + ks * 16) : 0u;
+          qb[nt][ks][1] = b < it.K ? *reinterpret_cast<const uint32_t*>(qrow + ks * 16 + 8) : 0u;
+        }
+      }
+    };
+    Item cur;
+    bool have = next_item(0, cur, false);
+    if (have) load_qb(cur);
+    while (have) {
+      float ot[4][NT][4];
+      float m_run[NT][2], l_run[NT][2];
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt) {
+        m_run[nt][0] = m_run[nt][1] = -INFINITY;
+        l_run[nt][0] = l_run[nt][1] = 0.f;
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+          for (int e = 0; e < 4; ++e) ot[j][nt][e] = 0.f;
+      }
+      for (int t = 0; t < cur.n_tiles; ++t) {
+        mbar_wait(bars + 8u * stage, phase);
+        const unsigned long long kmask = masks[stage];
+        const uint32_t sb = base + stage * XA_STAGE_BYTES;
+        flash_tile_t<NT>(qb, sb + hl * BOX_BYTES, sb + (XA_HEADS + hl) * BOX_BYTES, kmask, ot, m_run, l_run, lane);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bars + 8u * (XA_STAGES + stage));
+        if (++stage == XA_STAGES) { stage = 0; phase ^= 1u; }
+      }
+      const int out_row0 = cur.qrow0, out_rows = cur.K, h = cur.hg * XA_HEADS + hl;
+      have = next_item(cur.k + 1, cur, false);
+      if (have) load_qb(cur);                        // the next item's fragments: in flight under this epilogue
+      // ---- row sums over the key lanes, normalise, transpose back to beam-major pairs of d, store ----
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt) {
+        float inv[2];
+#pragma unroll
+        for (int e2 = 0; e2 < 2; ++e2) {
+          float l = l_run[nt][e2];
+          l += __shfl_xor_sync(0xffffffffu, l, 4);
+          l += __shfl_xor_sync(0xffffffffu, l, 8);
+          l += __shfl_xor_sync(0xffffffffu, l, 16);
+          inv[e2] = l > 0.f ? 1.0f / l : 0.f;
+        }
+        const int b = nt * 8 + g;                    // after the transpose this lane holds beam 8 nt + g, d pairs 2q, 2q + 1
+        bf16* orow = out + (size_t)(out_row0 + b) * HD + h * DK + 2 * q;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const uint32_t lo = movm_t(pack_bf16(ot[j][nt][0] * inv[0], ot[j][nt][1] * inv[1]));   // d = 16 j + 0..7
+          const uint32_t hi = movm_t(pack_bf16(ot[j][nt][2] * inv[0], ot[j][nt][3] * inv[1]));   // d = 16 j + 8..15
+          if (b < out_rows) {
+            *reinterpret_cast<uint32_t*>(orow + j * 16) = lo;
+            *reinterpret_cast<uint32_t*>(orow + j * 16 + 8) = hi;
+          }
+        }
+      }
+    }
+    return;
+  }
   uint32_t qf[MT][4][4];
   auto load_q = [&](const Item& it) {
     const int h = it.hg * XA_HEADS + hl;
@@ -826,6 +1000,25 @@ cudaError_t cross_attention_mma(const void* q, const void* kv, size_t kv_rows, s
         kern8<<<items < num_sms ? items : num_sms, fa::xa_threads(8), smem, s>>>(map, (const bf16*)q, (bf16*)out, ustart, uorder,
                                                                              tok_valid, K, H, k_off, v_off, live_start, live_count, users);
         return cudaGetLastError();
+      }
+      // up to 24 beams: transposed tiles, beams on the N dimension in units of 8 (GRAM_XATTN_T=0: the beams-on-M kernel, A/B)
+      static const bool transposed = [] { const char* e = getenv("GRAM_XATTN_T"); return !(e && e[0] == '0'); }();
+      if (transposed && K <= 24) {
+        static SmemAttr attr_t[3];
+        const int grid = items < num_sms ? items : num_sms;
+#define GRAM_XA_T(NTV)                                                                                                  \
+        {                                                                                                               \
+          auto kt = fa::cross_attention_persist_kernel<4, 1, 2, NTV>;                                                   \
+          cudaError_t et = attr_t[NTV - 1].ensure(kt, smem);                                                            \
+          if (et != cudaSuccess) return et;                                                                             \
+          kt<<<grid, fa::xa_threads(4), smem, s>>>(map, (const bf16*)q, (bf16*)out, ustart, uorder, tok_valid, K, H,    \
+                                                   k_off, v_off, live_start, live_count, users);                        \
+          return cudaGetLastError();                                                                                    \
+        }
+        if (K <= 8) GRAM_XA_T(1)
+        if (K <= 16) GRAM_XA_T(2)
+        GRAM_XA_T(3)
+#undef GRAM_XA_T
       }
       auto kern = fa::cross_attention_persist_kernel<4, 1>;
       cudaError_t e = attr[2].ensure(kern, smem);

@@ -135,7 +135,7 @@ def test_gemm_tcgen05_cta_pairs(shape, epi):
 
 
 @pytest.mark.parametrize("dtype,impl", [("fp32", 0), ("bf16", 0), ("bf16", 1), ("bf16", 2)])   # 1 = persistent, 2 = CTA per item
-@pytest.mark.parametrize("dk,H,K", [(16, 4, 4), (64, 8, 20), (64, 12, 50), (64, 8, 1), (64, 4, 33)])
+@pytest.mark.parametrize("dk,H,K", [(16, 4, 4), (64, 8, 20), (64, 12, 50), (64, 8, 1), (64, 4, 33), (64, 8, 12), (64, 8, 24), (64, 8, 25)])
 def test_cross_attention_op(dtype, impl, dk, H, K):
     if impl >= 1 and dk != 64:
         pytest.skip("tensor-core kernel is specialised for d_kv = 64")
