@@ -37,7 +37,7 @@ sys.path.insert(0, ROOT)
 import numpy as np  # noqa: E402
 import torch  # noqa: E402
 
-PROFILE_TAG = "r2b"
+PROFILE_TAG = "r2c"
 
 
 def parse():
@@ -304,7 +304,7 @@ def ncu_metrics(name, tag=PROFILE_TAG):
     """Per-launch means of the committed `ncu --set full` capture profiles/<tag>_<name>_metrics.csv (same command at the
     default batch): DRAM traffic (dram__bytes_read.sum + dram__bytes_write.sum), duration; None when no capture is present."""
     import csv
-    for t in (tag, "r2", "r1"):
+    for t in (tag, "r2b", "r2", "r1"):
         path = os.path.join(ROOT, "profiles", f"{t}_{name}_metrics.csv")
         if os.path.exists(path):
             break
@@ -677,7 +677,7 @@ def main():
     kernels = {c: dict(ms_per_step=v["ms"] / S, launches_per_step=v["launches"] // S,
                        share=v["ms"] / total_all if total_all else 0.0) for c, v in prof_all.items()}
     xcap = ncu_metrics("xattn")
-    roofline_cross = dict(bound="hbm", kernel="cross_attention_persist_kernel (cross_attention_mma_kernel with --flags 8192)", achieved=xa_gbs, peak=peaks["hbm"], unit="GB/s",
+    roofline_cross = dict(bound="hbm", kernel="cross_attention_persist_kernel, transposed tiles (cross_attention_mma_kernel with --flags 8192)", achieved=xa_gbs, peak=peaks["hbm"], unit="GB/s",
                           frac=xa_gbs / peaks["hbm"], work="executed bytes (K and V of users that still have live beams)",
                           algorithmic_gbs=xa_alg_bytes / (xa_ms / 1000.0) / 1e9 if xa_ms > 0 else 0.0,
                           traffic=xcap["traffic"] if xcap else None,

@@ -1,0 +1,19 @@
+#!/bin/bash
+# round 2, call 27: final verification of the shipped tree (transposed cross-attention): smoke, full suite, driver-shaped bench,
+# other configs, launch list + ncu captures (tag r2c)
+cd "$GRAFT_REPO_ROOT" 2>/dev/null || cd "$(dirname "$0")/.."
+O=gpurun_out; mkdir -p $O; tag=c27
+( timeout 300 python -c "import __graft_entry__ as g; g.smoke()" ) > $O/${tag}_smoke.log 2>&1
+echo "smoke rc=$?" >> $O/${tag}_smoke.log
+( time timeout 1500 python -m pytest tests -m gpu -q ) > $O/${tag}_pytest.log 2>&1
+echo "pytest rc=$?" >> $O/${tag}_pytest.log
+timeout 600 python bench.py > $O/${tag}_bench.json 2> $O/${tag}_bench.err
+for cfg in toys sports yelp; do
+  timeout 600 python bench.py --config $cfg --steps 10 --warmup 3 --cpu-users 0 > $O/${tag}_cfg_$cfg.json 2> $O/${tag}_cfg_$cfg.err
+done
+timeout 900 python bench.py --config scale5 --steps 4 --warmup 3 --cpu-users 0 > $O/${tag}_cfg_scale5.json 2> $O/${tag}_cfg_scale5.err
+P="python bench.py --steps 1 --warmup 1 --no-item-cache --cpu-users 0 --no-e2e"
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 6000 --csv --log-file $O/launches_r2c.csv $P > $O/${tag}_launches.log 2>&1
+timeout 400 ncu --set full --clock-control none --import-source on -k regex:cross_attention -s 20 -c 2 -o $O/prof_xattn_r2c -f $P > $O/${tag}_ncu_xattn.log 2>&1
+timeout 400 ncu --set full --clock-control none --import-source on -k regex:gemm_tc_kernel -s 0 -c 5 -o $O/prof_gemm_enc_r2c -f $P > $O/${tag}_ncu_gemm.log 2>&1
+echo done > $O/${tag}_done
