@@ -277,14 +277,18 @@ enc_chain_kernel(const __grid_constant__ CUtensorMap map_ao, const __grid_consta
         const uint32_t stg = xs(xround + 1u);                 // the buffer that does NOT hold the prefetched x round
 #pragma unroll 1
         for (int rd = 0; rd < 2; ++rd) {
+          // TMEM reads software-pipelined as in gemm_tc.cu: chunk cc + 1 is in flight while chunk cc is converted and staged
+          uint32_t vv[2][32];
+          const uint32_t taddr0 = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN + rd * 128);
+          tmem_ld32(taddr0, vv[0]);
           if (issuer && rd > 0) tma_store_wait_read();
           epi_bar();
-#pragma unroll 1
+#pragma unroll
           for (int cc = 0; cc < 4; ++cc) {
             const int c = rd * 4 + cc;
-            uint32_t v[32];
-            tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN + c * 32), v);
             tmem_ld_wait();
+            if (cc + 1 < 4) tmem_ld32(taddr0 + (uint32_t)((cc + 1) * 32), vv[(cc + 1) & 1]);
+            uint32_t (&v)[32] = vv[cc & 1];
             const uint32_t box = stg + (uint32_t)(cc >> 1) * 16384u + (uint32_t)r * 128u;
 #pragma unroll
             for (int g = 0; g < 4; ++g) {
@@ -337,14 +341,17 @@ enc_chain_kernel(const __grid_constant__ CUtensorMap map_ao, const __grid_consta
             }
             if (more) request_x(ns, nr, xround + 1u);
           }
+          uint32_t vv[2][32];
+          const uint32_t taddr0 = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN + rd * 64);
+          tmem_ld32(taddr0, vv[0]);
           epi_bar();                                          // the bf16 box is free again
           mbar_wait_wd(xfull_bar(xround & 1u), (xround >> 1) & 1u, a.err);
-#pragma unroll 1
+#pragma unroll
           for (int cc = 0; cc < 2; ++cc) {
             const int c = rd * 2 + cc;
-            uint32_t v[32];
-            tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN + c * 32), v);
             tmem_ld_wait();
+            if (cc == 0) tmem_ld32(taddr0 + 32u, vv[1]);
+            uint32_t (&v)[32] = vv[cc];
             const uint32_t xrow = x_cur + (uint32_t)cc * 16384u + (uint32_t)r * 128u;
             const uint32_t brow = xbox + (uint32_t)r * 128u;
             const float* gw = emit ? lnw + t.sub * BN + c * 32 : nullptr;
