@@ -332,15 +332,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
               tma_load_2d(xb_nxt + 16384u, &map_c, xfull_bar((xround & 1u) ^ 1u), ncol + 32, nrow);
             }
           }
+          uint32_t vv[2][32];                              // TMEM reads software-pipelined over the round's two chunks
+          const uint32_t taddr0 = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BLOCK_N + rd * 64);
+          tmem_ld32(taddr0, vv[0]);
           epi_bar();                                       // the bf16 box is free again
           mbar_wait(xfull_bar(xround & 1u), (xround >> 1) & 1u);
-#pragma unroll 1
+#pragma unroll
           for (int cc = 0; cc < 2; ++cc) {
             const int c = rd * 2 + cc;
-            uint32_t v[32];
-            const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BLOCK_N + c * 32);
-            tmem_ld32(taddr, v);
             tmem_ld_wait();
+            if (cc == 0) tmem_ld32(taddr0 + 32u, vv[1]);
+            uint32_t (&v)[32] = vv[cc];
             const uint32_t xrow = xb_cur + (uint32_t)cc * 16384u + (uint32_t)r * 128u;
             const uint32_t brow = cstage + 2 * CSTAGE_BYTES + (uint32_t)r * 128u;
             const float* gw = na.ln_w + n_blk * BLOCK_N + c * 32;
