@@ -280,7 +280,8 @@ __device__ __forceinline__ uint32_t movm_t(uint32_t a) {
 //   qb      B fragments of Q^T: [beam n-tile][16-wide step over d][2]
 //   ot      O^T accumulators [d m-tile][beam n-tile][4]: rows d = 16 j + g (+ 8), columns beam = 8 nt + 2q (+ 1)
 //   m_run / l_run  per beam column held by this lane; l_run is this lane's partial over its keys (summed over g at the end)
-template <int NT>
+//   MASK    false: every key of the tile is visible (kmask == ~0, all tiles of a user but the last): no visibility selects
+template <int NT, bool MASK>
 __device__ __forceinline__ void flash_tile_t(const uint32_t (&qb)[NT][4][2], uint32_t kbase, uint32_t vbase,
                                              unsigned long long kmask, float (&ot)[4][NT][4], float (&m_run)[NT][2],
                                              float (&l_run)[NT][2], int lane) {
@@ -307,8 +308,8 @@ __device__ __forceinline__ void flash_tile_t(const uint32_t (&qb)[NT][4][2], uin
   bool vis[4][2];
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    vis[i][0] = (kmask >> (i * 16 + g)) & 1ull;
-    vis[i][1] = (kmask >> (i * 16 + g + 8)) & 1ull;
+    vis[i][0] = !MASK || ((kmask >> (i * 16 + g)) & 1ull);
+    vis[i][1] = !MASK || ((kmask >> (i * 16 + g + 8)) & 1ull);
   }
 #pragma unroll
   for (int nt = 0; nt < NT; ++nt) {
@@ -319,8 +320,8 @@ __device__ __forceinline__ void flash_tile_t(const uint32_t (&qb)[NT][4][2], uin
       for (int i = 0; i < 4; ++i) {
 #pragma unroll
         for (int hf = 0; hf < 2; ++hf) {
-          const float v = vis[i][hf] ? st[i][nt][hf * 2 + e2] : -INFINITY;
-          st[i][nt][hf * 2 + e2] = v;
+          const float v = (!MASK || vis[i][hf]) ? st[i][nt][hf * 2 + e2] : -INFINITY;
+          if (MASK) st[i][nt][hf * 2 + e2] = v;
           t = fmaxf(t, v);
         }
       }
@@ -575,7 +576,7 @@ __global__ void __launch_bounds__(xa_threads(HEADS * BH), 1)
 cross_attention_persist_kernel(const __grid_constant__ CUtensorMap map_kv, const bf16* __restrict__ qg,
                                bf16* __restrict__ out, const int* __restrict__ ustart, const int* __restrict__ uorder,
                                const uint8_t* __restrict__ tok_valid, int K_all, int H, int k_col0, int v_col0,
-                               const int* __restrict__ live_start, const int* __restrict__ live_count, int users) {
+                               const int* __restrict__ live_start, const int* __restrict__ live_count, int users, int fast_path) {
   constexpr int XA_HEADS = HEADS;
   constexpr uint32_t XA_STAGE_BYTES = 2 * HEADS * BOX_BYTES;   // K boxes then V boxes
   constexpr int XA_STAGES = 3 * XA_STAGE_TARGET / (int)XA_STAGE_BYTES;
@@ -724,7 +725,10 @@ cross_attention_persist_kernel(const __grid_constant__ CUtensorMap map_kv, const
         mbar_wait(bars + 8u * stage, phase);
         const unsigned long long kmask = masks[stage];
         const uint32_t sb = base + stage * XA_STAGE_BYTES;
-        flash_tile_t<NT>(qb, sb + hl * BOX_BYTES, sb + (XA_HEADS + hl) * BOX_BYTES, kmask, ot, m_run, l_run, lane);
+        if (kmask == ~0ull && fast_path)                 // warp-uniform: two straight-line copies of the tile
+          flash_tile_t<NT, false>(qb, sb + hl * BOX_BYTES, sb + (XA_HEADS + hl) * BOX_BYTES, kmask, ot, m_run, l_run, lane);
+        else
+          flash_tile_t<NT, true>(qb, sb + hl * BOX_BYTES, sb + (XA_HEADS + hl) * BOX_BYTES, kmask, ot, m_run, l_run, lane);
         __syncwarp();
         if (lane == 0) mbar_arrive(bars + 8u * (XA_STAGES + stage));
         if (++stage == XA_STAGES) { stage = 0; phase ^= 1u; }
@@ -986,6 +990,7 @@ cudaError_t cross_attention_mma(const void* q, const void* kv, size_t kv_rows, s
   if (!fa::get_kv_map(kv, kv_rows, kv_stride, &map)) return cudaErrorUnknown;
   constexpr size_t smem = (size_t)3 * fa::XA_STAGE_TARGET + 1024 + 256;
   static SmemAttr attr[4];
+  static const int xa_fast = [] { const char* e = getenv("GRAM_XATTN_NOMASK"); return (e && e[0] == '0') ? 0 : 1; }();   // A/B
   const bool persist = num_sms > 0;          // num_sms <= 0: one CTA per (user, head group), the round-1 kernel (A/B timing)
   if (K <= 32 && (H % 4) == 0) {
     if (persist) {
@@ -998,7 +1003,7 @@ cudaError_t cross_attention_mma(const void* q, const void* kv, size_t kv_rows, s
         cudaError_t e8 = attr8.ensure(kern8, smem);
         if (e8 != cudaSuccess) return e8;
         kern8<<<items < num_sms ? items : num_sms, fa::xa_threads(8), smem, s>>>(map, (const bf16*)q, (bf16*)out, ustart, uorder,
-                                                                             tok_valid, K, H, k_off, v_off, live_start, live_count, users);
+                                                                             tok_valid, K, H, k_off, v_off, live_start, live_count, users, xa_fast);
         return cudaGetLastError();
       }
       // up to 24 beams: transposed tiles, beams on the N dimension in units of 8 (GRAM_XATTN_T=0: the beams-on-M kernel, A/B)
@@ -1012,7 +1017,7 @@ cudaError_t cross_attention_mma(const void* q, const void* kv, size_t kv_rows, s
           cudaError_t et = attr_t[NTV - 1].ensure(kt, smem);                                                            \
           if (et != cudaSuccess) return et;                                                                             \
           kt<<<grid, fa::xa_threads(4), smem, s>>>(map, (const bf16*)q, (bf16*)out, ustart, uorder, tok_valid, K, H,    \
-                                                   k_off, v_off, live_start, live_count, users);                        \
+                                                   k_off, v_off, live_start, live_count, users, xa_fast);                        \
           return cudaGetLastError();                                                                                    \
         }
         if (K <= 8) GRAM_XA_T(1)
@@ -1024,7 +1029,7 @@ cudaError_t cross_attention_mma(const void* q, const void* kv, size_t kv_rows, s
       cudaError_t e = attr[2].ensure(kern, smem);
       if (e != cudaSuccess) return e;
       kern<<<items < num_sms ? items : num_sms, fa::xa_threads(4), smem, s>>>(map, (const bf16*)q, (bf16*)out, ustart, uorder, tok_valid,
-                                                                          K, H, k_off, v_off, live_start, live_count, users);
+                                                                          K, H, k_off, v_off, live_start, live_count, users, xa_fast);
       return cudaGetLastError();
     }
     auto kern = fa::cross_attention_mma_kernel<4, 1, 1, 1>;
@@ -1041,7 +1046,7 @@ cudaError_t cross_attention_mma(const void* q, const void* kv, size_t kv_rows, s
       if (e != cudaSuccess) return e;
       const int items = users * (H / 2);
       kern<<<items < num_sms ? items : num_sms, fa::xa_threads(4), smem, s>>>(map, (const bf16*)q, (bf16*)out, ustart, uorder, tok_valid,
-                                                                          K, H, k_off, v_off, live_start, live_count, users);
+                                                                          K, H, k_off, v_off, live_start, live_count, users, xa_fast);
       return cudaGetLastError();
     }
     auto kern = fa::cross_attention_mma_kernel<2, 2, 1, 1>;
