@@ -278,7 +278,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         float mx = -INFINITY, sum = 0.f;
         const int row = row0 + r;
         // (pipelining these TMEM reads as in the store epilogues was measured and is slower here: the vocabulary head went
-        //  from 8.3-8.8 to 10.5-11.0 ms per step -- this loop is paced by its 256 ex2 per row, not by the load latency)
+        //  from 8.3-8.8 to 10.5-11.0 ms per step.  What paces this loop is its ALU issue slots: with one FFMA + MUFU + FADD
+        //  per logit and the column select confined to the last tile the head went from 8.8 to 6.8 ms per step)
         // EG = 2: group g reduces the tile's column half g to its own (max, sum) partial
 #pragma unroll 1
         for (int c = grp * (BLOCK_N / 32 / EG); c < (grp + 1) * (BLOCK_N / 32 / EG); ++c) {
@@ -288,17 +289,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           tmem_ld_wait();
           const int col0 = n_blk * BLOCK_N + c * 32;
           float cm = -INFINITY;
+          if (col0 + 32 > N) {                           // only the last column tile has columns past N (warp-uniform)
 #pragma unroll
-          for (int e = 0; e < 32; ++e) {
-            const float x = (col0 + e < N) ? __uint_as_float(v[e]) : -INFINITY;
-            v[e] = __float_as_uint(x);
-            cm = fmaxf(cm, x);
+            for (int e = 0; e < 32; ++e)
+              if (col0 + e >= N) v[e] = __float_as_uint(-INFINITY);
           }
+#pragma unroll
+          for (int e = 0; e < 32; ++e) cm = fmaxf(cm, __uint_as_float(v[e]));
           const float nm = fmaxf(mx, cm);
           if (nm > -INFINITY) {
+            // one FFMA + one MUFU + one FADD per logit: 2^(x log2e - m log2e)
+            const float nml = nm * 1.4426950408889634f;
             float cs = 0.f;
 #pragma unroll
-            for (int e = 0; e < 32; ++e) cs += ex2_ftz((__uint_as_float(v[e]) - nm) * 1.4426950408889634f);
+            for (int e = 0; e < 32; ++e) cs += ex2_ftz(fmaf(__uint_as_float(v[e]), 1.4426950408889634f, -nml));
             sum = sum * ex2_ftz((mx - nm) * 1.4426950408889634f) + cs;
             mx = nm;
           }
