@@ -1,7 +1,7 @@
 #!/bin/bash
-# round 2, call 31: verification of the shipped tree: smoke, full suite, driver-shaped bench, launch list + cross-attention capture (tag r2d)
+# round 2, call 33: verification of the shipped tree: smoke, full suite, driver-shaped bench, launch list + cross-attention capture (tag r2d)
 cd "$GRAFT_REPO_ROOT" 2>/dev/null || cd "$(dirname "$0")/.."
-O=gpurun_out; mkdir -p $O; tag=c31
+O=gpurun_out; mkdir -p $O; tag=c33
 ( timeout 300 python -c "import __graft_entry__ as g; g.smoke()" ) > $O/${tag}_smoke.log 2>&1
 echo "smoke rc=$?" >> $O/${tag}_smoke.log
 ( time timeout 1500 python -m pytest tests -m gpu -q ) > $O/${tag}_pytest.log 2>&1
