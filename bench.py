@@ -37,7 +37,7 @@ sys.path.insert(0, ROOT)
 import numpy as np  # noqa: E402
 import torch  # noqa: E402
 
-PROFILE_TAG = "r2c"
+PROFILE_TAG = "r2d"
 
 
 def parse():
@@ -304,7 +304,7 @@ def ncu_metrics(name, tag=PROFILE_TAG):
     """Per-launch means of the committed `ncu --set full` capture profiles/<tag>_<name>_metrics.csv (same command at the
     default batch): DRAM traffic (dram__bytes_read.sum + dram__bytes_write.sum), duration; None when no capture is present."""
     import csv
-    for t in (tag, "r2b", "r2", "r1"):
+    for t in (tag, "r2c", "r2b", "r2", "r1"):
         path = os.path.join(ROOT, "profiles", f"{t}_{name}_metrics.csv")
         if os.path.exists(path):
             break
